@@ -1,0 +1,185 @@
+/*
+ * sagan_b200.h -- C ABI of libsagan_b200.so: the SAGAN generator/discriminator hot path
+ * (self-attention block + spectrally-normalised conv / deconv / dense layers + the
+ * elementwise glue of one training step) as hand-written sm_100a CUDA.
+ *
+ * The reference (jimmYA-1995/Self-Attention-GAN) has no FFI / plugin registry: its
+ * boundary for this path is the Keras Layer protocol (`SpectralNormalization(layer)(x)`,
+ * `AttentionLayer()(x)`) and every FLOP runs inside TensorFlow library kernels.  Each
+ * entry point below cites the reference code whose arithmetic it replaces; the
+ * reference-side binding (ctypes from `layers.py`, or a TF REGISTER_OP shim) is shown
+ * in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / TF types.
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - activations are NHWC fp32, kernels use the Keras layouts
+ *       Conv2D [kh,kw,cin,cout], Conv2DTranspose [kh,kw,cout,cin], Dense [in,out].
+ *   - every call is asynchronous on the caller's stream (`stream` = cudaStream_t), never
+ *     allocates or synchronises, and is re-entrant across streams and devices.  The caller
+ *     owns all buffers, including workspaces sized by the `*_workspace_bytes` queries.
+ *   - return value: 0 = ok, < 0 = bad argument (SAGAN_E*), > 0 = cudaError_t.
+ *     `sagan_last_error()` returns a thread-local description of the last failure.
+ */
+#ifndef SAGAN_B200_H_
+#define SAGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAGAN_B200_ABI_VERSION 1
+
+#define SAGAN_EINVAL (-1)        /* bad argument (null pointer, non-positive size, Ip < 1 ...) */
+#define SAGAN_EUNSUPPORTED (-2)  /* shape / mode combination not built */
+#define SAGAN_EWORKSPACE (-3)    /* workspace too small */
+
+/* math_mode of the attention / conv kernels (the two tolerance tiers of BASELINE.json) */
+#define SAGAN_MATH_FP32_STRICT 0 /* fp32 operands, fp32 accumulate, CUDA cores           */
+#define SAGAN_MATH_BF16_TC 1     /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
+
+/* activation fused in conv / deconv epilogues */
+#define SAGAN_ACT_NONE 0
+#define SAGAN_ACT_LRELU 1 /* LeakyReLU(alpha = slope); generator.py:11, discriminator.py:10 */
+#define SAGAN_ACT_TANH 2  /* generator.py:36 */
+
+typedef void* sagan_stream_t; /* cudaStream_t */
+
+int sagan_abi_version(void);
+const char* sagan_last_error(void);
+/* number of kernels this library has launched in this process (all threads); bench.py's gpu_launches */
+unsigned long long sagan_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Spectral normalisation.  Replaces SpectralNormalization.update_uv, layers.py:50-68
+ * (l2normalize layers.py:4-5).  W is the wrapped layer's kernel viewed as the RAW row-major
+ * matrix [rows = last kernel axis, cols = numel / rows] (layers.py:56).  One call performs,
+ * `Ip` times, v <- l2n(u W), u <- l2n(v W^T); then sigma = sum((u W) * v) [/ factor] and
+ * W_bar = W / sigma.  u [rows] is read and updated in place, v [cols] is written.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sagan_sn_desc {
+  const float* W;     /* [rows, cols] */
+  float* u;           /* [rows] in/out */
+  float* v;           /* [cols] out */
+  float* W_bar;       /* [rows, cols] out (may alias nothing else) */
+  void* W_bar_bf16;   /* optional [rows, cols] bf16 copy of W_bar, or NULL */
+  float* sigma;       /* [1] out */
+  int32_t rows, cols;
+  int32_t Ip;         /* >= 1 (layers.py:17-18) */
+  float factor;       /* 0 = none (layers.py:65-66) */
+} sagan_sn_desc;
+
+typedef struct sagan_sn_plan sagan_sn_plan; /* opaque: device descriptor table + workspace */
+
+/* Builds a multi-tensor plan: ONE cooperative launch normalises all n matrices
+ * (the 13 / 8 spectrally-normalised kernels of G / D).  Allocates device memory (table +
+ * workspace) -- call outside the step loop.  `descs_host` is copied. */
+int sagan_sn_plan_create(const sagan_sn_desc* descs_host, int n, int device, sagan_sn_plan** plan_out);
+int sagan_sn_plan_run(sagan_sn_plan* plan, sagan_stream_t stream);
+/* Same plan, but only the matrices listed (indices into the plan) take part */
+int sagan_sn_plan_destroy(sagan_sn_plan* plan);
+/* algorithmic HBM bytes of one run of the plan (8 B/element, 10 with the bf16 copy,
+ * 16/18 when the matrix exceeds 64 MB) */
+unsigned long long sagan_sn_plan_algorithmic_bytes(const sagan_sn_plan* plan);
+
+/* d L / d W given d L / d W_bar, with u, v constants:
+ *   dW = (dW_bar - (sum dW_bar * W_bar) * reshape(u^T v) / factor) / sigma
+ * `ws` holds >= sagan_sn_backward_workspace_bytes(rows*cols) bytes. */
+size_t sagan_sn_backward_workspace_bytes(long long numel);
+int sagan_sn_backward(const float* dW_bar, const float* W_bar, const float* u, const float* v,
+                      const float* sigma, float factor, float* dW, int rows, int cols,
+                      void* ws, size_t ws_bytes, sagan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-attention block.  Replaces Attention_Layer.call, layers.py:93-120 (paper form):
+ *   theta = X Wq + bq, phi = X Wk + bk, g = X Wv + bv, P = softmax(theta phi^T), A = P g,
+ *   Y = X + gamma * (A Wo + bo).
+ * X, Y: [B, N, C] (NHWC, N = H*W).  d = C/8, dv = C/2 (layers.py:82-85).  Wq, Wk: [C, d];
+ * Wv: [C, dv]; Wo: [dv, C]  (Keras [1,1,cin,cout] kernels, already spectrally normalised).
+ * gamma: device scalar (`sigma`, layers.py:76-79).  Saved for backward: lse [B, N]
+ * (row-wise log-sum-exp of the logits) and A [B, N, dv].  The [B,N,N] map is never written.
+ * ------------------------------------------------------------------------------------------ */
+size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode);
+int sagan_attn_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                   const float* Wv, const float* bv, const float* Wo, const float* bo,
+                   const float* gamma, float* Y, float* lse, float* A_saved, int B, int N, int C,
+                   int math_mode, void* ws, size_t ws_bytes, sagan_stream_t stream);
+/* Gradients of the block.  Parameter gradients are OVERWRITTEN (not accumulated).
+ * Any of the d* parameter outputs may be NULL together with dX to skip it. */
+int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                   const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                   const float* gamma, const float* lse, const float* A_saved, float* dX, float* dWq,
+                   float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo,
+                   float* dgamma, int B, int N, int C, int math_mode, void* ws, size_t ws_bytes,
+                   sagan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Conv2D (generator.py:36, discriminator.py:8,35; the 1x1 convs of layers.py:82-85; Dense as
+ * the H=W=k=1 case, generator.py:25).  Geometry is explicit so TF 'same' padding asymmetry
+ * (k=4,s=1: 1 before / 2 after) is the caller's to state: pad_t / pad_l = padding before.
+ *   fwd   : y[b,ho,wo,co] = act(sum x[b,ho*s-pad_t+kh, wo*s-pad_l+kw, ci] w[kh,kw,ci,co] + bias[co])
+ *   dgrad : dx = conv^T(dy, w)      (also the forward of Conv2DTranspose, generator.py:8-9)
+ *   wgrad : dw[kh,kw,ci,co] = sum_m x[...] dy[m,co]; dbias[co] = sum_m dy[m,co] (dbias may be NULL)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sagan_conv_geom {
+  int32_t B, H, W, Cin;    /* input  [B,H,W,Cin]  */
+  int32_t Ho, Wo, Cout;    /* output [B,Ho,Wo,Cout] */
+  int32_t kh, kw, stride, pad_t, pad_l;
+} sagan_conv_geom;
+
+int sagan_conv2d_fwd(const float* x, const float* w, const float* bias, float* y,
+                     const sagan_conv_geom* g, int act, float slope, int math_mode, sagan_stream_t stream);
+int sagan_conv2d_dgrad(const float* dy, const float* w, float* dx, const sagan_conv_geom* g,
+                       int math_mode, sagan_stream_t stream);
+/* dw must hold kh*kw*Cin*Cout floats; it is overwritten. */
+int sagan_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias,
+                       const sagan_conv_geom* g, int math_mode, sagan_stream_t stream);
+
+/* dz = dy * act'(y) from the activation OUTPUT y (LeakyReLU: y>0 ? 1 : slope; tanh: 1 - y^2). */
+int sagan_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, float slope,
+                  sagan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNormalization(training) + LeakyReLU, generator.py:10-11.  x, y: [rows, C] (NHWC flattened).
+ * Batch statistics are per replica (plain BatchNormalization, not SyncBN).  save_mean/save_invstd [C]
+ * are kept for the backward; moving_mean / moving_var (may be NULL) get the Keras update
+ * m <- momentum*m + (1-momentum)*batch (biased variance).  ws: sagan_bn_workspace_bytes(C).
+ * ------------------------------------------------------------------------------------------ */
+size_t sagan_bn_workspace_bytes(int C);
+int sagan_bn_lrelu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean,
+                       float* save_invstd, float* moving_mean, float* moving_var, long long rows, int C,
+                       float eps, float momentum, float slope, void* ws, size_t ws_bytes,
+                       sagan_stream_t stream);
+int sagan_bn_lrelu_bwd(const float* dy, const float* x, const float* y, const float* gamma,
+                       const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
+                       float* dbeta, long long rows, int C, float slope, void* ws, size_t ws_bytes,
+                       sagan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hinge losses, sagan/main.py:21-27, with the scaling of main.py:184,201 folded in:
+ *   D: L = relu(1 - d_real) + relu(1 + d_fake);   G: L = -d_fake
+ * loss_sum[0] += sum(L) (caller zeroes it); gradients are d(scale * sum L)/d logits with
+ * scale = 1 / (n * global_batch).  g_real / g_fake may alias nothing.
+ * ------------------------------------------------------------------------------------------ */
+int sagan_hinge_d(const float* d_real, const float* d_fake, long long n, float scale, float* loss_sum,
+                  float* g_real, float* g_fake, sagan_stream_t stream);
+int sagan_hinge_g(const float* d_fake, long long n, float scale, float* loss_sum, float* g_fake,
+                  sagan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Keras Adam over one flat fp32 bucket (sagan/main.py:119-120: beta_1 = 0, epsilon = 1e-7):
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr_t * m / (sqrt(v) + eps)
+ * hyper [4] device floats = {lr_t, b1, b2, eps} (device-resident so a captured CUDA graph sees the
+ * per-step learning rate).  m may be NULL when b1 == 0 (then m == g).  grad_scale multiplies g
+ * first (1 for the SUM all-reduce convention of main.py:184).
+ * ------------------------------------------------------------------------------------------ */
+int sagan_adam_step(float* param, const float* grad, float* m, float* v, long long n,
+                    const float* hyper, float grad_scale, sagan_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGAN_B200_H_ */

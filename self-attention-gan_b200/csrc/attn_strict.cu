@@ -1,0 +1,501 @@
+// Self-attention block, FP32_STRICT math mode (CUDA cores, fp32 everywhere): the parity anchor of
+// the tensor-core path and the kernel used for the in-model channel counts C = 8..64
+// (d = C/8 in {1,2,4,8}, dv = C/2 in {4,8,16,32}), where one thread can own a whole query/key row.
+//
+// Replaces Attention_Layer.call (/root/reference/layers.py:93-120).  The [B,N,N] map is never
+// materialised: forward is a streaming (online-softmax) pass, backward recomputes P from the saved
+// row log-sum-exp.
+//
+//   fwd:  proj (theta, phi, g)  ->  flash (softmax(theta phi^T) g, out-proj, gamma residual fused)
+//   bwd:  pre  (dA = gamma dY Wo^T, D = rowsum(dA * A))
+//         main (per key tile: dK, dV in registers; dQ reduced per warp, atomics per tile)
+//         post (dX = dY + dQ Wq^T + dK Wk^T + dV Wv^T)
+//         weight grads as 1x1-conv wgrads (X^T dQ ...), dgamma / dWo / dbo from A^T dY.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sagan {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int AT_THREADS = 128;
+
+// ---------------------------------------------------------------------------- projections
+// one thread per token: q = x Wq + bq, k = x Wk + bk, v = x Wv + bv
+template <int C>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_proj_kernel(const float* __restrict__ X, const float* __restrict__ Wq, const float* __restrict__ bq,
+                 const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
+                 const float* __restrict__ bv, float* __restrict__ Q, float* __restrict__ K, float* __restrict__ V,
+                 long long T) {
+  constexpr int D = C / 8, DV = C / 2;
+  __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
+  for (int i = threadIdx.x; i < C * D; i += AT_THREADS) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
+  for (int i = threadIdx.x; i < C * DV; i += AT_THREADS) sWv[i] = Wv[i];
+  for (int i = threadIdx.x; i < D; i += AT_THREADS) { sbq[i] = bq[i]; sbk[i] = bk[i]; }
+  for (int i = threadIdx.x; i < DV; i += AT_THREADS) sbv[i] = bv[i];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * AT_THREADS + threadIdx.x;
+  if (t >= T) return;
+  float x[C];
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    const float4 v = ld4(X + t * C + c);
+    x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    float a = sbq[j], b = sbk[j];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      a = fmaf(x[c], sWq[c * D + j], a);
+      b = fmaf(x[c], sWk[c * D + j], b);
+    }
+    Q[t * D + j] = a;
+    K[t * D + j] = b;
+  }
+#pragma unroll
+  for (int j0 = 0; j0 < DV; j0 += 4) {
+    float a[4] = {sbv[j0], sbv[j0 + 1], sbv[j0 + 2], sbv[j0 + 3]};
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 w = *reinterpret_cast<const float4*>(&sWv[c * DV + j0]);
+      a[0] = fmaf(x[c], w.x, a[0]); a[1] = fmaf(x[c], w.y, a[1]);
+      a[2] = fmaf(x[c], w.z, a[2]); a[3] = fmaf(x[c], w.w, a[3]);
+    }
+    st4(V + t * DV + j0, make_float4(a[0], a[1], a[2], a[3]));
+  }
+}
+
+// ---------------------------------------------------------------------------- forward
+// grid (ceil(N/128), B); thread i owns query row i: q[D], o[DV], running max m (log2 units), sum l.
+template <int C>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_fwd_strict_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                       const float* __restrict__ X, const float* __restrict__ Wo, const float* __restrict__ bo,
+                       const float* __restrict__ gamma, float* __restrict__ Y, float* __restrict__ lse,
+                       float* __restrict__ A, int N) {
+  constexpr int D = C / 8, DV = C / 2, KT = 128;
+  __shared__ __align__(16) float Ks[KT * D];
+  __shared__ __align__(16) float Vs[KT * DV];
+  __shared__ __align__(16) float sWo[DV * C];
+  __shared__ float sbo[C];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int i = blockIdx.x * AT_THREADS + tid;
+  const bool valid = i < N;
+  const long long row = (long long)b * N + (valid ? i : 0);
+  for (int e = tid; e < DV * C; e += AT_THREADS) sWo[e] = Wo[e];
+  for (int e = tid; e < C; e += AT_THREADS) sbo[e] = bo[e];
+
+  float q[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) q[d] = Q[row * D + d] * LOG2E;
+  float o[DV];
+#pragma unroll
+  for (int v = 0; v < DV; ++v) o[v] = 0.f;
+  float m = -INFINITY, l = 0.f;
+
+  for (int kt = 0; kt < N; kt += KT) {
+    const int nk = min(KT, N - kt);
+    __syncthreads();
+    const float* Kg = K + ((long long)b * N + kt) * D;
+    const float* Vg = V + ((long long)b * N + kt) * DV;
+    for (int e = tid; e < KT * D; e += AT_THREADS) Ks[e] = e < nk * D ? Kg[e] : 0.f;
+    for (int e = tid * 4; e < KT * DV; e += AT_THREADS * 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < nk * DV) t = ld4(Vg + e);
+      *reinterpret_cast<float4*>(&Vs[e]) = t;
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < nk; j0 += 8) {
+      float s[8];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc = fmaf(q[d], Ks[(j0 + jj) * D + d], acc);
+        s[jj] = (j0 + jj < nk) ? acc : -INFINITY;
+        cmax = fmaxf(cmax, s[jj]);
+      }
+      if (cmax > m) {
+        const float corr = exp2f(m - cmax);
+        l *= corr;
+#pragma unroll
+        for (int v = 0; v < DV; ++v) o[v] *= corr;
+        m = cmax;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float p = exp2f(s[jj] - m);
+        l += p;
+#pragma unroll
+        for (int v = 0; v < DV; v += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(&Vs[(j0 + jj) * DV + v]);
+          o[v] = fmaf(p, vv.x, o[v]); o[v + 1] = fmaf(p, vv.y, o[v + 1]);
+          o[v + 2] = fmaf(p, vv.z, o[v + 2]); o[v + 3] = fmaf(p, vv.w, o[v + 3]);
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int v = 0; v < DV; ++v) o[v] *= inv;
+#pragma unroll
+  for (int v = 0; v < DV; v += 4) st4(A + row * DV + v, make_float4(o[v], o[v + 1], o[v + 2], o[v + 3]));
+  lse[row] = (m + log2f(l)) * LN2;
+  const float gm = *gamma;
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    float a[4] = {sbo[c], sbo[c + 1], sbo[c + 2], sbo[c + 3]};
+#pragma unroll
+    for (int v = 0; v < DV; ++v) {
+      const float4 w = *reinterpret_cast<const float4*>(&sWo[v * C + c]);
+      a[0] = fmaf(o[v], w.x, a[0]); a[1] = fmaf(o[v], w.y, a[1]);
+      a[2] = fmaf(o[v], w.z, a[2]); a[3] = fmaf(o[v], w.w, a[3]);
+    }
+    const float4 xx = ld4(X + row * C + c);
+    st4(Y + row * C + c, make_float4(fmaf(gm, a[0], xx.x), fmaf(gm, a[1], xx.y), fmaf(gm, a[2], xx.z),
+                                     fmaf(gm, a[3], xx.w)));
+  }
+}
+
+// ---------------------------------------------------------------------------- backward: pre
+// dA[t,:] = gamma * dY[t,:] Wo^T, Dd[t] = dA[t,:] . A[t,:]
+template <int C>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_pre_kernel(const float* __restrict__ dY, const float* __restrict__ A, const float* __restrict__ Wo,
+                    const float* __restrict__ gamma, float* __restrict__ dA, float* __restrict__ Dd, long long T) {
+  constexpr int DV = C / 2;
+  __shared__ __align__(16) float sWo[DV * C];
+  for (int e = threadIdx.x; e < DV * C; e += AT_THREADS) sWo[e] = Wo[e];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * AT_THREADS + threadIdx.x;
+  if (t >= T) return;
+  const float gm = *gamma;
+  float dy[C];
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    const float4 v = ld4(dY + t * C + c);
+    dy[c] = v.x; dy[c + 1] = v.y; dy[c + 2] = v.z; dy[c + 3] = v.w;
+  }
+  float dd = 0.f;
+#pragma unroll
+  for (int j0 = 0; j0 < DV; j0 += 4) {
+    float a[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; c += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&sWo[(j0 + jj) * C + c]);
+        acc = fmaf(dy[c], w.x, acc); acc = fmaf(dy[c + 1], w.y, acc);
+        acc = fmaf(dy[c + 2], w.z, acc); acc = fmaf(dy[c + 3], w.w, acc);
+      }
+      a[jj] = acc * gm;
+    }
+    const float4 av = ld4(A + t * DV + j0);
+    dd = fmaf(a[0], av.x, dd); dd = fmaf(a[1], av.y, dd); dd = fmaf(a[2], av.z, dd); dd = fmaf(a[3], av.w, dd);
+    st4(dA + t * DV + j0, make_float4(a[0], a[1], a[2], a[3]));
+  }
+  Dd[t] = dd;
+}
+
+// ---------------------------------------------------------------------------- backward: main
+// grid (ceil(N/128), B): thread j owns key row j (k[D], v[DV], dk[D], dv[DV]); loops over query tiles.
+template <int C>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_strict_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                       const float* __restrict__ dA, const float* __restrict__ lse, const float* __restrict__ Dd,
+                       float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV, int N) {
+  constexpr int D = C / 8, DV = C / 2, QT = 128, NW = AT_THREADS / 32;
+  __shared__ __align__(16) float Qs[QT * D];      // pre-scaled by log2(e)
+  __shared__ __align__(16) float dAs[QT * DV];
+  __shared__ float lses[QT], Dds[QT];
+  __shared__ float dqs[NW][QT * D];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.y;
+  const int j = blockIdx.x * AT_THREADS + tid;
+  const bool valid = j < N;
+  const long long krow = (long long)b * N + (valid ? j : 0);
+  float k[D], v[DV], dk[D], dv[DV];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { k[d] = K[krow * D + d]; dk[d] = 0.f; }
+#pragma unroll
+  for (int e = 0; e < DV; e += 4) {
+    const float4 t = ld4(V + krow * DV + e);
+    v[e] = t.x; v[e + 1] = t.y; v[e + 2] = t.z; v[e + 3] = t.w;
+    dv[e] = dv[e + 1] = dv[e + 2] = dv[e + 3] = 0.f;
+  }
+
+  for (int qt = 0; qt < N; qt += QT) {
+    const int nq = min(QT, N - qt);
+    __syncthreads();
+    const long long qrow0 = (long long)b * N + qt;
+    for (int e = tid; e < QT * D; e += AT_THREADS) Qs[e] = e < nq * D ? Q[qrow0 * D + e] * LOG2E : 0.f;
+    for (int e = tid * 4; e < QT * DV; e += AT_THREADS * 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < nq * DV) t = ld4(dA + qrow0 * DV + e);
+      *reinterpret_cast<float4*>(&dAs[e]) = t;
+    }
+    for (int e = tid; e < QT; e += AT_THREADS) {
+      lses[e] = e < nq ? lse[qrow0 + e] * LOG2E : 0.f;
+      Dds[e] = e < nq ? Dd[qrow0 + e] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < nq; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(Qs[i * D + d], k[d], s);
+      float p = exp2f(s - lses[i]);
+      p = valid ? p : 0.f;
+      float dp = 0.f;
+#pragma unroll
+      for (int e = 0; e < DV; e += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(&dAs[i * DV + e]);
+        dp = fmaf(g.x, v[e], dp); dp = fmaf(g.y, v[e + 1], dp);
+        dp = fmaf(g.z, v[e + 2], dp); dp = fmaf(g.w, v[e + 3], dp);
+        dv[e] = fmaf(p, g.x, dv[e]); dv[e + 1] = fmaf(p, g.y, dv[e + 1]);
+        dv[e + 2] = fmaf(p, g.z, dv[e + 2]); dv[e + 3] = fmaf(p, g.w, dv[e + 3]);
+      }
+      const float ds = p * (dp - Dds[i]);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        dk[d] = fmaf(ds, Qs[i * D + d], dk[d]);
+        const float r = warp_sum(ds * k[d]);
+        if (lane == 0) dqs[wid][i * D + d] = r;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < nq * D; e += AT_THREADS) {
+      float r = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) r += dqs[w][e];
+      atomicAdd(dQ + qrow0 * D + e, r);
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int d = 0; d < D; ++d) dK[krow * D + d] = dk[d] * LN2;   // Qs carried a log2(e) factor
+#pragma unroll
+  for (int e = 0; e < DV; e += 4) st4(dV + krow * DV + e, make_float4(dv[e], dv[e + 1], dv[e + 2], dv[e + 3]));
+}
+
+// ---------------------------------------------------------------------------- backward: post
+// dX = dY + dQ Wq^T + dK Wk^T + dV Wv^T
+template <int C>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_post_kernel(const float* __restrict__ dY, const float* __restrict__ dQ, const float* __restrict__ dK,
+                     const float* __restrict__ dV, const float* __restrict__ Wq, const float* __restrict__ Wk,
+                     const float* __restrict__ Wv, float* __restrict__ dX, long long T) {
+  constexpr int D = C / 8, DV = C / 2;
+  __shared__ float sWq[C * D], sWk[C * D];
+  __shared__ __align__(16) float sWv[C * DV];
+  for (int i = threadIdx.x; i < C * D; i += AT_THREADS) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
+  for (int i = threadIdx.x; i < C * DV; i += AT_THREADS) sWv[i] = Wv[i];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * AT_THREADS + threadIdx.x;
+  if (t >= T) return;
+  float dq[D], dk[D], dv[DV];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { dq[d] = dQ[t * D + d]; dk[d] = dK[t * D + d]; }
+#pragma unroll
+  for (int e = 0; e < DV; e += 4) {
+    const float4 g = ld4(dV + t * DV + e);
+    dv[e] = g.x; dv[e + 1] = g.y; dv[e + 2] = g.z; dv[e + 3] = g.w;
+  }
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += 4) {
+    const float4 g = ld4(dY + t * C + c0);
+    float a[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = c0 + cc;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        a[cc] = fmaf(dq[d], sWq[c * D + d], a[cc]);
+        a[cc] = fmaf(dk[d], sWk[c * D + d], a[cc]);
+      }
+#pragma unroll
+      for (int e = 0; e < DV; e += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&sWv[c * DV + e]);
+        a[cc] = fmaf(dv[e], w.x, a[cc]); a[cc] = fmaf(dv[e + 1], w.y, a[cc]);
+        a[cc] = fmaf(dv[e + 2], w.z, a[cc]); a[cc] = fmaf(dv[e + 3], w.w, a[cc]);
+      }
+    }
+    st4(dX + t * C + c0, make_float4(a[0], a[1], a[2], a[3]));
+  }
+}
+
+// dgamma = sum_c bo[c] dbo'[c] + sum_{j,c} Wo[j,c] dWo'[j,c]  with dWo' = A^T dY, dbo' = colsum(dY);
+// then dWo = gamma dWo', dbo = gamma dbo'.  One CTA.
+__global__ void __launch_bounds__(256)
+attn_bwd_finalize_kernel(const float* __restrict__ Wo, const float* __restrict__ bo, const float* __restrict__ gamma,
+                         float* __restrict__ dWo, float* __restrict__ dbo, float* __restrict__ dgamma, int nW, int C) {
+  __shared__ float red[32];
+  const float gm = *gamma;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nW; i += 256) {
+    const float g = dWo[i];
+    acc = fmaf(Wo[i], g, acc);
+    dWo[i] = g * gm;
+  }
+  for (int i = threadIdx.x; i < C; i += 256) {
+    const float g = dbo[i];
+    acc = fmaf(bo[i], g, acc);
+    dbo[i] = g * gm;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) *dgamma = acc;
+}
+
+static sagan_conv_geom geom_1x1(long long T, int cin, int cout) {
+  sagan_conv_geom g;
+  g.B = 1; g.H = 1; g.W = (int)T; g.Cin = cin; g.Ho = 1; g.Wo = (int)T; g.Cout = cout;
+  g.kh = 1; g.kw = 1; g.stride = 1; g.pad_t = 0; g.pad_l = 0;
+  return g;
+}
+
+template <int C>
+static int attn_fwd_strict_t(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                             const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
+                             float* Y, float* lse, float* A, int B, int N, float* ws, cudaStream_t st) {
+  constexpr int D = C / 8, DV = C / 2;
+  const long long T = (long long)B * N;
+  float* Q = ws;
+  float* K = Q + T * D;
+  float* V = K + T * D;
+  attn_proj_kernel<C><<<(unsigned)ceil_div<long long>(T, AT_THREADS), AT_THREADS, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Q,
+                                                                                            K, V, T);
+  SAGAN_LAUNCH_CHECK();
+  attn_fwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, X, Wo, bo, gamma, Y, lse,
+                                                                                      A, N);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int C>
+static int attn_bwd_strict_t(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                             const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                             const float* gamma, const float* lse, const float* A, float* dX, float* dWq, float* dbq,
+                             float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma,
+                             int B, int N, float* ws, cudaStream_t st) {
+  constexpr int D = C / 8, DV = C / 2;
+  const long long T = (long long)B * N;
+  float* Q = ws;
+  float* K = Q + T * D;
+  float* V = K + T * D;
+  float* dA = V + T * DV;
+  float* Dd = dA + T * DV;
+  float* dQ = Dd + T;
+  float* dK = dQ + T * D;
+  float* dV = dK + T * D;
+  const unsigned tb = (unsigned)ceil_div<long long>(T, AT_THREADS);
+  attn_proj_kernel<C><<<tb, AT_THREADS, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Q, K, V, T);
+  SAGAN_LAUNCH_CHECK();
+  attn_bwd_pre_kernel<C><<<tb, AT_THREADS, 0, st>>>(dY, A, Wo, gamma, dA, Dd, T);
+  SAGAN_LAUNCH_CHECK();
+  SAGAN_CUDA(cudaMemsetAsync(dQ, 0, (size_t)T * D * sizeof(float), st));
+  attn_bwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, dA, lse, Dd, dQ, dK, dV, N);
+  SAGAN_LAUNCH_CHECK();
+  if (dX) {
+    attn_bwd_post_kernel<C><<<tb, AT_THREADS, 0, st>>>(dY, dQ, dK, dV, Wq, Wk, Wv, dX, T);
+    SAGAN_LAUNCH_CHECK();
+  }
+  if (dWq) {
+    int rc;
+    sagan_conv_geom g = geom_1x1(T, C, D);
+    if ((rc = sagan_conv2d_wgrad(X, dQ, dWq, dbq, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
+    if ((rc = sagan_conv2d_wgrad(X, dK, dWk, dbk, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
+    g = geom_1x1(T, C, DV);
+    if ((rc = sagan_conv2d_wgrad(X, dV, dWv, dbv, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
+    g = geom_1x1(T, DV, C);
+    if ((rc = sagan_conv2d_wgrad(A, dY, dWo, dbo, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
+    attn_bwd_finalize_kernel<<<1, 256, 0, st>>>(Wo, bo, gamma, dWo, dbo, dgamma, DV * C, C);
+    SAGAN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace sagan
+
+using namespace sagan;
+
+// implemented in attn_tc.cu
+namespace sagan {
+size_t attn_tc_workspace_bytes(int B, int N, int C);
+int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
+                const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
+                int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace sagan
+
+static bool strict_supported(int C) { return C == 8 || C == 16 || C == 32 || C == 64; }
+
+extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode) {
+  if (B <= 0 || N <= 0 || C <= 0) return 0;
+  const long long T = (long long)B * N;
+  const size_t strict = (size_t)(T * (2 * C + 1) + 64) * sizeof(float);
+  if (math_mode == SAGAN_MATH_BF16_TC) return std::max(strict, attn_tc_workspace_bytes(B, N, C));
+  return strict;
+}
+
+#define SAGAN_ATTN_DISPATCH(FN, ...)                      \
+  switch (C) {                                            \
+    case 8: return FN<8>(__VA_ARGS__);                    \
+    case 16: return FN<16>(__VA_ARGS__);                  \
+    case 32: return FN<32>(__VA_ARGS__);                  \
+    case 64: return FN<64>(__VA_ARGS__);                  \
+    default: break;                                       \
+  }
+
+extern "C" int sagan_attn_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                              const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
+                              float* Y, float* lse, float* A_saved, int B, int N, int C, int math_mode, void* ws,
+                              size_t ws_bytes, sagan_stream_t stream) {
+  SAGAN_REQUIRE(X && Wq && bq && Wk && bk && Wv && bv && Wo && bo && gamma && Y && lse && A_saved && ws,
+                "sagan_attn_fwd: null pointer");
+  SAGAN_REQUIRE(B > 0 && N > 0 && C >= 8 && C % 8 == 0, "sagan_attn_fwd: need B,N > 0 and C a positive multiple of 8 (C=%d)", C);
+  SAGAN_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)A_saved | (uintptr_t)ws) & 15) == 0,
+                "sagan_attn_fwd: X, Y, A_saved, ws must be 16-byte aligned");
+  if (ws_bytes < sagan_attn_workspace_bytes(B, N, C, math_mode)) {
+    set_err("sagan_attn_fwd: workspace %zu < %zu bytes", ws_bytes, sagan_attn_workspace_bytes(B, N, C, math_mode));
+    return SAGAN_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (math_mode == SAGAN_MATH_BF16_TC)
+    return attn_tc_fwd(X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, C, ws, ws_bytes, st);
+  if (math_mode != SAGAN_MATH_FP32_STRICT) {
+    set_err("sagan_attn_fwd: unknown math_mode %d", math_mode);
+    return SAGAN_EINVAL;
+  }
+  SAGAN_ATTN_DISPATCH(attn_fwd_strict_t, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, (float*)ws, st);
+  set_err("sagan_attn_fwd: FP32_STRICT supports C in {8,16,32,64} (C=%d); use SAGAN_MATH_BF16_TC", C);
+  return SAGAN_EUNSUPPORTED;
+}
+
+extern "C" int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                              const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                              const float* gamma, const float* lse, const float* A_saved, float* dX, float* dWq,
+                              float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo,
+                              float* dgamma, int B, int N, int C, int math_mode, void* ws, size_t ws_bytes,
+                              sagan_stream_t stream) {
+  SAGAN_REQUIRE(dY && X && Wq && bq && Wk && bk && Wv && bv && Wo && bo && gamma && lse && A_saved && ws,
+                "sagan_attn_bwd: null pointer");
+  SAGAN_REQUIRE(B > 0 && N > 0 && C >= 8 && C % 8 == 0, "sagan_attn_bwd: need B,N > 0 and C a positive multiple of 8 (C=%d)", C);
+  const bool all_w = dWq && dbq && dWk && dbk && dWv && dbv && dWo && dbo && dgamma;
+  const bool no_w = !dWq && !dbq && !dWk && !dbk && !dWv && !dbv && !dWo && !dbo && !dgamma;
+  SAGAN_REQUIRE(all_w || no_w, "sagan_attn_bwd: parameter-gradient outputs must be all set or all NULL");
+  SAGAN_REQUIRE(dX || all_w, "sagan_attn_bwd: nothing to compute");
+  if (ws_bytes < sagan_attn_workspace_bytes(B, N, C, math_mode)) {
+    set_err("sagan_attn_bwd: workspace %zu < %zu bytes", ws_bytes, sagan_attn_workspace_bytes(B, N, C, math_mode));
+    return SAGAN_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // round 1: the backward runs in fp32 on the CUDA cores for both math modes
+  SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
+                      dbk, dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, st);
+  set_err("sagan_attn_bwd: supports C in {8,16,32,64} (C=%d)", C);
+  return SAGAN_EUNSUPPORTED;
+}

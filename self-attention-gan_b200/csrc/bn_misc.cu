@@ -1,0 +1,312 @@
+// BatchNorm(training)+LeakyReLU (generator.py:10-11), hinge losses (sagan/main.py:21-27),
+// Keras Adam (sagan/main.py:119-120) -- the elementwise glue between the conv / attention kernels.
+#include "common.cuh"
+
+namespace sagan {
+
+// ------------------------------------------------------------------------------------ BatchNorm
+// x [rows, C] NHWC-flattened.  Stage 1: per-CTA partial (sum, sumsq) in fp32 -> ws[nblk][2][C];
+// stage 2 (apply): every CTA folds the partials in fp64 in a fixed order (deterministic), then
+// y = lrelu((x - mean) * invstd * gamma + beta).
+constexpr int BN_THREADS = 256;
+constexpr int BN_MAX_BLOCKS = 296;
+constexpr int BN_MAX_C = 1024;
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, long long rows, int C, int rows_per_block) {
+  extern __shared__ float sm[];   // [2][BN_THREADS]
+  const int cpt = min(C, BN_THREADS);
+  const int rl = BN_THREADS / cpt;
+  const int c_lane = threadIdx.x % cpt, r_lane = threadIdx.x / cpt;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int c0 = 0; c0 < C; c0 += cpt) {
+    const int c = c0 + c_lane;
+    float s = 0.f, q = 0.f;
+    if (c < C && r_lane < rl)
+      for (long long r = r0 + r_lane; r < r1; r += rl) {
+        const float v = x[r * C + c];
+        s += v;
+        q = fmaf(v, v, q);
+      }
+    sm[threadIdx.x] = s;
+    sm[BN_THREADS + threadIdx.x] = q;
+    __syncthreads();
+    if (r_lane == 0 && c < C) {
+      for (int j = 1; j < rl; ++j) {
+        s += sm[j * cpt + c_lane];
+        q += sm[BN_THREADS + j * cpt + c_lane];
+      }
+      part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
+      part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ y, const float* __restrict__ part, int nparts, float* __restrict__ save_mean,
+                float* __restrict__ save_invstd, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                long long rows, int C, float eps, float momentum, float slope) {
+  extern __shared__ float sm[];   // scale[C], shift[C]
+  float* scale = sm;
+  float* shift = sm + C;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+      s += (double)part[((size_t)p * 2 + 0) * C + c];
+      q += (double)part[((size_t)p * 2 + 1) * C + c];
+    }
+    const double mean = s / (double)rows;
+    double var = q / (double)rows - mean * mean;   // biased variance (Keras training mode)
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (blockIdx.x == 0) {
+      save_mean[c] = (float)mean;
+      save_invstd[c] = invstd;
+      if (moving_mean) moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)mean;
+      if (moving_var) moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)var;
+    }
+  }
+  __syncthreads();
+  const long long n = rows * C;
+  const long long stride = (long long)gridDim.x * BN_THREADS * 4;
+  for (long long i = ((long long)blockIdx.x * BN_THREADS + threadIdx.x) * 4; i < n; i += stride) {
+    const int c = (int)(i % C);   // C % 4 == 0 (checked by the wrapper)
+    const float4 v = ld4(x + i);
+    float4 o;
+    o.x = fmaf(v.x, scale[c + 0], shift[c + 0]); o.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
+    o.z = fmaf(v.z, scale[c + 2], shift[c + 2]); o.w = fmaf(v.w, scale[c + 3], shift[c + 3]);
+    o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+    o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+    st4(y + i, o);
+  }
+}
+
+// backward stage 1: partial dbeta = sum dz, dgamma = sum dz * xhat, with dz = dy * lrelu'(y)
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ part,
+                    long long rows, int C, int rows_per_block, float slope) {
+  extern __shared__ float sm[];
+  const int cpt = min(C, BN_THREADS);
+  const int rl = BN_THREADS / cpt;
+  const int c_lane = threadIdx.x % cpt, r_lane = threadIdx.x / cpt;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int c0 = 0; c0 < C; c0 += cpt) {
+    const int c = c0 + c_lane;
+    float s = 0.f, q = 0.f;
+    if (c < C && r_lane < rl) {
+      const float mu = mean[c], is = invstd[c];
+      for (long long r = r0 + r_lane; r < r1; r += rl) {
+        const float yy = y[r * C + c];
+        float dz = dy[r * C + c];
+        dz = yy > 0.f ? dz : dz * slope;
+        s += dz;
+        q = fmaf(dz, (x[r * C + c] - mu) * is, q);
+      }
+    }
+    sm[threadIdx.x] = s;
+    sm[BN_THREADS + threadIdx.x] = q;
+    __syncthreads();
+    if (r_lane == 0 && c < C) {
+      for (int j = 1; j < rl; ++j) {
+        s += sm[j * cpt + c_lane];
+        q += sm[BN_THREADS + j * cpt + c_lane];
+      }
+      part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
+      part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+    }
+    __syncthreads();
+  }
+}
+
+// backward stage 2: dx = gamma * invstd * (dz - dbeta/M - xhat * dgamma/M)
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ part, int nparts, float* __restrict__ dx, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, long long rows, int C, float slope) {
+  extern __shared__ float sm[];   // a[C], b[C], c0[C], mu[C], is[C]
+  float* ka = sm;            // gamma * invstd
+  float* kb = sm + C;        // dbeta / M
+  float* kc = sm + 2 * C;    // dgamma / M
+  float* kmu = sm + 3 * C;
+  float* kis = sm + 4 * C;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+      s += (double)part[((size_t)p * 2 + 0) * C + c];
+      q += (double)part[((size_t)p * 2 + 1) * C + c];
+    }
+    if (blockIdx.x == 0) {
+      dbeta[c] = (float)s;
+      dgamma[c] = (float)q;
+    }
+    ka[c] = gamma[c] * invstd[c];
+    kb[c] = (float)(s / (double)rows);
+    kc[c] = (float)(q / (double)rows);
+    kmu[c] = mean[c];
+    kis[c] = invstd[c];
+  }
+  __syncthreads();
+  const long long n = rows * C;
+  const long long stride = (long long)gridDim.x * BN_THREADS * 4;
+  for (long long i = ((long long)blockIdx.x * BN_THREADS + threadIdx.x) * 4; i < n; i += stride) {
+    const int c = (int)(i % C);
+    const float4 d = ld4(dy + i), xx = ld4(x + i), yy = ld4(y + i);
+    const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {xx.x, xx.y, xx.z, xx.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dz = yv[j] > 0.f ? dv[j] : dv[j] * slope;
+      const float xh = (xv[j] - kmu[c + j]) * kis[c + j];
+      o[j] = ka[c + j] * (dz - kb[c + j] - xh * kc[c + j]);
+    }
+    st4(dx + i, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------ hinge
+__global__ void __launch_bounds__(256)
+hinge_d_kernel(const float* __restrict__ dr, const float* __restrict__ df, long long n, float scale,
+               float* __restrict__ loss_sum, float* __restrict__ gr, float* __restrict__ gf) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a = 1.f - dr[i], b = 1.f + df[i];       // main.py:25-26
+    acc += fmaxf(a, 0.f) + fmaxf(b, 0.f);
+    gr[i] = a > 0.f ? -scale : 0.f;
+    gf[i] = b > 0.f ? scale : 0.f;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, acc);
+}
+
+__global__ void __launch_bounds__(256)
+hinge_g_kernel(const float* __restrict__ df, long long n, float scale, float* __restrict__ loss_sum,
+               float* __restrict__ gf) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    acc += -df[i];                                       // main.py:22
+    gf[i] = -scale;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, acc);
+}
+
+// ------------------------------------------------------------------------------------ Adam
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, const float* __restrict__ hyper, float grad_scale) {
+  const float lr_t = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gg = g[i] * grad_scale;
+    float mm = gg;
+    if (m) {
+      mm = b1 * m[i] + (1.f - b1) * gg;
+      m[i] = mm;
+    }
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    v[i] = vv;
+    p[i] -= lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace sagan
+
+using namespace sagan;
+
+extern "C" size_t sagan_bn_workspace_bytes(int C) { return (size_t)BN_MAX_BLOCKS * 2 * (size_t)(C > 0 ? C : 1) * sizeof(float); }
+
+static int bn_blocks(long long rows, int* rows_per_block) {
+  int nblk = (int)std::min<long long>(BN_MAX_BLOCKS, std::max<long long>(1, rows / 64));
+  *rows_per_block = (int)ceil_div<long long>(rows, nblk);
+  return (int)ceil_div<long long>(rows, *rows_per_block);
+}
+
+extern "C" int sagan_bn_lrelu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean,
+                                  float* save_invstd, float* moving_mean, float* moving_var, long long rows, int C,
+                                  float eps, float momentum, float slope, void* ws, size_t ws_bytes,
+                                  sagan_stream_t stream) {
+  SAGAN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, "sagan_bn_lrelu_fwd: null pointer");
+  SAGAN_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= BN_MAX_C, "sagan_bn_lrelu_fwd: need rows>0, C%%4==0, C<=%d (C=%d)", BN_MAX_C, C);
+  SAGAN_REQUIRE(al16(x) && al16(y), "sagan_bn_lrelu_fwd: x/y must be 16-byte aligned");
+  if (ws_bytes < sagan_bn_workspace_bytes(C)) {
+    set_err("sagan_bn_lrelu_fwd: workspace %zu < %zu", ws_bytes, sagan_bn_workspace_bytes(C));
+    return SAGAN_EWORKSPACE;
+  }
+  int rpb;
+  const int nblk = bn_blocks(rows, &rpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_stats_kernel<<<nblk, BN_THREADS, 2 * BN_THREADS * sizeof(float), st>>>(x, (float*)ws, rows, C, rpb);
+  SAGAN_LAUNCH_CHECK();
+  const int ablk = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(rows * C, BN_THREADS * 4));
+  bn_apply_kernel<<<ablk, BN_THREADS, 2 * C * sizeof(float), st>>>(x, gamma, beta, y, (const float*)ws, nblk, save_mean,
+                                                                   save_invstd, moving_mean, moving_var, rows, C, eps,
+                                                                   momentum, slope);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_bn_lrelu_bwd(const float* dy, const float* x, const float* y, const float* gamma,
+                                  const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
+                                  float* dbeta, long long rows, int C, float slope, void* ws, size_t ws_bytes,
+                                  sagan_stream_t stream) {
+  SAGAN_REQUIRE(dy && x && y && gamma && save_mean && save_invstd && dx && dgamma && dbeta && ws,
+                "sagan_bn_lrelu_bwd: null pointer");
+  SAGAN_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= BN_MAX_C, "sagan_bn_lrelu_bwd: need rows>0, C%%4==0, C<=%d (C=%d)", BN_MAX_C, C);
+  SAGAN_REQUIRE(al16(dy) && al16(x) && al16(y) && al16(dx), "sagan_bn_lrelu_bwd: tensors must be 16-byte aligned");
+  if (ws_bytes < sagan_bn_workspace_bytes(C)) {
+    set_err("sagan_bn_lrelu_bwd: workspace %zu < %zu", ws_bytes, sagan_bn_workspace_bytes(C));
+    return SAGAN_EWORKSPACE;
+  }
+  int rpb;
+  const int nblk = bn_blocks(rows, &rpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_bwd_stats_kernel<<<nblk, BN_THREADS, 2 * BN_THREADS * sizeof(float), st>>>(dy, x, y, save_mean, save_invstd,
+                                                                                 (float*)ws, rows, C, rpb, slope);
+  SAGAN_LAUNCH_CHECK();
+  const int ablk = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(rows * C, BN_THREADS * 4));
+  bn_bwd_apply_kernel<<<ablk, BN_THREADS, 5 * C * sizeof(float), st>>>(dy, x, y, gamma, save_mean, save_invstd,
+                                                                       (const float*)ws, nblk, dx, dgamma, dbeta, rows, C,
+                                                                       slope);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_hinge_d(const float* d_real, const float* d_fake, long long n, float scale, float* loss_sum,
+                             float* g_real, float* g_fake, sagan_stream_t stream) {
+  SAGAN_REQUIRE(d_real && d_fake && loss_sum && g_real && g_fake && n > 0, "sagan_hinge_d: bad argument");
+  const int blocks = (int)std::min<long long>(num_sms(), ceil_div<long long>(n, 256));
+  hinge_d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_real, d_fake, n, scale, loss_sum, g_real, g_fake);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_hinge_g(const float* d_fake, long long n, float scale, float* loss_sum, float* g_fake,
+                             sagan_stream_t stream) {
+  SAGAN_REQUIRE(d_fake && loss_sum && g_fake && n > 0, "sagan_hinge_g: bad argument");
+  const int blocks = (int)std::min<long long>(num_sms(), ceil_div<long long>(n, 256));
+  hinge_g_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_fake, n, scale, loss_sum, g_fake);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_adam_step(float* param, const float* grad, float* m, float* v, long long n, const float* hyper,
+                               float grad_scale, sagan_stream_t stream) {
+  SAGAN_REQUIRE(param && grad && v && hyper && n > 0, "sagan_adam_step: bad argument");
+  const int blocks = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(n, 256));
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, hyper, grad_scale);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}

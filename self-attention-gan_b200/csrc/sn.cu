@@ -1,0 +1,478 @@
+// Spectral-norm power iteration as ONE cooperative, multi-tensor, memory-bound kernel.
+//
+// Replaces SpectralNormalization.update_uv (/root/reference/layers.py:50-68): per wrapped kernel
+// the reference issues ~12 TF micro-ops (reshape, 3 GEMVs, 2 norms, divides, reduce).  Here all
+// spectrally-normalised kernels of a network are processed by one launch:
+//
+//   phase 1   part_s[rb][k] = sum_{r in row block rb} u[r] W[r,k]        (column pass, float4 along k)
+//   phase 1b  s[k] = sum_rb part_s, partial ||s||^2                      (fixed order: deterministic)
+//   phase 2   v[k] = s[k]/(||s||+eps);  t[r] = sum_k v[k] W[r,k]         (row pass, warp-shuffle reduce)
+//   phase 2b  t[r] = sum_cb part_t, partial ||t||^2
+//   phase 3   u[r] = t[r]/(||t||+eps); sigma = ||t||^2/(||t||+eps) [/factor]; W_bar = W / sigma
+//
+// sigma = sum((u W) * v) of layers.py:62 equals u . t = ||t||^2/(||t||+eps), so no third GEMV.
+// Phases are separated by grid-wide barriers (cooperative launch); W is read three times but
+// passes 2 and 3 hit the 126 MB L2 for every in-model matrix (5.6 MB in total) -- compulsory HBM
+// traffic is one read of W and one write of W_bar (8 B/element).
+#include <cooperative_groups.h>
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sagan {
+
+constexpr int SN_THREADS = 256;
+constexpr int SN_WARPS = SN_THREADS / 32;
+constexpr int SN_MAX_MATS = 64;
+constexpr float SN_EPS = 1e-12f;  // layers.py:4
+
+struct SnDev {
+  const float* W;
+  float* u;
+  float* v;
+  float* Wbar;
+  __nv_bfloat16* Wbar16;
+  float* sigma;
+  int R, K, Ip;
+  float factor;
+  int vec;        // K % 4 == 0 and 16-byte aligned bases
+  int vecflat;    // numel % 4 == 0 and aligned: phase 3 may use float4 over the flat tensor
+  int TR, nrb;    // phase 1: rows per row block, number of row blocks
+  int ncb1;       // phase 1/1b: 128-column blocks
+  int CB2, ncb2;  // phase 2: columns per block (multiple of 128), number of blocks
+  int nrc;        // phase 2b/3: 128-row chunks
+  float* part_s;  // [nrb][K]
+  float* s;       // [K]
+  float* part_t;  // [ncb2][R] (unused when ncb2 == 1)
+  float* t;       // [R]
+  float* nrm_s;   // [ncb1] partial squared norms
+  float* nrm_t;   // [nrc]
+  int off1, off1b, off2, off2b, off3;  // first work unit of this matrix in each phase
+  long long numel;
+};
+
+struct SnTotals {
+  int n;
+  int tot1, tot1b, tot2, tot2b, tot3;
+  int maxIp;
+};
+
+__device__ __forceinline__ float4 sn_load4(const float* row, int k, int K, int vec) {
+  if (vec) return ld4(row + k);
+  float4 r;
+  r.x = (k + 0 < K) ? row[k + 0] : 0.f;
+  r.y = (k + 1 < K) ? row[k + 1] : 0.f;
+  r.z = (k + 2 < K) ? row[k + 2] : 0.f;
+  r.w = (k + 3 < K) ? row[k + 3] : 0.f;
+  return r;
+}
+__device__ __forceinline__ void sn_store4(float* row, int k, int K, int vec, float4 a) {
+  if (vec) {
+    st4(row + k, a);
+    return;
+  }
+  if (k + 0 < K) row[k + 0] = a.x;
+  if (k + 1 < K) row[k + 1] = a.y;
+  if (k + 2 < K) row[k + 2] = a.z;
+  if (k + 3 < K) row[k + 3] = a.w;
+}
+
+// which matrix owns work unit `unit` of a phase (offsets cached in shared memory, ascending)
+__device__ __forceinline__ int sn_find(const int* offs, int n, int unit) {
+  int m = 0;
+  while (m + 1 < n && offs[m + 1] <= unit) ++m;
+  return m;
+}
+
+__global__ void __launch_bounds__(SN_THREADS, 2)
+sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ int s_off[5][SN_MAX_MATS];
+  __shared__ float s_inv[SN_MAX_MATS];   // 1/(||s||+eps) or 1/(||t||+eps) of the current phase
+  __shared__ float s_sig[SN_MAX_MATS];
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * SN_WARPS + wid;
+  const int nwarps = gridDim.x * SN_WARPS;
+  const int n = tot.n;
+
+  for (int i = threadIdx.x; i < n; i += SN_THREADS) {
+    s_off[0][i] = tab[i].off1;
+    s_off[1][i] = tab[i].off1b;
+    s_off[2][i] = tab[i].off2;
+    s_off[3][i] = tab[i].off2b;
+    s_off[4][i] = tab[i].off3;
+  }
+  __syncthreads();
+
+  for (int it = 0; it < tot.maxIp; ++it) {
+    // ---------------------------------------------------------------- phase 1: s partials = u W
+    for (int unit = gwarp; unit < tot.tot1; unit += nwarps) {
+      const int m = sn_find(s_off[0], n, unit);
+      const SnDev d = tab[m];
+      if (it >= d.Ip) continue;
+      const int local = unit - d.off1;
+      const int rb = local / d.ncb1, cb = local - rb * d.ncb1;
+      const int k = cb * 128 + lane * 4;
+      const int r0 = rb * d.TR, r1 = min(d.R, r0 + d.TR);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < d.K) {
+        int r = r0;
+        for (; r + 8 <= r1; r += 8) {
+          float4 w[8];
+          float uu[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w[j] = sn_load4(d.W + (size_t)(r + j) * d.K, k, d.K, d.vec);
+            uu[j] = d.u[r + j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc.x = fmaf(uu[j], w[j].x, acc.x);
+            acc.y = fmaf(uu[j], w[j].y, acc.y);
+            acc.z = fmaf(uu[j], w[j].z, acc.z);
+            acc.w = fmaf(uu[j], w[j].w, acc.w);
+          }
+        }
+        for (; r < r1; ++r) {
+          const float4 w = sn_load4(d.W + (size_t)r * d.K, k, d.K, d.vec);
+          const float uu = d.u[r];
+          acc.x = fmaf(uu, w.x, acc.x);
+          acc.y = fmaf(uu, w.y, acc.y);
+          acc.z = fmaf(uu, w.z, acc.z);
+          acc.w = fmaf(uu, w.w, acc.w);
+        }
+        sn_store4(d.part_s + (size_t)rb * d.K, k, d.K, d.vec, acc);
+      }
+    }
+    grid.sync();
+
+    // ---------------------------------------------------------------- phase 1b: s, ||s||^2 partials
+    for (int unit = gwarp; unit < tot.tot1b; unit += nwarps) {
+      const int m = sn_find(s_off[1], n, unit);
+      const SnDev d = tab[m];
+      if (it >= d.Ip) continue;
+      const int cb = unit - d.off1b;
+      const int k = cb * 128 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < d.K) {
+        for (int rb = 0; rb < d.nrb; ++rb) {
+          const float4 p = sn_load4(d.part_s + (size_t)rb * d.K, k, d.K, d.vec);
+          acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        sn_store4(d.s, k, d.K, d.vec, acc);
+      }
+      float q = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+      q = warp_sum(q);
+      if (lane == 0) d.nrm_s[cb] = q;
+    }
+    grid.sync();
+
+    // ---------------------------------------------------------------- phase 2: v, t partials = v W^T
+    for (int m = wid; m < n; m += SN_WARPS) {
+      const SnDev& d = tab[m];
+      float q = 0.f;
+      for (int i = lane; i < d.ncb1; i += 32) q += d.nrm_s[i];
+      q = warp_sum(q);
+      if (lane == 0) s_inv[m] = 1.0f / (sqrtf(q) + SN_EPS);
+    }
+    __syncthreads();
+    for (int unit = gwarp; unit < tot.tot2; unit += nwarps) {
+      const int m = sn_find(s_off[2], n, unit);
+      const SnDev d = tab[m];
+      if (it >= d.Ip) continue;
+      const int local = unit - d.off2;
+      const int rg = local / d.ncb2, cb = local - rg * d.ncb2;
+      const int r0 = rg * 4;
+      const int k0 = cb * d.CB2, k1 = min(d.K, k0 + d.CB2);
+      const float inv = s_inv[m];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = k0 + lane * 4; k < k1; k += 128) {
+        float4 vv = sn_load4(d.s, k, d.K, d.vec);
+        vv.x *= inv; vv.y *= inv; vv.z *= inv; vv.w *= inv;
+        if (rg == 0) sn_store4(d.v, k, d.K, d.vec, vv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (r0 + j < d.R) {
+            const float4 w = sn_load4(d.W + (size_t)(r0 + j) * d.K, k, d.K, d.vec);
+            acc[j] = fmaf(w.x, vv.x, acc[j]);
+            acc[j] = fmaf(w.y, vv.y, acc[j]);
+            acc[j] = fmaf(w.z, vv.z, acc[j]);
+            acc[j] = fmaf(w.w, vv.w, acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+      if (lane == 0) {
+        float* dst = (d.ncb2 == 1) ? d.t : d.part_t + (size_t)cb * d.R;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (r0 + j < d.R) dst[r0 + j] = acc[j];
+      }
+    }
+    grid.sync();
+
+    // ---------------------------------------------------------------- phase 2b: t, ||t||^2 partials
+    for (int unit = gwarp; unit < tot.tot2b; unit += nwarps) {
+      const int m = sn_find(s_off[3], n, unit);
+      const SnDev d = tab[m];
+      if (it >= d.Ip) continue;
+      const int rc = unit - d.off2b;
+      const int r = rc * 128 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < d.R) {
+        if (d.ncb2 == 1) {
+          acc = sn_load4(d.t, r, d.R, 0);
+        } else {
+          for (int cb = 0; cb < d.ncb2; ++cb) {
+            const float4 p = sn_load4(d.part_t + (size_t)cb * d.R, r, d.R, 0);
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+          }
+          sn_store4(d.t, r, d.R, 0, acc);
+        }
+      }
+      float q = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+      q = warp_sum(q);
+      if (lane == 0) d.nrm_t[rc] = q;
+    }
+    grid.sync();
+
+    // ---------------------------------------------------------------- phase 3: u, sigma, W_bar
+    __syncthreads();
+    for (int m = wid; m < n; m += SN_WARPS) {
+      const SnDev& d = tab[m];
+      float q = 0.f;
+      for (int i = lane; i < d.nrc; i += 32) q += d.nrm_t[i];
+      q = warp_sum(q);
+      if (lane == 0) {
+        const float nt = sqrtf(q);
+        s_inv[m] = 1.0f / (nt + SN_EPS);
+        float sg = nt * nt / (nt + SN_EPS);       // == sum((u W) * v), layers.py:62
+        if (d.factor != 0.f) sg = sg / d.factor;  // layers.py:65-66
+        s_sig[m] = sg;
+      }
+    }
+    __syncthreads();
+    for (int unit = gwarp; unit < tot.tot3; unit += nwarps) {
+      const int m = sn_find(s_off[4], n, unit);
+      const SnDev d = tab[m];
+      if (it >= d.Ip) continue;
+      const int local = unit - d.off3;
+      if (local < d.nrc) {  // u update (+ sigma)
+        const int r = local * 128 + lane * 4;
+        if (r < d.R) {
+          float4 tt = sn_load4(d.t, r, d.R, 0);
+          const float inv = s_inv[m];
+          tt.x *= inv; tt.y *= inv; tt.z *= inv; tt.w *= inv;
+          sn_store4(d.u, r, d.R, 0, tt);
+        }
+        if (local == 0 && lane == 0) *d.sigma = s_sig[m];
+      } else if (it == d.Ip - 1) {  // W_bar = W / sigma over a 2048-element chunk
+        const float sg = s_sig[m];
+        const long long base = (long long)(local - d.nrc) * 2048;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long e = base + (long long)j * 128 + lane * 4;
+          if (e < d.numel) {
+            if (d.vecflat) {
+              float4 w = ld4(d.W + e);
+              w.x = w.x / sg; w.y = w.y / sg; w.z = w.z / sg; w.w = w.w / sg;   // layers.py:68
+              st4(d.Wbar + e, w);
+              if (d.Wbar16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(d.Wbar16 + e) = pk;
+              }
+            } else {
+              for (int q = 0; q < 4 && e + q < d.numel; ++q) {
+                const float w = d.W[e + q] / sg;
+                d.Wbar[e + q] = w;
+                if (d.Wbar16) d.Wbar16[e + q] = __float2bfloat16_rn(w);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (it + 1 < tot.maxIp) grid.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward
+// c = sum dW_bar * W_bar (two-stage, fixed order), then dW = (dW_bar - c * u[r] v[k] / factor) / sigma
+constexpr int SNB_THREADS = 256;
+constexpr int SNB_MAX_BLOCKS = 1024;
+
+__global__ void __launch_bounds__(SNB_THREADS)
+sn_bwd_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ part) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * SNB_THREADS;
+  for (long long i = (long long)blockIdx.x * SNB_THREADS + threadIdx.x; i < n; i += stride) acc = fmaf(a[i], b[i], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(SNB_THREADS)
+sn_bwd_apply_kernel(const float* __restrict__ dWbar, const float* __restrict__ u, const float* __restrict__ v,
+                    const float* __restrict__ sigma, float factor, const float* __restrict__ part, int nparts,
+                    float* __restrict__ dW, int R, int K) {
+  __shared__ float red[32];
+  float c = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += SNB_THREADS) c += part[i];
+  c = block_sum(c, red);
+  const float sg = *sigma;
+  const float cf = (factor != 0.f) ? c / factor : c;
+  const long long n = (long long)R * K;
+  const long long stride = (long long)gridDim.x * SNB_THREADS;
+  for (long long i = (long long)blockIdx.x * SNB_THREADS + threadIdx.x; i < n; i += stride) {
+    const int r = (int)(i / K), k = (int)(i - (long long)r * K);
+    dW[i] = (dWbar[i] - cf * u[r] * v[k]) / sg;
+  }
+}
+
+}  // namespace sagan
+
+using namespace sagan;
+
+struct sagan_sn_plan {
+  int n = 0;
+  int device = 0;
+  SnDev* tab_dev = nullptr;
+  float* ws_dev = nullptr;
+  SnTotals tot{};
+  int grid = 0;
+  unsigned long long alg_bytes = 0;
+};
+
+extern "C" int sagan_sn_plan_create(const sagan_sn_desc* descs, int n, int device, sagan_sn_plan** plan_out) {
+  SAGAN_REQUIRE(descs && plan_out, "sagan_sn_plan_create: null argument");
+  SAGAN_REQUIRE(n >= 1 && n <= SN_MAX_MATS, "sagan_sn_plan_create: n=%d outside [1,%d]", n, SN_MAX_MATS);
+  std::vector<SnDev> tab(n);
+  size_t ws_floats = 0;
+  SnTotals tot{};
+  tot.n = n;
+  unsigned long long alg = 0;
+  for (int i = 0; i < n; ++i) {
+    const sagan_sn_desc& s = descs[i];
+    SAGAN_REQUIRE(s.W && s.u && s.v && s.W_bar && s.sigma, "sagan_sn_plan_create: null pointer in descriptor %d", i);
+    SAGAN_REQUIRE(s.rows >= 1 && s.cols >= 1, "sagan_sn_plan_create: bad shape [%d,%d] in descriptor %d", s.rows, s.cols, i);
+    // layers.py:17-18
+    SAGAN_REQUIRE(s.Ip >= 1, "The number of power iterations should be positive integer (descriptor %d: Ip=%d)", i, s.Ip);
+    SnDev& d = tab[i];
+    d.W = s.W; d.u = s.u; d.v = s.v; d.Wbar = s.W_bar; d.Wbar16 = (__nv_bfloat16*)s.W_bar_bf16; d.sigma = s.sigma;
+    d.R = s.rows; d.K = s.cols; d.Ip = s.Ip; d.factor = s.factor;
+    d.numel = (long long)s.rows * s.cols;
+    const bool al = (((uintptr_t)s.W | (uintptr_t)s.W_bar) & 15) == 0 && (((uintptr_t)s.W_bar_bf16) & 7) == 0;
+    d.vec = (al && (d.K % 4 == 0)) ? 1 : 0;
+    d.vecflat = (al && (d.numel % 4 == 0)) ? 1 : 0;
+    d.ncb1 = ceil_div(d.K, 128);
+    int nrb = ceil_div(4096, d.ncb1);
+    nrb = std::max(1, std::min(nrb, std::min(64, ceil_div(d.R, 8))));
+    d.TR = ceil_div(ceil_div(d.R, nrb), 4) * 4;
+    d.nrb = ceil_div(d.R, d.TR);
+    d.CB2 = std::min(ceil_div(d.K, 128) * 128, 4096);
+    d.ncb2 = ceil_div(d.K, d.CB2);
+    d.nrc = ceil_div(d.R, 128);
+    d.off1 = tot.tot1;   tot.tot1 += d.nrb * d.ncb1;
+    d.off1b = tot.tot1b; tot.tot1b += d.ncb1;
+    d.off2 = tot.tot2;   tot.tot2 += ceil_div(d.R, 4) * d.ncb2;
+    d.off2b = tot.tot2b; tot.tot2b += d.nrc;
+    d.off3 = tot.tot3;   tot.tot3 += d.nrc + (int)ceil_div(d.numel, (long long)2048);
+    tot.maxIp = std::max(tot.maxIp, d.Ip);
+    // workspace layout (float offsets, each region padded to 4 floats so the float4 path stays aligned)
+    auto take = [&](size_t cnt) { size_t o = ws_floats; ws_floats += (cnt + 3) / 4 * 4; return o; };
+    const size_t o_ps = take((size_t)d.nrb * d.K), o_s = take(d.K), o_pt = take((size_t)d.ncb2 * d.R), o_t = take(d.R);
+    const size_t o_ns = take(d.ncb1), o_nt = take(d.nrc);
+    d.part_s = (float*)o_ps; d.s = (float*)o_s; d.part_t = (float*)o_pt; d.t = (float*)o_t;
+    d.nrm_s = (float*)o_ns; d.nrm_t = (float*)o_nt;
+    const unsigned long long per = (s.W_bar_bf16 ? 10ull : 8ull) + ((d.numel * 4 > (64ll << 20)) ? 8ull : 0ull);
+    alg += per * (unsigned long long)d.numel;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  SAGAN_CUDA(cudaSetDevice(device));
+  sagan_sn_plan* p = new sagan_sn_plan();
+  p->n = n; p->device = device; p->tot = tot; p->alg_bytes = alg;
+  cudaError_t e = cudaMalloc(&p->ws_dev, ws_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&p->tab_dev, sizeof(SnDev) * n);
+  if (e != cudaSuccess) {
+    set_err("sagan_sn_plan_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    cudaFree(p->ws_dev);
+    delete p;
+    cudaSetDevice(prev);
+    return (int)e;
+  }
+  for (auto& d : tab) {
+    d.part_s = p->ws_dev + (size_t)d.part_s; d.s = p->ws_dev + (size_t)d.s;
+    d.part_t = p->ws_dev + (size_t)d.part_t; d.t = p->ws_dev + (size_t)d.t;
+    d.nrm_s = p->ws_dev + (size_t)d.nrm_s; d.nrm_t = p->ws_dev + (size_t)d.nrm_t;
+  }
+  e = cudaMemcpy(p->tab_dev, tab.data(), sizeof(SnDev) * n, cudaMemcpyHostToDevice);
+  int occ = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sn_power_iter_kernel, SN_THREADS, 0);
+  if (e != cudaSuccess || occ < 1) {
+    set_err("sagan_sn_plan_create: setup failed: %s", cudaGetErrorString(e));
+    cudaFree(p->ws_dev); cudaFree(p->tab_dev);
+    delete p;
+    cudaSetDevice(prev);
+    return e != cudaSuccess ? (int)e : SAGAN_EUNSUPPORTED;
+  }
+  const int max_units = std::max(std::max(tot.tot1, tot.tot2), tot.tot3);
+  const int want = std::max(1, ceil_div(max_units, SN_WARPS));
+  p->grid = std::min(num_sms() * std::min(occ, 2), want);
+  cudaSetDevice(prev);
+  *plan_out = p;
+  return 0;
+}
+
+extern "C" int sagan_sn_plan_run(sagan_sn_plan* p, sagan_stream_t stream) {
+  SAGAN_REQUIRE(p, "sagan_sn_plan_run: null plan");
+  const SnDev* tab = p->tab_dev;
+  SnTotals tot = p->tot;
+  void* args[] = {(void*)&tab, (void*)&tot};
+  SAGAN_CUDA(cudaLaunchCooperativeKernel((const void*)sn_power_iter_kernel, dim3(p->grid), dim3(SN_THREADS), args, 0,
+                                         (cudaStream_t)stream));
+  count_launch();
+  return 0;
+}
+
+extern "C" int sagan_sn_plan_destroy(sagan_sn_plan* p) {
+  if (!p) return 0;
+  cudaFree(p->ws_dev);
+  cudaFree(p->tab_dev);
+  delete p;
+  return 0;
+}
+
+extern "C" unsigned long long sagan_sn_plan_algorithmic_bytes(const sagan_sn_plan* p) { return p ? p->alg_bytes : 0ull; }
+
+extern "C" size_t sagan_sn_backward_workspace_bytes(long long numel) {
+  (void)numel;
+  return SNB_MAX_BLOCKS * sizeof(float);
+}
+
+extern "C" int sagan_sn_backward(const float* dW_bar, const float* W_bar, const float* u, const float* v,
+                                 const float* sigma, float factor, float* dW, int rows, int cols, void* ws,
+                                 size_t ws_bytes, sagan_stream_t stream) {
+  SAGAN_REQUIRE(dW_bar && W_bar && u && v && sigma && dW && ws, "sagan_sn_backward: null pointer");
+  SAGAN_REQUIRE(rows >= 1 && cols >= 1, "sagan_sn_backward: bad shape [%d,%d]", rows, cols);
+  if (ws_bytes < SNB_MAX_BLOCKS * sizeof(float)) {
+    set_err("sagan_sn_backward: workspace %zu < %zu bytes", ws_bytes, SNB_MAX_BLOCKS * sizeof(float));
+    return SAGAN_EWORKSPACE;
+  }
+  const long long n = (long long)rows * cols;
+  const int blocks = (int)std::min<long long>(SNB_MAX_BLOCKS, ceil_div<long long>(n, SNB_THREADS * 4));
+  sn_bwd_dot_kernel<<<blocks, SNB_THREADS, 0, (cudaStream_t)stream>>>(dW_bar, W_bar, n, (float*)ws);
+  SAGAN_LAUNCH_CHECK();
+  sn_bwd_apply_kernel<<<blocks, SNB_THREADS, 0, (cudaStream_t)stream>>>(dW_bar, u, v, sigma, factor, (const float*)ws,
+                                                                         blocks, dW, rows, cols);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}

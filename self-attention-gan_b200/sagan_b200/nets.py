@@ -1,0 +1,261 @@
+"""Vanilla SAGAN generator / discriminator builders, same config dict as the reference.
+
+Mirrors /root/reference/sagan/models/generator.py:7-37 (Block, get_generator) and
+/root/reference/sagan/models/discriminator.py:7-36 (Block, get_discriminator) on the layer
+surface of nn.py.  Two things are done at network level because they pay on B200:
+  * all trainable parameters (and their gradients) live in ONE flat fp32 buffer per network, so the
+    data-parallel gradient exchange and the Adam update are single-bucket operations;
+  * all spectrally-normalised kernels of a network are normalised by ONE cooperative launch
+    (functional.SpectralNormGroup) at the start of each training forward.
+"""
+import numpy as np
+import torch
+
+from . import functional as F
+from . import nn
+from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH
+
+LRELU = 0.1
+
+
+class GBlock(torch.nn.Module):
+    """generator.py:7-12: SN(Conv2DTranspose(c,4,2,'same',no bias)) -> BN -> LeakyReLU(0.1)."""
+
+    def __init__(self, output_channels):
+        super().__init__()
+        self.deconv = nn.SpectralNormalization(nn.Conv2DTranspose(output_channels, 4, 2, padding="same", use_bias=False))
+        self.bn = nn.BatchNormalization(leaky_slope=LRELU)
+
+    def forward(self, x):
+        return self.bn(self.deconv(x))
+
+
+class DBlock(torch.nn.Module):
+    """discriminator.py:7-11: SN(Conv2D(c,4,2,'same')) -> LeakyReLU(0.1) (fused in the conv epilogue)."""
+
+    def __init__(self, output_channels):
+        super().__init__()
+        self.conv = nn.SpectralNormalization(nn.Conv2D(output_channels, 4, 2, padding="same", leaky_slope=LRELU))
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Network(torch.nn.Module):
+    """Common plumbing: lazy build on first call, flat parameter bucket, grouped spectral norm."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = dict(config)
+        self.finalized = False
+        self.flat_params = self.flat_grads = None
+        self.sn_group = None
+        self._sn_layers = []
+
+    def finalize(self):
+        """Re-home every parameter into one flat buffer and every SN wrapper into one group."""
+        params = [p for p in self.parameters()]
+        pad = lambda k: (k + 63) // 64 * 64
+        total = sum(pad(p.numel()) for p in params)
+        dev = params[0].device
+        self.flat_params = torch.zeros(total, device=dev)
+        self.flat_grads = torch.zeros(total, device=dev)
+        self.param_slices = []
+        off = 0
+        for p in params:
+            n = p.numel()
+            self.flat_params[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_params[off:off + n].view(p.shape)
+            p.grad = self.flat_grads[off:off + n].view(p.shape)
+            self.param_slices.append((off, n))
+            off += pad(n)
+        self._sn_layers = [m for m in self.modules() if isinstance(m, nn.SpectralNormalization)]
+        if self._sn_layers:
+            ws = [m._kernel() for m in self._sn_layers]
+            us = [m.u for m in self._sn_layers]
+            self.sn_group = F.SpectralNormGroup(ws, us, [m.Ip for m in self._sn_layers],
+                                                [m.factor for m in self._sn_layers])
+            for i, m in enumerate(self._sn_layers):
+                m.adopt(self.sn_group, i)
+        self.finalized = True
+
+    def named_flat_parameters(self):
+        return list(self.named_parameters())
+
+    def zero_grad_flat(self):
+        self.flat_grads.zero_()
+
+    def _normalise_all(self, training):
+        """One launch for all spectrally-normalised kernels; hands W_bar to each wrapper."""
+        if not self._sn_layers:
+            return
+        wbars = self.sn_group.normalized(update=training)
+        for m, wb in zip(self._sn_layers, wbars):
+            m._pending = wb
+
+    def load_keras_weights(self, named_arrays, sn_u=None):
+        """Set parameters (Keras layouts) and spectral-norm `u` vectors by oracle-style names."""
+        own = dict(self.named_parameters_by_oracle_name())
+        with torch.no_grad():
+            for k, a in named_arrays.items():
+                t = torch.as_tensor(np.asarray(a), dtype=torch.float32)
+                if k not in own:
+                    raise KeyError(f"unknown parameter {k}; have {sorted(own)}")
+                if tuple(own[k].shape) != tuple(t.shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(own[k].shape)}")
+                own[k].copy_(t.to(own[k].device))
+            if sn_u:
+                sn = dict(self.sn_by_oracle_name())
+                for k, a in sn_u.items():
+                    m = sn[k]
+                    m._group.u(m._index).copy_(torch.as_tensor(np.asarray(a), dtype=torch.float32).reshape(-1).to(
+                        m._group.out.device))
+
+
+def _attn_names(prefix, layer):
+    phi, theta, g, o = layer.SN_conv
+    out = []
+    for nm, sn in (("phi", phi), ("theta", theta), ("g", g), ("o", o)):
+        out += [(f"{prefix}.{nm}.kernel", sn.module.kernel), (f"{prefix}.{nm}.bias", sn.module.bias)]
+    out.append((f"{prefix}.sigma", layer.sigma))
+    return out
+
+
+def _attn_sn(prefix, layer):
+    return [(f"{prefix}.{nm}.u", sn) for nm, sn in zip(("phi", "theta", "g", "o"), layer.SN_conv)]
+
+
+class Generator(Network):
+    """generator.py:14-37."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        gf = config["gf_dim"]
+        self.dense = nn.SpectralNormalization(nn.Dense(4 * 4 * gf * 16))                  # generator.py:25
+        self.power = int(np.log2(config["img_size"] / 4))                                  # generator.py:28
+        self.blocks = torch.nn.ModuleList()
+        self.attn = torch.nn.ModuleDict()
+        size = 4
+        for i, p in enumerate(reversed(range(self.power))):
+            self.blocks.append(GBlock(gf * (2 ** p)))                                      # generator.py:32
+            size *= 2
+            if config.get("use_attention") and size in config["attn_dim_G"]:              # generator.py:33-34
+                self.attn[str(i)] = nn.AttentionLayer()
+        self.head = nn.Conv2D(3, 4, 1, padding="same", use_bias=False, activation="tanh")  # generator.py:36
+
+    def forward(self, inputs, training=True):
+        z, labels = inputs if isinstance(inputs, (tuple, list)) else (inputs, None)
+        cfg = self.config
+        x = z
+        if cfg.get("use_label"):
+            # generator.py:19-21 (with the `x` -> `z` slip at :21 fixed)
+            onehot = torch.nn.functional.one_hot(labels.long(), cfg["num_classes"]).to(z.dtype)
+            x = torch.cat([z, onehot], dim=1).contiguous()
+        if self.finalized:
+            self._normalise_all(training)
+        x = self.dense(x)
+        x = x.reshape(-1, 4, 4, cfg["gf_dim"] * 16)                                        # generator.py:26
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            if str(i) in self.attn:
+                x = self.attn[str(i)](x)
+        out = self.head(x)
+        if not self.finalized:
+            self.finalize()
+        return out
+
+    def named_parameters_by_oracle_name(self):
+        out = [("dense.kernel", self.dense.module.kernel), ("dense.bias", self.dense.module.bias)]
+        for i, blk in enumerate(self.blocks):
+            out += [(f"block{i}.deconv.kernel", blk.deconv.module.kernel), (f"block{i}.bn.gamma", blk.bn.gamma),
+                    (f"block{i}.bn.beta", blk.bn.beta)]
+            if str(i) in self.attn:
+                out += _attn_names(f"block{i}.attn", self.attn[str(i)])
+        out.append(("head.kernel", self.head.kernel))
+        return out
+
+    def sn_by_oracle_name(self):
+        out = [("dense.u", self.dense)]
+        for i, blk in enumerate(self.blocks):
+            out.append((f"block{i}.deconv.u", blk.deconv))
+            if str(i) in self.attn:
+                out += _attn_sn(f"block{i}.attn", self.attn[str(i)])
+        return out
+
+
+class Discriminator(Network):
+    """discriminator.py:13-36."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        df = config["df_dim"]
+        self.power = int(np.log2(config["img_size"] / 4))                                  # discriminator.py:20
+        self.blocks = torch.nn.ModuleList()
+        self.attn = torch.nn.ModuleDict()
+        size = config["img_size"]
+        for i, p in enumerate(range(self.power)):
+            self.blocks.append(DBlock(df * 2 ** p))                                        # discriminator.py:22
+            size //= 2
+            # discriminator.py:23 reads attn_dim_G (sic); attn_dim_D is ignored, kept for drop-in parity
+            if config.get("use_attention") and size in config["attn_dim_G"]:
+                self.attn[str(i)] = nn.AttentionLayer()
+        if config.get("use_label"):
+            self.head_dense = nn.Dense(1)                                                  # discriminator.py:28
+            self.embedding = None
+        else:
+            self.head = nn.Conv2D(1, 4, 1, padding="same")                                 # discriminator.py:35
+
+    def forward(self, inputs, training=True):
+        img, labels = inputs if isinstance(inputs, (tuple, list)) else (inputs, None)
+        cfg = self.config
+        if self.finalized:
+            self._normalise_all(training)
+        x = img
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            if str(i) in self.attn:
+                x = self.attn[str(i)](x)
+        if cfg.get("use_label"):
+            if self.embedding is None:
+                c = x.shape[-1]
+                self.embedding = torch.nn.Parameter(
+                    (torch.rand(cfg["num_classes"], c) * 0.1 - 0.05).to(x.device))       # Keras Embedding: U(-0.05,0.05)
+            h = x.sum(dim=(1, 2))                                                          # discriminator.py:27
+            out = self.head_dense(h)                                                       # discriminator.py:28
+            out = out + torch.sum(h * self.embedding[labels.long()], dim=1, keepdim=True)  # discriminator.py:31-32
+        else:
+            out = self.head(x)
+        if not self.finalized:
+            self.finalize()
+        return out
+
+    def named_parameters_by_oracle_name(self):
+        out = []
+        for i, blk in enumerate(self.blocks):
+            out += [(f"block{i}.conv.kernel", blk.conv.module.kernel), (f"block{i}.conv.bias", blk.conv.module.bias)]
+            if str(i) in self.attn:
+                out += _attn_names(f"block{i}.attn", self.attn[str(i)])
+        if self.config.get("use_label"):
+            out += [("head.dense.kernel", self.head_dense.kernel), ("head.dense.bias", self.head_dense.bias),
+                    ("head.embedding", self.embedding)]
+        else:
+            out += [("head.kernel", self.head.kernel), ("head.bias", self.head.bias)]
+        return out
+
+    def sn_by_oracle_name(self):
+        out = []
+        for i, blk in enumerate(self.blocks):
+            out.append((f"block{i}.conv.u", blk.conv))
+            if str(i) in self.attn:
+                out += _attn_sn(f"block{i}.attn", self.attn[str(i)])
+        return out
+
+
+def get_generator(config):
+    """generator.py:14.  Returns a callable model: model([z, labels], training=True) -> images NHWC."""
+    return Generator(config)
+
+
+def get_discriminator(config):
+    """discriminator.py:13.  model([images, labels], training=True) -> patch logits [B,4,4,1] (or [B,1])."""
+    return Discriminator(config)

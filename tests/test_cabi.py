@@ -1,0 +1,77 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads, and exports every symbol
+include/sagan_b200.h declares; the host layer surface mirrors the reference's; the product has no CPU path."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sagan_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sagan_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    path = ge.lib_path()
+    if not os.path.exists(path):
+        ge.build()
+    return path
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for s in ("sagan_sn_plan_create", "sagan_sn_plan_run", "sagan_sn_backward", "sagan_attn_fwd", "sagan_attn_bwd",
+              "sagan_conv2d_fwd", "sagan_conv2d_dgrad", "sagan_conv2d_wgrad", "sagan_bn_lrelu_fwd",
+              "sagan_bn_lrelu_bwd", "sagan_hinge_d", "sagan_hinge_g", "sagan_adam_step", "sagan_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/sagan_b200.h but not exported"
+    lib.sagan_abi_version.restype = ctypes.c_int
+    assert lib.sagan_abi_version() == 1
+
+
+def test_binding_covers_every_declared_symbol(lib_path):
+    from sagan_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    _lib.load()
+
+
+def test_layer_surface_mirrors_reference():
+    """Names imported at sagan/models/generator.py:4, discriminator.py:4 and layers.py:71 resolve from `layers`."""
+    import inspect
+    import layers
+    for name in ("SpectralNormalization", "SNConv2D", "SNDense", "AttentionLayer", "Attention_Layer"):
+        assert hasattr(layers, name)
+    sig = inspect.signature(layers.SpectralNormalization.__init__)
+    assert list(sig.parameters)[1:5] == ["module", "name", "Ip", "factor"]      # layers.py:12
+    assert sig.parameters["name"].default == "weights" and sig.parameters["Ip"].default == 1
+    with pytest.raises(ValueError, match="positive integer"):                   # layers.py:17-18
+        layers.SpectralNormalization(layers.Dense(4), Ip=0)
+    assert len(inspect.signature(layers.AttentionLayer.__init__).parameters) == 2   # no-arg constructor (+ math_mode)
+
+
+def test_product_has_no_cpu_fallback_and_does_not_import_the_oracle():
+    import torch
+    import layers
+    pkg = os.path.join(ROOT, "self-attention-gan_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception, match="no CPU fallback|CUDA"):
+            layers.Dense(4)(torch.zeros(2, 3))

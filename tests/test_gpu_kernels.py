@@ -1,0 +1,330 @@
+"""GPU parity tests: every kernel of libsagan_b200.so (called through the C ABI via the ctypes
+binding) against the CPU oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): sigma / u / v <= 1e-5 relative; attention and model
+forward / gradients <= 1e-5 relative L2 in FP32_STRICT mode, <= 2e-3 in BF16_TC mode.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden as mg  # noqa: E402
+
+from oracle import attention as oattn  # noqa: E402
+from oracle import nets as onets  # noqa: E402
+from oracle import sn as osn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STRICT_TOL = 1e-5
+TC_TOL = 2e-3
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+@pytest.fixture(scope="module")
+def F():
+    import sagan_b200.functional as F
+    from sagan_b200 import _lib
+    _lib.load()
+    return F
+
+
+# ---------------------------------------------------------------------------------------- spectral norm
+@pytest.mark.parametrize("Ip,factor", [(1, None), (2, 1.5)])
+def test_sn_power_iteration_all_shapes_one_launch(F, Ip, factor):
+    """All in-model SN matrix shapes in ONE multi-tensor launch, vs the fp64 oracle and the golden file."""
+    gold = np.load(os.path.join(GOLD, "sn.npz"))
+    Ws, us, dWs = [], [], []
+    for i, (R, K) in enumerate(mg.SN_SHAPES):
+        W, u, dW = mg.sn_inputs(R, K, 100 + i)
+        Ws.append(W), us.append(u), dWs.append(dW)
+    tW = [cu(W).requires_grad_(True) for W in Ws]
+    group = F.SpectralNormGroup(tW, [cu(u) for u in us], Ip, [factor] * len(Ws))
+    wbars = group.normalized(update=True)
+    loss = sum((wb * cu(dW)).sum() for wb, dW in zip(wbars, dWs))
+    loss.backward()
+    torch.cuda.synchronize()
+    for i, (R, K) in enumerate(mg.SN_SHAPES):
+        u2, v2, sig, Wb = osn.power_iteration(Ws[i].astype(np.float64), us[i].astype(np.float64), Ip, factor)
+        tag = f"{R}x{K}_Ip{Ip}"
+        # oracle == golden
+        assert rel_l2(u2, gold[tag + "_u"]) < 1e-12 and abs(sig - gold[tag + "_sigma"]) < 1e-12 * abs(sig)
+        assert rel_l2(group.u(i).cpu().numpy(), u2) < STRICT_TOL, tag
+        assert rel_l2(group.v(i).cpu().numpy(), v2) < STRICT_TOL, tag
+        assert abs(float(group.sigma(i).cpu()) - sig) < STRICT_TOL * abs(sig), tag
+        assert rel_l2(wbars[i].detach().cpu().numpy(), Wb) < STRICT_TOL, tag
+        g = osn.backward(dWs[i].astype(np.float64), Wb, u2, v2, sig, factor)
+        assert rel_l2(tW[i].grad.cpu().numpy(), g) < 2e-5, tag
+        assert rel_l2(mg.summarize(tW[i].grad.cpu().numpy()), gold[tag + "_dW_sum"]) < 2e-5, tag
+
+
+def test_sn_persistence_and_idempotence(F):
+    """u persists across calls: k single-iteration calls == one call with Ip = k (size-independent property);
+    at the fixed point sigma equals the top singular value."""
+    R, K = 96, 200
+    W, u, _ = mg.sn_inputs(R, K, 7)
+    g1 = F.SpectralNormGroup([cu(W)], [cu(u)], 1)
+    for _ in range(3):
+        g1.run()
+    g3 = F.SpectralNormGroup([cu(W)], [cu(u)], 3)
+    g3.run()
+    torch.cuda.synchronize()
+    assert rel_l2(g1.u(0).cpu().numpy(), g3.u(0).cpu().numpy()) < 1e-6
+    assert abs(float(g1.sigma(0).cpu()) - float(g3.sigma(0).cpu())) < 1e-6 * float(g3.sigma(0).cpu())
+    for _ in range(300):
+        g1.run()
+    torch.cuda.synchronize()
+    top = np.linalg.svd(osn.matricize(W.astype(np.float64)), compute_uv=False)[0]
+    assert abs(float(g1.sigma(0).cpu()) - top) < 1e-4 * top
+
+
+def test_sn_large_matrix_property(F):
+    """Roofline-sized matrix (4096 x 4096): W_bar * sigma == W and ||u|| == ||v|| == 1."""
+    R = K = 4096
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    W = torch.randn(K, R, device="cuda", generator=gen) * 0.02
+    u = torch.randn(1, R, device="cuda", generator=gen)
+    g = F.SpectralNormGroup([W], [u / u.norm()], 1)
+    g.run()
+    torch.cuda.synchronize()
+    sig = g.sigma(0)
+    assert torch.allclose(g.w_bar(0) * sig, W, rtol=1e-6, atol=1e-9)
+    assert abs(float(g.u(0).norm()) - 1) < 1e-5 and abs(float(g.v(0).norm()) - 1) < 1e-5
+    # against torch fp64 on the device data
+    Wm = W.reshape(R, K).double()
+    v = (u.double() / u.double().norm()) @ Wm
+    v = v / (v.norm() + 1e-12)
+    t = v @ Wm.t()
+    assert abs(float(sig) - float(t.norm())) < 1e-5 * float(t.norm())
+
+
+def test_sn_rejects_bad_ip(F):
+    W, u, _ = mg.sn_inputs(8, 16, 1)
+    with pytest.raises(ValueError, match="positive integer"):
+        F.SpectralNormGroup([cu(W)], [cu(u)], 0)
+
+
+# ---------------------------------------------------------------------------------------- conv family
+CONV_CASES = [  # B, H, W, Cin, Cout, k, stride   (the D / G layer shapes at small batch + odd ones)
+    (2, 64, 64, 3, 16, 4, 2), (2, 32, 32, 16, 32, 4, 2), (2, 8, 8, 64, 128, 4, 2),
+    (2, 64, 64, 16, 3, 4, 1), (2, 4, 4, 128, 1, 4, 1), (3, 9, 7, 5, 6, 3, 2), (2, 16, 16, 16, 2, 1, 1),
+    (1, 5, 5, 8, 20, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fwd_dgrad_wgrad(F, case):
+    B, H, W, Cin, Cout, k, s = case
+    rng = np.random.Generator(np.random.PCG64(11))
+    x = rng.standard_normal((B, H, W, Cin))
+    w = rng.standard_normal((k, k, Cin, Cout)) * 0.1
+    b = rng.standard_normal(Cout) * 0.1
+    tx, tw, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, b))
+    ref = torch.nn.functional.leaky_relu(onets.conv2d_same(tx, tw, tb, s), 0.1)
+    dy = rng.standard_normal(tuple(ref.shape))
+    ref.backward(torch.tensor(dy))
+    gx, gw, gb = (cu(a).requires_grad_(True) for a in (x, w, b))
+    y = F.conv2d(gx, gw, gb, s, "same", F.ACT_LRELU, 0.1)
+    y.backward(cu(dy))
+    torch.cuda.synchronize()
+    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
+    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < STRICT_TOL
+    assert rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()) < STRICT_TOL
+    assert rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()) < STRICT_TOL
+
+
+def test_conv2d_tanh_head(F):
+    rng = np.random.Generator(np.random.PCG64(12))
+    x = rng.standard_normal((2, 16, 16, 16))
+    w = rng.standard_normal((4, 4, 16, 3)) * 0.1
+    tx, tw = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w))
+    ref = torch.tanh(onets.conv2d_same(tx, tw, None, 1))
+    dy = rng.standard_normal(tuple(ref.shape))
+    ref.backward(torch.tensor(dy))
+    gx, gw = (cu(a).requires_grad_(True) for a in (x, w))
+    y = F.conv2d(gx, gw, None, 1, "same", F.ACT_TANH)
+    y.backward(cu(dy))
+    torch.cuda.synchronize()
+    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
+    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < STRICT_TOL
+    assert rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()) < STRICT_TOL
+
+
+@pytest.mark.parametrize("case", [(2, 4, 4, 256, 128, 4, 2), (2, 16, 16, 64, 32, 4, 2), (2, 32, 32, 32, 16, 4, 2),
+                                  (2, 5, 6, 8, 12, 3, 2), (1, 4, 4, 8, 8, 4, 2)])
+def test_conv2d_transpose(F, case):
+    B, H, W, Cin, Cout, k, s = case
+    rng = np.random.Generator(np.random.PCG64(13))
+    x = rng.standard_normal((B, H, W, Cin))
+    w = rng.standard_normal((k, k, Cout, Cin)) * 0.1
+    tx, tw = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w))
+    ref = onets.conv2d_transpose_same(tx, tw, s)
+    dy = rng.standard_normal(tuple(ref.shape))
+    ref.backward(torch.tensor(dy))
+    gx, gw = (cu(a).requires_grad_(True) for a in (x, w))
+    y = F.conv2d_transpose(gx, gw, s, "same")
+    assert tuple(y.shape) == tuple(ref.shape)
+    y.backward(cu(dy))
+    torch.cuda.synchronize()
+    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
+    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < STRICT_TOL
+    assert rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()) < STRICT_TOL
+
+
+def test_dense(F):
+    rng = np.random.Generator(np.random.PCG64(14))
+    x, w, b = rng.standard_normal((8, 128)), rng.standard_normal((128, 4096)) * 0.05, rng.standard_normal(4096)
+    tx, tw, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, b))
+    ref = tx @ tw + tb
+    dy = rng.standard_normal((8, 4096))
+    ref.backward(torch.tensor(dy))
+    gx, gw, gb = (cu(a).requires_grad_(True) for a in (x, w, b))
+    y = F.dense(gx, gw, gb)
+    y.backward(cu(dy))
+    torch.cuda.synchronize()
+    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
+    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < STRICT_TOL
+    assert rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()) < STRICT_TOL
+    assert rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()) < STRICT_TOL
+
+
+@pytest.mark.parametrize("shape", [(4, 8, 8, 128), (2, 64, 64, 16), (3, 5, 7, 12)])
+def test_batchnorm_lrelu(F, shape):
+    rng = np.random.Generator(np.random.PCG64(15))
+    x = rng.standard_normal(shape) * 1.7 + 0.3
+    C = shape[-1]
+    gam, bet = rng.standard_normal(C) * 0.3 + 1, rng.standard_normal(C) * 0.2
+    tx, tg, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, gam, bet))
+    stats = {"bn.moving_mean": torch.zeros(C, dtype=torch.float64), "bn.moving_var": torch.ones(C, dtype=torch.float64)}
+    ref = torch.nn.functional.leaky_relu(onets.batchnorm_train(tx, tg, tb, stats, "bn"), 0.1)
+    dy = rng.standard_normal(shape)
+    ref.backward(torch.tensor(dy))
+    gx, gg, gb = (cu(a).requires_grad_(True) for a in (x, gam, bet))
+    mm, mv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    y = F.batchnorm_lrelu(gx, gg, gb, mm, mv, 1e-3, 0.99, 0.1)
+    y.backward(cu(dy))
+    torch.cuda.synchronize()
+    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
+    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < 2e-5
+    assert rel_l2(gg.grad.cpu().numpy(), tg.grad.numpy()) < 2e-5
+    assert rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()) < 2e-5
+    assert rel_l2(mm.cpu().numpy(), stats["bn.moving_mean"].numpy()) < STRICT_TOL
+    assert rel_l2(mv.cpu().numpy(), stats["bn.moving_var"].numpy()) < STRICT_TOL
+
+
+# ---------------------------------------------------------------------------------------- attention
+def _run_attn(F, X, dY, w, mode):
+    t = {k: cu(np.asarray(v)).requires_grad_(True) for k, v in w.items()}
+    tx = cu(X).requires_grad_(True)
+    y = F.attention(tx, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"], mode)
+    y.backward(cu(dY))
+    torch.cuda.synchronize()
+    return y.detach().cpu().numpy(), tx.grad.cpu().numpy(), {k: v.grad.cpu().numpy() for k, v in t.items()}
+
+
+@pytest.mark.parametrize("case", list(enumerate(mg.ATTN_CASES)))
+def test_attention_strict_vs_golden(F, case):
+    i, (B, N, C) = case
+    gold = np.load(os.path.join(GOLD, "attention.npz"))
+    X, dY, w = mg.attn_inputs(B, N, C, 200 + i)
+    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_FP32_STRICT)
+    tag = f"B{B}_N{N}_C{C}"
+    assert rel_l2(y, gold[tag + "_Y"]) < STRICT_TOL
+    assert rel_l2(dx, gold[tag + "_dX"]) < STRICT_TOL
+    for k in oattn.WEIGHT_NAMES:
+        if k == "bphi":   # mathematically zero (softmax is invariant to a per-row shift of the logits)
+            assert np.abs(gw[k]).max() < 1e-4 * np.abs(gw["btheta"]).max()
+            continue
+        assert rel_l2(gw[k], gold[tag + "_d" + k]) < 2e-5, k
+
+
+def test_attention_strict_vs_oracle_ragged_and_large_logits(F):
+    """N not a multiple of the tile (200) and un-scaled logits of magnitude ~30 (no 1/sqrt(d), layers.py:108)."""
+    B, N, C = 2, 200, 32
+    X, dY, w = oattn.make_inputs(B, N, C, seed=5, gamma=0.8, dtype=np.float32)
+    w["Wtheta"] = w["Wtheta"] * 6
+    w["Wphi"] = w["Wphi"] * 6
+    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    Y = oattn.forward(X.astype(np.float64), **w64)
+    g = oattn.backward(dY.astype(np.float64), X.astype(np.float64), **w64)
+    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_FP32_STRICT)
+    assert rel_l2(y, Y) < STRICT_TOL
+    assert rel_l2(dx, g["dX"]) < 5e-5
+    for k in oattn.WEIGHT_NAMES:
+        if k == "bphi":
+            assert np.abs(gw[k]).max() < 1e-4 * np.abs(gw["btheta"]).max()
+            continue
+        assert rel_l2(gw[k], g["d" + k]) < 5e-5, k
+
+
+def test_attention_gamma_zero_is_identity(F):
+    """gamma is zero-initialised (layers.py:76-79): the block is the identity and only dgamma is non-zero."""
+    X, dY, w = oattn.make_inputs(2, 128, 16, seed=9, gamma=0.0, dtype=np.float32)
+    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_FP32_STRICT)
+    assert np.array_equal(y, X)
+    assert np.array_equal(dx, dY)
+    assert abs(gw["gamma"]).max() > 0
+    assert all(np.abs(gw[k]).max() == 0 for k in ("Wphi", "Wtheta", "Wg", "Wo", "bo"))
+
+
+def test_attention_full_size_properties(F):
+    """church64_attn G attention at 64x64 (N = 4096, C = 16), B = 4: permutation equivariance over tokens
+    and row-stochasticity (constant values => A == that constant), which do not need the O(N^2) oracle."""
+    B, N, C = 4, 4096, 16
+    X, dY, w = oattn.make_inputs(B, N, C, seed=21, gamma=0.5, dtype=np.float32)
+    t = {k: cu(np.asarray(v)) for k, v in w.items()}
+    args = (t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"])
+    x = cu(X)
+    y = F.attention(x, *args)
+    perm = torch.randperm(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    yp = F.attention(x[:, perm].contiguous(), *args)
+    torch.cuda.synchronize()
+    assert rel_l2(yp.cpu().numpy(), y[:, perm].cpu().numpy()) < 1e-5
+    # values independent of the token (Wg = 0): O = bg Wo + bo for every row
+    zg = torch.zeros_like(t["Wg"])
+    y2 = F.attention(x, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], zg, t["bg"], t["Wo"], t["bo"], t["gamma"])
+    const = t["bg"] @ t["Wo"] + t["bo"]
+    torch.cuda.synchronize()
+    assert rel_l2(y2.cpu().numpy(), (x + t["gamma"] * const).cpu().numpy()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------- losses / optimiser
+def test_hinge_and_adam(F):
+    rng = np.random.Generator(np.random.PCG64(17))
+    dr, df = rng.standard_normal((4, 4, 4, 1)) * 2, rng.standard_normal((4, 4, 4, 1)) * 2
+    loss = torch.zeros(2, device="cuda")
+    gr, gf = F.hinge_d_grads(cu(dr), cu(df), 8, loss[0:1])
+    gg = F.hinge_g_grads(cu(df), 8, loss[1:2])
+    torch.cuda.synchronize()
+    n = dr.size
+    assert abs(float(loss[0]) - (np.maximum(1 - dr, 0) + np.maximum(1 + df, 0)).sum()) < 1e-4
+    assert abs(float(loss[1]) - (-df).sum()) < 1e-4
+    assert np.allclose(gr.cpu().numpy(), np.where(1 - dr > 0, -1.0, 0.0) / (n * 8))
+    assert np.allclose(gf.cpu().numpy(), np.where(1 + df > 0, 1.0, 0.0) / (n * 8))
+    assert np.allclose(gg.cpu().numpy(), -1.0 / (n * 8))
+    # Keras Adam, beta_1 = 0, three steps
+    p0, g = rng.standard_normal(1000), rng.standard_normal((3, 1000))
+    p, v = cu(p0), torch.zeros(1000, device="cuda")
+    pr, vr = p0.copy(), np.zeros(1000)
+    for t in range(1, 4):
+        lr_t = 7e-4 * np.sqrt(1 - 0.999 ** t)
+        hyper = cu(np.array([lr_t, 0.0, 0.999, 1e-7]))
+        F.adam_step(p, cu(g[t - 1]), v, hyper)
+        vr = 0.999 * vr + 0.001 * g[t - 1] ** 2
+        pr = pr - lr_t * g[t - 1] / (np.sqrt(vr) + 1e-7)
+    torch.cuda.synchronize()
+    assert rel_l2(p.cpu().numpy(), pr) < 1e-6
