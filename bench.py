@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- SAGAN (church64_attn) training throughput on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: the full training step of
+/root/reference/sagan/main.py:171-211 (D update + G update, `update_ratio` = 1) at the
+example_configs/church64_attn.py model (z 128, gf 16, df 16, 64x64, attention at 32x32 and 64x64),
+per-GPU batch 64, synthetic uniform[-1,1) images and N(0,1) noise.
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM (CUDA-graph replay of
+the whole step), `e2e` = images/s through the public Trainer API with the batch copied from pinned
+host memory and the two loss scalars read back every step.  `roofline` is the dominant kernel
+(self-attention at N = 4096) timed alone with CUDA events; `cpu_baseline` is the CPU oracle
+(torch-CPU restatement of the reference's TF graph; TensorFlow is not installable here) on a bounded
+sample.  `--impl reference` times that CPU oracle only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "self-attention-gan_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CHURCH64 = dict(  # /root/reference/example_configs/church64_attn.py:14-27 (model / training keys)
+    model="vanilla", z_dim=128, gf_dim=16, df_dim=16, lr_g=2e-4, lr_d=7e-4, decay_rate=0.99, use_attention=True,
+    attn_dim_G=[32, 64], attn_dim_D=[8, 4], use_label=False, batch_size=64, loss="hinge_loss", update_ratio=1,
+    img_size=64, num_classes=1)
+METRIC = "sagan_train_images_per_sec_64x64"
+UNIT = "images/s"
+WORKLOAD = "church64_attn train step (D update + G update), per-GPU batch 64, 64x64x3, synthetic"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle leg
+def cpu_oracle_images_per_sec(steps, warmup, sample_batch=8, threads=None):
+    """Times the CPU oracle (oracle.train.OracleTrainer: un-fused torch-CPU fp32 restatement of the TF graph)
+    on a bounded sample: `sample_batch` images per step instead of 64."""
+    from oracle import train as otrain
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(threads or cores)
+    cfg = dict(CHURCH64, batch_size=sample_batch)
+    tr = otrain.OracleTrainer(cfg, torch.float32, seed=0, attn_sigma=0.0, global_batch_size=sample_batch)
+    rng = np.random.Generator(np.random.PCG64(1234))
+    img = torch.tensor(rng.uniform(-1, 1, (sample_batch, 64, 64, 3)).astype(np.float32))
+    times = []
+    for s in range(warmup + steps):
+        nd = torch.tensor(rng.standard_normal((sample_batch, 128)).astype(np.float32))
+        ng = torch.tensor(rng.standard_normal((sample_batch, 128)).astype(np.float32))
+        t0 = time.perf_counter()
+        tr.train_step(img, [nd], ng)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    return dict(value=sample_batch / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"{sample_batch} of the 64 images of a step per iteration (full G+D train step, fp32, "
+                       f"{steps} timed + {warmup} warm-up iterations), oracle.train.OracleTrainer on torch-CPU"), dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base, dt = cpu_oracle_images_per_sec(max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "note": "CPU oracle (torch-CPU port of the reference TF2 graph; TensorFlow "
+                      "is not installable in this image), bounded sample per step"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- kernel rooflines
+def time_cuda(fn, iters, flush=None):
+    """Average device time of fn() over `iters` launches (CUDA events on the launching stream)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1.0)         # 512 MB write: evicts the 126 MB L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters * 1e-3
+
+
+def attn_flops(B, N, C, bwd=False):
+    d, dv = C // 8, C // 2
+    fwd = 2 * B * N * C * (2 * d + dv) + 2 * B * N * N * d + 2 * B * N * N * dv + 2 * B * N * dv * C
+    if not bwd:
+        return fwd
+    return 2 * B * N * N * (3 * d + 2 * dv) + 2 * (2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C)
+
+
+def kernel_rooflines(pk, math_mode):
+    """The dominant kernels of the step, timed alone: attention at G's 64x64 map (B=64, N=4096, C=16) and the
+    multi-tensor spectral-norm launch; plus a roofline-sized spectral norm (4096x4096)."""
+    import sagan_b200.functional as F
+    from oracle import attention as oattn
+    flush = torch.zeros(128 * 1024 * 1024, device="cuda")
+    B, N, C = 64, 4096, 16
+    X, dY, w = oattn.make_inputs(1, 8, C, seed=0, gamma=0.5, dtype=np.float32)
+    t = {k: torch.tensor(np.asarray(v, dtype=np.float32)).cuda().requires_grad_(True) for k, v in w.items()}
+    x = torch.randn(B, N, C, device="cuda", requires_grad=True)
+    dy = torch.randn(B, N, C, device="cuda")
+    args = (t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"])
+    with torch.no_grad():
+        t_fwd = time_cuda(lambda: F.attention(x, *args, math_mode), 10, flush)
+    y = F.attention(x, *args, math_mode)
+
+    def bwd():
+        torch.autograd.grad(y, [x] + list(t.values()), dy, retain_graph=True)
+    t_bwd = time_cuda(bwd, 5, flush)
+    out = {}
+    f_fwd, f_bwd = attn_flops(B, N, C), attn_flops(B, N, C, True)
+    out["attn_fwd"] = dict(bound="tensor", achieved=f_fwd / t_fwd / 1e12, peak=pk["tc_burst"], unit="TFLOP/s",
+                           frac=f_fwd / t_fwd / 1e12 / pk["tc_burst"], traffic=None, seconds=t_fwd,
+                           shape=f"B={B} N={N} C={C} (d=2, dv=8)", exps_per_s=B * N * N / t_fwd)
+    out["attn_bwd"] = dict(bound="tensor", achieved=f_bwd / t_bwd / 1e12, peak=pk["tc_burst"], unit="TFLOP/s",
+                           frac=f_bwd / t_bwd / 1e12 / pk["tc_burst"], traffic=None, seconds=t_bwd,
+                           shape=f"B={B} N={N} C={C} (d=2, dv=8)", exps_per_s=B * N * N / t_bwd)
+    # spectral norm at roofline size (64 MB matrix: 8 B/element rule of SURVEY.md §8d)
+    R = K = 4096
+    W = torch.randn(K, R, device="cuda") * 0.02
+    u = torch.randn(1, R, device="cuda")
+    g = F.SpectralNormGroup([W], [u / u.norm()], 1)
+    t_sn = time_cuda(g.run, 10, flush)
+    out["sn_4096x4096"] = dict(bound="hbm", achieved=g.algorithmic_bytes / t_sn / 1e9, peak=pk["hbm"], unit="GB/s",
+                               frac=g.algorithmic_bytes / t_sn / 1e9 / pk["hbm"], traffic=None, seconds=t_sn,
+                               rule="8 B/element (read W once + write W_bar; 64 MB matrix, passes 2-3 from L2)")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    from sagan_b200 import MATH_BF16_TC, MATH_FP32_STRICT, _lib
+    from sagan_b200 import nn as snn
+    from sagan_b200.trainer import Trainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    math_mode = MATH_BF16_TC if args.math == "bf16_tc" else MATH_FP32_STRICT
+    snn.set_default_math_mode(math_mode)
+    cfg = dict(CHURCH64)
+    B = cfg["batch_size"]
+    tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=126227 // (B * world), seed=0)   # LSUN church: 126 227 images
+    rng = np.random.Generator(np.random.PCG64(1234 + rank))
+    host_batches = [torch.tensor(rng.uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
+    dev_batches = [b.to(dev) for b in host_batches]
+
+    n0 = _lib.launch_count()
+    tr.capture(warmup=max(3, args.warmup))
+    # kernels launched while capturing == kernel nodes of this library in one replay of the step graph
+    n_cap0 = _lib.launch_count()
+    launches_per_step = None
+    # count by re-running one eager step (same launch sequence as the captured one)
+    c0 = _lib.launch_count()
+    tr.train_step(dev_batches[0])
+    launches_per_step = _lib.launch_count() - c0
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms) * 1e-3
+
+    # ---- value: inputs resident in HBM, whole-step CUDA graph
+    for s in range(args.warmup):
+        tr.graph_step(dev_batches[s % 4])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sec = timed(lambda s: tr.graph_step(dev_batches[s % 4]), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * args.steps / sec
+
+    # ---- e2e: pinned host batch -> device each step, losses read back each step
+    def e2e_step(s):
+        tr.graph_step(host_batches[s % 4])
+        tr.losses()                       # device -> host read of the two loss sums (synchronises)
+    for s in range(2):
+        e2e_step(s)
+    sec_e2e = timed(e2e_step, args.steps)
+    e2e = B * world * args.steps / sec_e2e
+    losses = tr.losses()
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    pk = peaks()
+    roofs = kernel_rooflines(pk, math_mode)
+    dom = max(("attn_fwd", "attn_bwd"), key=lambda k: roofs[k]["seconds"])
+    roofline = dict(roofs[dom], kernel=dom, peak_source=pk["src"],
+                    note="in-model attention dims (d=2, dv=8) are exp/MUFU-bound, not tensor-bound: see exps_per_s")
+    if args.cpu_baseline:
+        cpu, _ = cpu_oracle_images_per_sec(2, 1)
+    else:
+        cpu = None
+    act_mb = 4 * B * (64 * 64 * 16 * 12 + 32 * 32 * 32 * 10) / 1e6
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if math_mode == MATH_FP32_STRICT else "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "math_mode": args.math, "cuda_graph": True,
+                   "l2": f"no explicit flush: a step touches ~{act_mb:.0f} MB of saved activations (> 126 MB L2)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": sec_e2e / args.steps * 1e3,
+                "h2d_bytes_per_step": int(host_batches[0].numel() * 4 + 2 * 16), "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline,
+        "kernels": {k: {kk: vv for kk, vv in v.items()} for k, v in roofs.items()},
+        "cpu_baseline": cpu,
+        "final_losses": losses,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default="fp32_strict", choices=["fp32_strict", "bf16_tc"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: spawn one process per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
