@@ -1,11 +1,476 @@
-// placeholder, replaced by the tcgen05 kernel
+// Self-attention block, BF16_TC math mode: flash-style forward on the 5th-gen tensor cores.
+//
+// Replaces Attention_Layer.call (/root/reference/layers.py:93-120): S = theta phi^T and A = softmax(S) g are
+// tcgen05.mma (bf16 operands, fp32 accumulators in TMEM), K / V^T tiles arrive by TMA into 128-byte-swizzled
+// shared memory, the online softmax runs on fp32 rows read back with tcgen05.ld (one thread per query row),
+// and the output 1x1 conv + gamma residual are fused in the epilogue.  The [B,N,N] map is never written.
+//
+// CTA = one 128-query tile of one sample; 5 warps:
+//   warps 0-3  softmax / epilogue (thread r <-> TMEM lane r <-> query row r); thread 0 also issues the MMAs
+//   warp  4    TMA producer (one lane), TMEM allocator
+// Per 128-key tile j:   S_j = Q K_j^T   (M=128, N=128, K=16*kq_steps)   -> TMEM columns [S]
+//                       P_j = exp2(S_j - m)  -> bf16, written to shared memory in the UMMA K-major SW128 layout
+//                       O  += P_j V_j  (M=128, N=DVP, K=128)            -> TMEM columns [O]
+// The running-max rescale of O is lazy (only when the row max grows by > 2^8), so O stays in TMEM.
+// NS = number of S buffers: 2 lets QK_{j+1} run under softmax_j (ping-pong inside the CTA, one CTA per SM);
+// NS = 1 is used for small value dims where two CTAs share an SM and overlap each other instead.
+#include <math.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace sagan {
-size_t attn_tc_workspace_bytes(int B, int N, int C) { return 0; }
+
+using namespace tc;
+
+constexpr float TC_LOG2E = 1.4426950408889634f;
+constexpr float TC_LN2 = 0.6931471805599453f;
+constexpr int TC_THREADS = 160;
+constexpr int QK_COLS = 64;   // Q / K rows are padded to 64 bf16 = one 128-byte swizzle span
+
+// ------------------------------------------------------------------------------------ host: tensor maps
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                      uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_err("cuTensorMapEncodeTiled is not available from this driver");
+    return SAGAN_EUNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu stride=%llu box=%ux%u)", (int)r,
+            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_bytes, box_rows, box_cols);
+    return SAGAN_EINVAL;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ projections (small C)
+// one thread per PADDED token: Qb[b][n][64] = bf16(log2e * (x Wq + bq)), Kb[b][n][64] = bf16(x Wk + bk),
+// Vt[b][v][n] = bf16(x Wv + bv); rows n >= N are zero (so masked keys contribute exactly 0 to P V).
+template <int C>
+__global__ void __launch_bounds__(128)
+attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, const float* __restrict__ bq,
+                    const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
+                    const float* __restrict__ bv, __nv_bfloat16* __restrict__ Qb, __nv_bfloat16* __restrict__ Kb,
+                    __nv_bfloat16* __restrict__ Vt, int B, int N, int Npad) {
+  constexpr int D = C / 8, DV = C / 2, DVP = DV < 16 ? 16 : DV;
+  __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
+  for (int i = threadIdx.x; i < C * D; i += 128) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
+  for (int i = threadIdx.x; i < C * DV; i += 128) sWv[i] = Wv[i];
+  for (int i = threadIdx.x; i < D; i += 128) { sbq[i] = bq[i]; sbk[i] = bk[i]; }
+  for (int i = threadIdx.x; i < DV; i += 128) sbv[i] = bv[i];
+  __syncthreads();
+  const long long tp = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (tp >= (long long)B * Npad) return;
+  const int b = (int)(tp / Npad), n = (int)(tp - (long long)b * Npad);
+  const bool valid = n < N;
+  float x[C];
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v = ld4(X + ((long long)b * N + n) * C + c);
+    x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
+  }
+  float q[16], k[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { q[j] = 0.f; k[j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    float a = sbq[j], kk = sbk[j];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      a = fmaf(x[c], sWq[c * D + j], a);
+      kk = fmaf(x[c], sWk[c * D + j], kk);
+    }
+    q[j] = valid ? a * TC_LOG2E : 0.f;
+    k[j] = valid ? kk : 0.f;
+  }
+  uint4 pq[2], pk[2];
+  pq[0] = make_uint4(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]), pack_bf16x2(q[4], q[5]), pack_bf16x2(q[6], q[7]));
+  pq[1] = make_uint4(pack_bf16x2(q[8], q[9]), pack_bf16x2(q[10], q[11]), pack_bf16x2(q[12], q[13]), pack_bf16x2(q[14], q[15]));
+  pk[0] = make_uint4(pack_bf16x2(k[0], k[1]), pack_bf16x2(k[2], k[3]), pack_bf16x2(k[4], k[5]), pack_bf16x2(k[6], k[7]));
+  pk[1] = make_uint4(pack_bf16x2(k[8], k[9]), pack_bf16x2(k[10], k[11]), pack_bf16x2(k[12], k[13]), pack_bf16x2(k[14], k[15]));
+  uint4* qd = reinterpret_cast<uint4*>(Qb + tp * QK_COLS);
+  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * QK_COLS);
+  qd[0] = pq[0]; qd[1] = pq[1];
+  kd[0] = pk[0]; kd[1] = pk[1];
+#pragma unroll
+  for (int v = 0; v < DVP; ++v) {
+    float a = 0.f;
+    if (v < DV) {
+      a = sbv[v];
+#pragma unroll
+      for (int c = 0; c < C; ++c) a = fmaf(x[c], sWv[c * DV + v], a);
+    }
+    Vt[((long long)b * DVP + v) * Npad + n] = __float2bfloat16_rn(valid ? a : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------ flash forward
+template <int DVP, int NS, int NP>
+struct FwdSmem {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int K_BYTES = 128 * 128;
+  static constexpr int V_BYTES = 2 * DVP * 128;      // two 64-key sub-tiles of [DVP rows][128 B]
+  static constexpr int P_BYTES = 2 * 128 * 128;      // two 64-key sub-tiles of [128 rows][128 B]
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
+  static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
+  static constexpr int OFF_W = OFF_P + NP * P_BYTES;         // fp32 Wo [dv][C] + bo [C] for the fused epilogue
+  static constexpr int W_BYTES = (32 * 64 + 64) * 4;
+  static constexpr int OFF_BAR = OFF_W + W_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;          // + alignment slack
+  static constexpr int TMEM_COLS = (NS * 128 + DVP) <= 256 ? 256 : 512;
+  static constexpr int OCOL = NS * 128;
+};
+
+// CEPI: channel count C when the out-projection + residual are fused on the CUDA cores (C <= 64), 0 otherwise
+template <int DVP, int NS, int NP, int CEPI>
+__global__ void __launch_bounds__(TC_THREADS, NS == 1 ? 2 : 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const float* __restrict__ X, const float* __restrict__ Wo,
+                   const float* __restrict__ bo, const float* __restrict__ gamma, float* __restrict__ Y,
+                   float* __restrict__ lse, float* __restrict__ A_saved, __nv_bfloat16* __restrict__ A_bf16, int N,
+                   int Npad, int dv, int kq_steps) {
+  using L = FwdSmem<DVP, NS, NP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + L::OFF_Q;
+  uint8_t* sK = smem + L::OFF_K;
+  uint8_t* sV = smem + L::OFF_V;
+  uint8_t* sP = smem + L::OFF_P;
+  float* sW = reinterpret_cast<float*>(smem + L::OFF_W);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* barQ = bars + 0;
+  uint64_t* barKV = bars + 1;   // [2]
+  uint64_t* barS = bars + 3;    // [2]
+  uint64_t* barPV = bars + 5;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, qt = blockIdx.x;
+  const int nt = Npad / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(barQ, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(barKV + i, 1); mbar_init(barS + i, 1); mbar_init(barPV + i, 1); }
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      mbar_expect_tx(barQ, L::Q_BYTES);
+      tma_load_2d(sQ, &tmQ, barQ, 0, b * Npad + qt * 128);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(barPV + s, ((j - 2) >> 1) & 1);   // PV_{j-2} done (=> QK_{j-2} done): stage s is free
+        mbar_expect_tx(barKV + s, L::K_BYTES + L::V_BYTES);
+        tma_load_2d(sK + s * L::K_BYTES, &tmK, barKV + s, 0, b * Npad + j * 128);
+        tma_load_2d(sV + s * L::V_BYTES, &tmV, barKV + s, j * 128, b * DVP);
+        tma_load_2d(sV + s * L::V_BYTES + DVP * 128, &tmV, barKV + s, j * 128 + 64, b * DVP);
+      }
+    }
+  } else {
+    // ================================================================ softmax warps (+ MMA issue by thread 0)
+    const int row = threadIdx.x;                                   // query row inside the tile == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+    constexpr uint32_t IDESC_O = make_idesc_bf16(128, DVP);
+    const uint64_t descQ = make_desc_sw128(smem_u32(sQ));
+
+    if (CEPI > 0) {
+      const int nW = dv * CEPI;
+      for (int e = threadIdx.x; e < nW; e += 128) sW[e] = Wo[e];
+      for (int e = threadIdx.x; e < CEPI; e += 128) sW[32 * 64 + e] = bo[e];
+    }
+
+    auto issue_qk = [&](int j) {
+      const int s = j & 1;
+      mbar_wait(barKV + s, (j >> 1) & 1);
+      tc_fence_after();
+      const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
+      const uint32_t d = tmem_base + (uint32_t)((j % NS) * 128);
+      for (int ks = 0; ks < kq_steps; ++ks) mma_bf16_ss(d, descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+      mma_commit(barS + (j % NS));
+    };
+    auto issue_pv = [&](int j) {
+      const int s = j & 1, pb = j % NP;
+      const uint64_t descP = make_desc_sw128(smem_u32(sP + pb * L::P_BYTES));
+      const uint64_t descV = make_desc_sw128(smem_u32(sV + s * L::V_BYTES));
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t a = descP + (uint64_t)((ks >> 2) * ((128 * 128) >> 4) + (ks & 3) * 2);
+        const uint64_t bb = descV + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2);
+        mma_bf16_ss(tmem_base + L::OCOL, a, bb, IDESC_O, (j > 0) || (ks > 0));
+      }
+      mma_commit(barPV + s);
+    };
+
+    if (threadIdx.x == 0) {
+      mbar_wait(barQ, 0);
+      issue_qk(0);
+    }
+    __syncwarp();
+
+    float m_used = -INFINITY, l = 0.f;
+    const bool ragged = (N % 128) != 0;
+
+    for (int j = 0; j < nt; ++j) {
+      if (NS == 2) {
+        if (threadIdx.x == 0 && j + 1 < nt) issue_qk(j + 1);   // runs under softmax_j
+        __syncwarp();
+      }
+      mbar_wait(barS + (j % NS), (j / NS) & 1);
+      tc_fence_after();
+      const uint32_t t_s = t_row + (uint32_t)((j % NS) * 128);
+      const int kvalid = (ragged && j == nt - 1) ? (N - j * 128) : 128;   // keys of this tile that exist
+
+      // ---- pass 1: row max (logits are already in log2 units: Q carries log2(e))
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = __uint_as_float(r[i]);
+          mx = fmaxf(mx, (c * 32 + i < kvalid) ? sv : -INFINITY);
+        }
+      }
+      // ---- lazy rescale of the running accumulators
+      const bool need = mx > m_used + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        if (j > 0) {
+          mbar_wait(barPV + ((j - 1) & 1), ((j - 1) >> 1) & 1);       // every PV issued so far has completed
+          tc_fence_after();
+          const float scale = need ? exp2f(m_used - mx) : 1.0f;
+          l *= scale;
+#pragma unroll
+          for (int c = 0; c < DVP / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(t_row + L::OCOL + c * 16, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * scale);
+            tmem_st16(t_row + L::OCOL + c * 16, r);
+          }
+          tmem_wait_st();
+        }
+        if (need) m_used = mx;
+      }
+      // ---- P buffer free?  (PV_{j-NP} has finished reading it)
+      const int pb = j % NP;
+      if (j >= NP) mbar_wait(barPV + ((j - NP) & 1), ((j - NP) >> 1) & 1);
+      uint8_t* sPj = sP + pb * L::P_BYTES;
+      // ---- pass 2: P = exp2(S - m), row sum, bf16 pack, swizzled store
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2_approx(__uint_as_float(r[i]) - m_used);
+          float p1 = ex2_approx(__uint_as_float(r[i + 1]) - m_used);
+          p0 = (c * 32 + i < kvalid) ? p0 : 0.f;
+          p1 = (c * 32 + i + 1 < kvalid) ? p1 : 0.f;
+          l += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        uint8_t* sub = sPj + (c >> 1) * (128 * 128);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = (c & 1) * 4 + q4;
+          *reinterpret_cast<uint4*>(sub + sw128_offset(row, chunk)) =
+              make_uint4(pk[q4 * 4 + 0], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
+      tc_fence_before();             // orders this thread's tcgen05.ld / st before the barrier
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        if (NS == 1 && j + 1 < nt) issue_qk(j + 1);   // S is free again; QK_{j+1} queues ahead of the long PV_j
+        issue_pv(j);
+      }
+      __syncwarp();
+    }
+
+    // ---- epilogue: O / l, saved tensors, (fused) output conv + gamma residual
+    mbar_wait(barPV + ((nt - 1) & 1), ((nt - 1) >> 1) & 1);
+    tc_fence_after();
+    const int i_tok = qt * 128 + row;
+    const bool valid = i_tok < N;
+    const long long grow = (long long)b * N + (valid ? i_tok : 0);
+    const float inv = 1.0f / l;
+    if (CEPI > 0) {
+      constexpr int C = CEPI > 0 ? CEPI : 16;
+      constexpr int DV = C / 2;
+      float a[DVP];
+#pragma unroll
+      for (int c = 0; c < DVP / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(t_row + L::OCOL + c * 16, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[c * 16 + i] = __uint_as_float(r[i]) * inv;
+      }
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < DV; v += 4) st4(A_saved + grow * DV + v, make_float4(a[v], a[v + 1], a[v + 2], a[v + 3]));
+        lse[grow] = (m_used + log2f(l)) * TC_LN2;
+        const float gm = *gamma;
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+          float o[4] = {sW[32 * 64 + c], sW[32 * 64 + c + 1], sW[32 * 64 + c + 2], sW[32 * 64 + c + 3]};
+#pragma unroll
+          for (int v = 0; v < DV; ++v) {
+            const float4 w = *reinterpret_cast<const float4*>(&sW[v * C + c]);
+            o[0] = fmaf(a[v], w.x, o[0]); o[1] = fmaf(a[v], w.y, o[1]);
+            o[2] = fmaf(a[v], w.z, o[2]); o[3] = fmaf(a[v], w.w, o[3]);
+          }
+          const float4 xx = ld4(X + grow * C + c);
+          st4(Y + grow * C + c,
+              make_float4(fmaf(gm, o[0], xx.x), fmaf(gm, o[1], xx.y), fmaf(gm, o[2], xx.z), fmaf(gm, o[3], xx.w)));
+        }
+      }
+    } else {
+      // un-fused: A (normalised) as fp32 [B,N,dv] for the backward and as bf16 [B*Npad, DVP] for the out-proj GEMM
+      const long long prow = (long long)b * Npad + qt * 128 + row;
+#pragma unroll
+      for (int c = 0; c < DVP / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(t_row + L::OCOL + c * 16, r);
+        tmem_wait_ld();
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = valid ? __uint_as_float(r[i]) * inv : 0.f;
+        uint4 p0 = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+        uint4 p1 = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
+        uint4* dst = reinterpret_cast<uint4*>(A_bf16 + prow * DVP + c * 16);
+        dst[0] = p0; dst[1] = p1;
+        if (valid && A_saved) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            if (c * 16 + i < dv) st4(A_saved + grow * dv + c * 16 + i, make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]));
+        }
+      }
+      if (valid) lse[grow] = (m_used + log2f(l)) * TC_LN2;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct TcLayout {
+  int Npad, DVP, kq_steps;
+  size_t off_q, off_k, off_v, off_a, total;
+};
+
+static TcLayout tc_layout(int B, int N, int C) {
+  TcLayout t;
+  const int d = C / 8, dv = C / 2;
+  t.Npad = round_up(N, 128);
+  t.DVP = std::max(16, round_up(dv, 16));
+  t.kq_steps = (d + 15) / 16;
+  const size_t T = (size_t)B * t.Npad;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+  t.off_q = take(T * QK_COLS * 2);
+  t.off_k = take(T * QK_COLS * 2);
+  t.off_v = take((size_t)B * t.DVP * t.Npad * 2);
+  t.off_a = take(T * t.DVP * 2);
+  t.total = o + 1024;
+  return t;
+}
+
+size_t attn_tc_workspace_bytes(int B, int N, int C) { return tc_layout(B, N, C).total; }
+
+template <int DVP, int NS, int NP, int CEPI>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const float* X,
+                      const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
+                      __nv_bfloat16* Ab, int B, int N, int Npad, int dv, int kq_steps, cudaStream_t st) {
+  using L = FwdSmem<DVP, NS, NP>;
+  auto kern = attn_fwd_tc_kernel<DVP, NS, NP, CEPI>;
+  static bool configured = false;
+  if (!configured) {
+    SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<dim3(Npad / 128, B), TC_THREADS, L::TOTAL, st>>>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, Ab, N, Npad, dv,
+                                                          kq_steps);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
                 const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
                 int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
-  set_err("BF16_TC attention not built yet");
+  if (!(C == 16 || C == 32 || C == 64)) {
+    set_err("sagan_attn_fwd: BF16_TC currently supports C in {16,32,64} (C=%d)", C);
+    return SAGAN_EUNSUPPORTED;
+  }
+  const TcLayout t = tc_layout(B, N, C);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(base + t.off_q);
+  __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(base + t.off_k);
+  __nv_bfloat16* Vt = reinterpret_cast<__nv_bfloat16*>(base + t.off_v);
+  const long long Tp = (long long)B * t.Npad;
+  const unsigned pb = (unsigned)ceil_div<long long>(Tp, 128);
+  switch (C) {
+    case 16: attn_proj_tc_kernel<16><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad); break;
+    case 32: attn_proj_tc_kernel<32><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad); break;
+    case 64: attn_proj_tc_kernel<64><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad); break;
+  }
+  SAGAN_LAUNCH_CHECK();
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, Qb, (uint64_t)Tp, QK_COLS, QK_COLS * 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tp, QK_COLS, QK_COLS * 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Npad, (uint64_t)t.Npad * 2, (uint32_t)t.DVP))) return rc;
+  const int dv = C / 2;
+  switch (C) {
+    case 16: return launch_fwd<16, 1, 1, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 32: return launch_fwd<16, 1, 1, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 64: return launch_fwd<32, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+  }
   return SAGAN_EUNSUPPORTED;
 }
+
 }  // namespace sagan

@@ -328,3 +328,38 @@ def test_hinge_and_adam(F):
         pr = pr - lr_t * g[t - 1] / (np.sqrt(vr) + 1e-7)
     torch.cuda.synchronize()
     assert rel_l2(p.cpu().numpy(), pr) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------- attention, BF16_TC (tcgen05)
+@pytest.mark.parametrize("case", list(enumerate(mg.ATTN_CASES)))
+def test_attention_tc_vs_golden(F, case):
+    """tcgen05 / TMEM / TMA forward (bf16 operands, fp32 accumulate) against the fp64 golden: <= 2e-3 rel-L2."""
+    i, (B, N, C) = case
+    gold = np.load(os.path.join(GOLD, "attention.npz"))
+    X, dY, w = mg.attn_inputs(B, N, C, 200 + i)
+    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_BF16_TC)
+    tag = f"B{B}_N{N}_C{C}"
+    assert rel_l2(y, gold[tag + "_Y"]) < TC_TOL
+    # the attention contribution alone (Y - X) must also be accurate, not just hidden behind the residual
+    assert rel_l2(y - X, gold[tag + "_Y"] - X) < 1e-2
+    assert rel_l2(dx, gold[tag + "_dX"]) < TC_TOL
+    for k in oattn.WEIGHT_NAMES:
+        if k == "bphi":
+            continue
+        assert rel_l2(gw[k], gold[tag + "_d" + k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("shape", [(4, 4096, 16), (4, 1024, 32), (2, 1024, 64), (3, 1000, 16)])
+def test_attention_tc_vs_strict_full_size(F, shape):
+    """In-model sizes (N = 4096 / 1024): the tensor-core forward against the fp32 CUDA-core forward."""
+    B, N, C = shape
+    X, dY, w = oattn.make_inputs(B, N, C, seed=31, gamma=0.7, dtype=np.float32)
+    w["Wtheta"] = w["Wtheta"] * 3      # un-scaled logits of a few units, like a trained model
+    t = {k: cu(np.asarray(v)) for k, v in w.items()}
+    args = (t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"])
+    x = cu(X)
+    ys = F.attention(x, *args, F.MATH_FP32_STRICT)
+    yt = F.attention(x, *args, F.MATH_BF16_TC)
+    torch.cuda.synchronize()
+    assert rel_l2(yt.cpu().numpy(), ys.cpu().numpy()) < TC_TOL
+    assert rel_l2((yt - x).cpu().numpy(), (ys - x).cpu().numpy()) < 1e-2
