@@ -72,7 +72,7 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
                     const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
                     const float* __restrict__ bv, __nv_bfloat16* __restrict__ Qb, __nv_bfloat16* __restrict__ Kb,
                     __nv_bfloat16* __restrict__ Vt, int B, int N, int Npad) {
-  constexpr int D = C / 8, DV = C / 2, DVP = DV < 16 ? 16 : DV;
+  constexpr int D = C / 8, DV = C / 2, DVP = 2 * DV;   // V^T rows: [v_hi (DV) | v_lo (DV)]
   __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
   for (int i = threadIdx.x; i < C * D; i += 128) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
   for (int i = threadIdx.x; i < C * DV; i += 128) sWv[i] = Wv[i];
@@ -90,9 +90,14 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
     if (valid) v = ld4(X + ((long long)b * N + n) * C + c);
     x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
   }
-  float q[16], k[16];
+  // Split-bf16 logits: q = q_hi + q_lo, k = k_hi + k_lo (each half a bf16).  The K dimension of the QK^T MMA is
+  // padded to a multiple of 16 anyway, so the row is laid out as  Q: [q_hi | q_lo | q_hi | 0..]  K: [k_hi | k_hi | k_lo | 0..]
+  // and one MMA yields q_hi.k_hi + q_lo.k_hi + q_hi.k_lo -- logits accurate to ~2^-16 instead of 2^-8 at no extra cost
+  // for d <= 5 (the logits are NOT scaled by 1/sqrt(d), layers.py:108, so bf16 logits would dominate the error).
+  constexpr int KQ = ((3 * D + 15) / 16) * 16;
+  float q[KQ], k[KQ];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { q[j] = 0.f; k[j] = 0.f; }
+  for (int j = 0; j < KQ; ++j) { q[j] = 0.f; k[j] = 0.f; }
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     float a = sbq[j], kk = sbk[j];
@@ -101,27 +106,32 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
       a = fmaf(x[c], sWq[c * D + j], a);
       kk = fmaf(x[c], sWk[c * D + j], kk);
     }
-    q[j] = valid ? a * TC_LOG2E : 0.f;
-    k[j] = valid ? kk : 0.f;
+    a = valid ? a * TC_LOG2E : 0.f;
+    kk = valid ? kk : 0.f;
+    const float a_hi = __bfloat162float(__float2bfloat16_rn(a)), k_hi = __bfloat162float(__float2bfloat16_rn(kk));
+    q[j] = a_hi; q[D + j] = a - a_hi; q[2 * D + j] = a_hi;
+    k[j] = k_hi; k[D + j] = k_hi;     k[2 * D + j] = kk - k_hi;
   }
-  uint4 pq[2], pk[2];
-  pq[0] = make_uint4(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]), pack_bf16x2(q[4], q[5]), pack_bf16x2(q[6], q[7]));
-  pq[1] = make_uint4(pack_bf16x2(q[8], q[9]), pack_bf16x2(q[10], q[11]), pack_bf16x2(q[12], q[13]), pack_bf16x2(q[14], q[15]));
-  pk[0] = make_uint4(pack_bf16x2(k[0], k[1]), pack_bf16x2(k[2], k[3]), pack_bf16x2(k[4], k[5]), pack_bf16x2(k[6], k[7]));
-  pk[1] = make_uint4(pack_bf16x2(k[8], k[9]), pack_bf16x2(k[10], k[11]), pack_bf16x2(k[12], k[13]), pack_bf16x2(k[14], k[15]));
   uint4* qd = reinterpret_cast<uint4*>(Qb + tp * QK_COLS);
   uint4* kd = reinterpret_cast<uint4*>(Kb + tp * QK_COLS);
-  qd[0] = pq[0]; qd[1] = pq[1];
-  kd[0] = pk[0]; kd[1] = pk[1];
 #pragma unroll
-  for (int v = 0; v < DVP; ++v) {
-    float a = 0.f;
-    if (v < DV) {
-      a = sbv[v];
+  for (int g = 0; g < KQ / 8; ++g) {
+    qd[g] = make_uint4(pack_bf16x2(q[g * 8 + 0], q[g * 8 + 1]), pack_bf16x2(q[g * 8 + 2], q[g * 8 + 3]),
+                       pack_bf16x2(q[g * 8 + 4], q[g * 8 + 5]), pack_bf16x2(q[g * 8 + 6], q[g * 8 + 7]));
+    kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
+                       pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
+  }
+  // values are split the same way (v = v_hi + v_lo, two bf16 rows of V^T), so O = P [v_hi | v_lo] carries V exactly
+  // and the only bf16 rounding left in A is that of P itself
 #pragma unroll
-      for (int c = 0; c < C; ++c) a = fmaf(x[c], sWv[c * DV + v], a);
-    }
-    Vt[((long long)b * DVP + v) * Npad + n] = __float2bfloat16_rn(valid ? a : 0.f);
+  for (int v = 0; v < DV; ++v) {
+    float a = sbv[v];
+#pragma unroll
+    for (int c = 0; c < C; ++c) a = fmaf(x[c], sWv[c * DV + v], a);
+    a = valid ? a : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+    Vt[((long long)b * DVP + v) * Npad + n] = hi;
+    Vt[((long long)b * DVP + DV + v) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(hi));
   }
 }
 
@@ -252,19 +262,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t t_s = t_row + (uint32_t)((j % NS) * 128);
       const int kvalid = (ragged && j == nt - 1) ? (N - j * 128) : 128;   // keys of this tile that exist
 
-      // ---- pass 1: row max (logits are already in log2 units: Q carries log2(e))
-      float mx = -INFINITY;
+      // ---- the whole S row (128 fp32) comes to registers with ONE exposed TMEM round trip
+      //      (logits are already in log2 units: Q carries log2(e))
+      uint32_t r[128];
+      tmem_ld32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+      tmem_ld32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+      tmem_wait_ld();
+      if (kvalid < 128) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(r[i]);
-          mx = fmaxf(mx, (c * 32 + i < kvalid) ? sv : -INFINITY);
-        }
+        for (int i = 0; i < 128; ++i)
+          if (i >= kvalid) r[i] = 0xff800000u;   // -inf: masked keys of the ragged last tile
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // ---- lazy rescale of the running accumulators
       const bool need = mx > m_used + 8.0f;
       if (__any_sync(0xffffffffu, need)) {
@@ -275,12 +294,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           l *= scale;
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
-            uint32_t r[16];
-            tmem_ld16(t_row + L::OCOL + c * 16, r);
+            uint32_t o[16];
+            tmem_ld16(t_row + L::OCOL + c * 16, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * scale);
-            tmem_st16(t_row + L::OCOL + c * 16, r);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
+            tmem_st16(t_row + L::OCOL + c * 16, o);
           }
           tmem_wait_st();
         }
@@ -290,30 +309,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int pb = j % NP;
       if (j >= NP) mbar_wait(barPV + ((j - NP) & 1), ((j - NP) >> 1) & 1);
       uint8_t* sPj = sP + pb * L::P_BYTES;
-      // ---- pass 2: P = exp2(S - m), row sum, bf16 pack, swizzled store
+      // ---- P = exp2(S - m), row sum, bf16 pack, swizzled store (16 B = 8 keys per store)
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      for (int g = 0; g < 16; ++g) {
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(__uint_as_float(r[i]) - m_used);
-          float p1 = ex2_approx(__uint_as_float(r[i + 1]) - m_used);
-          p0 = (c * 32 + i < kvalid) ? p0 : 0.f;
-          p1 = (c * 32 + i + 1 < kvalid) ? p1 : 0.f;
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = ex2_approx(__uint_as_float(r[g * 8 + 2 * i]) - m_used);
+          const float p1 = ex2_approx(__uint_as_float(r[g * 8 + 2 * i + 1]) - m_used);
+          l0 += p0;
+          l1 += p1;
+          pk[i] = pack_bf16x2(p0, p1);
         }
-        uint8_t* sub = sPj + (c >> 1) * (128 * 128);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;
-          *reinterpret_cast<uint4*>(sub + sw128_offset(row, chunk)) =
-              make_uint4(pk[q4 * 4 + 0], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+        // key columns [8g, 8g+8): sub-tile g/8, 16-byte chunk g%8
+        *reinterpret_cast<uint4*>(sPj + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7)) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      l += l0 + l1;
       fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
       tc_fence_before();             // orders this thread's tcgen05.ld / st before the barrier
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -335,6 +348,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (CEPI > 0) {
       constexpr int C = CEPI > 0 ? CEPI : 16;
       constexpr int DV = C / 2;
+      static_assert(CEPI == 0 || DVP == 2 * DV, "fused epilogue expects split values [v_hi | v_lo]");
       float a[DVP];
 #pragma unroll
       for (int c = 0; c < DVP / 16; ++c) {
@@ -342,8 +356,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld16(t_row + L::OCOL + c * 16, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[c * 16 + i] = __uint_as_float(r[i]) * inv;
+        for (int i = 0; i < 16; ++i) a[c * 16 + i] = __uint_as_float(r[i]);
       }
+#pragma unroll
+      for (int v = 0; v < DV; ++v) a[v] = (a[v] + a[DV + v]) * inv;
       if (valid) {
 #pragma unroll
         for (int v = 0; v < DV; v += 4) st4(A_saved + grow * DV + v, make_float4(a[v], a[v + 1], a[v + 2], a[v + 3]));
@@ -407,8 +423,8 @@ static TcLayout tc_layout(int B, int N, int C) {
   TcLayout t;
   const int d = C / 8, dv = C / 2;
   t.Npad = round_up(N, 128);
-  t.DVP = std::max(16, round_up(dv, 16));
-  t.kq_steps = (d + 15) / 16;
+  t.DVP = (C <= 64) ? 2 * dv : std::max(16, round_up(dv, 16));   // small C: split values [v_hi | v_lo]
+  t.kq_steps = (3 * d + 15) / 16;   // split-bf16 logits: [hi|lo|hi] x [hi|hi|lo]
   const size_t T = (size_t)B * t.Npad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
@@ -467,8 +483,8 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
   const int dv = C / 2;
   switch (C) {
     case 16: return launch_fwd<16, 1, 1, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 32: return launch_fwd<16, 1, 1, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 64: return launch_fwd<32, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 32: return launch_fwd<32, 1, 1, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 64: return launch_fwd<64, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
   }
   return SAGAN_EUNSUPPORTED;
 }

@@ -343,10 +343,12 @@ def test_attention_tc_vs_golden(F, case):
     # the attention contribution alone (Y - X) must also be accurate, not just hidden behind the residual
     assert rel_l2(y - X, gold[tag + "_Y"] - X) < 1e-2
     assert rel_l2(dx, gold[tag + "_dX"]) < TC_TOL
-    for k in oattn.WEIGHT_NAMES:
-        if k == "bphi":
-            continue
-        assert rel_l2(gw[k], gold[tag + "_d" + k]) < 1e-2, k
+    errs = {k: rel_l2(gw[k], gold[tag + "_d" + k]) for k in oattn.WEIGHT_NAMES if k != "bphi"}
+    print(tag, "Y", rel_l2(y, gold[tag + "_Y"]), "Y-X", rel_l2(y - X, gold[tag + "_Y"] - X), "dX", rel_l2(dx, gold[tag + "_dX"]), errs)
+    # parameter gradients: the theta / phi gradients are cancellation-prone (sum_j dS_ij = 0) and inherit the bf16
+    # rounding of P through D = rowsum(dA * A); measured <= 3e-3, asserted at 5e-3 (everything else is < 2e-3)
+    for k, e in errs.items():
+        assert e < (5e-3 if k in ("Wtheta", "Wphi", "btheta") else TC_TOL), (k, e)
 
 
 @pytest.mark.parametrize("shape", [(4, 4096, 16), (4, 1024, 32), (2, 1024, 64), (3, 1000, 16)])
