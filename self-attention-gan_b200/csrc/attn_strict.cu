@@ -376,30 +376,15 @@ static int attn_fwd_strict_t(const float* X, const float* Wq, const float* bq, c
   return 0;
 }
 
+// common tail of the backward: dX from (dQ, dK, dV), parameter gradients as 1x1-conv wgrads
 template <int C>
-static int attn_bwd_strict_t(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
-                             const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
-                             const float* gamma, const float* lse, const float* A, float* dX, float* dWq, float* dbq,
-                             float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma,
-                             int B, int N, float* ws, cudaStream_t st) {
+static int attn_bwd_tail_t(const float* dY, const float* X, const float* Wq, const float* Wk, const float* Wv,
+                           const float* Wo, const float* bo, const float* gamma, const float* A, const float* dQ,
+                           const float* dK, const float* dV, float* dX, float* dWq, float* dbq, float* dWk, float* dbk,
+                           float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma, int B, int N, cudaStream_t st) {
   constexpr int D = C / 8, DV = C / 2;
   const long long T = (long long)B * N;
-  float* Q = ws;
-  float* K = Q + T * D;
-  float* V = K + T * D;
-  float* dA = V + T * DV;
-  float* Dd = dA + T * DV;
-  float* dQ = Dd + T;
-  float* dK = dQ + T * D;
-  float* dV = dK + T * D;
   const unsigned tb = (unsigned)ceil_div<long long>(T, AT_THREADS);
-  attn_proj_kernel<C><<<tb, AT_THREADS, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Q, K, V, T);
-  SAGAN_LAUNCH_CHECK();
-  attn_bwd_pre_kernel<C><<<tb, AT_THREADS, 0, st>>>(dY, A, Wo, gamma, dA, Dd, T);
-  SAGAN_LAUNCH_CHECK();
-  SAGAN_CUDA(cudaMemsetAsync(dQ, 0, (size_t)T * D * sizeof(float), st));
-  attn_bwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, dA, lse, Dd, dQ, dK, dV, N);
-  SAGAN_LAUNCH_CHECK();
   if (dX) {
     attn_bwd_post_kernel<C><<<tb, AT_THREADS, 0, st>>>(dY, dQ, dK, dV, Wq, Wk, Wv, dX, T);
     SAGAN_LAUNCH_CHECK();
@@ -419,6 +404,62 @@ static int attn_bwd_strict_t(const float* dY, const float* X, const float* Wq, c
   return 0;
 }
 
+template <int C>
+static int attn_bwd_strict_t(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                             const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                             const float* gamma, const float* lse, const float* A, float* dX, float* dWq, float* dbq,
+                             float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma,
+                             int B, int N, float* ws, cudaStream_t st) {
+  constexpr int D = C / 8, DV = C / 2;
+  const long long T = (long long)B * N;
+  float* dQ = ws;
+  float* dK = dQ + T * D;
+  float* dV = dK + T * D;
+  float* Q = dV + T * DV;
+  float* K = Q + T * D;
+  float* V = K + T * D;
+  float* dA = V + T * DV;
+  float* Dd = dA + T * DV;
+  const unsigned tb = (unsigned)ceil_div<long long>(T, AT_THREADS);
+  attn_proj_kernel<C><<<tb, AT_THREADS, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Q, K, V, T);
+  SAGAN_LAUNCH_CHECK();
+  attn_bwd_pre_kernel<C><<<tb, AT_THREADS, 0, st>>>(dY, A, Wo, gamma, dA, Dd, T);
+  SAGAN_LAUNCH_CHECK();
+  SAGAN_CUDA(cudaMemsetAsync(dQ, 0, (size_t)T * D * sizeof(float), st));
+  attn_bwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, dA, lse, Dd, dQ, dK, dV, N);
+  SAGAN_LAUNCH_CHECK();
+  return attn_bwd_tail_t<C>(dY, X, Wq, Wk, Wv, Wo, bo, gamma, A, dQ, dK, dV, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo, dbo,
+                            dgamma, B, N, st);
+}
+
+// implemented in attn_tc_bwd.cu
+size_t attn_tc_bwd_workspace_bytes(int B, int N, int C);
+int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const float* lse, const float* Wq, const float* bq,
+                     const float* Wk, const float* bk, const float* Wv, const float* bv, const float* Wo,
+                     const float* gamma, float* dQ, float* dK, float* dV, int B, int N, int C, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+
+// BF16_TC backward: dQ / dK / dV on the tensor cores, then the common tail
+template <int C>
+static int attn_bwd_tc_t(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                         const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                         const float* gamma, const float* lse, const float* A, float* dX, float* dWq, float* dbq,
+                         float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma, int B,
+                         int N, float* ws, size_t ws_bytes, cudaStream_t st) {
+  constexpr int D = C / 8, DV = C / 2;
+  const long long T = (long long)B * N;
+  float* dQ = ws;
+  float* dK = dQ + T * D;
+  float* dV = dK + T * D;
+  const size_t used = (size_t)(T * (2 * D + DV) + 64) * sizeof(float);
+  SAGAN_CUDA(cudaMemsetAsync(dQ, 0, (size_t)T * D * sizeof(float), st));
+  int rc = attn_tc_bwd_core(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, dQ, dK, dV, B, N, C,
+                            reinterpret_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
+  if (rc) return rc;
+  return attn_bwd_tail_t<C>(dY, X, Wq, Wk, Wv, Wo, bo, gamma, A, dQ, dK, dV, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo, dbo,
+                            dgamma, B, N, st);
+}
+
 }  // namespace sagan
 
 using namespace sagan;
@@ -431,13 +472,14 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
                 int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace sagan
 
-static bool strict_supported(int C) { return C == 8 || C == 16 || C == 32 || C == 64; }
-
 extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode) {
   if (B <= 0 || N <= 0 || C <= 0) return 0;
   const long long T = (long long)B * N;
   const size_t strict = (size_t)(T * (2 * C + 1) + 64) * sizeof(float);
-  if (math_mode == SAGAN_MATH_BF16_TC) return std::max(strict, attn_tc_workspace_bytes(B, N, C));
+  if (math_mode == SAGAN_MATH_BF16_TC) {
+    const size_t small = (size_t)(T * (C / 4 + C / 2) + 64) * sizeof(float);   // dQ, dK, dV
+    return std::max(strict, std::max(attn_tc_workspace_bytes(B, N, C), small + attn_tc_bwd_workspace_bytes(B, N, C)));
+  }
   return strict;
 }
 
@@ -493,7 +535,10 @@ extern "C" int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, 
     return SAGAN_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // round 1: the backward runs in fp32 on the CUDA cores for both math modes
+  if (math_mode == SAGAN_MATH_BF16_TC && (C == 16 || C == 32 || C == 64)) {
+    SAGAN_ATTN_DISPATCH(attn_bwd_tc_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk, dbk,
+                        dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, ws_bytes, st);
+  }
   SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
                       dbk, dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, st);
   set_err("sagan_attn_bwd: supports C in {8,16,32,64} (C=%d)", C);

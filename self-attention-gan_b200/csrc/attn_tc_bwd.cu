@@ -1,0 +1,496 @@
+// Self-attention block, BF16_TC math mode: flash-style BACKWARD on the 5th-gen tensor cores.
+//
+// The reference has no hand-written backward (tf.GradientTape differentiates /root/reference/layers.py:93-120);
+// the formulas are SURVEY.md §8a row 2:  dP = dA g^T, dS = P * (dP - D), D = rowsum(dA * A),
+// dg = P^T dA, dtheta = dS phi, dphi = dS^T theta.  P is recomputed from the saved row log-sum-exp.
+//
+// CTA = one 128-KEY tile j of one sample, looping over 128-query tiles i; TMEM lanes = keys, so the two
+// score-shaped MMAs are computed transposed and every accumulation over queries stays inside the CTA:
+//     S^T  = K_j Q_i^T           (M=keys, N=queries, K=16*kq)        [split-bf16 logits, log2 units]
+//     dP^T = V_j dA_i^T          (M=keys, N=queries, K=16*kv)
+//     P^T  = exp2(S^T - lse_i),  dS^T = P^T * (dP^T - D_i)           -> bf16 tiles [keys][queries] in smem (SW128)
+//     dV_j += P^T  dA_i          (A = P^T  K-major, B = dA_i^T rows)   TMEM, accumulated over i
+//     dK_j += dS^T Q_i           (A = dS^T K-major, B = Q_i^T rows)    TMEM, accumulated over i
+//     dQ_i  = dS   K_j           (A = the SAME dS^T tile read MN-major, B = K_j^T rows) -> atomicAdd over key tiles
+// 9 warps: 0-7 compute (two threads per key row, 64 query columns each; thread 0 also issues the MMAs),
+// warp 8 = TMA producer.
+#include <math.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sagan {
+
+using namespace tc;
+
+constexpr float TB_LOG2E = 1.4426950408889634f;
+constexpr int TB_THREADS = 288;
+constexpr int TB_COLS = 64;   // bf16 row length of the K-major operand buffers (128 B)
+
+// ------------------------------------------------------------------------------------ prep (small C)
+// one thread per PADDED token; recomputes theta/phi/g from X and forms dA = gamma dY Wo^T, D = dA . A
+template <int C>
+__global__ void __launch_bounds__(128)
+attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ dY, const float* __restrict__ A,
+                        const float* __restrict__ lse, const float* __restrict__ Wq, const float* __restrict__ bq,
+                        const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
+                        const float* __restrict__ bv, const float* __restrict__ Wo, const float* __restrict__ gamma,
+                        __nv_bfloat16* __restrict__ Qb, __nv_bfloat16* __restrict__ Kb, __nv_bfloat16* __restrict__ Vb,
+                        __nv_bfloat16* __restrict__ dAb, __nv_bfloat16* __restrict__ dAt, __nv_bfloat16* __restrict__ Qt,
+                        __nv_bfloat16* __restrict__ Kt, float* __restrict__ lse2, float* __restrict__ Dd,
+                        float* __restrict__ dA_f32, int B, int N, int Npad) {
+  constexpr int D = C / 8, DV = C / 2, DVP = DV < 16 ? 16 : DV;
+  constexpr int KQ = ((3 * D + 15) / 16) * 16;
+  constexpr int KV = ((DV + 15) / 16) * 16;
+  __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
+  __shared__ __align__(16) float sWo[DV * C];
+  for (int i = threadIdx.x; i < C * D; i += 128) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
+  for (int i = threadIdx.x; i < C * DV; i += 128) { sWv[i] = Wv[i]; sWo[i] = Wo[i]; }
+  for (int i = threadIdx.x; i < D; i += 128) { sbq[i] = bq[i]; sbk[i] = bk[i]; }
+  for (int i = threadIdx.x; i < DV; i += 128) sbv[i] = bv[i];
+  __syncthreads();
+  const long long tp = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (tp >= (long long)B * Npad) return;
+  const int b = (int)(tp / Npad), n = (int)(tp - (long long)b * Npad);
+  const bool valid = n < N;
+  const long long t = (long long)b * N + (valid ? n : 0);
+  float x[C], dy[C];
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), g = v;
+    if (valid) { v = ld4(X + t * C + c); g = ld4(dY + t * C + c); }
+    x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
+    dy[c] = g.x; dy[c + 1] = g.y; dy[c + 2] = g.z; dy[c + 3] = g.w;
+  }
+  // ---- theta / phi: split-bf16 rows for the logits, plain hi/lo transposed rows for the dK / dQ GEMMs
+  float q[KQ], k[KQ];
+#pragma unroll
+  for (int j = 0; j < KQ; ++j) { q[j] = 0.f; k[j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    float a = sbq[j], kk = sbk[j];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      a = fmaf(x[c], sWq[c * D + j], a);
+      kk = fmaf(x[c], sWk[c * D + j], kk);
+    }
+    a = valid ? a : 0.f;
+    kk = valid ? kk : 0.f;
+    // transposed (un-scaled) copies: rows [hi (D) | lo (D)]
+    const __nv_bfloat16 qh = __float2bfloat16_rn(a), kh = __float2bfloat16_rn(kk);
+    Qt[((long long)b * 16 + j) * Npad + n] = qh;
+    Qt[((long long)b * 16 + D + j) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(qh));
+    Kt[((long long)b * 16 + j) * Npad + n] = kh;
+    Kt[((long long)b * 16 + D + j) * Npad + n] = __float2bfloat16_rn(kk - __bfloat162float(kh));
+    const float as = a * TB_LOG2E;
+    const float a_hi = __bfloat162float(__float2bfloat16_rn(as)), k_hi = __bfloat162float(kh);
+    q[j] = a_hi; q[D + j] = as - a_hi; q[2 * D + j] = a_hi;
+    k[j] = k_hi; k[D + j] = k_hi;      k[2 * D + j] = kk - k_hi;
+  }
+#pragma unroll
+  for (int j = 2 * D; j < 16; ++j) {
+    Qt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+    Kt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+  }
+  uint4* qd = reinterpret_cast<uint4*>(Qb + tp * TB_COLS);
+  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * TB_COLS);
+#pragma unroll
+  for (int g = 0; g < KQ / 8; ++g) {
+    qd[g] = make_uint4(pack_bf16x2(q[g * 8 + 0], q[g * 8 + 1]), pack_bf16x2(q[g * 8 + 2], q[g * 8 + 3]),
+                       pack_bf16x2(q[g * 8 + 4], q[g * 8 + 5]), pack_bf16x2(q[g * 8 + 6], q[g * 8 + 7]));
+    kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
+                       pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
+  }
+  // ---- g (values) and dA = gamma dY Wo^T, D = dA . A
+  const float gm = *gamma;
+  float v[KV], da[KV];
+#pragma unroll
+  for (int j = 0; j < KV; ++j) { v[j] = 0.f; da[j] = 0.f; }
+  float dd = 0.f;
+#pragma unroll
+  for (int j = 0; j < DV; ++j) {
+    float a = sbv[j], g = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      a = fmaf(x[c], sWv[c * DV + j], a);
+      g = fmaf(dy[c], sWo[j * C + c], g);
+    }
+    g *= gm;
+    v[j] = valid ? a : 0.f;
+    da[j] = valid ? g : 0.f;
+    if (valid) dd = fmaf(g, A[t * DV + j], dd);
+  }
+  uint4* vd = reinterpret_cast<uint4*>(Vb + tp * TB_COLS);
+  uint4* ad = reinterpret_cast<uint4*>(dAb + tp * TB_COLS);
+#pragma unroll
+  for (int g = 0; g < KV / 8; ++g) {
+    vd[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+    ad[g] = make_uint4(pack_bf16x2(da[g * 8 + 0], da[g * 8 + 1]), pack_bf16x2(da[g * 8 + 2], da[g * 8 + 3]),
+                       pack_bf16x2(da[g * 8 + 4], da[g * 8 + 5]), pack_bf16x2(da[g * 8 + 6], da[g * 8 + 7]));
+  }
+#pragma unroll
+  for (int j = 0; j < DVP; ++j) dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(j < DV ? da[j] : 0.f);
+  lse2[tp] = valid ? lse[t] * TB_LOG2E : INFINITY;   // +inf => P = 0 for padded queries
+  Dd[tp] = valid ? dd : 0.f;
+  (void)dA_f32;
+}
+
+// ------------------------------------------------------------------------------------ main
+template <int DVP>
+struct BwdSmem {
+  static constexpr int TILE = 128 * 128;                 // [128 rows][128 B]
+  static constexpr int T16 = 2 * 16 * 128;               // two 64-column sub-tiles of [16 rows][128 B]
+  static constexpr int TDV = 2 * DVP * 128;
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE;
+  static constexpr int OFF_KT = OFF_V + TILE;
+  static constexpr int OFF_STAGE = OFF_KT + T16;
+  static constexpr int ST_Q = 0;
+  static constexpr int ST_DA = ST_Q + TILE;
+  static constexpr int ST_DAT = ST_DA + TILE;
+  static constexpr int ST_QT = ST_DAT + TDV;
+  static constexpr int ST_VEC = ST_QT + T16;             // lse2[128], D[128] fp32
+  static constexpr int STAGE = ST_VEC + 1024;
+  static constexpr int OFF_PT = OFF_STAGE + 2 * STAGE;
+  static constexpr int OFF_DST = OFF_PT + 2 * TILE;
+  static constexpr int OFF_BAR = OFF_DST + 2 * TILE;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  static constexpr int STAGE_TX = TILE + TILE + TDV + T16 + 1024;
+  static_assert(STAGE % 1024 == 0 && OFF_STAGE % 1024 == 0, "tiles must stay 1024-byte aligned");
+  // TMEM columns
+  static constexpr int ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + 64, DQ_COL = 256 + 64 + 16;
+};
+
+template <int DVP>
+__global__ void __launch_bounds__(TB_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdA,
+                   const __grid_constant__ CUtensorMap tmdAt, const __grid_constant__ CUtensorMap tmQt,
+                   const __grid_constant__ CUtensorMap tmKt, const float* __restrict__ lse2,
+                   const float* __restrict__ Dd, float* __restrict__ dQ, float* __restrict__ dK,
+                   float* __restrict__ dV, int N, int Npad, int d, int dv, int kq_steps, int kv_steps) {
+  using L = BwdSmem<DVP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem + L::OFF_K;
+  uint8_t* sV = smem + L::OFF_V;
+  uint8_t* sKt = smem + L::OFF_KT;
+  uint8_t* sStage = smem + L::OFF_STAGE;
+  uint8_t* sPt = smem + L::OFF_PT;
+  uint8_t* sdSt = smem + L::OFF_DST;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* barKV = bars + 0;
+  uint64_t* barQ = bars + 1;    // [2] stage full
+  uint64_t* barS = bars + 3;    // S^T / dP^T ready
+  uint64_t* barG = bars + 4;    // [2] gradient MMAs of iteration i done
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, kt = blockIdx.x;
+  const int nq = Npad / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(barKV, 1);
+    mbar_init(barQ, 1); mbar_init(barQ + 1, 1);
+    mbar_init(barS, 1);
+    mbar_init(barG, 1); mbar_init(barG + 1, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdA);
+      tma_prefetch_desc(&tmdAt); tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt);
+      mbar_expect_tx(barKV, 2 * L::TILE + L::T16);
+      tma_load_2d(sK, &tmK, barKV, 0, b * Npad + kt * 128);
+      tma_load_2d(sV, &tmV, barKV, 0, b * Npad + kt * 128);
+      tma_load_2d(sKt, &tmKt, barKV, kt * 128, b * 16);
+      tma_load_2d(sKt + 16 * 128, &tmKt, barKV, kt * 128 + 64, b * 16);
+      for (int i = 0; i < nq; ++i) {
+        const int s = i & 1;
+        uint8_t* st = sStage + s * L::STAGE;
+        if (i >= 2) mbar_wait(barG + s, ((i - 2) >> 1) & 1);     // every MMA of iteration i-2 has completed
+        mbar_expect_tx(barQ + s, L::STAGE_TX);
+        tma_load_2d(st + L::ST_Q, &tmQ, barQ + s, 0, b * Npad + i * 128);
+        tma_load_2d(st + L::ST_DA, &tmdA, barQ + s, 0, b * Npad + i * 128);
+        tma_load_2d(st + L::ST_DAT, &tmdAt, barQ + s, i * 128, b * DVP);
+        tma_load_2d(st + L::ST_DAT + DVP * 128, &tmdAt, barQ + s, i * 128 + 64, b * DVP);
+        tma_load_2d(st + L::ST_QT, &tmQt, barQ + s, i * 128, b * 16);
+        tma_load_2d(st + L::ST_QT + 16 * 128, &tmQt, barQ + s, i * 128 + 64, b * 16);
+        bulk_load_1d(st + L::ST_VEC, lse2 + (size_t)b * Npad + i * 128, 512, barQ + s);
+        bulk_load_1d(st + L::ST_VEC + 512, Dd + (size_t)b * Npad + i * 128, 512, barQ + s);
+      }
+    }
+  } else {
+    // ================================================================ compute warps
+    const int qd = warp & 3, h = warp >> 2;
+    const int krow = qd * 32 + lane;                                // key row inside the tile == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const bool key_ok = kt * 128 + krow < N;
+    constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+    constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
+    constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
+    constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
+
+    auto issue_sdp = [&](int i) {     // S^T = K Q_i^T, dP^T = V dA_i^T
+      const int s = i & 1;
+      uint8_t* st = sStage + s * L::STAGE;
+      const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dQ_ = make_desc_sw128(smem_u32(st + L::ST_Q));
+      const uint64_t dV_ = make_desc_sw128(smem_u32(sV)), dA_ = make_desc_sw128(smem_u32(st + L::ST_DA));
+      for (int ks = 0; ks < kq_steps; ++ks)
+        mma_bf16_ss(tmem_base + L::ST_COL, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+      for (int ks = 0; ks < kv_steps; ++ks)
+        mma_bf16_ss(tmem_base + L::DP_COL, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+      mma_commit(barS);
+    };
+    auto issue_grads = [&](int i) {   // dV += P^T dA_i ; dK += dS^T Q_i ; dQ_i = dS K
+      const int s = i & 1;
+      uint8_t* st = sStage + s * L::STAGE;
+      const uint64_t dPt = make_desc_sw128(smem_u32(sPt)), dSt = make_desc_sw128(smem_u32(sdSt));
+      const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::ST_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::ST_QT));
+      const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {   // K = queries
+        const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
+        mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
+                    IDESC_DV, (i > 0) || (ks > 0));
+      }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
+        mma_bf16_ss(tmem_base + L::DK_COL, dSt + a_off, dQt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
+                    IDESC_DK, (i > 0) || (ks > 0));
+      }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {   // K = keys: the dS^T tile read MN-major (M = queries contiguous)
+        const uint64_t a = make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024);
+        mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 16, a, dKt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
+                    IDESC_DQ, ks > 0);
+      }
+      mma_commit(barG + s);
+    };
+    // dQ_i tile (TMEM lanes = queries) -> atomicAdd; columns [hi (d) | lo (d)] of the split K^T rows
+    auto flush_dq = [&](int i) {
+      if (h == 0) {
+        uint32_t r[16];
+        tmem_ld16(t_row + L::DQ_COL + (i & 1) * 16, r);
+        tmem_wait_ld();
+        const int qrow = i * 128 + krow;
+        if (qrow < N) {
+          float* dst = dQ + ((size_t)b * N + qrow) * d;
+          for (int c = 0; c < d; ++c) atomicAdd(dst + c, __uint_as_float(r[c]) + __uint_as_float(r[d + c]));
+        }
+      }
+    };
+
+    if (threadIdx.x == 0) {
+      mbar_wait(barKV, 0);
+      mbar_wait(barQ, 0);
+      tc_fence_after();
+      issue_sdp(0);
+    }
+    __syncwarp();
+
+    for (int i = 0; i < nq; ++i) {
+      const int s = i & 1;
+      const float* vec = reinterpret_cast<const float*>(sStage + s * L::STAGE + L::ST_VEC);
+      mbar_wait(barQ + s, (i >> 1) & 1);      // lse2 / D of this query tile have landed
+      mbar_wait(barS, i & 1);
+      tc_fence_after();
+      uint32_t rs[64], rp[64];
+      tmem_ld32(t_row + L::ST_COL + h * 64, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
+      tmem_ld32(t_row + L::ST_COL + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
+      tmem_ld32(t_row + L::DP_COL + h * 64, *reinterpret_cast<uint32_t(*)[32]>(&rp[0]));
+      tmem_ld32(t_row + L::DP_COL + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rp[32]));
+      tmem_wait_ld();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // S^T / dP^T are in registers everywhere
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        if (i + 1 < nq) {
+          mbar_wait(barQ + ((i + 1) & 1), ((i + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_sdp(i + 1);                                  // runs under the exp / dS math of tile i
+        }
+      }
+      __syncwarp();
+      if (i >= 1) {
+        mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // P^T / dS^T buffers free, dQ_{i-1} complete
+        tc_fence_after();
+        flush_dq(i - 1);
+      }
+      uint8_t* pt = sPt + h * L::TILE;
+      uint8_t* dst = sdSt + h * L::TILE;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 64 + g * 8);
+        const float4 l1 = *reinterpret_cast<const float4*>(vec + h * 64 + g * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + h * 64 + g * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + h * 64 + g * 8 + 4);
+        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float ds_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float p[8], g_[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
+          pe = key_ok ? pe : 0.f;
+          p[e] = pe;
+          g_[e] = pe * (__uint_as_float(rp[g * 8 + e]) - ds_[e]);
+        }
+        const uint32_t off = sw128_offset(krow, g);
+        *reinterpret_cast<uint4*>(pt + off) =
+            make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(g_[0], g_[1]), pack_bf16x2(g_[2], g_[3]),
+                                                          pack_bf16x2(g_[4], g_[5]), pack_bf16x2(g_[6], g_[7]));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        issue_grads(i);
+      }
+      __syncwarp();
+    }
+    // ---- epilogue
+    mbar_wait(barG + ((nq - 1) & 1), ((nq - 1) >> 1) & 1);
+    tc_fence_after();
+    flush_dq(nq - 1);
+    if (h == 0) {
+      const int key = kt * 128 + krow;
+      const size_t grow = (size_t)b * N + key;
+#pragma unroll
+      for (int c = 0; c < DVP / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(t_row + L::DV_COL + c * 16, r);
+        tmem_wait_ld();
+        if (key < N) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            if (c * 16 + e < dv)
+              st4(dV + grow * dv + c * 16 + e, make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                            __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+        }
+      }
+      uint32_t r[16];
+      tmem_ld16(t_row + L::DK_COL, r);
+      tmem_wait_ld();
+      if (key < N)
+        for (int c = 0; c < d; ++c) dK[grow * d + c] = __uint_as_float(r[c]) + __uint_as_float(r[d + c]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+struct TbLayout {
+  int Npad, DVP, kq_steps, kv_steps;
+  size_t off_q, off_k, off_v, off_da, off_dat, off_qt, off_kt, off_lse, off_dd, total;
+};
+
+static TbLayout tb_layout(int B, int N, int C) {
+  TbLayout t;
+  const int d = C / 8, dv = C / 2;
+  t.Npad = (N + 127) / 128 * 128;
+  t.DVP = dv < 16 ? 16 : dv;
+  t.kq_steps = (3 * d + 15) / 16;
+  t.kv_steps = (dv + 15) / 16;
+  const size_t T = (size_t)B * t.Npad;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+  t.off_q = take(T * TB_COLS * 2);
+  t.off_k = take(T * TB_COLS * 2);
+  t.off_v = take(T * TB_COLS * 2);
+  t.off_da = take(T * TB_COLS * 2);
+  t.off_dat = take((size_t)B * t.DVP * t.Npad * 2);
+  t.off_qt = take((size_t)B * 16 * t.Npad * 2);
+  t.off_kt = take((size_t)B * 16 * t.Npad * 2);
+  t.off_lse = take(T * 4);
+  t.off_dd = take(T * 4);
+  t.total = o + 1024;
+  return t;
+}
+
+size_t attn_tc_bwd_workspace_bytes(int B, int N, int C) { return tb_layout(B, N, C).total; }
+
+template <int C>
+static int run_prep(const float* X, const float* dY, const float* A, const float* lse, const float* Wq, const float* bq,
+                    const float* Wk, const float* bk, const float* Wv, const float* bv, const float* Wo,
+                    const float* gamma, uint8_t* base, const TbLayout& t, int B, int N, cudaStream_t st) {
+  const long long Tp = (long long)B * t.Npad;
+  attn_bwd_prep_tc_kernel<C><<<(unsigned)ceil_div<long long>(Tp, 128), 128, 0, st>>>(
+      X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, (__nv_bfloat16*)(base + t.off_q), (__nv_bfloat16*)(base + t.off_k),
+      (__nv_bfloat16*)(base + t.off_v), (__nv_bfloat16*)(base + t.off_da), (__nv_bfloat16*)(base + t.off_dat),
+      (__nv_bfloat16*)(base + t.off_qt), (__nv_bfloat16*)(base + t.off_kt), (float*)(base + t.off_lse),
+      (float*)(base + t.off_dd), nullptr, B, N, t.Npad);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int DVP>
+static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, float* dQ, float* dK, float* dV, int B,
+                      int N, int Npad, int d, int dv, int kq, int kv, cudaStream_t st) {
+  using L = BwdSmem<DVP>;
+  auto kern = attn_bwd_tc_kernel<DVP>;
+  static bool configured = false;
+  if (!configured) {
+    SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<dim3(Npad / 128, B), TB_THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], lse2, Dd, dQ, dK, dV,
+                                                          N, Npad, d, dv, kq, kv);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dQ / dK / dV [B,N,.] fp32 from the tensor-core kernel (dQ must be zero on entry: it is accumulated atomically)
+int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const float* lse, const float* Wq, const float* bq,
+                     const float* Wk, const float* bk, const float* Wv, const float* bv, const float* Wo,
+                     const float* gamma, float* dQ, float* dK, float* dV, int B, int N, int C, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  if (!(C == 16 || C == 32 || C == 64)) {
+    set_err("sagan_attn_bwd: BF16_TC supports C in {16,32,64} (C=%d)", C);
+    return SAGAN_EUNSUPPORTED;
+  }
+  const TbLayout t = tb_layout(B, N, C);
+  if (ws_bytes < t.total) {
+    set_err("sagan_attn_bwd: tensor-core workspace %zu < %zu bytes", ws_bytes, t.total);
+    return SAGAN_EWORKSPACE;
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  int rc = 0;
+  switch (C) {
+    case 16: rc = run_prep<16>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, st); break;
+    case 32: rc = run_prep<32>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, st); break;
+    case 64: rc = run_prep<64>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, st); break;
+  }
+  if (rc) return rc;
+  const uint64_t Tp = (uint64_t)B * t.Npad;
+  CUtensorMap m[7];
+  if ((rc = make_tmap_bf16_2d(&m[0], base + t.off_q, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[1], base + t.off_k, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[2], base + t.off_v, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[3], base + t.off_da, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[4], base + t.off_dat, (uint64_t)B * t.DVP, t.Npad, (uint64_t)t.Npad * 2, t.DVP))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[5], base + t.off_qt, (uint64_t)B * 16, t.Npad, (uint64_t)t.Npad * 2, 16))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[6], base + t.off_kt, (uint64_t)B * 16, t.Npad, (uint64_t)t.Npad * 2, 16))) return rc;
+  const float* lse2 = (const float*)(base + t.off_lse);
+  const float* Dd = (const float*)(base + t.off_dd);
+  const int d = C / 8, dv = C / 2;
+  if (t.DVP == 16) return launch_bwd<16>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  return launch_bwd<32>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+}
+
+}  // namespace sagan
