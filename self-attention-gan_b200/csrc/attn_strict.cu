@@ -329,6 +329,86 @@ attn_bwd_post_kernel(const float* __restrict__ dY, const float* __restrict__ dQ,
   }
 }
 
+// ---------------------------------------------------------------------------- backward: parameter gradients
+// All parameter gradients of the block in ONE launch (they are skinny GEMMs over the token axis):
+//   G1 = [X | 1]^T [dQ dK dV]   ((C+1) x (2d+dv))   -> dWq, dWk, dWv, dbq, dbk, dbv
+//   G2 = [A | 1]^T dY           ((dv+1) x C)        -> dWo' = A^T dY, dbo' = colsum(dY)   (scaled by gamma in finalize)
+// One thread per output element (strided when there are more outputs than threads), tokens staged through shared
+// memory in tiles of 32; per-CTA partial sums are combined with fp32 atomics (outputs zeroed by the caller).
+template <int C>
+__global__ void __launch_bounds__(256)
+attn_wgrad_small_kernel(const float* __restrict__ X, const float* __restrict__ A, const float* __restrict__ dY,
+                        const float* __restrict__ dQ, const float* __restrict__ dK, const float* __restrict__ dV,
+                        float* __restrict__ dWq, float* __restrict__ dbq, float* __restrict__ dWk,
+                        float* __restrict__ dbk, float* __restrict__ dWv, float* __restrict__ dbv,
+                        float* __restrict__ dWo, float* __restrict__ dbo, long long T, int tokens_per_block) {
+  constexpr int D = C / 8, DV = C / 2, TT = 32;
+  constexpr int LW = C + 1, RW = 2 * D + DV;          // G1: left width (X | 1), right width (dQ dK dV)
+  constexpr int L2 = DV + 1, R2 = C;                  // G2: (A | 1), dY
+  constexpr int N1 = LW * RW, N2 = L2 * R2, NOUT = N1 + N2;
+  constexpr int PER = (NOUT + 255) / 256;
+  __shared__ float sL1[TT][LW + 1], sR1[TT][RW + 1], sL2[TT][L2 + 1], sR2[TT][R2 + 1];
+  float acc[PER];
+  int li[PER], ri[PER], which[PER];
+#pragma unroll
+  for (int p = 0; p < PER; ++p) {
+    acc[p] = 0.f;
+    const int o = threadIdx.x + p * 256;
+    which[p] = o < N1 ? 1 : (o < NOUT ? 2 : 0);
+    const int oo = o < N1 ? o : o - N1;
+    li[p] = which[p] == 1 ? oo / RW : oo / R2;
+    ri[p] = which[p] == 1 ? oo % RW : oo % R2;
+  }
+  const long long t0 = (long long)blockIdx.x * tokens_per_block;
+  const long long t1 = min(T, t0 + tokens_per_block);
+  for (long long tb = t0; tb < t1; tb += TT) {
+    const int nt = (int)min((long long)TT, t1 - tb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < TT * LW; e += 256) {
+      const int r = e / LW, c = e % LW;
+      sL1[r][c] = r < nt ? (c < C ? X[(tb + r) * C + c] : 1.f) : 0.f;
+    }
+    for (int e = threadIdx.x; e < TT * RW; e += 256) {
+      const int r = e / RW, c = e % RW;
+      float v = 0.f;
+      if (r < nt) v = c < D ? dQ[(tb + r) * D + c] : (c < 2 * D ? dK[(tb + r) * D + c - D] : dV[(tb + r) * DV + c - 2 * D]);
+      sR1[r][c] = v;
+    }
+    for (int e = threadIdx.x; e < TT * L2; e += 256) {
+      const int r = e / L2, c = e % L2;
+      sL2[r][c] = r < nt ? (c < DV ? A[(tb + r) * DV + c] : 1.f) : 0.f;
+    }
+    for (int e = threadIdx.x; e < TT * R2; e += 256) {
+      const int r = e / R2, c = e % R2;
+      sR2[r][c] = r < nt ? dY[(tb + r) * C + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      if (which[p] == 1) {
+#pragma unroll 8
+        for (int r = 0; r < TT; ++r) acc[p] = fmaf(sL1[r][li[p]], sR1[r][ri[p]], acc[p]);
+      } else if (which[p] == 2) {
+#pragma unroll 8
+        for (int r = 0; r < TT; ++r) acc[p] = fmaf(sL2[r][li[p]], sR2[r][ri[p]], acc[p]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PER; ++p) {
+    if (which[p] == 1) {
+      const int l = li[p], r = ri[p];
+      float* dst;
+      if (l < C) dst = r < D ? dWq + l * D + r : (r < 2 * D ? dWk + l * D + (r - D) : dWv + l * DV + (r - 2 * D));
+      else dst = r < D ? dbq + r : (r < 2 * D ? dbk + (r - D) : dbv + (r - 2 * D));
+      atomicAdd(dst, acc[p]);
+    } else if (which[p] == 2) {
+      const int l = li[p], r = ri[p];
+      atomicAdd(l < DV ? dWo + l * C + r : dbo + r, acc[p]);
+    }
+  }
+}
+
 // dgamma = sum_c bo[c] dbo'[c] + sum_{j,c} Wo[j,c] dWo'[j,c]  with dWo' = A^T dY, dbo' = colsum(dY);
 // then dWo = gamma dWo', dbo = gamma dbo'.  One CTA.
 __global__ void __launch_bounds__(256)
@@ -390,14 +470,19 @@ static int attn_bwd_tail_t(const float* dY, const float* X, const float* Wq, con
     SAGAN_LAUNCH_CHECK();
   }
   if (dWq) {
-    int rc;
-    sagan_conv_geom g = geom_1x1(T, C, D);
-    if ((rc = sagan_conv2d_wgrad(X, dQ, dWq, dbq, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
-    if ((rc = sagan_conv2d_wgrad(X, dK, dWk, dbk, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
-    g = geom_1x1(T, C, DV);
-    if ((rc = sagan_conv2d_wgrad(X, dV, dWv, dbv, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
-    g = geom_1x1(T, DV, C);
-    if ((rc = sagan_conv2d_wgrad(A, dY, dWo, dbo, &g, SAGAN_MATH_FP32_STRICT, st))) return rc;
+    SAGAN_CUDA(cudaMemsetAsync(dWq, 0, sizeof(float) * C * D, st));
+    SAGAN_CUDA(cudaMemsetAsync(dWk, 0, sizeof(float) * C * D, st));
+    SAGAN_CUDA(cudaMemsetAsync(dWv, 0, sizeof(float) * C * DV, st));
+    SAGAN_CUDA(cudaMemsetAsync(dWo, 0, sizeof(float) * DV * C, st));
+    SAGAN_CUDA(cudaMemsetAsync(dbq, 0, sizeof(float) * D, st));
+    SAGAN_CUDA(cudaMemsetAsync(dbk, 0, sizeof(float) * D, st));
+    SAGAN_CUDA(cudaMemsetAsync(dbv, 0, sizeof(float) * DV, st));
+    SAGAN_CUDA(cudaMemsetAsync(dbo, 0, sizeof(float) * C, st));
+    const int blocks = (int)std::min<long long>(num_sms() * 2, ceil_div<long long>(T, 256));
+    const int tpb = (int)(ceil_div<long long>(ceil_div<long long>(T, blocks), 32) * 32);
+    attn_wgrad_small_kernel<C><<<(unsigned)ceil_div<long long>(T, tpb), 256, 0, st>>>(X, A, dY, dQ, dK, dV, dWq, dbq, dWk,
+                                                                                    dbk, dWv, dbv, dWo, dbo, T, tpb);
+    SAGAN_LAUNCH_CHECK();
     attn_bwd_finalize_kernel<<<1, 256, 0, st>>>(Wo, bo, gamma, dWo, dbo, dgamma, DV * C, C);
     SAGAN_LAUNCH_CHECK();
   }

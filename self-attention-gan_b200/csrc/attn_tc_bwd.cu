@@ -12,8 +12,9 @@
 //     dV_j += P^T  dA_i          (A = P^T  K-major, B = dA_i^T rows)   TMEM, accumulated over i
 //     dK_j += dS^T Q_i           (A = dS^T K-major, B = Q_i^T rows)    TMEM, accumulated over i
 //     dQ_i  = dS   K_j           (A = the SAME dS^T tile read MN-major, B = K_j^T rows) -> atomicAdd over key tiles
-// 9 warps: 0-7 compute (two threads per key row, 64 query columns each; thread 0 also issues the MMAs),
-// warp 8 = TMA producer.
+// 10 warps: 0-7 compute (two threads per key row, 64 query columns each), warp 8 = TMA producer,
+// warp 9 = MMA issuer.  Compute warps never wait for each other: they signal the issuer through mbarriers
+// (S/dP registers loaded -> next S/dP MMA may overwrite TMEM; P/dS tiles written -> gradient MMAs may start).
 #include <math.h>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@ namespace sagan {
 using namespace tc;
 
 constexpr float TB_LOG2E = 1.4426950408889634f;
-constexpr int TB_THREADS = 288;
+constexpr int TB_THREADS = 320;   // 8 compute warps + TMA producer warp + MMA issuer warp
 constexpr int TB_COLS = 64;   // bf16 row length of the K-major operand buffers (128 B)
 
 // ------------------------------------------------------------------------------------ prep (small C)
@@ -184,6 +185,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* barQ = bars + 1;    // [2] stage full
   uint64_t* barS = bars + 3;    // S^T / dP^T ready
   uint64_t* barG = bars + 4;    // [2] gradient MMAs of iteration i done
+  uint64_t* barSfree = bars + 6;   // 256 arrivals: S^T / dP^T of tile i are in registers
+  uint64_t* barTiles = bars + 7;   // 256 arrivals: P^T / dS^T tiles of tile i are in shared memory
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,6 +198,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(barQ, 1); mbar_init(barQ + 1, 1);
     mbar_init(barS, 1);
     mbar_init(barG, 1); mbar_init(barG + 1, 1);
+    mbar_init(barSfree, 256); mbar_init(barTiles, 256);
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(tmem_ptr, 512);
@@ -228,54 +232,72 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         bulk_load_1d(st + L::ST_VEC + 512, Dd + (size_t)b * Npad + i * 128, 512, barQ + s);
       }
     }
+  } else if (warp == 9) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+      constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
+      constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
+      constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
+      auto issue_sdp = [&](int i) {     // S^T = K Q_i^T, dP^T = V dA_i^T
+        const int s = i & 1;
+        uint8_t* st = sStage + s * L::STAGE;
+        const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dQ_ = make_desc_sw128(smem_u32(st + L::ST_Q));
+        const uint64_t dV_ = make_desc_sw128(smem_u32(sV)), dA_ = make_desc_sw128(smem_u32(st + L::ST_DA));
+        for (int ks = 0; ks < kq_steps; ++ks)
+          mma_bf16_ss(tmem_base + L::ST_COL, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        for (int ks = 0; ks < kv_steps; ++ks)
+          mma_bf16_ss(tmem_base + L::DP_COL, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barS);
+      };
+      auto issue_grads = [&](int i) {   // dV += P^T dA_i ; dK += dS^T Q_i ; dQ_i = dS K
+        const int s = i & 1;
+        uint8_t* st = sStage + s * L::STAGE;
+        const uint64_t dPt = make_desc_sw128(smem_u32(sPt)), dSt = make_desc_sw128(smem_u32(sdSt));
+        const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::ST_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::ST_QT));
+        const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // K = queries
+          const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
+          mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
+                      IDESC_DV, (i > 0) || (ks > 0));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
+          mma_bf16_ss(tmem_base + L::DK_COL, dSt + a_off, dQt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
+                      IDESC_DK, (i > 0) || (ks > 0));
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // K = keys: the dS^T tile read MN-major (M = queries contiguous)
+          const uint64_t a = make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 16, a, dKt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
+                      IDESC_DQ, ks > 0);
+        }
+        mma_commit(barG + s);
+      };
+      mbar_wait(barKV, 0);
+      mbar_wait(barQ, 0);
+      tc_fence_after();
+      issue_sdp(0);
+      for (int i = 0; i < nq; ++i) {
+        if (i + 1 < nq) {
+          mbar_wait(barQ + ((i + 1) & 1), ((i + 1) >> 1) & 1);
+          mbar_wait(barSfree, i & 1);            // every compute thread holds S^T_i / dP^T_i in registers
+          tc_fence_after();
+          issue_sdp(i + 1);                      // runs under the exp / dS math of tile i
+        }
+        mbar_wait(barTiles, i & 1);              // P^T_i / dS^T_i are in shared memory
+        tc_fence_after();
+        issue_grads(i);
+      }
+    }
   } else {
     // ================================================================ compute warps
     const int qd = warp & 3, h = warp >> 2;
     const int krow = qd * 32 + lane;                                // key row inside the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
     const bool key_ok = kt * 128 + krow < N;
-    constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
-    constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
-    constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
-    constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
-
-    auto issue_sdp = [&](int i) {     // S^T = K Q_i^T, dP^T = V dA_i^T
-      const int s = i & 1;
-      uint8_t* st = sStage + s * L::STAGE;
-      const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dQ_ = make_desc_sw128(smem_u32(st + L::ST_Q));
-      const uint64_t dV_ = make_desc_sw128(smem_u32(sV)), dA_ = make_desc_sw128(smem_u32(st + L::ST_DA));
-      for (int ks = 0; ks < kq_steps; ++ks)
-        mma_bf16_ss(tmem_base + L::ST_COL, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-      for (int ks = 0; ks < kv_steps; ++ks)
-        mma_bf16_ss(tmem_base + L::DP_COL, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-      mma_commit(barS);
-    };
-    auto issue_grads = [&](int i) {   // dV += P^T dA_i ; dK += dS^T Q_i ; dQ_i = dS K
-      const int s = i & 1;
-      uint8_t* st = sStage + s * L::STAGE;
-      const uint64_t dPt = make_desc_sw128(smem_u32(sPt)), dSt = make_desc_sw128(smem_u32(sdSt));
-      const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::ST_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::ST_QT));
-      const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {   // K = queries
-        const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
-        mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
-                    IDESC_DV, (i > 0) || (ks > 0));
-      }
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
-        mma_bf16_ss(tmem_base + L::DK_COL, dSt + a_off, dQt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
-                    IDESC_DK, (i > 0) || (ks > 0));
-      }
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {   // K = keys: the dS^T tile read MN-major (M = queries contiguous)
-        const uint64_t a = make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024);
-        mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 16, a, dKt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
-                    IDESC_DQ, ks > 0);
-      }
-      mma_commit(barG + s);
-    };
     // dQ_i tile (TMEM lanes = queries) -> atomicAdd; columns [hi (d) | lo (d)] of the split K^T rows
     auto flush_dq = [&](int i) {
       if (h == 0) {
@@ -290,14 +312,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     };
 
-    if (threadIdx.x == 0) {
-      mbar_wait(barKV, 0);
-      mbar_wait(barQ, 0);
-      tc_fence_after();
-      issue_sdp(0);
-    }
-    __syncwarp();
-
     for (int i = 0; i < nq; ++i) {
       const int s = i & 1;
       const float* vec = reinterpret_cast<const float*>(sStage + s * L::STAGE + L::ST_VEC);
@@ -311,16 +325,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld32(t_row + L::DP_COL + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rp[32]));
       tmem_wait_ld();
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");          // S^T / dP^T are in registers everywhere
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        if (i + 1 < nq) {
-          mbar_wait(barQ + ((i + 1) & 1), ((i + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_sdp(i + 1);                                  // runs under the exp / dS math of tile i
-        }
-      }
-      __syncwarp();
+      mbar_arrive(barSfree);                                  // this thread's S^T / dP^T are in registers
       if (i >= 1) {
         mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // P^T / dS^T buffers free, dQ_{i-1} complete
         tc_fence_after();
@@ -352,12 +357,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        issue_grads(i);
-      }
-      __syncwarp();
+      mbar_arrive(barTiles);                                  // this thread's part of P^T / dS^T is written
     }
     // ---- epilogue
     mbar_wait(barG + ((nq - 1) & 1), ((nq - 1) >> 1) & 1);

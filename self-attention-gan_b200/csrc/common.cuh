@@ -61,6 +61,13 @@ inline int num_sms() {
 template <typename T>
 inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// convolution geometry shared by the CUDA-core and tensor-core conv kernels
+struct CG {
+  int B, H, W, Cin, Ho, Wo, Cout, KH, KW, S, PT, PL;
+  int M;  // B*Ho*Wo
+  int K;  // KH*KW*Cin
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

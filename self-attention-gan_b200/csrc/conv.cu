@@ -16,11 +16,13 @@
 
 namespace sagan {
 
-struct CG {
-  int B, H, W, Cin, Ho, Wo, Cout, KH, KW, S, PT, PL;
-  int M;  // B*Ho*Wo
-  int K;  // KH*KW*Cin
-};
+// tensor-core variants (conv_tc.cu)
+bool conv_tc_fwd_ok(const CG& g, const float* x, const float* w);
+bool conv_tc_dgrad_ok(const CG& g, const float* dy, const float* w);
+bool conv_tc_wgrad_ok(const CG& g, const float* x, const float* dy);
+int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope, cudaStream_t st);
+int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st);
+int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st);
 
 constexpr int CV_THREADS = 256;
 constexpr int CV_BK = 16;
@@ -515,10 +517,11 @@ extern "C" int sagan_conv2d_fwd(const float* x, const float* w, const float* bia
                                 const sagan_conv_geom* geom, int act, float slope, int math_mode,
                                 sagan_stream_t stream) {
   SAGAN_REQUIRE(x && w && y, "sagan_conv2d_fwd: null pointer");
-  (void)math_mode;
   CG g;
   int rc = make_geom(geom, &g, "sagan_conv2d_fwd");
   if (rc) return rc;
+  if (math_mode == SAGAN_MATH_BF16_TC && conv_tc_fwd_ok(g, x, w))
+    return conv_tc_fwd(x, w, bias, y, g, act, slope, (cudaStream_t)stream);
   const int vecA = (g.Cin % 4 == 0 && al16(x)) ? 1 : 0;
   const int vecB = (g.Cout % 4 == 0 && al16(w)) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -536,7 +539,6 @@ extern "C" int sagan_conv2d_fwd(const float* x, const float* w, const float* bia
 extern "C" int sagan_conv2d_dgrad(const float* dy, const float* w, float* dx, const sagan_conv_geom* geom,
                                   int math_mode, sagan_stream_t stream) {
   SAGAN_REQUIRE(dy && w && dx, "sagan_conv2d_dgrad: null pointer");
-  (void)math_mode;
   CG g;
   int rc = make_geom(geom, &g, "sagan_conv2d_dgrad");
   if (rc) return rc;
@@ -546,6 +548,7 @@ extern "C" int sagan_conv2d_dgrad(const float* dy, const float* w, float* dx, co
   for (int r = 0; r < g.S; ++r)
     if (r >= g.KH || r >= g.KW) full_cover = false;
   if (!full_cover) SAGAN_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.B * g.H * g.W * g.Cin * sizeof(float), st));
+  if (math_mode == SAGAN_MATH_BF16_TC && conv_tc_dgrad_ok(g, dy, w)) return conv_tc_dgrad(dy, w, dx, g, st);
   const int vecA = (g.Cout % 4 == 0 && al16(dy)) ? 1 : 0;
   const int Hc = ceil_div(g.H, g.S), Wc = ceil_div(g.W, g.S);
   const int Mc = g.B * Hc * Wc;
@@ -563,12 +566,15 @@ extern "C" int sagan_conv2d_dgrad(const float* dy, const float* w, float* dx, co
 extern "C" int sagan_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias,
                                   const sagan_conv_geom* geom, int math_mode, sagan_stream_t stream) {
   SAGAN_REQUIRE(x && dy && dw, "sagan_conv2d_wgrad: null pointer");
-  (void)math_mode;
   CG g;
   int rc = make_geom(geom, &g, "sagan_conv2d_wgrad");
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SAGAN_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.K * g.Cout * sizeof(float), st));
+  if (math_mode == SAGAN_MATH_BF16_TC && conv_tc_wgrad_ok(g, x, dy)) {
+    if (dbias) SAGAN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st));
+    return conv_tc_wgrad(x, dy, dw, dbias, g, st);
+  }
   const int vecA = (g.Cin % 4 == 0 && al16(x)) ? 1 : 0;
   const int vecB = (g.Cout % 4 == 0 && al16(dy)) ? 1 : 0;
   const int tiles = ceil_div(g.K, 64) * ceil_div(g.Cout, 64);

@@ -1,0 +1,374 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (BF16_TC math mode): forward, backward-data
+// (= Conv2DTranspose forward) and backward-filter of the spectrally-normalised Conv2D / Conv2DTranspose /
+// Dense layers (/root/reference/sagan/models/generator.py:8-9,25,36, discriminator.py:8,35).
+//
+// One kernel template, three gather modes.  fp32 NHWC activations and fp32 Keras-layout kernels are read
+// directly: the producer warps gather 8-element chunks, convert to bf16 and store them into the 128-byte-
+// swizzled UMMA operand layouts (software im2col -- no intermediate tensors in HBM); accumulation is fp32 in TMEM.
+//
+//   FWD    D[m][n] = sum_k A[m][k] W[k][n]      A = im2col(x) (K-major tile), W = HWIO kernel read as an MN-major B tile
+//   DGRAD  per stride-parity class: D[m][n] = sum_k dY[m][k] Wc[n][k]   both K-major (W[kh,kw,n,:] rows are contiguous in co)
+//   WGRAD  D[kk][n] = sum_m A[m][kk] dY[m][n]   both operands MN-major (the same im2col rows, dY rows); split over
+//          pixel ranges with fp32 atomics; an extra im2col column of ones yields the bias gradient for free
+//
+// CTA tile 128 x NT (NT in {16,32,64,128}), K blocks of 64, 3-stage shared-memory ring.
+// 9 warps: 0-7 producers + epilogue, warp 8 = MMA issuer / TMEM owner.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sagan {
+
+using namespace tc;
+
+enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
+constexpr int CT_THREADS = 288;
+constexpr int CT_STAGES = 3;
+
+struct ConvTcP {
+  const float* a_src;   // FWD: x     DGRAD: dy    WGRAD: x
+  const float* b_src;   // FWD: w     DGRAD: w     WGRAD: dy
+  const float* bias;    // FWD (may be null)
+  float* out;           // FWD: y     DGRAD: dx    WGRAD: dw (zeroed by the caller)
+  float* dbias;         // WGRAD (may be null; zeroed by the caller)
+  CG g;
+  int act;
+  float slope;
+  int m_per_split;      // WGRAD: pixels per blockIdx.z
+};
+
+__device__ __forceinline__ float ct_act(float v, int act, float slope) {
+  if (act == SAGAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == SAGAN_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__device__ __forceinline__ void st_chunk(uint8_t* dst, const float4& a, const float4& b) {
+  *reinterpret_cast<uint4*>(dst) =
+      make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
+template <int MODE, int NT>
+struct ConvTcSmem {
+  static constexpr int A_BYTES = 128 * 128;                                              // 16 KB either major
+  static constexpr int B_BYTES = MODE == TC_DGRAD ? NT * 128 : 8192 * ((NT + 63) / 64);  // K-major rows / MN-major sub-tiles
+  static constexpr int STAGE = A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES);
+  static constexpr int OFF_BAR = CT_STAGES * STAGE;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+};
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+conv_tc_kernel(const ConvTcP p) {
+  using L = ConvTcSmem<MODE, NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* full = bars;                 // [CT_STAGES], 256 arrivals
+  uint64_t* empty = bars + CT_STAGES;    // [CT_STAGES], tcgen05.commit
+  uint64_t* accum = bars + 2 * CT_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * CT_STAGES + 1);
+  const CG& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+
+  // ---- GEMM view of this CTA
+  int Mg, Ng, k_begin, k_end;            // rows, cols, reduction range
+  int rh = 0, rw = 0, hi_first = 0, wi_first = 0, Hc = 1, Wc = 1, ntw = 1;   // DGRAD class geometry
+  if (MODE == TC_FWD) {
+    Mg = g.M; Ng = g.Cout; k_begin = 0; k_end = g.K;
+  } else if (MODE == TC_DGRAD) {
+    rh = blockIdx.z / g.S; rw = blockIdx.z - rh * g.S;
+    hi_first = ((rh - g.PT) % g.S + g.S) % g.S;
+    wi_first = ((rw - g.PL) % g.S + g.S) % g.S;
+    Hc = hi_first < g.H ? (g.H - hi_first + g.S - 1) / g.S : 0;
+    Wc = wi_first < g.W ? (g.W - wi_first + g.S - 1) / g.S : 0;
+    const int nth = rh < g.KH ? (g.KH - rh + g.S - 1) / g.S : 0;
+    ntw = rw < g.KW ? (g.KW - rw + g.S - 1) / g.S : 0;
+    Mg = g.B * Hc * Wc; Ng = g.Cin; k_begin = 0; k_end = nth * ntw * g.Cout;
+  } else {
+    Mg = g.K + (p.dbias ? 1 : 0); Ng = g.Cout;
+    k_begin = blockIdx.z * p.m_per_split; k_end = min(g.M, k_begin + p.m_per_split);
+  }
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
+  if (m0 >= Mg || k_begin >= k_end) return;      // uniform per CTA (before any barrier / TMEM use)
+  const int nkb = (k_end - k_begin + 63) / 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < CT_STAGES; ++i) { mbar_init(full + i, 256); mbar_init(empty + i, 1); }
+    mbar_init(accum, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc_bf16(128, NT, MODE == TC_WGRAD ? 1 : 0, MODE == TC_DGRAD ? 0 : 1);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % CT_STAGES;
+        mbar_wait(full + s, (kb / CT_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t aA = smem_u32(smem + s * L::STAGE), aB = aA + L::A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t da, db;
+          if (MODE == TC_WGRAD) da = make_desc_sw128_mn(aA + ks * 2048, 8192, 1024);
+          else da = make_desc_sw128(aA) + (uint64_t)(ks * 2);
+          if (MODE == TC_DGRAD) db = make_desc_sw128(aB) + (uint64_t)(ks * 2);
+          else db = make_desc_sw128_mn(aB + ks * 2048, 8192, 1024);
+          mma_bf16_ss(tmem_base, da, db, IDESC, (kb > 0) || (ks > 0));
+        }
+        mma_commit(empty + s);
+      }
+      mma_commit(accum);
+    }
+  } else {
+    // ================================================================ producers
+    // A tile: 1024 chunks of 8 elements, 4 per thread.  K-major modes: thread -> rows (tid>>3) + 32 j, chunk tid & 7.
+    //                                                   WGRAD:         thread -> m-rows (tid>>4) + 16 j, kk-chunk tid & 15.
+    const int a_chunk = MODE == TC_WGRAD ? (tid & 15) : (tid & 7);
+    int a_base[4];        // element offset of the row's pixel origin in a_src (FWD / DGRAD), -1 = row out of range
+    int a_h0[4], a_w0[4];
+    if (MODE != TC_WGRAD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + (tid >> 3) + 32 * j;
+        if (m >= Mg) { a_base[j] = -1; a_h0[j] = 0; a_w0[j] = 0; continue; }
+        if (MODE == TC_FWD) {
+          const int b = m / (g.Ho * g.Wo), rem = m - b * (g.Ho * g.Wo);
+          const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+          a_base[j] = b; a_h0[j] = ho * g.S - g.PT; a_w0[j] = wo * g.S - g.PL;
+        } else {
+          const int b = m / (Hc * Wc), rem = m - b * (Hc * Wc);
+          const int ih = rem / Wc, iw = rem - ih * Wc;
+          const int hi = hi_first + ih * g.S, wi = wi_first + iw * g.S;
+          a_base[j] = b; a_h0[j] = (hi + g.PT - rh) / g.S; a_w0[j] = (wi + g.PL - rw) / g.S;   // ho = h0 - th
+        }
+      }
+    }
+    // WGRAD: the kk columns of this thread's chunk are fixed: decode (kh, kw, ci0) once
+    int wg_kh = 0, wg_kw = 0, wg_ci = 0, wg_kind = 0;   // kind: 0 = im2col, 1 = ones column (bias), 2 = beyond range
+    if (MODE == TC_WGRAD) {
+      const int kk = m0 + a_chunk * 8;
+      if (kk >= g.K) wg_kind = (kk == g.K && p.dbias) ? 1 : 2;
+      else { const int tap = kk / g.Cin; wg_ci = kk - tap * g.Cin; wg_kh = tap / g.KW; wg_kw = tap - wg_kh * g.KW; }
+    }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % CT_STAGES;
+      if (kb >= CT_STAGES) mbar_wait(empty + s, ((kb / CT_STAGES) - 1) & 1);
+      uint8_t* sA = smem + s * L::STAGE;
+      uint8_t* sB = sA + L::A_BYTES;
+      const int kbase = k_begin + kb * 64;
+      // ------------------------------------------------ A tile
+      if (MODE == TC_FWD || MODE == TC_DGRAD) {
+        const int k0 = kbase + a_chunk * 8;
+        const int cch = MODE == TC_FWD ? g.Cin : g.Cout;          // channels per tap
+        const int tap = k0 / cch, c0 = k0 - tap * cch;
+        int dh, dw;
+        if (MODE == TC_FWD) { dh = tap / g.KW; dw = tap - dh * g.KW; }
+        else { dh = tap / ntw; dw = tap - dh * ntw; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 v0 = z4, v1 = z4;
+          if (a_base[j] >= 0 && k0 < k_end) {
+            if (MODE == TC_FWD) {
+              const int hi = a_h0[j] + dh, wi = a_w0[j] + dw;
+              if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
+                const float* src = p.a_src + ((size_t)(a_base[j] * g.H + hi) * g.W + wi) * g.Cin + c0;
+                v0 = ld4(src); v1 = ld4(src + 4);
+              }
+            } else {
+              const int ho = a_h0[j] - dh, wo = a_w0[j] - dw;
+              if (ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo) {
+                const float* src = p.a_src + ((size_t)(a_base[j] * g.Ho + ho) * g.Wo + wo) * g.Cout + c0;
+                v0 = ld4(src); v1 = ld4(src + 4);
+              }
+            }
+          }
+          st_chunk(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk), v0, v1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int mr = (tid >> 4) + 16 * j;          // pixel row inside the 64-pixel block
+          const int m = kbase + mr;
+          float4 v0 = z4, v1 = z4;
+          if (m < k_end) {
+            if (wg_kind == 0) {
+              const int b = m / (g.Ho * g.Wo), rem = m - b * (g.Ho * g.Wo);
+              const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+              const int hi = ho * g.S - g.PT + wg_kh, wi = wo * g.S - g.PL + wg_kw;
+              if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
+                const float* src = p.a_src + ((size_t)(b * g.H + hi) * g.W + wi) * g.Cin + wg_ci;
+                v0 = ld4(src); v1 = ld4(src + 4);
+              }
+            } else if (wg_kind == 1) {
+              v0.x = 1.0f;                              // ones column -> bias gradient row
+            }
+          }
+          st_chunk(sA + (a_chunk >> 3) * 8192 + sw128_offset(mr, a_chunk & 7), v0, v1);
+        }
+      }
+      // ------------------------------------------------ B tile
+      if (MODE == TC_DGRAD) {
+        // K-major rows n (NT), 8 chunks of k: source w[(tap * Cin + n) * Cout + co0 ..]
+        constexpr int NCH = NT * 8;
+        for (int c = tid; c < NCH; c += 256) {
+          const int n = c >> 3, ch = c & 7;
+          const int k0 = kbase + ch * 8;
+          float4 v0 = z4, v1 = z4;
+          if (n0 + n < Ng && k0 < k_end) {
+            const int tap = k0 / g.Cout, co0 = k0 - tap * g.Cout;
+            const int th = tap / ntw, tw = tap - th * ntw;
+            const int kh = rh + th * g.S, kw = rw + tw * g.S;
+            const float* src = p.b_src + ((size_t)(kh * g.KW + kw) * g.Cin + n0 + n) * g.Cout + co0;
+            v0 = ld4(src); v1 = ld4(src + 4);
+          }
+          st_chunk(sB + sw128_offset(n, ch), v0, v1);
+        }
+      } else {
+        // MN-major: 64 reduction rows, NT/8 chunks of n: source rows are contiguous in n (w[k][:] or dy[m][:])
+        constexpr int CPR = NT / 8;                    // chunks per row
+        constexpr int NCH = 64 * CPR;
+        for (int c = tid; c < NCH; c += 256) {
+          const int r = c / CPR, ch = c - r * CPR;
+          const int kk = kbase + r, n = n0 + ch * 8;
+          float4 v0 = z4, v1 = z4;
+          if (kk < k_end && n < Ng) {
+            const float* src = p.b_src + (size_t)kk * g.Cout + n;
+            if ((g.Cout & 7) == 0) {
+              v0 = ld4(src); v1 = ld4(src + 4);
+            } else {   // ragged channel count (the 3-channel image head): guarded scalar loads
+              float t8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t8[e] = (n + e < Ng) ? src[e] : 0.f;
+              v0 = make_float4(t8[0], t8[1], t8[2], t8[3]); v1 = make_float4(t8[4], t8[5], t8[6], t8[7]);
+            }
+          }
+          st_chunk(sB + (ch >> 3) * 8192 + sw128_offset(r, ch & 7), v0, v1);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full + s);
+    }
+
+    // ================================================================ epilogue
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int qd = warp & 3, hh = warp >> 2;           // TMEM lane quarter, column half
+    const int row = qd * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
+    constexpr int HALF = NT >= 32 ? NT / 2 : NT;       // NT = 16: only the hh == 0 warps work
+    if (NT >= 32 || hh == 0) {
+      const int cbase = NT >= 32 ? hh * HALF : 0;
+      const int m = m0 + row;
+      float* orow = nullptr;
+      if (m < Mg) {
+        if (MODE == TC_FWD) orow = p.out + (size_t)m * g.Cout;
+        else if (MODE == TC_DGRAD) {
+          const int b = m / (Hc * Wc), rem = m - b * (Hc * Wc);
+          const int ih = rem / Wc, iw = rem - ih * Wc;
+          orow = p.out + ((size_t)(b * g.H + hi_first + ih * g.S) * g.W + wi_first + iw * g.S) * g.Cin;
+        } else orow = (m < g.K) ? p.out + (size_t)m * g.Cout : p.dbias;
+      }
+#pragma unroll
+      for (int c = 0; c < HALF; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + cbase + c, r);
+        tmem_wait_ld();
+        if (orow) {
+          const int nb = n0 + cbase + c;
+          if (MODE == TC_WGRAD) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (nb + e < Ng) atomicAdd(orow + nb + e, __uint_as_float(r[e]));
+          } else if (nb + 16 <= Ng) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              float v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[q] = __uint_as_float(r[e + q]);
+                if (MODE == TC_FWD) v[q] = ct_act(v[q] + (p.bias ? p.bias[nb + e + q] : 0.f), p.act, p.slope);
+              }
+              st4(orow + nb + e, make_float4(v[0], v[1], v[2], v[3]));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (nb + e < Ng) {
+                float v = __uint_as_float(r[e]);
+                if (MODE == TC_FWD) v = ct_act(v + (p.bias ? p.bias[nb + e] : 0.f), p.act, p.slope);
+                orow[nb + e] = v;
+              }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int MODE, int NT>
+static int launch_conv_tc(const ConvTcP& p, dim3 grid, cudaStream_t st) {
+  using L = ConvTcSmem<MODE, NT>;
+  auto kern = conv_tc_kernel<MODE, NT>;
+  static bool configured = false;
+  if (!configured) {
+    SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, CT_THREADS, L::TOTAL, st>>>(p);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int MODE>
+static int dispatch_nt(const ConvTcP& p, int Ng, int gx, int gz, cudaStream_t st) {
+  if (Ng <= 16) return launch_conv_tc<MODE, 16>(p, dim3(gx, 1, gz), st);
+  if (Ng <= 32) return launch_conv_tc<MODE, 32>(p, dim3(gx, 1, gz), st);
+  if (Ng <= 64) return launch_conv_tc<MODE, 64>(p, dim3(gx, 1, gz), st);
+  return launch_conv_tc<MODE, 128>(p, dim3(gx, ceil_div(Ng, 128), gz), st);
+}
+
+static inline bool al16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
+
+// eligibility: 8-element chunks must stay inside one tap and be 16-byte aligned
+bool conv_tc_fwd_ok(const CG& g, const float* x, const float* w) { return g.Cin % 8 == 0 && al16(x) && al16(w); }
+bool conv_tc_dgrad_ok(const CG& g, const float* dy, const float* w) { return g.Cout % 8 == 0 && g.Cin % 4 == 0 && al16(dy) && al16(w); }
+bool conv_tc_wgrad_ok(const CG& g, const float* x, const float* dy) { return g.Cin % 8 == 0 && al16(x) && al16(dy); }
+
+int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope,
+                cudaStream_t st) {
+  ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0};
+  return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
+}
+
+int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st) {
+  ConvTcP p{dy, w, nullptr, dx, nullptr, g, 0, 0.f, 0};
+  const int Hc = ceil_div(g.H, g.S), Wc = ceil_div(g.W, g.S);
+  return dispatch_nt<TC_DGRAD>(p, g.Cin, ceil_div(g.B * Hc * Wc, 128), g.S * g.S, st);
+}
+
+int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st) {
+  const int Mg = g.K + (dbias ? 1 : 0);
+  const int tiles = ceil_div(Mg, 128) * ceil_div(g.Cout, 128);
+  int splits = std::max(1, std::min(ceil_div(g.M, 256), ceil_div(num_sms() * 2, tiles)));
+  int mps = ceil_div(ceil_div(g.M, splits), 64) * 64;
+  splits = ceil_div(g.M, mps);
+  ConvTcP p{x, dy, nullptr, dw, dbias, g, 0, 0.f, mps};
+  return dispatch_nt<TC_WGRAD>(p, g.Cout, ceil_div(Mg, 128), splits, st);
+}
+
+}  // namespace sagan
