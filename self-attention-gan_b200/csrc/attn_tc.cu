@@ -12,6 +12,12 @@
 //                       P_j = exp2(S_j - m)  -> bf16, written to shared memory in the UMMA K-major SW128 layout
 //                       O  += P_j V_j  (M=128, N=DVP, K=128)            -> TMEM columns [O]
 // The running-max rescale of O is lazy (only when the row max grows by > 2^8), so O stays in TMEM.
+//
+// Consistent rounding.  The softmax weights enter the PV MMA as bf16.  To keep the block and its backward an exact
+// (fp32-accurate) function / gradient pair of ONE well-defined set of weights, the running max is kept INTEGER-valued
+// (log2 units), so P'_ij = bf16(exp2(S_ij - m)) does not depend on which m was current (bf16 rounding commutes with
+// powers of two); the row sum l' = sum_j P'_ij is accumulated by the same MMA through a ones row appended to V^T, and
+// A = (P' V) / l'.  The backward (attn_tc_bwd.cu) regenerates exactly these P' from S and lse' = m + log2 l'.
 // NS = number of S buffers: 2 lets QK_{j+1} run under softmax_j (ping-pong inside the CTA, one CTA per SM);
 // NS = 1 is used for small value dims where two CTAs share an SM and overlap each other instead.
 #include <math.h>
@@ -72,7 +78,8 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
                     const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
                     const float* __restrict__ bv, __nv_bfloat16* __restrict__ Qb, __nv_bfloat16* __restrict__ Kb,
                     __nv_bfloat16* __restrict__ Vt, int B, int N, int Npad) {
-  constexpr int D = C / 8, DV = C / 2, DVP = 2 * DV;   // V^T rows: [v_hi (DV) | v_lo (DV)]
+  constexpr int D = C / 8, DV = C / 2;
+  constexpr int DVP = ((2 * DV + 1 + 15) / 16) * 16;   // V^T rows: [v_hi (DV) | v_lo (DV) | ones | 0 ...]
   __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
   for (int i = threadIdx.x; i < C * D; i += 128) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
   for (int i = threadIdx.x; i < C * DV; i += 128) sWv[i] = Wv[i];
@@ -133,10 +140,14 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
     Vt[((long long)b * DVP + v) * Npad + n] = hi;
     Vt[((long long)b * DVP + DV + v) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(hi));
   }
+  // ones row: column 2 DV of O accumulates l' = sum_j P'_ij (masked / padded keys contribute 0)
+  Vt[((long long)b * DVP + 2 * DV) * Npad + n] = __float2bfloat16_rn(valid ? 1.0f : 0.0f);
+#pragma unroll
+  for (int v = 2 * DV + 1; v < DVP; ++v) Vt[((long long)b * DVP + v) * Npad + n] = __float2bfloat16_rn(0.0f);
 }
 
 // ------------------------------------------------------------------------------------ flash forward
-template <int DVP, int NS, int NP>
+template <int DVP, int NS, int NP, int CEPI>
 struct FwdSmem {
   static constexpr int Q_BYTES = 128 * 128;
   static constexpr int K_BYTES = 128 * 128;
@@ -147,7 +158,7 @@ struct FwdSmem {
   static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
   static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
   static constexpr int OFF_W = OFF_P + NP * P_BYTES;         // fp32 Wo [dv][C] + bo [C] for the fused epilogue
-  static constexpr int W_BYTES = (32 * 64 + 64) * 4;
+  static constexpr int W_BYTES = (((CEPI / 2) * CEPI + CEPI) * 4 + 127) / 128 * 128;
   static constexpr int OFF_BAR = OFF_W + W_BYTES;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;          // + alignment slack
   static constexpr int TMEM_COLS = (NS * 128 + DVP) <= 256 ? 256 : 512;
@@ -162,7 +173,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const float* __restrict__ bo, const float* __restrict__ gamma, float* __restrict__ Y,
                    float* __restrict__ lse, float* __restrict__ A_saved, __nv_bfloat16* __restrict__ A_bf16, int N,
                    int Npad, int dv, int kq_steps) {
-  using L = FwdSmem<DVP, NS, NP>;
+  using L = FwdSmem<DVP, NS, NP, CEPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem + L::OFF_Q;
@@ -218,7 +229,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (CEPI > 0) {
       const int nW = dv * CEPI;
       for (int e = threadIdx.x; e < nW; e += 128) sW[e] = Wo[e];
-      for (int e = threadIdx.x; e < CEPI; e += 128) sW[32 * 64 + e] = bo[e];
+      for (int e = threadIdx.x; e < CEPI; e += 128) sW[nW + e] = bo[e];
     }
 
     auto issue_qk = [&](int j) {
@@ -249,7 +260,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     __syncwarp();
 
-    float m_used = -INFINITY, l = 0.f;
+    float m_used = -INFINITY;      // integer-valued (log2 units) once set: see "consistent rounding" above
     const bool ragged = (N % 128) != 0;
 
     for (int j = 0; j < nt; ++j) {
@@ -290,8 +301,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (j > 0) {
           mbar_wait(barPV + ((j - 1) & 1), ((j - 1) >> 1) & 1);       // every PV issued so far has completed
           tc_fence_after();
-          const float scale = need ? exp2f(m_used - mx) : 1.0f;
-          l *= scale;
+          const float scale = need ? exp2f(m_used - ceilf(mx)) : 1.0f;   // exact power of two
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
             uint32_t o[16];
@@ -303,14 +313,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           tmem_wait_st();
         }
-        if (need) m_used = mx;
+        if (need) m_used = ceilf(mx);
       }
       // ---- P buffer free?  (PV_{j-NP} has finished reading it)
       const int pb = j % NP;
       if (j >= NP) mbar_wait(barPV + ((j - NP) & 1), ((j - NP) >> 1) & 1);
       uint8_t* sPj = sP + pb * L::P_BYTES;
-      // ---- P = exp2(S - m), row sum, bf16 pack, swizzled store (16 B = 8 keys per store)
-      float l0 = 0.f, l1 = 0.f;
+      // ---- P' = bf16(exp2(S - m)), swizzled store (16 B = 8 keys per store); the row sum comes out of the PV MMA
 #pragma unroll
       for (int g = 0; g < 16; ++g) {
         uint32_t pk[4];
@@ -318,15 +327,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 0; i < 4; ++i) {
           const float p0 = ex2_approx(__uint_as_float(r[g * 8 + 2 * i]) - m_used);
           const float p1 = ex2_approx(__uint_as_float(r[g * 8 + 2 * i + 1]) - m_used);
-          l0 += p0;
-          l1 += p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
         // key columns [8g, 8g+8): sub-tile g/8, 16-byte chunk g%8
         *reinterpret_cast<uint4*>(sPj + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7)) =
             make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      l += l0 + l1;
       fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
       tc_fence_before();             // orders this thread's tcgen05.ld / st before the barrier
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -338,17 +344,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
     }
 
-    // ---- epilogue: O / l, saved tensors, (fused) output conv + gamma residual
+    // ---- epilogue: A = (P' V) / l', saved tensors, fused output conv + gamma residual
     mbar_wait(barPV + ((nt - 1) & 1), ((nt - 1) >> 1) & 1);
     tc_fence_after();
     const int i_tok = qt * 128 + row;
     const bool valid = i_tok < N;
     const long long grow = (long long)b * N + (valid ? i_tok : 0);
-    const float inv = 1.0f / l;
-    if (CEPI > 0) {
-      constexpr int C = CEPI > 0 ? CEPI : 16;
+    {
+      constexpr int C = CEPI;
       constexpr int DV = C / 2;
-      static_assert(CEPI == 0 || DVP == 2 * DV, "fused epilogue expects split values [v_hi | v_lo]");
+      static_assert(DVP >= 2 * DV + 1, "V^T rows are [v_hi | v_lo | ones]");
       float a[DVP];
 #pragma unroll
       for (int c = 0; c < DVP / 16; ++c) {
@@ -358,6 +363,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[c * 16 + i] = __uint_as_float(r[i]);
       }
+      const float l = a[2 * DV];           // l' = sum_j P'_ij, accumulated by the MMA through the ones row
+      const float inv = 1.0f / l;
 #pragma unroll
       for (int v = 0; v < DV; ++v) a[v] = (a[v] + a[DV + v]) * inv;
       if (valid) {
@@ -367,7 +374,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float gm = *gamma;
 #pragma unroll
         for (int c = 0; c < C; c += 4) {
-          float o[4] = {sW[32 * 64 + c], sW[32 * 64 + c + 1], sW[32 * 64 + c + 2], sW[32 * 64 + c + 3]};
+          float o[4] = {sW[DV * C + c], sW[DV * C + c + 1], sW[DV * C + c + 2], sW[DV * C + c + 3]};
 #pragma unroll
           for (int v = 0; v < DV; ++v) {
             const float4 w = *reinterpret_cast<const float4*>(&sW[v * C + c]);
@@ -379,28 +386,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               make_float4(fmaf(gm, o[0], xx.x), fmaf(gm, o[1], xx.y), fmaf(gm, o[2], xx.z), fmaf(gm, o[3], xx.w)));
         }
       }
-    } else {
-      // un-fused: A (normalised) as fp32 [B,N,dv] for the backward and as bf16 [B*Npad, DVP] for the out-proj GEMM
-      const long long prow = (long long)b * Npad + qt * 128 + row;
-#pragma unroll
-      for (int c = 0; c < DVP / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(t_row + L::OCOL + c * 16, r);
-        tmem_wait_ld();
-        float a[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = valid ? __uint_as_float(r[i]) * inv : 0.f;
-        uint4 p0 = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
-        uint4 p1 = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
-        uint4* dst = reinterpret_cast<uint4*>(A_bf16 + prow * DVP + c * 16);
-        dst[0] = p0; dst[1] = p1;
-        if (valid && A_saved) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            if (c * 16 + i < dv) st4(A_saved + grow * dv + c * 16 + i, make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]));
-        }
-      }
-      if (valid) lse[grow] = (m_used + log2f(l)) * TC_LN2;
     }
     tc_fence_before();
   }
@@ -416,14 +401,14 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct TcLayout {
   int Npad, DVP, kq_steps;
-  size_t off_q, off_k, off_v, off_a, total;
+  size_t off_q, off_k, off_v, total;
 };
 
 static TcLayout tc_layout(int B, int N, int C) {
   TcLayout t;
   const int d = C / 8, dv = C / 2;
   t.Npad = round_up(N, 128);
-  t.DVP = (C <= 64) ? 2 * dv : std::max(16, round_up(dv, 16));   // small C: split values [v_hi | v_lo]
+  t.DVP = round_up(2 * dv + 1, 16);   // V^T rows [v_hi | v_lo | ones | 0 ...]
   t.kq_steps = (3 * d + 15) / 16;   // split-bf16 logits: [hi|lo|hi] x [hi|hi|lo]
   const size_t T = (size_t)B * t.Npad;
   size_t o = 0;
@@ -431,7 +416,6 @@ static TcLayout tc_layout(int B, int N, int C) {
   t.off_q = take(T * QK_COLS * 2);
   t.off_k = take(T * QK_COLS * 2);
   t.off_v = take((size_t)B * t.DVP * t.Npad * 2);
-  t.off_a = take(T * t.DVP * 2);
   t.total = o + 1024;
   return t;
 }
@@ -442,7 +426,7 @@ template <int DVP, int NS, int NP, int CEPI>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const float* X,
                       const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
                       __nv_bfloat16* Ab, int B, int N, int Npad, int dv, int kq_steps, cudaStream_t st) {
-  using L = FwdSmem<DVP, NS, NP>;
+  using L = FwdSmem<DVP, NS, NP, CEPI>;
   auto kern = attn_fwd_tc_kernel<DVP, NS, NP, CEPI>;
   static bool configured = false;
   if (!configured) {
@@ -482,9 +466,9 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
   if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Npad, (uint64_t)t.Npad * 2, (uint32_t)t.DVP))) return rc;
   const int dv = C / 2;
   switch (C) {
-    case 16: return launch_fwd<16, 1, 1, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 32: return launch_fwd<32, 1, 1, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 64: return launch_fwd<64, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 16: return launch_fwd<32, 1, 1, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 32: return launch_fwd<48, 1, 1, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 64: return launch_fwd<80, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
   }
   return SAGAN_EUNSUPPORTED;
 }

@@ -8,7 +8,10 @@
 // score-shaped MMAs are computed transposed and every accumulation over queries stays inside the CTA:
 //     S^T  = K_j Q_i^T           (M=keys, N=queries, K=16*kq)        [split-bf16 logits, log2 units]
 //     dP^T = V_j dA_i^T          (M=keys, N=queries, K=16*kv)
-//     P^T  = exp2(S^T - lse_i),  dS^T = P^T * (dP^T - D_i)           -> bf16 tiles [keys][queries] in smem (SW128)
+//     P'^T = bf16(exp2(S^T - M_i)), dS^T = P'^T * (dP'^T - D'_i)     -> bf16 tiles [keys][queries] in smem (SW128)
+//            M_i = ceil(lse'_i) integer, so P' reproduces the forward's bf16 weights exactly (attn_tc.cu, "consistent
+//            rounding"); the per-query factor 2^(M_i - lse'_i) that normalises P' is folded into dA and D by the prep
+//            kernel (dA' = f dA, D' = f D), so sum_j dS_ij = 0 holds to fp32 accuracy and nothing is amplified
 //     dV_j += P^T  dA_i          (A = P^T  K-major, B = dA_i^T rows)   TMEM, accumulated over i
 //     dK_j += dS^T Q_i           (A = dS^T K-major, B = Q_i^T rows)    TMEM, accumulated over i
 //     dQ_i  = dS   K_j           (A = the SAME dS^T tile read MN-major, B = K_j^T rows) -> atomicAdd over key tiles
@@ -40,9 +43,13 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
                         __nv_bfloat16* __restrict__ dAb, __nv_bfloat16* __restrict__ dAt, __nv_bfloat16* __restrict__ Qt,
                         __nv_bfloat16* __restrict__ Kt, float* __restrict__ lse2, float* __restrict__ Dd,
                         float* __restrict__ dA_f32, int B, int N, int Npad) {
-  constexpr int D = C / 8, DV = C / 2, DVP = DV < 16 ? 16 : DV;
+  constexpr int D = C / 8, DV = C / 2;
+  constexpr bool SPLIT3 = DV <= 16;                  // 3-term split of the dP contraction fits a 64-column row
+  constexpr bool SPLIT_DA = DV <= 16;                // dA^T rows [hi | lo] for the dV GEMM
+  constexpr int DVP = SPLIT_DA ? (2 * DV < 16 ? 16 : 2 * DV) : DV;
   constexpr int KQ = ((3 * D + 15) / 16) * 16;
-  constexpr int KV = ((DV + 15) / 16) * 16;
+  constexpr int KV = SPLIT3 ? ((3 * DV + 15) / 16) * 16 : 2 * DV;
+  static_assert(KV <= TB_COLS, "dP operand row must fit one 128-byte swizzle span");
   __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
   __shared__ __align__(16) float sWo[DV * C];
   for (int i = threadIdx.x; i < C * D; i += 128) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
@@ -102,8 +109,10 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
                        pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
   }
-  // ---- g (values) and dA = gamma dY Wo^T, D = dA . A
-  const float gm = *gamma;
+  // ---- g (values) and dA' = f gamma dY Wo^T, D' = dA' . A, with f = 2^(M - lse') the normaliser of P' (see top)
+  const float l2 = valid ? lse[t] * TB_LOG2E : 0.f;
+  const float Mi = ceilf(l2);
+  const float gm = *gamma * exp2f(Mi - l2);
   float v[KV], da[KV];
 #pragma unroll
   for (int j = 0; j < KV; ++j) { v[j] = 0.f; da[j] = 0.f; }
@@ -117,9 +126,25 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
       g = fmaf(dy[c], sWo[j * C + c], g);
     }
     g *= gm;
-    v[j] = valid ? a : 0.f;
-    da[j] = valid ? g : 0.f;
-    if (valid) dd = fmaf(g, A[t * DV + j], dd);
+    a = valid ? a : 0.f;
+    g = valid ? g : 0.f;
+    // split-bf16 operands of dP^T = V dA^T (dP - D cancels, so bf16 V / dA would dominate the gradient error):
+    //   V row [v_hi | v_hi | v_lo], dA row [da_hi | da_lo | da_hi]  ->  v_hi da_hi + v_hi da_lo + v_lo da_hi
+    // dv = 32: only two terms fit the 64-column row: [v_hi | v_lo] x [da_hi | da_hi] = v . bf16(dA), and D uses the
+    // same rounded dA so that D_i = sum_j P'_ij dP_ij stays consistent
+    const float vh = __bfloat162float(__float2bfloat16_rn(a)), gh = __bfloat162float(__float2bfloat16_rn(g));
+    if (SPLIT3) {
+      v[j] = vh; v[DV + j] = vh; v[2 * DV + j] = a - vh;
+      da[j] = gh; da[DV + j] = g - gh; da[2 * DV + j] = gh;
+      if (valid) dd = fmaf(g, A[t * DV + j], dd);
+    } else {
+      v[j] = vh; v[DV + j] = a - vh;
+      da[j] = gh; da[DV + j] = gh;
+      if (valid) dd = fmaf(gh, A[t * DV + j], dd);
+    }
+    // transposed dA rows for dV = P^T dA: [hi | lo] when they fit
+    dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(g);
+    if (SPLIT_DA) dAt[((long long)b * DVP + DV + j) * Npad + n] = __float2bfloat16_rn(g - gh);
   }
   uint4* vd = reinterpret_cast<uint4*>(Vb + tp * TB_COLS);
   uint4* ad = reinterpret_cast<uint4*>(dAb + tp * TB_COLS);
@@ -131,8 +156,8 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
                        pack_bf16x2(da[g * 8 + 4], da[g * 8 + 5]), pack_bf16x2(da[g * 8 + 6], da[g * 8 + 7]));
   }
 #pragma unroll
-  for (int j = 0; j < DVP; ++j) dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(j < DV ? da[j] : 0.f);
-  lse2[tp] = valid ? lse[t] * TB_LOG2E : INFINITY;   // +inf => P = 0 for padded queries
+  for (int j = (SPLIT_DA ? 2 * DV : DV); j < DVP; ++j) dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(0.f);
+  lse2[tp] = valid ? Mi : INFINITY;                  // integer shift M_i; +inf => P' = 0 for padded queries
   Dd[tp] = valid ? dd : 0.f;
   (void)dA_f32;
 }
@@ -155,7 +180,8 @@ struct BwdSmem {
   static constexpr int STAGE = ST_VEC + 1024;
   static constexpr int OFF_PT = OFF_STAGE + 2 * STAGE;
   static constexpr int OFF_DST = OFF_PT + 2 * TILE;
-  static constexpr int OFF_BAR = OFF_DST + 2 * TILE;
+  static constexpr int OFF_DSL = OFF_DST + 2 * TILE;      // dS^T - bf16(dS^T): second bf16 term of the split
+  static constexpr int OFF_BAR = OFF_DSL + 2 * TILE;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;
   static constexpr int STAGE_TX = TILE + TILE + TDV + T16 + 1024;
   static_assert(STAGE % 1024 == 0 && OFF_STAGE % 1024 == 0, "tiles must stay 1024-byte aligned");
@@ -163,7 +189,7 @@ struct BwdSmem {
   static constexpr int ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + 64, DQ_COL = 256 + 64 + 16;
 };
 
-template <int DVP>
+template <int DVP, bool SPLIT_DA>
 __global__ void __launch_bounds__(TB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdA,
@@ -180,6 +206,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sStage = smem + L::OFF_STAGE;
   uint8_t* sPt = smem + L::OFF_PT;
   uint8_t* sdSt = smem + L::OFF_DST;
+  uint8_t* sdSl = smem + L::OFF_DSL;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* barKV = bars + 0;
   uint64_t* barQ = bars + 1;    // [2] stage full
@@ -262,16 +289,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
                       IDESC_DV, (i > 0) || (ks > 0));
         }
+        const uint64_t dSl = make_desc_sw128(smem_u32(sdSl));
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
-          mma_bf16_ss(tmem_base + L::DK_COL, dSt + a_off, dQt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
-                      IDESC_DK, (i > 0) || (ks > 0));
+        for (int ks = 0; ks < 16; ++ks) {  // dS^T = hi tile (ks < 8) + lo tile
+          const int k8 = ks & 7;
+          const uint64_t a_off = (uint64_t)((k8 >> 2) * (L::TILE >> 4) + (k8 & 3) * 2);
+          mma_bf16_ss(tmem_base + L::DK_COL, (ks < 8 ? dSt : dSl) + a_off,
+                      dQt_ + (uint64_t)((k8 >> 2) * ((16 * 128) >> 4) + (k8 & 3) * 2), IDESC_DK, (i > 0) || (ks > 0));
         }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // K = keys: the dS^T tile read MN-major (M = queries contiguous)
-          const uint64_t a = make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024);
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 16, a, dKt_ + (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2),
+        for (int ks = 0; ks < 16; ++ks) {  // K = keys: the dS^T tiles read MN-major (M = queries contiguous)
+          const int k8 = ks & 7;
+          const uint64_t a = make_desc_sw128_mn(smem_u32(ks < 8 ? sdSt : sdSl) + k8 * 16 * 128, L::TILE, 1024);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 16, a, dKt_ + (uint64_t)((k8 >> 2) * ((16 * 128) >> 4) + (k8 & 3) * 2),
                       IDESC_DQ, ks > 0);
         }
         mma_commit(barG + s);
@@ -333,6 +363,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       uint8_t* pt = sPt + h * L::TILE;
       uint8_t* dst = sdSt + h * L::TILE;
+      uint8_t* dsl = sdSl + h * L::TILE;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 64 + g * 8);
@@ -342,18 +373,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float ds_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         float p[8], g_[8];
+        uint32_t pp[4];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
-          pe = key_ok ? pe : 0.f;
-          p[e] = pe;
-          g_[e] = pe * (__uint_as_float(rp[g * 8 + e]) - ds_[e]);
+          const float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
+          p[e] = key_ok ? pe : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pp[e] = pack_bf16x2(p[2 * e], p[2 * e + 1]);       // P' = bf16(exp2(S - M)): the weights the forward used
+          g_[2 * e] = __uint_as_float(pp[e] << 16) * (__uint_as_float(rp[g * 8 + 2 * e]) - ds_[2 * e]);
+          g_[2 * e + 1] = __uint_as_float(pp[e] & 0xffff0000u) * (__uint_as_float(rp[g * 8 + 2 * e + 1]) - ds_[2 * e + 1]);
         }
         const uint32_t off = sw128_offset(krow, g);
-        *reinterpret_cast<uint4*>(pt + off) =
-            make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-        *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(g_[0], g_[1]), pack_bf16x2(g_[2], g_[3]),
-                                                          pack_bf16x2(g_[4], g_[5]), pack_bf16x2(g_[6], g_[7]));
+        *reinterpret_cast<uint4*>(pt + off) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+        // dS^T = hi + lo (two bf16 terms): sum_j dS_ij = 0, so the theta / phi gradients cancel and need the extra bits
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[e] = pack_bf16x2(g_[2 * e], g_[2 * e + 1]);
+          lo[e] = pack_bf16x2(g_[2 * e] - __uint_as_float(hi[e] << 16), g_[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
+        }
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dsl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -366,17 +408,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (h == 0) {
       const int key = kt * 128 + krow;
       const size_t grow = (size_t)b * N + key;
+      if (SPLIT_DA) {
+        // columns [dV from dA_hi (dv) | dV from dA_lo (dv)]
+        float acc[DVP];
 #pragma unroll
-      for (int c = 0; c < DVP / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(t_row + L::DV_COL + c * 16, r);
-        tmem_wait_ld();
+        for (int c = 0; c < DVP / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(t_row + L::DV_COL + c * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[c * 16 + e] = __uint_as_float(r[e]);
+        }
+        constexpr int DVH = DVP / 2;   // == dv
         if (key < N) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            if (c * 16 + e < dv)
-              st4(dV + grow * dv + c * 16 + e, make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
-                                                            __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+          for (int e = 0; e < DVH; e += 4)
+            st4(dV + grow * DVH + e, make_float4(acc[e] + acc[DVH + e], acc[e + 1] + acc[DVH + e + 1],
+                                                 acc[e + 2] + acc[DVH + e + 2], acc[e + 3] + acc[DVH + e + 3]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < DVP / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(t_row + L::DV_COL + c * 16, r);
+          tmem_wait_ld();
+          if (key < N) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              if (c * 16 + e < dv)
+                st4(dV + grow * dv + c * 16 + e, make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                              __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+          }
         }
       }
       uint32_t r[16];
@@ -404,9 +466,9 @@ static TbLayout tb_layout(int B, int N, int C) {
   TbLayout t;
   const int d = C / 8, dv = C / 2;
   t.Npad = (N + 127) / 128 * 128;
-  t.DVP = dv < 16 ? 16 : dv;
+  t.DVP = C == 16 ? 16 : 32;                              // C <= 32: [dA_hi | dA_lo] rows; C = 64: dA rows unsplit
   t.kq_steps = (3 * d + 15) / 16;
-  t.kv_steps = (dv + 15) / 16;
+  t.kv_steps = dv <= 16 ? (3 * dv + 15) / 16 : (2 * dv) / 16;   // split-bf16 dP contraction (see the prep kernel)
   const size_t T = (size_t)B * t.Npad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
@@ -439,11 +501,11 @@ static int run_prep(const float* X, const float* dY, const float* A, const float
   return 0;
 }
 
-template <int DVP>
+template <int DVP, bool SPLIT_DA>
 static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, float* dQ, float* dK, float* dV, int B,
                       int N, int Npad, int d, int dv, int kq, int kv, cudaStream_t st) {
   using L = BwdSmem<DVP>;
-  auto kern = attn_bwd_tc_kernel<DVP>;
+  auto kern = attn_bwd_tc_kernel<DVP, SPLIT_DA>;
   static bool configured = false;
   if (!configured) {
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -489,8 +551,9 @@ int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const floa
   const float* lse2 = (const float*)(base + t.off_lse);
   const float* Dd = (const float*)(base + t.off_dd);
   const int d = C / 8, dv = C / 2;
-  if (t.DVP == 16) return launch_bwd<16>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
-  return launch_bwd<32>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  if (C == 16) return launch_bwd<16, true>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  if (C == 32) return launch_bwd<32, true>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  return launch_bwd<32, false>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
 }
 
 }  // namespace sagan

@@ -347,10 +347,14 @@ def test_attention_tc_vs_golden(F, case):
     # the attention contribution alone (Y - X) must also be accurate, not just hidden behind the residual
     assert e_att < 1e-2
     assert e_dx < TC_TOL
-    # parameter gradients in BF16_TC mode: P, dS, dA and V enter the backward GEMMs as bf16 (2^-9 rounding) and the
-    # theta / phi gradients are cancellation-prone (sum_j dS_ij = 0): measured 3e-3 .. 8e-3, asserted at 1.5e-2
+    # parameter gradients: the cancellation-prone operands of the backward GEMMs (V, dA in dP = dA g^T; dS in the
+    # theta / phi gradients) are carried as split bf16 pairs, so only the bf16 rounding of P itself is left for
+    # C <= 32.  C = 64 (dv = 32): the 3-term split of dP does not fit the 64-column operand row, V stays rounded.
+    tol_w = TC_TOL if C <= 32 else 6e-3
     for k, e in errs.items():
-        assert e < 1.5e-2, (k, e)
+        # d gamma = sum(dY * O) is ONE scalar summed over zero-mean terms (this test's dY is independent of O), so its
+        # relative error is a ratio of two random-walk sums: loose bound
+        assert e < (1e-2 if k == "gamma" else tol_w), (k, e)
 
 
 @pytest.mark.parametrize("shape", [(4, 4096, 16), (4, 1024, 32), (2, 1024, 64), (3, 1000, 16)])
@@ -409,6 +413,10 @@ def test_conv2d_tc(F, case):
     tx, tw = bf16r(x).requires_grad_(True), bf16r(w).requires_grad_(True)
     onets.conv2d_same(tx, tw, None, s).backward(bf16r(dz))
     e_dx, e_dw = rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()), rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy())
+    if Cout % 8:   # ragged channel count (the 3-channel image head): dgrad is not tensor-core eligible and runs in fp32
+        ux = torch.tensor(x, requires_grad=True)
+        onets.conv2d_same(ux, torch.tensor(w), None, s).backward(dz)
+        e_dx = rel_l2(gx.grad.cpu().numpy(), ux.grad.numpy())
     e_db = rel_l2(gb.grad.cpu().numpy(), bf16r(dz).sum(dim=(0, 1, 2)).numpy())
     # (2) un-rounded reference, forward
     ref = torch.nn.functional.leaky_relu(onets.conv2d_same(torch.tensor(x), torch.tensor(w), tb, s), 0.1)
@@ -438,240 +446,6 @@ def test_conv2d_tc_linear_vs_fp64(F, case):
             rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()), rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()))
     print(case, "y %.2e dx %.2e dw %.2e db %.2e" % errs)
     assert max(errs) < 2 * TC_TOL
-
-
-@pytest.mark.parametrize("case", [(2, 4, 4, 256, 128, 4, 2), (2, 16, 16, 64, 32, 4, 2), (2, 32, 32, 32, 16, 4, 2),
-                                  (2, 5, 6, 8, 12, 3, 2), (1, 4, 4, 8, 8, 4, 2)])
-def test_conv2d_transpose(F, case):
-    B, H, W, Cin, Cout, k, s = case
-    rng = np.random.Generator(np.random.PCG64(13))
-    x = rng.standard_normal((B, H, W, Cin))
-    w = rng.standard_normal((k, k, Cout, Cin)) * 0.1
-    tx, tw = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w))
-    ref = onets.conv2d_transpose_same(tx, tw, s)
-    dy = rng.standard_normal(tuple(ref.shape))
-    ref.backward(torch.tensor(dy))
-    gx, gw = (cu(a).requires_grad_(True) for a in (x, w))
-    y = F.conv2d_transpose(gx, gw, s, "same")
-    assert tuple(y.shape) == tuple(ref.shape)
-    y.backward(cu(dy))
-    torch.cuda.synchronize()
-    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
-    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < STRICT_TOL
-    assert rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()) < STRICT_TOL
-
-
-def test_dense(F):
-    rng = np.random.Generator(np.random.PCG64(14))
-    x, w, b = rng.standard_normal((8, 128)), rng.standard_normal((128, 4096)) * 0.05, rng.standard_normal(4096)
-    tx, tw, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, b))
-    ref = tx @ tw + tb
-    dy = rng.standard_normal((8, 4096))
-    ref.backward(torch.tensor(dy))
-    gx, gw, gb = (cu(a).requires_grad_(True) for a in (x, w, b))
-    y = F.dense(gx, gw, gb)
-    y.backward(cu(dy))
-    torch.cuda.synchronize()
-    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
-    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < STRICT_TOL
-    assert rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()) < STRICT_TOL
-    assert rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()) < STRICT_TOL
-
-
-@pytest.mark.parametrize("shape", [(4, 8, 8, 128), (2, 64, 64, 16), (3, 5, 7, 12)])
-def test_batchnorm_lrelu(F, shape):
-    rng = np.random.Generator(np.random.PCG64(15))
-    x = rng.standard_normal(shape) * 1.7 + 0.3
-    C = shape[-1]
-    gam, bet = rng.standard_normal(C) * 0.3 + 1, rng.standard_normal(C) * 0.2
-    tx, tg, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, gam, bet))
-    stats = {"bn.moving_mean": torch.zeros(C, dtype=torch.float64), "bn.moving_var": torch.ones(C, dtype=torch.float64)}
-    ref = torch.nn.functional.leaky_relu(onets.batchnorm_train(tx, tg, tb, stats, "bn"), 0.1)
-    dy = rng.standard_normal(shape)
-    ref.backward(torch.tensor(dy))
-    gx, gg, gb = (cu(a).requires_grad_(True) for a in (x, gam, bet))
-    mm, mv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
-    y = F.batchnorm_lrelu(gx, gg, gb, mm, mv, 1e-3, 0.99, 0.1)
-    y.backward(cu(dy))
-    torch.cuda.synchronize()
-    assert rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()) < STRICT_TOL
-    assert rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()) < 2e-5
-    assert rel_l2(gg.grad.cpu().numpy(), tg.grad.numpy()) < 2e-5
-    assert rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()) < 2e-5
-    assert rel_l2(mm.cpu().numpy(), stats["bn.moving_mean"].numpy()) < STRICT_TOL
-    assert rel_l2(mv.cpu().numpy(), stats["bn.moving_var"].numpy()) < STRICT_TOL
-
-
-# ---------------------------------------------------------------------------------------- attention
-def _run_attn(F, X, dY, w, mode):
-    t = {k: cu(np.asarray(v)).requires_grad_(True) for k, v in w.items()}
-    tx = cu(X).requires_grad_(True)
-    y = F.attention(tx, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"], mode)
-    y.backward(cu(dY))
-    torch.cuda.synchronize()
-    return y.detach().cpu().numpy(), tx.grad.cpu().numpy(), {k: v.grad.cpu().numpy() for k, v in t.items()}
-
-
-@pytest.mark.parametrize("case", list(enumerate(mg.ATTN_CASES)))
-def test_attention_strict_vs_golden(F, case):
-    i, (B, N, C) = case
-    gold = np.load(os.path.join(GOLD, "attention.npz"))
-    X, dY, w = mg.attn_inputs(B, N, C, 200 + i)
-    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_FP32_STRICT)
-    tag = f"B{B}_N{N}_C{C}"
-    assert rel_l2(y, gold[tag + "_Y"]) < STRICT_TOL
-    assert rel_l2(dx, gold[tag + "_dX"]) < STRICT_TOL
-    for k in oattn.WEIGHT_NAMES:
-        if k == "bphi":   # mathematically zero (softmax is invariant to a per-row shift of the logits)
-            assert np.abs(gw[k]).max() < 1e-4 * np.abs(gw["btheta"]).max()
-            continue
-        assert rel_l2(gw[k], gold[tag + "_d" + k]) < 2e-5, k
-
-
-def test_attention_strict_vs_oracle_ragged_and_large_logits(F):
-    """N not a multiple of the tile (200) and un-scaled logits of magnitude ~30 (no 1/sqrt(d), layers.py:108)."""
-    B, N, C = 2, 200, 32
-    X, dY, w = oattn.make_inputs(B, N, C, seed=5, gamma=0.8, dtype=np.float32)
-    w["Wtheta"] = w["Wtheta"] * 6
-    w["Wphi"] = w["Wphi"] * 6
-    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
-    Y = oattn.forward(X.astype(np.float64), **w64)
-    g = oattn.backward(dY.astype(np.float64), X.astype(np.float64), **w64)
-    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_FP32_STRICT)
-    assert rel_l2(y, Y) < STRICT_TOL
-    assert rel_l2(dx, g["dX"]) < 5e-5
-    for k in oattn.WEIGHT_NAMES:
-        if k == "bphi":
-            assert np.abs(gw[k]).max() < 1e-4 * np.abs(gw["btheta"]).max()
-            continue
-        assert rel_l2(gw[k], g["d" + k]) < 5e-5, k
-
-
-def test_attention_gamma_zero_is_identity(F):
-    """gamma is zero-initialised (layers.py:76-79): the block is the identity and only dgamma is non-zero."""
-    X, dY, w = oattn.make_inputs(2, 128, 16, seed=9, gamma=0.0, dtype=np.float32)
-    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_FP32_STRICT)
-    assert np.array_equal(y, X)
-    assert np.array_equal(dx, dY)
-    assert abs(gw["gamma"]).max() > 0
-    assert all(np.abs(gw[k]).max() == 0 for k in ("Wphi", "Wtheta", "Wg", "Wo", "bo"))
-
-
-def test_attention_full_size_properties(F):
-    """church64_attn G attention at 64x64 (N = 4096, C = 16), B = 4: permutation equivariance over tokens
-    and row-stochasticity (constant values => A == that constant), which do not need the O(N^2) oracle."""
-    B, N, C = 4, 4096, 16
-    X, dY, w = oattn.make_inputs(B, N, C, seed=21, gamma=0.5, dtype=np.float32)
-    t = {k: cu(np.asarray(v)) for k, v in w.items()}
-    args = (t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"])
-    x = cu(X)
-    y = F.attention(x, *args)
-    perm = torch.randperm(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
-    yp = F.attention(x[:, perm].contiguous(), *args)
-    torch.cuda.synchronize()
-    assert rel_l2(yp.cpu().numpy(), y[:, perm].cpu().numpy()) < 1e-5
-    # values independent of the token (Wg = 0): O = bg Wo + bo for every row
-    zg = torch.zeros_like(t["Wg"])
-    y2 = F.attention(x, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], zg, t["bg"], t["Wo"], t["bo"], t["gamma"])
-    const = t["bg"] @ t["Wo"] + t["bo"]
-    torch.cuda.synchronize()
-    assert rel_l2(y2.cpu().numpy(), (x + t["gamma"] * const).cpu().numpy()) < 1e-6
-
-
-# ---------------------------------------------------------------------------------------- losses / optimiser
-def test_hinge_and_adam(F):
-    rng = np.random.Generator(np.random.PCG64(17))
-    dr, df = rng.standard_normal((4, 4, 4, 1)) * 2, rng.standard_normal((4, 4, 4, 1)) * 2
-    loss = torch.zeros(2, device="cuda")
-    gr, gf = F.hinge_d_grads(cu(dr), cu(df), 8, loss[0:1])
-    gg = F.hinge_g_grads(cu(df), 8, loss[1:2])
-    torch.cuda.synchronize()
-    n = dr.size
-    assert abs(float(loss[0]) - (np.maximum(1 - dr, 0) + np.maximum(1 + df, 0)).sum()) < 1e-4
-    assert abs(float(loss[1]) - (-df).sum()) < 1e-4
-    assert np.allclose(gr.cpu().numpy(), np.where(1 - dr > 0, -1.0, 0.0) / (n * 8))
-    assert np.allclose(gf.cpu().numpy(), np.where(1 + df > 0, 1.0, 0.0) / (n * 8))
-    assert np.allclose(gg.cpu().numpy(), -1.0 / (n * 8))
-    # Keras Adam, beta_1 = 0, three steps
-    p0, g = rng.standard_normal(1000), rng.standard_normal((3, 1000))
-    p, v = cu(p0), torch.zeros(1000, device="cuda")
-    pr, vr = p0.copy(), np.zeros(1000)
-    for t in range(1, 4):
-        lr_t = 7e-4 * np.sqrt(1 - 0.999 ** t)
-        hyper = cu(np.array([lr_t, 0.0, 0.999, 1e-7]))
-        F.adam_step(p, cu(g[t - 1]), v, hyper)
-        vr = 0.999 * vr + 0.001 * g[t - 1] ** 2
-        pr = pr - lr_t * g[t - 1] / (np.sqrt(vr) + 1e-7)
-    torch.cuda.synchronize()
-    assert rel_l2(p.cpu().numpy(), pr) < 1e-6
-
-
-# ---------------------------------------------------------------------------------------- attention, BF16_TC (tcgen05)
-@pytest.mark.parametrize("case", list(enumerate(mg.ATTN_CASES)))
-def test_attention_tc_vs_golden(F, case):
-    """tcgen05 / TMEM / TMA forward (bf16 operands, fp32 accumulate) against the fp64 golden: <= 2e-3 rel-L2."""
-    i, (B, N, C) = case
-    gold = np.load(os.path.join(GOLD, "attention.npz"))
-    X, dY, w = mg.attn_inputs(B, N, C, 200 + i)
-    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_BF16_TC)
-    tag = f"B{B}_N{N}_C{C}"
-    errs = {k: rel_l2(gw[k], gold[tag + "_d" + k]) for k in oattn.WEIGHT_NAMES if k != "bphi"}
-    e_y, e_att, e_dx = rel_l2(y, gold[tag + "_Y"]), rel_l2(y - X, gold[tag + "_Y"] - X), rel_l2(dx, gold[tag + "_dX"])
-    print(tag, "Y %.2e Y-X %.2e dX %.2e dX-dY %.2e" % (e_y, e_att, e_dx, rel_l2(dx - dY, gold[tag + "_dX"] - dY)),
-          {k: "%.1e" % v for k, v in errs.items()})
-    assert e_y < TC_TOL
-    # the attention contribution alone (Y - X) must also be accurate, not just hidden behind the residual
-    assert e_att < 1e-2
-    assert e_dx < TC_TOL
-    # parameter gradients in BF16_TC mode: P, dS, dA and V enter the backward GEMMs as bf16 (2^-9 rounding) and the
-    # theta / phi gradients are cancellation-prone (sum_j dS_ij = 0): measured 3e-3 .. 8e-3, asserted at 1.5e-2
-    for k, e in errs.items():
-        assert e < 1.5e-2, (k, e)
-
-
-@pytest.mark.parametrize("shape", [(4, 4096, 16), (4, 1024, 32), (2, 1024, 64), (3, 1000, 16)])
-def test_attention_tc_vs_strict_full_size(F, shape):
-    """In-model sizes (N = 4096 / 1024): the tensor-core forward against the fp32 CUDA-core forward."""
-    B, N, C = shape
-    X, dY, w = oattn.make_inputs(B, N, C, seed=31, gamma=0.7, dtype=np.float32)
-    w["Wtheta"] = w["Wtheta"] * 3      # un-scaled logits of a few units, like a trained model
-    t = {k: cu(np.asarray(v)) for k, v in w.items()}
-    args = (t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"])
-    x = cu(X)
-    ys = F.attention(x, *args, F.MATH_FP32_STRICT)
-    yt = F.attention(x, *args, F.MATH_BF16_TC)
-    torch.cuda.synchronize()
-    assert rel_l2(yt.cpu().numpy(), ys.cpu().numpy()) < TC_TOL
-    assert rel_l2((yt - x).cpu().numpy(), (ys - x).cpu().numpy()) < 1e-2
-
-
-# ---------------------------------------------------------------------------------------- conv family, BF16_TC (tcgen05)
-TC_CONV_CASES = [  # B, H, W, Cin, Cout, k, stride
-    (2, 32, 32, 16, 32, 4, 2), (2, 16, 16, 32, 64, 4, 2), (2, 8, 8, 64, 128, 4, 2), (4, 64, 64, 16, 3, 4, 1),
-    (2, 4, 4, 128, 8, 4, 1), (3, 9, 7, 8, 24, 3, 2), (2, 16, 16, 16, 16, 1, 1), (1, 5, 5, 8, 200, 3, 1),
-]
-
-
-@pytest.mark.parametrize("case", TC_CONV_CASES)
-def test_conv2d_tc(F, case):
-    """tcgen05 implicit-GEMM conv (bf16 operands, fp32 accumulate): fwd, dgrad, wgrad + bias grad vs fp64 torch."""
-    B, H, W, Cin, Cout, k, s = case
-    rng = np.random.Generator(np.random.PCG64(41))
-    x = rng.standard_normal((B, H, W, Cin))
-    w = rng.standard_normal((k, k, Cin, Cout)) * 0.1
-    b = rng.standard_normal(Cout) * 0.1
-    tx, tw, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, b))
-    ref = torch.nn.functional.leaky_relu(onets.conv2d_same(tx, tw, tb, s), 0.1)
-    dy = rng.standard_normal(tuple(ref.shape))
-    ref.backward(torch.tensor(dy))
-    gx, gw, gb = (cu(a).requires_grad_(True) for a in (x, w, b))
-    y = F.conv2d(gx, gw, gb, s, "same", F.ACT_LRELU, 0.1, F.MATH_BF16_TC)
-    y.backward(cu(dy))
-    torch.cuda.synchronize()
-    errs = (rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()), rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()),
-            rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()), rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()))
-    print(case, "y %.2e dx %.2e dw %.2e db %.2e" % errs)
-    assert max(errs) < 5e-3
 
 
 @pytest.mark.parametrize("case", [(2, 4, 4, 256, 128, 4, 2), (2, 16, 16, 64, 32, 4, 2), (2, 32, 32, 32, 16, 4, 2),
