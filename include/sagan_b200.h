@@ -81,6 +81,9 @@ int sagan_sn_plan_create(const sagan_sn_desc* descs_host, int n, int device, sag
 int sagan_sn_plan_run(sagan_sn_plan* plan, sagan_stream_t stream);
 /* Same plan, but only the matrices listed (indices into the plan) take part */
 int sagan_sn_plan_destroy(sagan_sn_plan* plan);
+/* Diagnostics: device-side durations (ms, %globaltimer) of the five phases of the plan's most recent run
+ * [u W partials, s + ||s||, v W^T partials, t + ||t||, u / sigma / W_bar].  Synchronises the device. */
+int sagan_sn_plan_phase_times(sagan_sn_plan* plan, float* ms_host /* [5] */);
 /* algorithmic HBM bytes of one run of the plan (8 B/element, 10 with the bf16 copy,
  * 16/18 when the matrix exceeds 64 MB) */
 unsigned long long sagan_sn_plan_algorithmic_bytes(const sagan_sn_plan* plan);

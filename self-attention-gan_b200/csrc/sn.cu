@@ -58,7 +58,40 @@ struct SnTotals {
   int n;
   int tot1, tot1b, tot2, tot2b, tot3;
   int maxIp;
+  unsigned long long* stamps;   // optional [8] %globaltimer values at the phase boundaries of the last iteration
 };
+
+__device__ __forceinline__ unsigned long long sn_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SN_STAMP(i)                                                                    \
+  do {                                                                                 \
+    if (tot.stamps && blockIdx.x == 0 && threadIdx.x == 0) tot.stamps[i] = sn_now();   \
+  } while (0)
+
+// cache-hinted accesses: W is read three times (passes 1-2: keep in L2; pass 3: last use), W_bar is write-once
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld4_keep(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float4 ld4_last(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ float4 sn_load4(const float* row, int k, int K, int vec) {
   if (vec) return ld4(row + k);
@@ -87,17 +120,23 @@ __device__ __forceinline__ int sn_find(const int* offs, int n, int unit) {
   return m;
 }
 
+__device__ __forceinline__ float4 sn_load4_keep(const float* row, int k, int K, int vec, uint64_t pol) {
+  return vec ? ld4_keep(row + k, pol) : sn_load4(row, k, K, 0);
+}
+
 __global__ void __launch_bounds__(SN_THREADS, 2)
 sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
   cg::grid_group grid = cg::this_grid();
   __shared__ int s_off[5][SN_MAX_MATS];
   __shared__ float s_inv[SN_MAX_MATS];   // 1/(||s||+eps) or 1/(||t||+eps) of the current phase
   __shared__ float s_sig[SN_MAX_MATS];
+  __shared__ float4 s_red[SN_WARPS][32];
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * SN_WARPS + wid;
   const int nwarps = gridDim.x * SN_WARPS;
   const int n = tot.n;
+  const uint64_t pol = l2_policy_evict_last();
 
   for (int i = threadIdx.x; i < n; i += SN_THREADS) {
     s_off[0][i] = tab[i].off1;
@@ -107,9 +146,11 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
     s_off[4][i] = tab[i].off3;
   }
   __syncthreads();
+  SN_STAMP(0);
 
   for (int it = 0; it < tot.maxIp; ++it) {
     // ---------------------------------------------------------------- phase 1: s partials = u W
+    // warp unit = TR rows x 128 columns; 8 independent 16-byte loads in flight per lane
     for (int unit = gwarp; unit < tot.tot1; unit += nwarps) {
       const int m = sn_find(s_off[0], n, unit);
       const SnDev d = tab[m];
@@ -126,7 +167,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
           float uu[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            w[j] = sn_load4(d.W + (size_t)(r + j) * d.K, k, d.K, d.vec);
+            w[j] = sn_load4_keep(d.W + (size_t)(r + j) * d.K, k, d.K, d.vec, pol);
             uu[j] = d.u[r + j];
           }
 #pragma unroll
@@ -138,7 +179,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
           }
         }
         for (; r < r1; ++r) {
-          const float4 w = sn_load4(d.W + (size_t)r * d.K, k, d.K, d.vec);
+          const float4 w = sn_load4_keep(d.W + (size_t)r * d.K, k, d.K, d.vec, pol);
           const float uu = d.u[r];
           acc.x = fmaf(uu, w.x, acc.x);
           acc.y = fmaf(uu, w.y, acc.y);
@@ -149,27 +190,50 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
       }
     }
     grid.sync();
+    SN_STAMP(1);
 
     // ---------------------------------------------------------------- phase 1b: s, ||s||^2 partials
-    for (int unit = gwarp; unit < tot.tot1b; unit += nwarps) {
+    // CTA unit = 128 columns: warp w folds row blocks w, w+8, ... (4 loads in flight), then warp 0 folds the 8 warp
+    // sums -- a fixed order, so the result is deterministic
+    for (int unit = blockIdx.x; unit < tot.tot1b; unit += gridDim.x) {
       const int m = sn_find(s_off[1], n, unit);
       const SnDev d = tab[m];
-      if (it >= d.Ip) continue;
+      if (it >= d.Ip) continue;                 // uniform per CTA
       const int cb = unit - d.off1b;
       const int k = cb * 128 + lane * 4;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < d.K) {
-        for (int rb = 0; rb < d.nrb; ++rb) {
+        int rb = wid;
+        for (; rb + 3 * SN_WARPS < d.nrb; rb += 4 * SN_WARPS) {
+          float4 p[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) p[j] = sn_load4(d.part_s + (size_t)(rb + j * SN_WARPS) * d.K, k, d.K, d.vec);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc.x += p[j].x; acc.y += p[j].y; acc.z += p[j].z; acc.w += p[j].w; }
+        }
+        for (; rb < d.nrb; rb += SN_WARPS) {
           const float4 p = sn_load4(d.part_s + (size_t)rb * d.K, k, d.K, d.vec);
           acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
         }
-        sn_store4(d.s, k, d.K, d.vec, acc);
       }
-      float q = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
-      q = warp_sum(q);
-      if (lane == 0) d.nrm_s[cb] = q;
+      s_red[wid][lane] = acc;
+      __syncthreads();
+      if (wid == 0) {
+        acc = s_red[0][lane];
+#pragma unroll
+        for (int w = 1; w < SN_WARPS; ++w) {
+          const float4 p = s_red[w][lane];
+          acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        if (k < d.K) sn_store4(d.s, k, d.K, d.vec, acc);
+        float q = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+        q = warp_sum(q);
+        if (lane == 0) d.nrm_s[cb] = q;
+      }
+      __syncthreads();
     }
     grid.sync();
+    SN_STAMP(2);
 
     // ---------------------------------------------------------------- phase 2: v, t partials = v W^T
     for (int m = wid; m < n; m += SN_WARPS) {
@@ -180,7 +244,10 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
       if (lane == 0) s_inv[m] = 1.0f / (sqrtf(q) + SN_EPS);
     }
     __syncthreads();
-    for (int unit = gwarp; unit < tot.tot2; unit += nwarps) {
+    // warp unit = 4 rows x CB2 columns, visited in REVERSE order: pass 1 ended on the last rows, which are the
+    // lines most recently brought into L2
+    for (int uu_ = gwarp; uu_ < tot.tot2; uu_ += nwarps) {
+      const int unit = tot.tot2 - 1 - uu_;
       const int m = sn_find(s_off[2], n, unit);
       const SnDev d = tab[m];
       if (it >= d.Ip) continue;
@@ -190,14 +257,38 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
       const int k0 = cb * d.CB2, k1 = min(d.K, k0 + d.CB2);
       const float inv = s_inv[m];
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = k0 + lane * 4; k < k1; k += 128) {
+      const bool full = (r0 + 4 <= d.R) && d.vec;
+      int k = k0 + lane * 4;
+      if (full) {
+        const float* w0 = d.W + (size_t)r0 * d.K;
+        for (; k + 128 < k1; k += 256) {          // two column steps: 8 independent W loads in flight
+          float4 va = ld4(d.s + k), vb = ld4(d.s + k + 128);
+          float4 wa[4], wb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            wa[j] = ld4_keep(w0 + (size_t)j * d.K + k, pol);
+            wb[j] = ld4_keep(w0 + (size_t)j * d.K + k + 128, pol);
+          }
+          va.x *= inv; va.y *= inv; va.z *= inv; va.w *= inv;
+          vb.x *= inv; vb.y *= inv; vb.z *= inv; vb.w *= inv;
+          if (rg == 0) { st4(d.v + k, va); st4(d.v + k + 128, vb); }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j] = fmaf(wa[j].x, va.x, acc[j]); acc[j] = fmaf(wa[j].y, va.y, acc[j]);
+            acc[j] = fmaf(wa[j].z, va.z, acc[j]); acc[j] = fmaf(wa[j].w, va.w, acc[j]);
+            acc[j] = fmaf(wb[j].x, vb.x, acc[j]); acc[j] = fmaf(wb[j].y, vb.y, acc[j]);
+            acc[j] = fmaf(wb[j].z, vb.z, acc[j]); acc[j] = fmaf(wb[j].w, vb.w, acc[j]);
+          }
+        }
+      }
+      for (; k < k1; k += 128) {
         float4 vv = sn_load4(d.s, k, d.K, d.vec);
         vv.x *= inv; vv.y *= inv; vv.z *= inv; vv.w *= inv;
         if (rg == 0) sn_store4(d.v, k, d.K, d.vec, vv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (r0 + j < d.R) {
-            const float4 w = sn_load4(d.W + (size_t)(r0 + j) * d.K, k, d.K, d.vec);
+            const float4 w = sn_load4_keep(d.W + (size_t)(r0 + j) * d.K, k, d.K, d.vec, pol);
             acc[j] = fmaf(w.x, vv.x, acc[j]);
             acc[j] = fmaf(w.y, vv.y, acc[j]);
             acc[j] = fmaf(w.z, vv.z, acc[j]);
@@ -215,6 +306,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
       }
     }
     grid.sync();
+    SN_STAMP(3);
 
     // ---------------------------------------------------------------- phase 2b: t, ||t||^2 partials
     for (int unit = gwarp; unit < tot.tot2b; unit += nwarps) {
@@ -240,6 +332,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
       if (lane == 0) d.nrm_t[rc] = q;
     }
     grid.sync();
+    SN_STAMP(4);
 
     // ---------------------------------------------------------------- phase 3: u, sigma, W_bar
     __syncthreads();
@@ -257,6 +350,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
       }
     }
     __syncthreads();
+    // forward order again: pass 2 ended on the first rows
     for (int unit = gwarp; unit < tot.tot3; unit += nwarps) {
       const int m = sn_find(s_off[4], n, unit);
       const SnDev d = tab[m];
@@ -271,16 +365,29 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
           sn_store4(d.u, r, d.R, 0, tt);
         }
         if (local == 0 && lane == 0) *d.sigma = s_sig[m];
-      } else if (it == d.Ip - 1) {  // W_bar = W / sigma over a 2048-element chunk
-        const float sg = s_sig[m];
+      } else if (it == d.Ip - 1) {  // W_bar = W / sigma over a 2048-element chunk (layers.py:68)
+        // W / sigma (layers.py:68) as a multiplication by the correctly-rounded reciprocal (<= 1.5 ulp from the quotient)
+        const float rs = 1.0f / s_sig[m];
         const long long base = (long long)(local - d.nrc) * 2048;
+        if (d.vecflat && !d.Wbar16 && base + 2048 <= d.numel) {
+          // streaming fast path: 16 loads in flight, last use of W (evict-first), write-once W_bar
+          float4 w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = ld4_last(d.W + base + j * 128 + lane * 4);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            w[j].x *= rs; w[j].y *= rs; w[j].z *= rs; w[j].w *= rs;
+            st4_stream(d.Wbar + base + j * 128 + lane * 4, w[j]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const long long e = base + (long long)j * 128 + lane * 4;
           if (e < d.numel) {
             if (d.vecflat) {
               float4 w = ld4(d.W + e);
-              w.x = w.x / sg; w.y = w.y / sg; w.z = w.z / sg; w.w = w.w / sg;   // layers.py:68
+              w.x *= rs; w.y *= rs; w.z *= rs; w.w *= rs;
               st4(d.Wbar + e, w);
               if (d.Wbar16) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
@@ -291,7 +398,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
               }
             } else {
               for (int q = 0; q < 4 && e + q < d.numel; ++q) {
-                const float w = d.W[e + q] / sg;
+                const float w = d.W[e + q] * rs;
                 d.Wbar[e + q] = w;
                 if (d.Wbar16) d.Wbar16[e + q] = __float2bfloat16_rn(w);
               }
@@ -302,6 +409,7 @@ sn_power_iter_kernel(const SnDev* __restrict__ tab, SnTotals tot) {
     }
     if (it + 1 < tot.maxIp) grid.sync();
   }
+  SN_STAMP(5);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -346,6 +454,7 @@ struct sagan_sn_plan {
   int device = 0;
   SnDev* tab_dev = nullptr;
   float* ws_dev = nullptr;
+  unsigned long long* stamps_dev = nullptr;
   SnTotals tot{};
   int grid = 0;
   unsigned long long alg_bytes = 0;
@@ -359,6 +468,10 @@ extern "C" int sagan_sn_plan_create(const sagan_sn_desc* descs, int n, int devic
   SnTotals tot{};
   tot.n = n;
   unsigned long long alg = 0;
+  long long total_numel = 0;
+  for (int i = 0; i < n; ++i) total_numel += (long long)std::max(descs[i].rows, 0) * std::max(descs[i].cols, 0);
+  if (total_numel <= 0) total_numel = 1;
+  const int resident_warps = num_sms() * 2 * SN_WARPS;
   for (int i = 0; i < n; ++i) {
     const sagan_sn_desc& s = descs[i];
     SAGAN_REQUIRE(s.W && s.u && s.v && s.W_bar && s.sigma, "sagan_sn_plan_create: null pointer in descriptor %d", i);
@@ -372,12 +485,18 @@ extern "C" int sagan_sn_plan_create(const sagan_sn_desc* descs, int n, int devic
     const bool al = (((uintptr_t)s.W | (uintptr_t)s.W_bar) & 15) == 0 && (((uintptr_t)s.W_bar_bf16) & 7) == 0;
     d.vec = (al && (d.K % 4 == 0)) ? 1 : 0;
     d.vecflat = (al && (d.numel % 4 == 0)) ? 1 : 0;
+    // work decomposition: ~3 warp units per resident warp for the matrices that dominate the plan, so that both
+    // GEMV passes keep every SM's load queues full (2 CTAs x 8 warps x 8 x 16 B in flight per SM)
+    const double share = (double)d.numel / (double)total_numel;
+    const int want_units = std::max(1, (int)(3.0 * resident_warps * share));
     d.ncb1 = ceil_div(d.K, 128);
-    int nrb = ceil_div(4096, d.ncb1);
-    nrb = std::max(1, std::min(nrb, std::min(64, ceil_div(d.R, 8))));
+    int nrb = ceil_div(want_units, d.ncb1);
+    nrb = std::max(1, std::min(nrb, std::min(128, ceil_div(d.R, 16))));   // >= 16 rows per unit, <= 128 partials to fold
     d.TR = ceil_div(ceil_div(d.R, nrb), 4) * 4;
     d.nrb = ceil_div(d.R, d.TR);
-    d.CB2 = std::min(ceil_div(d.K, 128) * 128, 4096);
+    int ncb2 = ceil_div(want_units, ceil_div(d.R, 4));
+    ncb2 = std::max(1, std::min(ncb2, ceil_div(d.K, 512)));       // >= 512 columns per unit
+    d.CB2 = ceil_div(ceil_div(d.K, ncb2), 256) * 256;
     d.ncb2 = ceil_div(d.K, d.CB2);
     d.nrc = ceil_div(d.R, 128);
     d.off1 = tot.tot1;   tot.tot1 += d.nrb * d.ncb1;
@@ -415,6 +534,9 @@ extern "C" int sagan_sn_plan_create(const sagan_sn_desc* descs, int n, int devic
     d.nrm_s = p->ws_dev + (size_t)d.nrm_s; d.nrm_t = p->ws_dev + (size_t)d.nrm_t;
   }
   e = cudaMemcpy(p->tab_dev, tab.data(), sizeof(SnDev) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&p->stamps_dev, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(p->stamps_dev, 0, 8 * sizeof(unsigned long long));
+  p->tot.stamps = p->stamps_dev;
   int occ = 0;
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sn_power_iter_kernel, SN_THREADS, 0);
   if (e != cudaSuccess || occ < 1) {
@@ -447,7 +569,16 @@ extern "C" int sagan_sn_plan_destroy(sagan_sn_plan* p) {
   if (!p) return 0;
   cudaFree(p->ws_dev);
   cudaFree(p->tab_dev);
+  cudaFree(p->stamps_dev);
   delete p;
+  return 0;
+}
+
+extern "C" int sagan_sn_plan_phase_times(sagan_sn_plan* p, float* ms_host) {
+  SAGAN_REQUIRE(p && ms_host, "sagan_sn_plan_phase_times: null argument");
+  unsigned long long st[8];
+  SAGAN_CUDA(cudaMemcpy(st, p->stamps_dev, sizeof(st), cudaMemcpyDeviceToHost));   // synchronises
+  for (int i = 0; i < 5; ++i) ms_host[i] = st[i + 1] >= st[i] ? (float)((double)(st[i + 1] - st[i]) * 1e-6) : 0.f;
   return 0;
 }
 

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sagan_sn_plan_run": (_I, [_P, _P]),
     "sagan_sn_plan_destroy": (_I, [_P]),
     "sagan_sn_plan_algorithmic_bytes": (C.c_ulonglong, [_P]),
+    "sagan_sn_plan_phase_times": (_I, [_P, C.POINTER(C.c_float)]),
     "sagan_sn_backward_workspace_bytes": (_SZ, [_LL]),
     "sagan_sn_backward": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _P, _SZ, _P]),
     "sagan_attn_workspace_bytes": (_SZ, [_I, _I, _I, _I]),

@@ -315,6 +315,12 @@ class SpectralNormGroup:
         """Power iteration + W/sigma for every kernel of the group (layers.py:50-68), one launch."""
         check(_lib.load().sagan_sn_plan_run(self.plan, _stream()), "sagan_sn_plan_run")
 
+    def phase_times_ms(self):
+        """Device-side durations of the five phases of the last run (diagnostics; synchronises)."""
+        out = (C.c_float * 5)()
+        check(_lib.load().sagan_sn_plan_phase_times(self.plan, out), "sagan_sn_plan_phase_times")
+        return list(out)
+
     def views(self, snap, i):
         R, K = self.shapes[i]
         wbar = snap[self.off_w[i]:self.off_w[i] + R * K].view(self.weights[i].shape)

@@ -37,7 +37,7 @@ def timed(fn, iters, flush):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["attn", "sn"])
+    ap.add_argument("op", choices=["attn", "sn", "snmodel"])
     ap.add_argument("--B", type=int, default=64)
     ap.add_argument("--N", type=int, default=4096)
     ap.add_argument("--C", type=int, default=16)
@@ -71,6 +71,16 @@ def main():
             t_b = timed(lambda: torch.autograd.grad(y, [x] + w, dy, retain_graph=True), a.iters, flush)
             fl_b = 2 * B * N * N * (3 * d + 2 * dv) + 2 * (2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C)
             out.update(bwd_ms=t_b[0] * 1e3, bwd_tflops=fl_b / t_b[0] / 1e12, bwd_exps_per_s=B * N * N / t_b[0])
+    elif a.op == "snmodel":
+        # the 13 spectrally-normalised kernels of the church64 generator in ONE launch
+        shapes = [(4096, 128), (256, 2048), (128, 1024), (64, 512), (32, 256), (4, 32), (4, 32), (16, 32), (32, 16),
+                  (2, 16), (2, 16), (8, 16), (16, 8)]
+        Ws = [torch.randn(K, R, device="cuda") * 0.02 for R, K in shapes]
+        us = [torch.randn(1, R, device="cuda") for R, K in shapes]
+        grp = F.SpectralNormGroup(Ws, [u / u.norm() for u in us], 1)
+        t = timed(grp.run, a.iters, flush)
+        out.update(ms=t[0] * 1e3, min_ms=t[1] * 1e3, algorithmic_bytes=grp.algorithmic_bytes,
+                   gbs=grp.algorithmic_bytes / t[0] / 1e9, phases_ms=grp.phase_times_ms())
     else:
         R, K = a.rows, a.cols
         W = torch.randn(K, R, device="cuda") * 0.02
@@ -78,7 +88,8 @@ def main():
         grp = F.SpectralNormGroup([W], [u / u.norm()], 1)
         t = timed(grp.run, a.iters, flush)
         out.update(shape=[R, K], ms=t[0] * 1e3, min_ms=t[1] * 1e3, algorithmic_bytes=grp.algorithmic_bytes,
-                   gbs=grp.algorithmic_bytes / t[0] / 1e9)
+                   gbs=grp.algorithmic_bytes / t[0] / 1e9, gbs_best=grp.algorithmic_bytes / t[1] / 1e9,
+                   traffic_3r1w_gbs=16.0 * R * K / t[0] / 1e9, phases_ms=grp.phase_times_ms())
     print(json.dumps(out))
 
 
