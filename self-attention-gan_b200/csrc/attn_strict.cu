@@ -562,6 +562,7 @@ extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode)
   const long long T = (long long)B * N;
   const size_t strict = (size_t)(T * (2 * C + 1) + 64) * sizeof(float);
   if (math_mode == SAGAN_MATH_BF16_TC) {
+    if (C > 64) return attn_tc_workspace_bytes(B, N, C);                      // forward only (large-C path)
     const size_t small = (size_t)(T * (C / 4 + C / 2) + 64) * sizeof(float);   // dQ, dK, dV
     return std::max(strict, std::max(attn_tc_workspace_bytes(B, N, C), small + attn_tc_bwd_workspace_bytes(B, N, C)));
   }
@@ -626,6 +627,6 @@ extern "C" int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, 
   }
   SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
                       dbk, dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, st);
-  set_err("sagan_attn_bwd: supports C in {8,16,32,64} (C=%d)", C);
+  set_err("sagan_attn_bwd: supports C in {8,16,32,64} (C=%d); the large-C tensor-core path is forward-only so far", C);
   return SAGAN_EUNSUPPORTED;
 }

@@ -420,7 +420,17 @@ static TcLayout tc_layout(int B, int N, int C) {
   return t;
 }
 
-size_t attn_tc_workspace_bytes(int B, int N, int C) { return tc_layout(B, N, C).total; }
+// attn_tc_big.cu: C in {128, 256, 512}
+bool attn_tc_big_supported(int N, int C);
+size_t attn_tc_big_workspace_bytes(int B, int N, int C);
+int attn_tc_big_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
+                    const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
+                    int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+
+size_t attn_tc_workspace_bytes(int B, int N, int C) {
+  if (C > 64) return attn_tc_big_workspace_bytes(B, N, C);
+  return tc_layout(B, N, C).total;
+}
 
 template <int DVP, int NS, int NP, int CEPI>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const float* X,
@@ -442,8 +452,9 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
 int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
                 const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
                 int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (C > 64) return attn_tc_big_fwd(X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A, B, N, C, ws, ws_bytes, st);
   if (!(C == 16 || C == 32 || C == 64)) {
-    set_err("sagan_attn_fwd: BF16_TC currently supports C in {16,32,64} (C=%d)", C);
+    set_err("sagan_attn_fwd: BF16_TC supports C in {16,32,64} (small-d kernel) and {128,256,512} (C=%d)", C);
     return SAGAN_EUNSUPPORTED;
   }
   const TcLayout t = tc_layout(B, N, C);

@@ -1,0 +1,356 @@
+// Self-attention block, BF16_TC math mode, LARGE channel counts (C = 128 / 256 / 512: d = 16 / 32 / 64 logit
+// dims, dv = 64 / 128 / 256 value dims) -- the regime of the stand-alone kernel sweep (BASELINE.json configs[4]),
+// where the two contractions S = theta phi^T and A = softmax(S) g are real tensor-core work.
+//
+// Replaces Attention_Layer.call (/root/reference/layers.py:93-120) as four launches:
+//   1. gemm_tf32_qkv     X [T,C] x [Wtheta | Wphi | Wg] -> bf16 Q (pre-scaled by log2 e), K (rows of 64), V [T,dv]
+//                        (TMA-fed tcgen05 kind::tf32 GEMM, gemm_tf32.cu, projection epilogue; X is read once)
+//   2. attn_fwd_big      flash forward, this file
+//   3. gemm_tf32_residual Y = X + gamma (A Wo + bo)  (same GEMM core, residual epilogue)
+//
+// attn_fwd_big: CTA = one 128-query tile of one sample, 6 warps:
+//   warps 0-3  softmax + epilogue: thread r <-> TMEM lane r <-> query row r; the whole S row (128 fp32) is pulled
+//              into registers with one exposed tcgen05.ld round trip, P = exp2(S - m) goes back to shared memory as
+//              bf16 in the UMMA K-major SW128 layout
+//   warp 4     TMA producer: K tile [128 keys][64] and V tile as dv/64 slabs of [128 keys][64 values] (V is used in its
+//              natural [token][dv] layout, as the MN-major B operand of the PV MMA -- no transposed copy)
+//   warp 5     MMA issuer: S_{j+1} = Q K_{j+1}^T is issued BEFORE it waits for P_j, so the tensor core computes the
+//              next logits under the softmax of the current tile (two S buffers in TMEM); O += P_j V_j
+// TMEM: S0 [0,128) S1 [128,256) O [256, 256+dv) -> all 512 columns at dv = 256, one CTA per SM.
+// The O rescale is lazy (row max grows by > 2^32), so O stays in TMEM across key tiles.
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sagan {
+
+using namespace tc;
+
+// gemm_tf32.cu
+int gemm_tf32_qkv(const float* x, const float* wt, const float* bcat, __nv_bfloat16* q, __nv_bfloat16* k,
+                  __nv_bfloat16* v, long long M, int K, int d, int dv, float q_scale, cudaStream_t st);
+int gemm_tf32_residual(const float* x, const float* wt, const float* bias, const float* res, const float* res_scale,
+                       float* y, long long M, int K, int N, cudaStream_t st);
+
+constexpr float BG_LOG2E = 1.4426950408889634f;
+constexpr float BG_LN2 = 0.6931471805599453f;
+constexpr int BG_THREADS = 192;
+
+template <int DV>
+struct BigSmem {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int K_BYTES = 128 * 128;
+  static constexpr int V_BYTES = (DV / 64) * 128 * 128;   // DV/64 slabs of [128 keys][64 values = 128 B]
+  static constexpr int P_BYTES = 2 * 128 * 128;           // two 64-key sub-tiles of [128 queries][128 B]
+  static constexpr int NP = DV <= 128 ? 2 : 1;            // P buffers
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
+  static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int OCOL = 256;
+};
+
+template <int DV>
+__global__ void __launch_bounds__(BG_THREADS, 1)
+attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, float* __restrict__ lse, float* __restrict__ A_saved,
+                    int N, int kq_steps, int dbg) {
+  using L = BigSmem<DV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + L::OFF_Q;
+  uint8_t* sK = smem + L::OFF_K;
+  uint8_t* sV = smem + L::OFF_V;
+  uint8_t* sP = smem + L::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* barQ = bars + 0;
+  uint64_t* barKV = bars + 1;   // [2] K / V stage full (TMA)
+  uint64_t* barS = bars + 3;    // [2] S buffer ready (MMA commit)
+  uint64_t* barPV = bars + 5;   // [2] PV_j done: K / V stage and P buffer free, O up to date
+  uint64_t* barP = bars + 7;    // [2] 128 arrivals each: P_j is in shared memory (and S_j has been read); two
+                                //     barriers so that a warp running one tile ahead cannot complete tile j's phase
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, qt = blockIdx.x;
+  const int nt = N / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(barQ, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(barKV + i, 1); mbar_init(barS + i, 1); mbar_init(barPV + i, 1); }
+    mbar_init(barP, 128); mbar_init(barP + 1, 128);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      mbar_expect_tx(barQ, L::Q_BYTES);
+      tma_load_2d(sQ, &tmQ, barQ, 0, b * N + qt * 128);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(barPV + s, ((j - 2) >> 1) & 1);
+        mbar_expect_tx(barKV + s, L::K_BYTES + L::V_BYTES);
+        tma_load_2d(sK + s * L::K_BYTES, &tmK, barKV + s, 0, b * N + j * 128);
+#pragma unroll
+        for (int sl = 0; sl < DV / 64; ++sl)
+          tma_load_2d(sV + s * L::V_BYTES + sl * (128 * 128), &tmV, barKV + s, sl * 64, b * N + j * 128);
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+      constexpr uint32_t IDESC_O = make_idesc_bf16(128, DV, 0, /*b_mn_major=*/1);
+      const uint64_t descQ = make_desc_sw128(smem_u32(sQ));
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(barKV + s, (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
+        for (int ks = 0; ks < ((dbg & 4) ? 0 : kq_steps); ++ks)
+          mma_bf16_ss(tmem_base + (uint32_t)(s * 128), descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barS + s);
+      };
+      mbar_wait(barQ, 0);
+      issue_qk(0);
+      for (int j = 0; j < nt; ++j) {
+        // S buffer (j+1)&1 held S_{j-1}: every softmax thread read it before arriving on barP for tile j-1
+        if (j + 1 < nt) issue_qk(j + 1);
+        mbar_wait(barP + (j & 1), (j >> 1) & 1);
+        tc_fence_after();
+        const int s = j & 1, pb = j % L::NP;
+        const uint64_t descP = make_desc_sw128(smem_u32(sP + pb * L::P_BYTES));
+        const uint32_t vbase = smem_u32(sV + s * L::V_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step
+          const uint64_t a = descP + (uint64_t)((ks >> 2) * ((128 * 128) >> 4) + (ks & 3) * 2);
+          if (dbg & 2) continue;   // TIMING EXPERIMENT: no PV MMAs
+          if (dbg & 1) {   // TIMING EXPERIMENT ONLY (wrong results): same bytes read as a K-major B operand
+            const uint64_t bk = make_desc_sw128(vbase) + (uint64_t)((ks >> 2) * ((DV * 128) >> 4) + (ks & 3) * 2);
+            mma_bf16_ss(tmem_base + L::OCOL, a, bk, make_idesc_bf16(128, DV, 0, 0), (j > 0) || (ks > 0));
+            continue;
+          }
+          const uint64_t bb = make_desc_sw128_mn(vbase + ks * 2048, 128 * 128, 1024);
+          mma_bf16_ss(tmem_base + L::OCOL, a, bb, IDESC_O, (j > 0) || (ks > 0));
+        }
+        mma_commit(barPV + s);
+      }
+    }
+  } else {
+    // ================================================================ softmax warps
+    const int row = threadIdx.x;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float m_used = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(barS + (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = t_row + (uint32_t)((j & 1) * 128);
+      uint32_t r[128];
+      tmem_ld32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+      tmem_ld32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+      tmem_wait_ld();
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // ---- lazy rescale of the running accumulators
+      // threshold 2^32: P and the fp32 accumulators share the 8-bit exponent range, so a stale max costs no precision;
+      // the rescale (which has to wait for the tensor core and touch all of O) then only ever runs in the first tiles
+      const bool need = mx > m_used + 32.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        if (j > 0) {
+          mbar_wait(barPV + ((j - 1) & 1), ((j - 1) >> 1) & 1);     // every PV issued so far has completed
+          tc_fence_after();
+          const float scale = need ? exp2f(m_used - mx) : 1.0f;
+          l *= scale;
+#pragma unroll
+          for (int c = 0; c < DV / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_row + L::OCOL + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
+            tmem_st32(t_row + L::OCOL + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+        if (need) m_used = mx;
+      }
+      // ---- P = exp2(S - m) (logits are in log2 units: Q carries log2 e), packed to bf16 in registers
+      uint32_t pk[64];
+      float l0 = 0.f, l1 = 0.f;
+      if (dbg & 8) {   // TIMING EXPERIMENT: no exponentials
+#pragma unroll
+        for (int i = 0; i < 64; ++i) pk[i] = r[2 * i] ^ r[2 * i + 1];
+        l0 = 1.f;
+      } else
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p0 = ex2_approx(__uint_as_float(r[2 * i]) - m_used);
+        const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) - m_used);
+        l0 += p0;
+        l1 += p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      l += l0 + l1;
+      // ---- P buffer free?  (PV_{j-NP} has finished reading it) -- the exponentials above ran under that MMA
+      const int pb = j % L::NP;
+      if (j >= L::NP) mbar_wait(barPV + ((j - L::NP) & 1), ((j - L::NP) >> 1) & 1);
+      uint8_t* sPj = sP + pb * L::P_BYTES;
+#pragma unroll
+      for (int g = 0; g < 16; ++g)   // key columns [8g, 8g+8): sub-tile g/8, 16-byte chunk g%8
+        *reinterpret_cast<uint4*>(sPj + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7)) =
+            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
+      tc_fence_before();             // orders this thread's tcgen05.ld / st before the arrive
+      mbar_arrive(barP + (j & 1));
+    }
+
+    // ---- epilogue: A = O / l (fp32, saved for the backward and read by the output-conv GEMM), lse
+    mbar_wait(barPV + ((nt - 1) & 1), ((nt - 1) >> 1) & 1);
+    tc_fence_after();
+    const long long grow = (long long)b * N + qt * 128 + row;
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int c = 0; c < DV / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(t_row + L::OCOL + c * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        st4(A_saved + grow * DV + c * 32 + i,
+            make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
+                        __uint_as_float(o[i + 3]) * inv));
+    }
+    lse[grow] = (m_used + log2f(l)) * BG_LN2;
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// K-major (transposed) weight operands of the two GEMMs: Wt [2d+dv][C] = [Wq | Wk | Wv]^T, bcat, WoT [C][dv] = Wo^T
+__global__ void attn_big_weights_kernel(const float* __restrict__ Wq, const float* __restrict__ bq,
+                                        const float* __restrict__ Wk, const float* __restrict__ bk,
+                                        const float* __restrict__ Wv, const float* __restrict__ bv,
+                                        const float* __restrict__ Wo, float* __restrict__ Wt, float* __restrict__ bcat,
+                                        float* __restrict__ WoT, int C, int d, int dv) {
+  const int NN = 2 * d + dv;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * NN) {
+    const int n = i / C, c = i - n * C;
+    Wt[i] = n < d ? Wq[c * d + n] : (n < 2 * d ? Wk[c * d + n - d] : Wv[c * dv + n - 2 * d]);
+  }
+  if (i < C * dv) {
+    const int c = i / dv, v = i - c * dv;
+    WoT[i] = Wo[v * C + c];
+  }
+  if (i < NN) bcat[i] = i < d ? bq[i] : (i < 2 * d ? bk[i - d] : bv[i - 2 * d]);
+}
+
+struct BigLayout {
+  size_t off_w, off_b, off_wo, off_q, off_k, off_v, total;
+};
+
+static BigLayout big_layout(int B, int N, int C) {
+  const int d = C / 8, dv = C / 2;
+  const size_t T = (size_t)B * N;
+  BigLayout t;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+  t.off_w = take((size_t)C * (2 * d + dv) * 4);
+  t.off_b = take((size_t)(2 * d + dv) * 4);
+  t.off_wo = take((size_t)C * dv * 4);
+  t.off_q = take(T * 64 * 2);
+  t.off_k = take(T * 64 * 2);
+  t.off_v = take(T * dv * 2);
+  t.total = o + 1024;
+  return t;
+}
+
+bool attn_tc_big_supported(int N, int C) { return (C == 128 || C == 256 || C == 512) && N % 128 == 0; }
+size_t attn_tc_big_workspace_bytes(int B, int N, int C) { return big_layout(B, N, C).total; }
+
+template <int DV>
+static int launch_big(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, float* lse, float* A, int B,
+                      int N, int kq_steps, cudaStream_t st) {
+  using L = BigSmem<DV>;
+  auto kern = attn_fwd_big_kernel<DV>;
+  static bool configured = false;
+  if (!configured) {
+    SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  static const int dbg = getenv("SAGAN_BIG_DEBUG") ? atoi(getenv("SAGAN_BIG_DEBUG")) : 0;
+  kern<<<dim3(N / 128, B), BG_THREADS, L::TOTAL, st>>>(tq, tk, tv, lse, A, N, kq_steps, dbg);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+int attn_tc_big_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
+                    const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
+                    int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!attn_tc_big_supported(N, C)) {
+    set_err("sagan_attn_fwd: large-C tensor-core path needs C in {128,256,512} and N %% 128 == 0 (C=%d, N=%d)", C, N);
+    return SAGAN_EUNSUPPORTED;
+  }
+  const BigLayout t = big_layout(B, N, C);
+  if (ws_bytes < t.total) {
+    set_err("sagan_attn_fwd: workspace %zu < %zu bytes", ws_bytes, t.total);
+    return SAGAN_EWORKSPACE;
+  }
+  const int d = C / 8, dv = C / 2;
+  const long long T = (long long)B * N;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  float* Wt = reinterpret_cast<float*>(base + t.off_w);
+  float* bcat = reinterpret_cast<float*>(base + t.off_b);
+  float* WoT = reinterpret_cast<float*>(base + t.off_wo);
+  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(base + t.off_q);
+  __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(base + t.off_k);
+  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(base + t.off_v);
+  const int nn = C * (2 * d + dv);
+  attn_big_weights_kernel<<<ceil_div(nn, 256), 256, 0, st>>>(Wq, bq, Wk, bk, Wv, bv, Wo, Wt, bcat, WoT, C, d, dv);
+  SAGAN_LAUNCH_CHECK();
+  if (d < 64) {   // rows of Q / K are padded to one 128-byte swizzle span
+    SAGAN_CUDA(cudaMemsetAsync(Qb, 0, (size_t)T * 64 * 2, st));
+    SAGAN_CUDA(cudaMemsetAsync(Kb, 0, (size_t)T * 64 * 2, st));
+  }
+  int rc = gemm_tf32_qkv(X, Wt, bcat, Qb, Kb, Vb, T, C, d, dv, BG_LOG2E, st);
+  if (rc) return rc;
+  CUtensorMap tq, tk, tv;
+  if ((rc = make_tmap_bf16_2d(&tq, Qb, (uint64_t)T, 64, 128, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)T, 64, 128, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, Vb, (uint64_t)T, (uint64_t)dv, (uint64_t)dv * 2, 128, 64))) return rc;
+  const int kq = d / 16;
+  switch (dv) {
+    case 64: rc = launch_big<64>(tq, tk, tv, lse, A, B, N, kq, st); break;
+    case 128: rc = launch_big<128>(tq, tk, tv, lse, A, B, N, kq, st); break;
+    default: rc = launch_big<256>(tq, tk, tv, lse, A, B, N, kq, st); break;
+  }
+  if (rc) return rc;
+  return gemm_tf32_residual(A, WoT, bo, X, gamma, Y, T, dv, C, st);
+}
+
+}  // namespace sagan

@@ -34,6 +34,14 @@ struct ConvTcP {
   int act;
   float slope;
   int m_per_split;      // WGRAD: pixels per blockIdx.z
+  // FWD epilogue variants used by the large-C attention block (attn_tc_big.cu):
+  const float* res;         // out = res + (*res_scale) * (acc + bias)   (gamma residual, layers.py:120)
+  const float* res_scale;
+  __nv_bfloat16* q_out;     // when set: columns [0,d) -> q_out[m][64] * q_scale, [d,2d) -> k_out[m][64], [2d,2d+dv) -> v_out[m][dv]
+  __nv_bfloat16* k_out;
+  __nv_bfloat16* v_out;
+  int qk_d, v_dv;
+  float q_scale;
 };
 
 __device__ __forceinline__ float ct_act(float v, int act, float slope) {
@@ -277,14 +285,53 @@ conv_tc_kernel(const ConvTcP p) {
           orow = p.out + ((size_t)(b * g.H + hi_first + ih * g.S) * g.W + wi_first + iw * g.S) * g.Cin;
         } else orow = (m < g.K) ? p.out + (size_t)m * g.Cout : p.dbias;
       }
+      const bool row_ok = m < Mg;
+      const float res_gm = (MODE == TC_FWD && p.res) ? *p.res_scale : 0.f;
 #pragma unroll
       for (int c = 0; c < HALF; c += 16) {
         uint32_t r[16];
         tmem_ld16(t_row + cbase + c, r);
         tmem_wait_ld();
-        if (orow) {
+        if (row_ok) {
           const int nb = n0 + cbase + c;
-          if (MODE == TC_WGRAD) {
+          if (MODE == TC_FWD && p.q_out) {
+            // fused q / k / v projection epilogue: bf16 rows in the layouts the flash kernel's TMA boxes read
+            if (nb < Ng) {
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + (p.bias ? p.bias[nb + e] : 0.f);
+              __nv_bfloat16* dst;
+              if (nb < p.qk_d) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] *= p.q_scale;
+                dst = p.q_out + (size_t)m * 64 + nb;
+              } else if (nb < 2 * p.qk_d) {
+                dst = p.k_out + (size_t)m * 64 + (nb - p.qk_d);
+              } else {
+                dst = p.v_out + (size_t)m * p.v_dv + (nb - 2 * p.qk_d);
+              }
+              uint4* d4 = reinterpret_cast<uint4*>(dst);
+              d4[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              d4[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
+          } else if (MODE == TC_FWD && p.res) {
+            if (nb + 16 <= Ng) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 x4 = ld4(p.res + (size_t)m * g.Cout + nb + e);
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = __uint_as_float(r[e + q]) + (p.bias ? p.bias[nb + e + q] : 0.f);
+                st4(orow + nb + e, make_float4(fmaf(res_gm, v[0], x4.x), fmaf(res_gm, v[1], x4.y), fmaf(res_gm, v[2], x4.z),
+                                               fmaf(res_gm, v[3], x4.w)));
+              }
+            } else {
+              for (int e = 0; e < 16; ++e)
+                if (nb + e < Ng)
+                  orow[nb + e] = fmaf(res_gm, __uint_as_float(r[e]) + (p.bias ? p.bias[nb + e] : 0.f),
+                                      p.res[(size_t)m * g.Cout + nb + e]);
+            }
+          } else if (MODE == TC_WGRAD) {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               if (nb + e < Ng) atomicAdd(orow + nb + e, __uint_as_float(r[e]));
@@ -351,12 +398,35 @@ bool conv_tc_wgrad_ok(const CG& g, const float* x, const float* dy) { return g.C
 
 int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope,
                 cudaStream_t st) {
-  ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0};
+  ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
+}
+
+static CG gemm_geom(long long M, int K, int N) {
+  CG g{};
+  g.B = (int)M; g.H = 1; g.W = 1; g.Cin = K; g.Ho = 1; g.Wo = 1; g.Cout = N; g.KH = 1; g.KW = 1; g.S = 1; g.PT = 0; g.PL = 0;
+  g.M = (int)M; g.K = K;
+  return g;
+}
+
+// [M, K] fp32 x [K, 2d + dv] fp32 (+ bias) -> bf16 q (scaled) / k rows of 64 columns and v rows of dv columns
+int gemm_tc_qkv(const float* x, const float* wcat, const float* bcat, __nv_bfloat16* q, __nv_bfloat16* k,
+                __nv_bfloat16* v, long long M, int K, int d, int dv, float q_scale, cudaStream_t st) {
+  const CG g = gemm_geom(M, K, 2 * d + dv);
+  ConvTcP p{x, wcat, bcat, nullptr, nullptr, g, 0, 0.f, 0, nullptr, nullptr, q, k, v, d, dv, q_scale};
+  return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
+}
+
+// y = res + (*res_scale) * (x [M, K] * w [K, N] + bias)
+int gemm_tc_residual(const float* x, const float* w, const float* bias, const float* res, const float* res_scale, float* y,
+                     long long M, int K, int N, cudaStream_t st) {
+  const CG g = gemm_geom(M, K, N);
+  ConvTcP p{x, w, bias, y, nullptr, g, 0, 0.f, 0, res, res_scale, nullptr, nullptr, nullptr, 0, 0, 0.f};
   return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
 }
 
 int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st) {
-  ConvTcP p{dy, w, nullptr, dx, nullptr, g, 0, 0.f, 0};
+  ConvTcP p{dy, w, nullptr, dx, nullptr, g, 0, 0.f, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   const int Hc = ceil_div(g.H, g.S), Wc = ceil_div(g.W, g.S);
   return dispatch_nt<TC_DGRAD>(p, g.Cin, ceil_div(g.B * Hc * Wc, 128), g.S * g.S, st);
 }
@@ -367,7 +437,7 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, cons
   int splits = std::max(1, std::min(ceil_div(g.M, 256), ceil_div(num_sms() * 2, tiles)));
   int mps = ceil_div(ceil_div(g.M, splits), 64) * 64;
   splits = ceil_div(g.M, mps);
-  ConvTcP p{x, dy, nullptr, dw, dbias, g, 0, 0.f, mps};
+  ConvTcP p{x, dy, nullptr, dw, dbias, g, 0, 0.f, mps, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   return dispatch_nt<TC_WGRAD>(p, g.Cout, ceil_div(Mg, 128), splits, st);
 }
 

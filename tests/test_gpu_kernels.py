@@ -373,6 +373,43 @@ def test_attention_tc_vs_strict_full_size(F, shape):
     assert rel_l2((yt - x).cpu().numpy(), (ys - x).cpu().numpy()) < 1e-2
 
 
+# ---------------------------------------------------------------------------------------- attention, large C (sweep regime)
+@pytest.mark.parametrize("shape", [(2, 256, 128), (2, 384, 256), (1, 512, 512), (1, 128, 512)])
+def test_attention_tc_large_c_forward(F, shape):
+    """BASELINE.json configs[4] regime (C = 128..512: d = 16..64, dv = 64..256): projection GEMM -> flash forward ->
+    output-conv GEMM with the gamma residual, all on tcgen05, against the fp64 oracle.  Logits here are plain bf16
+    products (no room for the split-bf16 trick at d >= 16), so the inputs keep them at a few units (std 1.5), the
+    regime a spectrally-normalised trained block lives in; the error grows linearly with the logit scale."""
+    B, N, C = shape
+    d = C // 8
+    X, dY, w = oattn.make_inputs(B, N, C, seed=77 + C, gamma=0.8, dtype=np.float64)
+    w["Wtheta"] = w["Wtheta"] * (1.5 ** 0.5) / d ** 0.25
+    w["Wphi"] = w["Wphi"] * (1.5 ** 0.5) / d ** 0.25
+    ref, cache = oattn.forward(X, **w, return_cache=True)
+    t = {k: cu(np.asarray(v)) for k, v in w.items()}
+    x = cu(X)
+    y = F.attention(x, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"],
+                    F.MATH_BF16_TC)
+    torch.cuda.synchronize()
+    yk = y.cpu().numpy()
+    e_y, e_att = rel_l2(yk, ref), rel_l2(yk - X, ref - X)
+    print(shape, "Y %.2e Y-X %.2e" % (e_y, e_att))
+    assert e_y < TC_TOL
+    assert e_att < 1e-2
+
+
+def test_attention_tc_large_c_backward_is_refused(F):
+    """The large-C tensor-core path is forward-only so far: the backward must fail loudly, not fall back."""
+    from sagan_b200 import _lib
+    X, dY, w = oattn.make_inputs(1, 128, 128, seed=3, gamma=0.5, dtype=np.float32)
+    t = {k: cu(np.asarray(v)).requires_grad_(True) for k, v in w.items()}
+    x = cu(X).requires_grad_(True)
+    y = F.attention(x, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"],
+                    F.MATH_BF16_TC)
+    with pytest.raises(_lib.SaganError, match="forward-only"):
+        y.backward(cu(dY))
+
+
 # ---------------------------------------------------------------------------------------- conv family, BF16_TC (tcgen05)
 TC_CONV_CASES = [  # B, H, W, Cin, Cout, k, stride
     (2, 32, 32, 16, 32, 4, 2), (2, 16, 16, 32, 64, 4, 2), (2, 8, 8, 64, 128, 4, 2), (4, 64, 64, 16, 3, 4, 1),

@@ -60,13 +60,16 @@ def main():
         mk = lambda *s: (torch.randn(*s, device="cuda", generator=g) / np.sqrt(s[0])).requires_grad_(True)
         w = [mk(C, d), mk(d), mk(C, d), mk(d), mk(C, dv), mk(dv), mk(dv, C), mk(C),
              torch.tensor(0.5, device="cuda", requires_grad=True)]
+        with torch.no_grad():      # un-scaled logits (layers.py:108) of a few units, std 1.5, whatever d is
+            w[0] *= 1.5 ** 0.5 / d ** 0.25
+            w[2] *= 1.5 ** 0.5 / d ** 0.25
         dy = torch.randn(B, N, C, device="cuda", generator=g)
         with torch.no_grad():
             t_f = timed(lambda: F.attention(x, *w, mode), a.iters, flush)
         fl_f = 2 * B * N * C * (2 * d + dv) + 2 * B * N * N * (d + dv) + 2 * B * N * dv * C
         out.update(shape=[B, N, C], math=a.math, fwd_ms=t_f[0] * 1e3, fwd_min_ms=t_f[1] * 1e3,
                    fwd_tflops=fl_f / t_f[0] / 1e12, fwd_exps_per_s=B * N * N / t_f[0])
-        if a.bwd:
+        if a.bwd and C <= 64:
             y = F.attention(x, *w, mode)
             t_b = timed(lambda: torch.autograd.grad(y, [x] + w, dy, retain_graph=True), a.iters, flush)
             fl_b = 2 * B * N * N * (3 * d + 2 * dv) + 2 * (2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C)
