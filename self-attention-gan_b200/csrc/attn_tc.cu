@@ -5,13 +5,14 @@
 // shared memory, the online softmax runs on fp32 rows read back with tcgen05.ld (one thread per query row),
 // and the output 1x1 conv + gamma residual are fused in the epilogue.  The [B,N,N] map is never written.
 //
-// CTA = one 128-query tile of one sample; 5 warps:
-//   warps 0-3  softmax / epilogue (thread r <-> TMEM lane r <-> query row r); thread 0 also issues the MMAs
-//   warp  4    TMA producer (one lane), TMEM allocator
+// CTA = one 128-query tile of one sample; 6 warps:
+//   warps 0-3  softmax / epilogue (thread r <-> TMEM lane r <-> query row r)
+//   warp  4    TMA producer (one elected lane), TMEM allocator
+//   warp  5    MMA issuer (one elected lane)
 // Per 128-key tile j:   S_j = Q K_j^T   (M=128, N=128, K=16*kq_steps)   -> TMEM columns [S]
 //                       P_j = exp2(S_j - m)  -> bf16, written to shared memory in the UMMA K-major SW128 layout
 //                       O  += P_j V_j  (M=128, N=DVP, K=128)            -> TMEM columns [O]
-// The running-max rescale of O is lazy (only when the row max grows by > 2^8), so O stays in TMEM.
+// The running-max rescale of O is lazy (only when the row max grows by > 2^32), so O stays in TMEM.
 //
 // Consistent rounding.  The softmax weights enter the PV MMA as bf16.  To keep the block and its backward an exact
 // (fp32-accurate) function / gradient pair of ONE well-defined set of weights, the running max is kept INTEGER-valued
@@ -31,7 +32,7 @@ using namespace tc;
 
 constexpr float TC_LOG2E = 1.4426950408889634f;
 constexpr float TC_LN2 = 0.6931471805599453f;
-constexpr int TC_THREADS = 160;
+constexpr int TC_THREADS = 192;
 constexpr int QK_COLS = 64;   // Q / K rows are padded to 64 bf16 = one 128-byte swizzle span
 
 // ------------------------------------------------------------------------------------ host: tensor maps
@@ -161,7 +162,10 @@ struct FwdSmem {
   static constexpr int W_BYTES = (((CEPI / 2) * CEPI + CEPI) * 4 + 127) / 128 * 128;
   static constexpr int OFF_BAR = OFF_W + W_BYTES;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;          // + alignment slack
-  static constexpr int TMEM_COLS = (NS * 128 + DVP) <= 256 ? 256 : 512;
+  // O is spread over NACC accumulators (key steps ks % NACC): small-N MMAs that accumulate into the SAME TMEM tile run
+  // back to back at the full pipeline latency, independent accumulators pipeline; they are summed in the epilogue
+  static constexpr int NACC = (NS * 128 + 4 * DVP <= 256 || DVP > 64) ? 4 : 2;
+  static constexpr int TMEM_COLS = (NS * 128 + NACC * DVP) <= 256 ? 256 : 512;
   static constexpr int OCOL = NS * 128;
 };
 
@@ -186,7 +190,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* barKV = bars + 1;   // [2]
   uint64_t* barS = bars + 3;    // [2]
   uint64_t* barPV = bars + 5;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* barP = bars + 7;    // [2] 128 arrivals each: P_j is in shared memory (and S_j has been read)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, qt = blockIdx.x;
@@ -195,6 +200,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(barQ, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(barKV + i, 1); mbar_init(barS + i, 1); mbar_init(barPV + i, 1); }
+    mbar_init(barP, 128); mbar_init(barP + 1, 128);
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(tmem_ptr, L::TMEM_COLS);
@@ -205,7 +211,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 4) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       mbar_expect_tx(barQ, L::Q_BYTES);
       tma_load_2d(sQ, &tmQ, barQ, 0, b * Npad + qt * 128);
@@ -218,56 +224,59 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_2d(sV + s * L::V_BYTES + DVP * 128, &tmV, barKV + s, j * 128 + 64, b * DVP);
       }
     }
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer (one elected thread)
+    if (elect_one_sync()) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+      constexpr uint32_t IDESC_O = make_idesc_bf16(128, DVP);
+      const uint64_t descQ = make_desc_sw128(smem_u32(sQ));
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(barKV + s, (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
+        const uint32_t d = tmem_base + (uint32_t)((j % NS) * 128);
+        for (int ks = 0; ks < kq_steps; ++ks) mma_bf16_ss(d, descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barS + (j % NS));
+      };
+      auto issue_pv = [&](int j) {
+        const int s = j & 1, pb = j % NP;
+        const uint64_t descP = make_desc_sw128(smem_u32(sP + pb * L::P_BYTES));
+        const uint64_t descV = make_desc_sw128(smem_u32(sV + s * L::V_BYTES));
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = descP + (uint64_t)((ks >> 2) * ((128 * 128) >> 4) + (ks & 3) * 2);
+          const uint64_t bb = descV + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2);
+          mma_bf16_ss(tmem_base + L::OCOL + (ks % L::NACC) * DVP, a, bb, IDESC_O, (j > 0) || (ks >= L::NACC));
+        }
+        mma_commit(barPV + s);
+      };
+      mbar_wait(barQ, 0);
+      issue_qk(0);
+      for (int j = 0; j < nt; ++j) {
+        if (NS == 2 && j + 1 < nt) issue_qk(j + 1);   // second S buffer: runs under softmax_j
+        mbar_wait(barP + (j & 1), (j >> 1) & 1);      // P_j written, S_j consumed by every softmax thread
+        tc_fence_after();
+        if (NS == 1 && j + 1 < nt) issue_qk(j + 1);   // S is free again; QK_{j+1} queues ahead of PV_j
+        issue_pv(j);
+      }
+    }
   } else {
-    // ================================================================ softmax warps (+ MMA issue by thread 0)
+    // ================================================================ softmax warps
     const int row = threadIdx.x;                                   // query row inside the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
-    constexpr uint32_t IDESC_O = make_idesc_bf16(128, DVP);
-    const uint64_t descQ = make_desc_sw128(smem_u32(sQ));
 
     if (CEPI > 0) {
       const int nW = dv * CEPI;
       for (int e = threadIdx.x; e < nW; e += 128) sW[e] = Wo[e];
       for (int e = threadIdx.x; e < CEPI; e += 128) sW[nW + e] = bo[e];
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the epilogue of every softmax thread reads all of sW
     }
-
-    auto issue_qk = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(barKV + s, (j >> 1) & 1);
-      tc_fence_after();
-      const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
-      const uint32_t d = tmem_base + (uint32_t)((j % NS) * 128);
-      for (int ks = 0; ks < kq_steps; ++ks) mma_bf16_ss(d, descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-      mma_commit(barS + (j % NS));
-    };
-    auto issue_pv = [&](int j) {
-      const int s = j & 1, pb = j % NP;
-      const uint64_t descP = make_desc_sw128(smem_u32(sP + pb * L::P_BYTES));
-      const uint64_t descV = make_desc_sw128(smem_u32(sV + s * L::V_BYTES));
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t a = descP + (uint64_t)((ks >> 2) * ((128 * 128) >> 4) + (ks & 3) * 2);
-        const uint64_t bb = descV + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2);
-        mma_bf16_ss(tmem_base + L::OCOL, a, bb, IDESC_O, (j > 0) || (ks > 0));
-      }
-      mma_commit(barPV + s);
-    };
-
-    if (threadIdx.x == 0) {
-      mbar_wait(barQ, 0);
-      issue_qk(0);
-    }
-    __syncwarp();
 
     float m_used = -INFINITY;      // integer-valued (log2 units) once set: see "consistent rounding" above
     const bool ragged = (N % 128) != 0;
 
     for (int j = 0; j < nt; ++j) {
-      if (NS == 2) {
-        if (threadIdx.x == 0 && j + 1 < nt) issue_qk(j + 1);   // runs under softmax_j
-        __syncwarp();
-      }
       mbar_wait(barS + (j % NS), (j / NS) & 1);
       tc_fence_after();
       const uint32_t t_s = t_row + (uint32_t)((j % NS) * 128);
@@ -296,14 +305,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // ---- lazy rescale of the running accumulators
-      const bool need = mx > m_used + 8.0f;
+      const bool need = mx > m_used + 32.0f;   // P and the fp32 accumulators share the exponent range: a stale max costs no precision
       if (__any_sync(0xffffffffu, need)) {
         if (j > 0) {
           mbar_wait(barPV + ((j - 1) & 1), ((j - 1) >> 1) & 1);       // every PV issued so far has completed
           tc_fence_after();
           const float scale = need ? exp2f(m_used - ceilf(mx)) : 1.0f;   // exact power of two
 #pragma unroll
-          for (int c = 0; c < DVP / 16; ++c) {
+          for (int c = 0; c < L::NACC * DVP / 16; ++c) {
             uint32_t o[16];
             tmem_ld16(t_row + L::OCOL + c * 16, o);
             tmem_wait_ld();
@@ -334,14 +343,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
-      tc_fence_before();             // orders this thread's tcgen05.ld / st before the barrier
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        if (NS == 1 && j + 1 < nt) issue_qk(j + 1);   // S is free again; QK_{j+1} queues ahead of the long PV_j
-        issue_pv(j);
-      }
-      __syncwarp();
+      tc_fence_before();             // orders this thread's tcgen05.ld / st before the arrive
+      mbar_arrive(barP + (j & 1));
     }
 
     // ---- epilogue: A = (P' V) / l', saved tensors, fused output conv + gamma residual
@@ -356,12 +359,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       static_assert(DVP >= 2 * DV + 1, "V^T rows are [v_hi | v_lo | ones]");
       float a[DVP];
 #pragma unroll
-      for (int c = 0; c < DVP / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(t_row + L::OCOL + c * 16, r);
-        tmem_wait_ld();
+      for (int i = 0; i < DVP; ++i) a[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[c * 16 + i] = __uint_as_float(r[i]);
+      for (int acc = 0; acc < L::NACC; ++acc) {
+#pragma unroll
+        for (int c = 0; c < DVP / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(t_row + L::OCOL + acc * DVP + c * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[c * 16 + i] += __uint_as_float(r[i]);
+        }
       }
       const float l = a[2 * DV];           // l' = sum_j P'_ij, accumulated by the MMA through the ones row
       const float inv = 1.0f / l;

@@ -93,7 +93,7 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 4) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       mbar_expect_tx(barQ, L::Q_BYTES);
       tma_load_2d(sQ, &tmQ, barQ, 0, b * N + qt * 128);
@@ -109,7 +109,7 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 5) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, DV, 0, /*b_mn_major=*/1);
       const uint64_t descQ = make_desc_sw128(smem_u32(sQ));

@@ -15,10 +15,11 @@
 //     dV_j += P^T  dA_i          (A = P^T  K-major, B = dA_i^T rows)   TMEM, accumulated over i
 //     dK_j += dS^T Q_i           (A = dS^T K-major, B = Q_i^T rows)    TMEM, accumulated over i
 //     dQ_i  = dS   K_j           (A = the SAME dS^T tile read MN-major, B = K_j^T rows) -> atomicAdd over key tiles
-// 10 warps: 0-7 compute (two threads per key row, 64 query columns each), warp 8 = TMA producer,
-// warp 9 = MMA issuer.  Compute warps never wait for each other: they signal the issuer through mbarriers
+// 18 warps: 0-15 compute (four threads per key row, 32 query columns each), warp 16 = TMA producer,
+// warp 17 = MMA issuer.  Compute warps never wait for each other: they signal the issuer through mbarriers
 // (S/dP registers loaded -> next S/dP MMA may overwrite TMEM; P/dS tiles written -> gradient MMAs may start).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -28,7 +29,8 @@ namespace sagan {
 using namespace tc;
 
 constexpr float TB_LOG2E = 1.4426950408889634f;
-constexpr int TB_THREADS = 320;   // 8 compute warps + TMA producer warp + MMA issuer warp
+constexpr int TB_THREADS = 576;   // 16 compute warps + TMA producer warp + MMA issuer warp
+constexpr int TB_CWARPS = 16;
 constexpr int TB_COLS = 64;   // bf16 row length of the K-major operand buffers (128 B)
 
 // ------------------------------------------------------------------------------------ prep (small C)
@@ -84,21 +86,23 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     }
     a = valid ? a : 0.f;
     kk = valid ? kk : 0.f;
-    // transposed (un-scaled) copies: rows [hi (D) | lo (D)]
+    // transposed (un-scaled) copies: rows [hi at 0..7 | lo at 8..15]
     const __nv_bfloat16 qh = __float2bfloat16_rn(a), kh = __float2bfloat16_rn(kk);
     Qt[((long long)b * 16 + j) * Npad + n] = qh;
-    Qt[((long long)b * 16 + D + j) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(qh));
+    Qt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(qh));
     Kt[((long long)b * 16 + j) * Npad + n] = kh;
-    Kt[((long long)b * 16 + D + j) * Npad + n] = __float2bfloat16_rn(kk - __bfloat162float(kh));
+    Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(kk - __bfloat162float(kh));
     const float as = a * TB_LOG2E;
     const float a_hi = __bfloat162float(__float2bfloat16_rn(as)), k_hi = __bfloat162float(kh);
     q[j] = a_hi; q[D + j] = as - a_hi; q[2 * D + j] = a_hi;
     k[j] = k_hi; k[D + j] = k_hi;      k[2 * D + j] = kk - k_hi;
   }
 #pragma unroll
-  for (int j = 2 * D; j < 16; ++j) {
+  for (int j = D; j < 8; ++j) {      // rows [hi (0..7) | lo (8..15)]: unused rows are zero
     Qt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+    Qt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(0.f);
     Kt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+    Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(0.f);
   }
   uint4* qd = reinterpret_cast<uint4*>(Qb + tp * TB_COLS);
   uint4* kd = reinterpret_cast<uint4*>(Kb + tp * TB_COLS);
@@ -186,7 +190,10 @@ struct BwdSmem {
   static constexpr int STAGE_TX = TILE + TILE + TDV + T16 + 1024;
   static_assert(STAGE % 1024 == 0 && OFF_STAGE % 1024 == 0, "tiles must stay 1024-byte aligned");
   // TMEM columns
-  static constexpr int ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + 64, DQ_COL = 256 + 64 + 16;
+  // Small-N MMAs that accumulate into the SAME TMEM tile execute back to back at the full pipeline latency, so the
+  // gradient GEMMs are spread over five independent accumulators issued round-robin: dV, dK from dS_hi, dK from dS_lo,
+  // dQ from dS_hi, dQ from dS_lo (the hi / lo partial sums are added in the epilogue)
+  static constexpr int ST_COL = 0, DP_COL = 128, DV_COL = 256, DKH_COL = 320, DKL_COL = 336, DQ_COL = 352;   // DQ: 2 x [hi 16 | lo 16]
 };
 
 template <int DVP, bool SPLIT_DA>
@@ -225,18 +232,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(barQ, 1); mbar_init(barQ + 1, 1);
     mbar_init(barS, 1);
     mbar_init(barG, 1); mbar_init(barG + 1, 1);
-    mbar_init(barSfree, 256); mbar_init(barTiles, 256);
+    mbar_init(barSfree, TB_CWARPS * 32); mbar_init(barTiles, TB_CWARPS * 32);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(tmem_ptr, 512);
+  if (warp == TB_CWARPS) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == TB_CWARPS) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdA);
       tma_prefetch_desc(&tmdAt); tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt);
       mbar_expect_tx(barKV, 2 * L::TILE + L::T16);
@@ -259,9 +266,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         bulk_load_1d(st + L::ST_VEC + 512, Dd + (size_t)b * Npad + i * 128, 512, barQ + s);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TB_CWARPS + 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
       constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
@@ -283,26 +290,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint64_t dPt = make_desc_sw128(smem_u32(sPt)), dSt = make_desc_sw128(smem_u32(sdSt));
         const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::ST_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::ST_QT));
         const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // K = queries
-          const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
-          mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
-                      IDESC_DV, (i > 0) || (ks > 0));
-        }
         const uint64_t dSl = make_desc_sw128(smem_u32(sdSl));
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {  // dS^T = hi tile (ks < 8) + lo tile
-          const int k8 = ks & 7;
-          const uint64_t a_off = (uint64_t)((k8 >> 2) * (L::TILE >> 4) + (k8 & 3) * 2);
-          mma_bf16_ss(tmem_base + L::DK_COL, (ks < 8 ? dSt : dSl) + a_off,
-                      dQt_ + (uint64_t)((k8 >> 2) * ((16 * 128) >> 4) + (k8 & 3) * 2), IDESC_DK, (i > 0) || (ks > 0));
-        }
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {  // K = keys: the dS^T tiles read MN-major (M = queries contiguous)
-          const int k8 = ks & 7;
-          const uint64_t a = make_desc_sw128_mn(smem_u32(ks < 8 ? sdSt : sdSl) + k8 * 16 * 128, L::TILE, 1024);
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 16, a, dKt_ + (uint64_t)((k8 >> 2) * ((16 * 128) >> 4) + (k8 & 3) * 2),
-                      IDESC_DQ, ks > 0);
+        for (int ks = 0; ks < 8; ++ks) {   // 16 queries (dV, dK) / 16 keys (dQ) per step; five independent accumulators
+          const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
+          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+          const bool acc = (i > 0) || (ks > 0);
+          mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
+                      IDESC_DV, acc);
+          mma_bf16_ss(tmem_base + L::DKH_COL, dSt + a_off, dQt_ + b16, IDESC_DK, acc);
+          // dQ: the dS^T tiles read MN-major (M = queries contiguous), K = keys
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024),
+                      dKt_ + b16, IDESC_DQ, ks > 0);
+          mma_bf16_ss(tmem_base + L::DKL_COL, dSl + a_off, dQt_ + b16, IDESC_DK, acc);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(smem_u32(sdSl) + ks * 16 * 128, L::TILE, 1024),
+                      dKt_ + b16, IDESC_DQ, ks > 0);
         }
         mma_commit(barG + s);
       };
@@ -324,20 +326,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ================================================================ compute warps
+    // thread <-> key row krow (TMEM lane) x 32 of the tile's 128 query columns: warp w owns lane quarter w & 3 and
+    // query columns [32 h, 32 h + 32), h = w >> 2.  Four warps per scheduler hide the MUFU / LDS latencies of the chain
+    // exp2 -> bf16 -> (dP - D) -> split, which two warps per scheduler could not (measured 0.4 IPC).
     const int qd = warp & 3, h = warp >> 2;
     const int krow = qd * 32 + lane;                                // key row inside the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
     const bool key_ok = kt * 128 + krow < N;
-    // dQ_i tile (TMEM lanes = queries) -> atomicAdd; columns [hi (d) | lo (d)] of the split K^T rows
+    // dQ_i tile (TMEM lanes = queries) -> atomicAdd; the four column groups take turns so the atomics are spread evenly
     auto flush_dq = [&](int i) {
-      if (h == 0) {
-        uint32_t r[16];
-        tmem_ld16(t_row + L::DQ_COL + (i & 1) * 16, r);
+      if (h == (i & 3)) {
+        uint32_t r[32];
+        tmem_ld32(t_row + L::DQ_COL + (i & 1) * 32, r);      // [from dS_hi: K_hi (8) K_lo (8) | from dS_lo: K_hi K_lo]
         tmem_wait_ld();
         const int qrow = i * 128 + krow;
         if (qrow < N) {
           float* dst = dQ + ((size_t)b * N + qrow) * d;
-          for (int c = 0; c < d; ++c) atomicAdd(dst + c, __uint_as_float(r[c]) + __uint_as_float(r[d + c]));
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < d)
+              atomicAdd(dst + c, (__uint_as_float(r[c]) + __uint_as_float(r[8 + c])) +
+                                     (__uint_as_float(r[16 + c]) + __uint_as_float(r[24 + c])));
         }
       }
     };
@@ -348,32 +357,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(barQ + s, (i >> 1) & 1);      // lse2 / D of this query tile have landed
       mbar_wait(barS, i & 1);
       tc_fence_after();
-      uint32_t rs[64], rp[64];
-      tmem_ld32(t_row + L::ST_COL + h * 64, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
-      tmem_ld32(t_row + L::ST_COL + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
-      tmem_ld32(t_row + L::DP_COL + h * 64, *reinterpret_cast<uint32_t(*)[32]>(&rp[0]));
-      tmem_ld32(t_row + L::DP_COL + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rp[32]));
+      uint32_t rs[32], rp[32];
+      tmem_ld32(t_row + L::ST_COL + h * 32, rs);
+      tmem_ld32(t_row + L::DP_COL + h * 32, rp);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(barSfree);                                  // this thread's S^T / dP^T are in registers
-      if (i >= 1) {
-        mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // P^T / dS^T buffers free, dQ_{i-1} complete
-        tc_fence_after();
-        flush_dq(i - 1);
-      }
-      uint8_t* pt = sPt + h * L::TILE;
-      uint8_t* dst = sdSt + h * L::TILE;
-      uint8_t* dsl = sdSl + h * L::TILE;
+      // ---- all of this tile's math goes to registers first: it overlaps the gradient MMAs of tile i-1, which still
+      //      read the single-buffered P^T / dS^T tiles; only the stores below have to wait for them
+      uint32_t pp[16], hi[16], lo[16];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 64 + g * 8);
-        const float4 l1 = *reinterpret_cast<const float4*>(vec + h * 64 + g * 8 + 4);
-        const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + h * 64 + g * 8);
-        const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + h * 64 + g * 8 + 4);
+      for (int g = 0; g < 4; ++g) {
+        const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8);
+        const float4 l1 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8 + 4);
         const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float ds_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         float p[8], g_[8];
-        uint32_t pp[4];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
@@ -381,21 +382,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          pp[e] = pack_bf16x2(p[2 * e], p[2 * e + 1]);       // P' = bf16(exp2(S - M)): the weights the forward used
-          g_[2 * e] = __uint_as_float(pp[e] << 16) * (__uint_as_float(rp[g * 8 + 2 * e]) - ds_[2 * e]);
-          g_[2 * e + 1] = __uint_as_float(pp[e] & 0xffff0000u) * (__uint_as_float(rp[g * 8 + 2 * e + 1]) - ds_[2 * e + 1]);
+          const uint32_t pk = pack_bf16x2(p[2 * e], p[2 * e + 1]);   // P' = bf16(exp2(S - M)): the weights the forward used
+          pp[g * 4 + e] = pk;
+          g_[2 * e] = __uint_as_float(pk << 16) * (__uint_as_float(rp[g * 8 + 2 * e]) - ds_[2 * e]);
+          g_[2 * e + 1] = __uint_as_float(pk & 0xffff0000u) * (__uint_as_float(rp[g * 8 + 2 * e + 1]) - ds_[2 * e + 1]);
         }
-        const uint32_t off = sw128_offset(krow, g);
-        *reinterpret_cast<uint4*>(pt + off) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
         // dS^T = hi + lo (two bf16 terms): sum_j dS_ij = 0, so the theta / phi gradients cancel and need the extra bits
-        uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          hi[e] = pack_bf16x2(g_[2 * e], g_[2 * e + 1]);
-          lo[e] = pack_bf16x2(g_[2 * e] - __uint_as_float(hi[e] << 16), g_[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
+          const uint32_t hk = pack_bf16x2(g_[2 * e], g_[2 * e + 1]);
+          hi[g * 4 + e] = hk;
+          lo[g * 4 + e] = pack_bf16x2(g_[2 * e] - __uint_as_float(hk << 16), g_[2 * e + 1] - __uint_as_float(hk & 0xffff0000u));
         }
-        *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(dsl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      if (i >= 1) {
+        mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // P^T / dS^T buffers free, dQ_{i-1} complete
+        tc_fence_after();
+        flush_dq(i - 1);
+      }
+      // query columns [32 h, 32 h + 32): 64-query sub-tile h >> 1, 16-byte chunks (h & 1) * 4 + g
+      uint8_t* pt = sPt + (h >> 1) * L::TILE;
+      uint8_t* dst = sdSt + (h >> 1) * L::TILE;
+      uint8_t* dsl = sdSl + (h >> 1) * L::TILE;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t off = sw128_offset(krow, (h & 1) * 4 + g);
+        *reinterpret_cast<uint4*>(pt + off) = make_uint4(pp[g * 4], pp[g * 4 + 1], pp[g * 4 + 2], pp[g * 4 + 3]);
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
+        *reinterpret_cast<uint4*>(dsl + off) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -441,16 +455,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      uint32_t r[16];
-      tmem_ld16(t_row + L::DK_COL, r);
+      uint32_t r[32];
+      tmem_ld32(t_row + L::DKH_COL, r);                       // [from dS_hi: Q_hi (8) Q_lo (8) | from dS_lo: Q_hi Q_lo]
       tmem_wait_ld();
-      if (key < N)
-        for (int c = 0; c < d; ++c) dK[grow * d + c] = __uint_as_float(r[c]) + __uint_as_float(r[d + c]);
+      if (key < N) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < d)
+            dK[grow * d + c] = (__uint_as_float(r[c]) + __uint_as_float(r[8 + c])) +
+                               (__uint_as_float(r[16 + c]) + __uint_as_float(r[24 + c]));
+      }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TB_CWARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -114,7 +114,7 @@ conv_tc_kernel(const ConvTcP p) {
 
   if (warp == 8) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC = make_idesc_bf16(128, NT, MODE == TC_WGRAD ? 1 : 0, MODE == TC_DGRAD ? 0 : 1);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % CT_STAGES;

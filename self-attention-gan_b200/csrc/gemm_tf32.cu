@@ -84,7 +84,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % GT_STAGES;
@@ -95,7 +95,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC = make_idesc_tf32(128, 128);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % GT_STAGES;

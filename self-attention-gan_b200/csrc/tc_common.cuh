@@ -12,6 +12,20 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp is elected.  Role code that issues TMA / tcgen05.mma must be gated with THIS, not
+// with `lane == 0`: ptxas recognises the elect pattern as "exactly one active thread" and moves the descriptors to
+// uniform registers with a plain R2UR; behind `lane == 0` it wraps every UTCHMMA in a BRA.U.ANY uniformisation loop
+// (measured: 76 cycles per MMA issue instead of ~15).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
