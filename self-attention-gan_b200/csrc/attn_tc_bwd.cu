@@ -15,8 +15,8 @@
 //     dV_j += P^T  dA_i          (A = P^T  K-major, B = dA_i^T rows)   TMEM, accumulated over i
 //     dK_j += dS^T Q_i           (A = dS^T K-major, B = Q_i^T rows)    TMEM, accumulated over i
 //     dQ_i  = dS   K_j           (A = the SAME dS^T tile read MN-major, B = K_j^T rows) -> atomicAdd over key tiles
-// 18 warps: 0-15 compute (four threads per key row, 32 query columns each), warp 16 = TMA producer,
-// warp 17 = MMA issuer.  Compute warps never wait for each other: they signal the issuer through mbarriers
+// 19 warps: 0-15 compute (four threads per key row, 32 query columns each), warp 16 = TMA producer,
+// warps 17, 18 = MMA issuers (S^T / dP^T / dV / dK and dQ).  Compute warps never wait for each other: they signal the issuer through mbarriers
 // (S/dP registers loaded -> next S/dP MMA may overwrite TMEM; P/dS tiles written -> gradient MMAs may start).
 #include <math.h>
 #include <stdlib.h>
@@ -29,7 +29,7 @@ namespace sagan {
 using namespace tc;
 
 constexpr float TB_LOG2E = 1.4426950408889634f;
-constexpr int TB_THREADS = 576;   // 16 compute warps + TMA producer warp + MMA issuer warp
+constexpr int TB_THREADS = 608;   // 16 compute warps + TMA producer warp + 2 MMA issuer warps
 constexpr int TB_CWARPS = 16;
 constexpr int TB_COLS = 64;   // bf16 row length of the K-major operand buffers (128 B)
 
@@ -231,7 +231,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(barKV, 1);
     mbar_init(barQ, 1); mbar_init(barQ + 1, 1);
     mbar_init(barS, 1);
-    mbar_init(barG, 1); mbar_init(barG + 1, 1);
+    mbar_init(barG, 2); mbar_init(barG + 1, 2);     // both issuer warps commit
     mbar_init(barSfree, TB_CWARPS * 32); mbar_init(barTiles, TB_CWARPS * 32);
     mbar_fence_init();
   }
@@ -272,7 +272,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
       constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
-      constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
       auto issue_sdp = [&](int i) {     // S^T = K Q_i^T, dP^T = V dA_i^T
         const int s = i & 1;
         uint8_t* st = sStage + s * L::STAGE;
@@ -289,22 +288,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint8_t* st = sStage + s * L::STAGE;
         const uint64_t dPt = make_desc_sw128(smem_u32(sPt)), dSt = make_desc_sw128(smem_u32(sdSt));
         const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::ST_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::ST_QT));
-        const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
         const uint64_t dSl = make_desc_sw128(smem_u32(sdSl));
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // 16 queries (dV, dK) / 16 keys (dQ) per step; five independent accumulators
+        for (int ks = 0; ks < 8; ++ks) {   // 16 queries per step; three independent accumulators (dQ: second issuer warp)
           const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
           const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
           const bool acc = (i > 0) || (ks > 0);
           mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
                       IDESC_DV, acc);
           mma_bf16_ss(tmem_base + L::DKH_COL, dSt + a_off, dQt_ + b16, IDESC_DK, acc);
-          // dQ: the dS^T tiles read MN-major (M = queries contiguous), K = keys
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024),
-                      dKt_ + b16, IDESC_DQ, ks > 0);
           mma_bf16_ss(tmem_base + L::DKL_COL, dSl + a_off, dQt_ + b16, IDESC_DK, acc);
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(smem_u32(sdSl) + ks * 16 * 128, L::TILE, 1024),
-                      dKt_ + b16, IDESC_DQ, ks > 0);
         }
         mma_commit(barG + s);
       };
@@ -322,6 +315,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(barTiles, i & 1);              // P^T_i / dS^T_i are in shared memory
         tc_fence_after();
         issue_grads(i);
+      }
+    }
+  } else if (warp == TB_CWARPS + 2) {
+    // ================================================================ second MMA issuer: dQ_i = dS_i K_j
+    // (issuing one tcgen05.mma costs the elected thread ~35 cycles; 43 per tile from one thread were the critical path)
+    if (elect_one_sync()) {
+      constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
+      const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
+      mbar_wait(barKV, 0);
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(barTiles, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // K = 16 keys per step: the dS^T tiles read MN-major (M = queries contiguous)
+          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024),
+                      dKt_ + b16, IDESC_DQ, ks > 0);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(smem_u32(sdSl) + ks * 16 * 128, L::TILE, 1024),
+                      dKt_ + b16, IDESC_DQ, ks > 0);
+        }
+        mma_commit(barG + (i & 1));
       }
     }
   } else {
