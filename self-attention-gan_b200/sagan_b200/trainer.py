@@ -17,7 +17,8 @@ import torch
 
 from . import functional as F
 from . import nets
-from ._lib import MATH_FP32_STRICT
+from ._lib import MATH_FP32_STRICT  # noqa: F401
+from .parallel import ReplicaGradientSum
 
 ADAM_B1, ADAM_B2, ADAM_EPS = 0.0, 0.999, 1e-7      # main.py:119-120 (Keras defaults, beta_1 = 0)
 
@@ -54,12 +55,10 @@ class Trainer:
         self.config = dict(config)
         cfg = self.config
         self.B = cfg["batch_size"]
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+        self.dp = ReplicaGradientSum(process_group)
+        self.world = self.dp.world
         # main.py:358: global_batch_size = batch_size * len(gpu)
-        self.global_batch = global_batch_size or self.B * self.world
+        self.global_batch = global_batch_size or self.dp.global_batch(self.B)
         self.device = torch.device("cuda", torch.cuda.current_device())
         torch.manual_seed(seed)
         self.G = nets.get_generator(cfg)
@@ -69,11 +68,8 @@ class Trainer:
             lab = torch.zeros(self.B, dtype=torch.int64, device=self.device) if cfg.get("use_label") else None
             img = self.G([z, lab])
             self.D([img, lab])
-        if self.world > 1:      # identical initial weights on every replica (MirroredStrategy variables)
-            torch.distributed.broadcast(self.G.flat_params, 0, group=self.pg)
-            torch.distributed.broadcast(self.D.flat_params, 0, group=self.pg)
-            torch.distributed.broadcast(self.G.sn_group.out, 0, group=self.pg)
-            torch.distributed.broadcast(self.D.sn_group.out, 0, group=self.pg)
+        # identical initial weights and spectral-norm state on every replica (MirroredStrategy variables)
+        self.dp.broadcast_(self.G.flat_params, self.D.flat_params, self.G.sn_group.out, self.D.sn_group.out)
         ur = cfg.get("update_ratio", 1)
         self.opt_G = FlatAdam(self.G, cfg["lr_g"], steps_per_epoch, cfg["decay_rate"])          # main.py:111-114
         self.opt_D = FlatAdam(self.D, cfg["lr_d"], steps_per_epoch * ur, cfg["decay_rate"])     # main.py:115-118
@@ -83,8 +79,7 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------
     def _allreduce(self, flat):
-        if self.world > 1:
-            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self.dp.sum_(flat)
 
     def _d_phase(self, images, labels, noise, fake_labels):
         G, D = self.G, self.D

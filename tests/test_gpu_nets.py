@@ -120,6 +120,96 @@ def test_forward_and_gradients_vs_oracle_and_golden():
         assert rel_l2(m.u.cpu().numpy(), ref.numpy()) < 1e-5, k
 
 
+def _phase_grads(tr, cfg, img, nd, ng, labels=None, fake_labels=None):
+    """D-phase and G-phase gradients of the GPU trainer (sagan/main.py:176-204) -> (D loss elems, G loss elems)."""
+    import sagan_b200.functional as F
+    lab = None if labels is None else torch.as_tensor(labels).cuda()
+    flab = None if fake_labels is None else torch.as_tensor(fake_labels).cuda()
+    with torch.no_grad():
+        fake = tr.G([cu(nd), flab], training=True)
+    tr.D.zero_grad_flat()
+    d_real = tr.D([cu(img), lab], training=True)
+    d_fake = tr.D([fake, flab], training=True)
+    loss = torch.zeros(1, device="cuda")
+    g_real, g_fake = F.hinge_d_grads(d_real, d_fake, cfg["batch_size"], loss)
+    torch.autograd.backward([d_real, d_fake], [g_real, g_fake])
+    le_d = (torch.relu(1 - d_real) + torch.relu(1 + d_fake)).detach().cpu().numpy()
+    tr.G.zero_grad_flat()
+    for p in tr.D.parameters():
+        p.requires_grad_(False)
+    fake = tr.G([cu(ng), flab], training=True)
+    d_fake = tr.D([fake, flab], training=True)
+    g = F.hinge_g_grads(d_fake, cfg["batch_size"], loss)
+    d_fake.backward(g)
+    for p in tr.D.parameters():
+        p.requires_grad_(True)
+    torch.cuda.synchronize()
+    return le_d, (-d_fake).detach().cpu().numpy()
+
+
+def test_forward_and_gradients_bf16_tc_mode():
+    """The same D-phase / G-phase evaluation with every conv / deconv / dense / attention layer on the tcgen05 path
+    (BF16_TC): losses and per-parameter gradients against the fp64 oracle, BASELINE.json tolerance 2e-3 rel-L2 on the
+    forward; gradients are reported per parameter and bounded (LeakyReLU / hinge masks flip for the few activations
+    that bf16 rounding moves across zero, which no bf16 implementation can avoid)."""
+    from sagan_b200 import nn as snn
+    from sagan_b200 import MATH_BF16_TC, MATH_FP32_STRICT
+    cfg = dict(mg.TEST_CFG)
+    snn.set_default_math_mode(MATH_BF16_TC)
+    try:
+        orc, tr = make_pair(cfg, attn_sigma=0.37, bias_scale=0.05)
+    finally:
+        snn.set_default_math_mode(MATH_FP32_STRICT)
+    img, nd, ng = mg.step_inputs(cfg, 0)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    dgr, dl = orc.d_grads(t64(img), t64(nd))
+    # the oracle's G phase must see the same D state as ours: evaluate it before any update (no optimiser step here)
+    ggr, gl = orc.g_grads(t64(ng))
+    le_d, le_g = _phase_grads(tr, cfg, img, nd, ng)
+    e_d, e_g = rel_l2(le_d, dl.numpy()), rel_l2(le_g, gl.numpy())
+    print("BF16_TC loss elems: D %.2e G %.2e" % (e_d, e_g))
+    assert e_d < 2e-3 and e_g < 2e-3
+    errs = {}
+    for net, ref in ((tr.D, dgr), (tr.G, ggr)):
+        for k, p in net.named_parameters_by_oracle_name():
+            if k.endswith("phi.bias"):
+                continue
+            errs[("D." if net is tr.D else "G.") + k] = rel_l2(p.grad.cpu().numpy(), ref[k].numpy())
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("BF16_TC worst per-parameter gradient rel-L2:", [(k, "%.2e" % v) for k, v in worst])
+    print("BF16_TC median per-parameter gradient rel-L2: %.2e" % float(np.median(list(errs.values()))))
+    assert max(errs.values()) < 2e-2
+
+
+def test_conditional_128_forward_and_gradients():
+    """BASELINE.json configs[3]: 128x128 class-conditional SAGAN (one-hot concat in G, projection head in D,
+    attention at 32x32 and 64x64), B = 2, against the fp64 oracle (FP32_STRICT tier)."""
+    cfg = dict(mg.TEST_CFG, img_size=128, use_label=True, num_classes=10, batch_size=2, attn_dim_G=[32, 64])
+    orc, tr = make_pair(cfg, attn_sigma=0.3, bias_scale=0.05)
+    # the projection-head embedding is created lazily by the GPU discriminator: give both sides the oracle's values
+    rng = np.random.Generator(np.random.PCG64(5))
+    img = rng.uniform(-1, 1, (2, 128, 128, 3)).astype(np.float32)
+    nd = rng.standard_normal((2, cfg["z_dim"])).astype(np.float32)
+    ng = rng.standard_normal((2, cfg["z_dim"])).astype(np.float32)
+    labels = np.array([3, 7], dtype=np.int64)
+    fake_labels = np.array([1, 9], dtype=np.int64)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    dgr, dl = orc.d_grads(t64(img), t64(nd), torch.tensor(labels), torch.tensor(fake_labels))
+    ggr, gl = orc.g_grads(t64(ng), torch.tensor(fake_labels))
+    le_d, le_g = _phase_grads(tr, cfg, img, nd, ng, labels, fake_labels)
+    assert le_d.shape == (2, 1)                                  # discriminator.py:33 -> [B, 1]
+    assert rel_l2(le_d, dl.numpy()) < 1e-5 and rel_l2(le_g, gl.numpy()) < 1e-5
+    worst = 0.0
+    for net, ref in ((tr.D, dgr), (tr.G, ggr)):
+        for k, p in net.named_parameters_by_oracle_name():
+            if k.endswith("phi.bias") or ref[k] is None:
+                continue
+            e = rel_l2(p.grad.cpu().numpy(), ref[k].numpy())
+            worst = max(worst, e)
+            assert e < 2e-4, (k, e)
+    print("128x128 conditional: worst per-parameter gradient rel-L2 %.2e" % worst)
+
+
 def test_train_steps_match_oracle_fp32():
     """5 full steps (both Adam updates, LR schedule) against the fp32 oracle: losses and weights."""
     cfg = dict(mg.TEST_CFG)
