@@ -59,7 +59,7 @@ def _worker(rank, world, port, out):
     state = torch.full((4,), float(rank))
     dp.broadcast_(state)
     dp.sum_(flat)
-    losses = dp.sum_losses_(torch.tensor([loss_sum]))
+    losses = dp.sum_losses_(torch.tensor([loss_sum], dtype=torch.float64))
     if rank == 0:
         torch.save(dict(flat=flat, loss=losses, state=state, gb=gb, world=dp.world), out)
     dist.barrier()
