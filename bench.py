@@ -119,7 +119,7 @@ def cpu_oracle_images_per_sec(steps, warmup, sample_batch=8, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    base, dt = cpu_oracle_images_per_sec(max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    base, dt = cpu_oracle_images_per_sec(max(1, min(args.steps, 30)), max(1, min(args.warmup, 5)))
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -157,42 +157,79 @@ def attn_flops(B, N, C, bwd=False):
     return 2 * B * N * N * (3 * d + 2 * dv) + 2 * (2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C)
 
 
-def kernel_rooflines(pk, math_mode):
-    """The dominant kernels of the step, timed alone: attention at G's 64x64 map (B=64, N=4096, C=16) and the
-    multi-tensor spectral-norm launch; plus a roofline-sized spectral norm (4096x4096)."""
-    import sagan_b200.functional as F
-    from oracle import attention as oattn
-    flush = torch.zeros(128 * 1024 * 1024, device="cuda")
-    B, N, C = 64, 4096, 16
-    X, dY, w = oattn.make_inputs(1, 8, C, seed=0, gamma=0.5, dtype=np.float32)
-    t = {k: torch.tensor(np.asarray(v, dtype=np.float32)).cuda().requires_grad_(True) for k, v in w.items()}
-    x = torch.randn(B, N, C, device="cuda", requires_grad=True)
-    dy = torch.randn(B, N, C, device="cuda")
-    args = (t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"])
-    with torch.no_grad():
-        t_fwd = time_cuda(lambda: F.attention(x, *args, math_mode), 10, flush)
-    y = F.attention(x, *args, math_mode)
+def _traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this kernel at this
+    shape (profiles/r1_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(name)
+    return None
 
-    def bwd():
-        torch.autograd.grad(y, [x] + list(t.values()), dy, retain_graph=True)
-    t_bwd = time_cuda(bwd, 5, flush)
+
+def kernel_rooflines(pk, math_mode):
+    """The dominant kernels, each timed alone with CUDA events (L2 flushed between iterations):
+      * self-attention at G's 64x64 map (B=64, N=4096, C=16), forward and backward  -- the step's top kernels
+      * self-attention forward in the sweep regime (B=16, N=4096, C=512)           -- where the block is tensor-bound
+      * spectral norm: 4096x16384 (256 MB, 16 B/element rule), 4096x4096 (64 MB, 8 B/element rule), and the 13
+        matrices of the church64 generator in one launch."""
+    import sagan_b200.functional as F
+    from sagan_b200 import MATH_BF16_TC
+    flush = torch.zeros(128 * 1024 * 1024, device="cuda")
+    mufu_peak = 148 * 16 * 1.965e9       # ex2 / s: 16 per clock per SM at the maximum SM clock
     out = {}
-    f_fwd, f_bwd = attn_flops(B, N, C), attn_flops(B, N, C, True)
-    out["attn_fwd"] = dict(bound="tensor", achieved=f_fwd / t_fwd / 1e12, peak=pk["tc_burst"], unit="TFLOP/s",
-                           frac=f_fwd / t_fwd / 1e12 / pk["tc_burst"], traffic=None, seconds=t_fwd,
-                           shape=f"B={B} N={N} C={C} (d=2, dv=8)", exps_per_s=B * N * N / t_fwd)
-    out["attn_bwd"] = dict(bound="tensor", achieved=f_bwd / t_bwd / 1e12, peak=pk["tc_burst"], unit="TFLOP/s",
-                           frac=f_bwd / t_bwd / 1e12 / pk["tc_burst"], traffic=None, seconds=t_bwd,
-                           shape=f"B={B} N={N} C={C} (d=2, dv=8)", exps_per_s=B * N * N / t_bwd)
-    # spectral norm at roofline size (64 MB matrix: 8 B/element rule of SURVEY.md §8d)
-    R = K = 4096
-    W = torch.randn(K, R, device="cuda") * 0.02
-    u = torch.randn(1, R, device="cuda")
-    g = F.SpectralNormGroup([W], [u / u.norm()], 1)
-    t_sn = time_cuda(g.run, 10, flush)
-    out["sn_4096x4096"] = dict(bound="hbm", achieved=g.algorithmic_bytes / t_sn / 1e9, peak=pk["hbm"], unit="GB/s",
-                               frac=g.algorithmic_bytes / t_sn / 1e9 / pk["hbm"], traffic=None, seconds=t_sn,
-                               rule="8 B/element (read W once + write W_bar; 64 MB matrix, passes 2-3 from L2)")
+
+    def attn_case(B, N, C, mode, bwd, iters):
+        d, dv = C // 8, C // 2
+        g = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.randn(B, N, C, device="cuda", generator=g, requires_grad=True)
+        mk = lambda *sh: (torch.randn(*sh, device="cuda", generator=g) / np.sqrt(sh[0])).requires_grad_(True)
+        w = [mk(C, d), mk(d), mk(C, d), mk(d), mk(C, dv), mk(dv), mk(dv, C), mk(C),
+             torch.tensor(0.5, device="cuda", requires_grad=True)]
+        with torch.no_grad():      # un-scaled logits (layers.py:108) of a few units (std 1.5) whatever d is
+            w[0] *= 1.5 ** 0.5 / d ** 0.25
+            w[2] *= 1.5 ** 0.5 / d ** 0.25
+        dy = torch.randn(B, N, C, device="cuda", generator=g)
+        with torch.no_grad():
+            t_f = time_cuda(lambda: F.attention(x, *w, mode), iters, flush)
+        t_b = None
+        if bwd:
+            y = F.attention(x, *w, mode)
+            t_b = time_cuda(lambda: torch.autograd.grad(y, [x] + w, dy, retain_graph=True), max(3, iters // 2), flush)
+        return t_f, t_b
+
+    def attn_entry(name, B, N, C, t, bwd):
+        fl = attn_flops(B, N, C, bwd)
+        d, dv = C // 8, C // 2
+        return dict(bound="tensor", achieved=fl / t / 1e12, peak=pk["tc_burst"], unit="TFLOP/s",
+                    frac=fl / t / 1e12 / pk["tc_burst"], traffic=_traffic(name), seconds=t,
+                    shape=f"B={B} N={N} C={C} (d={d}, dv={dv})", exps_per_s=B * N * N / t,
+                    mufu_frac=B * N * N / t / mufu_peak)
+
+    B, N, C = 64, 4096, 16
+    t_f, t_b = attn_case(B, N, C, math_mode, True, 10)
+    out["attn_fwd"] = attn_entry("attn_fwd", B, N, C, t_f, False)
+    out["attn_bwd"] = attn_entry("attn_bwd", B, N, C, t_b, True)
+    if math_mode == MATH_BF16_TC:
+        B, N, C = 16, 4096, 512
+        t_f, _ = attn_case(B, N, C, math_mode, False, 10)
+        out["attn_fwd_C512"] = attn_entry("attn_fwd_C512", B, N, C, t_f, False)
+        out["attn_fwd_C512"]["note"] = ("sweep regime (BASELINE.json configs[4]): projection GEMM + flash forward + "
+                                        "output-conv GEMM, whole block; forward only")
+
+    def sn_entry(name, shapes, rule):
+        Ws = [torch.randn(K, R, device="cuda") * 0.02 for R, K in shapes]
+        us = [torch.randn(1, R, device="cuda") for R, K in shapes]
+        grp = F.SpectralNormGroup(Ws, [u / u.norm() for u in us], 1)
+        t = time_cuda(grp.run, 10, flush)
+        out[name] = dict(bound="hbm", achieved=grp.algorithmic_bytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
+                         frac=grp.algorithmic_bytes / t / 1e9 / pk["hbm"], traffic=_traffic(name), seconds=t, rule=rule)
+        del grp, Ws, us
+
+    sn_entry("sn_4096x16384", [(4096, 16384)], "16 B/element (256 MB matrix: three reads of W + one write of W_bar)")
+    sn_entry("sn_4096x4096", [(4096, 4096)], "8 B/element (64 MB matrix: read W once + write W_bar, passes 2-3 from L2)")
+    sn_entry("sn_church64_G", [(4096, 128), (256, 2048), (128, 1024), (64, 512), (32, 256), (4, 32), (4, 32), (16, 32),
+                               (32, 16), (2, 16), (2, 16), (8, 16), (16, 8)],
+             "8 B/element; the 13 spectrally-normalised kernels of the generator in ONE launch (4.9 MB: latency-bound)")
     return out
 
 
@@ -278,9 +315,12 @@ def run_ours(args, rank, world, local_rank):
     roofs = kernel_rooflines(pk, math_mode)
     dom = max(("attn_fwd", "attn_bwd"), key=lambda k: roofs[k]["seconds"])
     roofline = dict(roofs[dom], kernel=dom, peak_source=pk["src"],
-                    note="in-model attention dims (d=2, dv=8) are exp/MUFU-bound, not tensor-bound: see exps_per_s")
+                    note="dominant kernel of the step.  BASELINE.json names the tensor pipe as this block's roof, but at "
+                         "the in-model dims (d=2, dv=8: 20 useful FLOPs per score against one exp2) the MUFU pipe is the "
+                         "binding unit: mufu_frac = exps_per_s / (148 SMs x 16 ex2/clk x 1.965 GHz).  The tensor-bound "
+                         "regime is kernels.attn_fwd_C512.")
     if args.cpu_baseline:
-        cpu, _ = cpu_oracle_images_per_sec(2, 1)
+        cpu, _ = cpu_oracle_images_per_sec(8, 2)
     else:
         cpu = None
     act_mb = 4 * B * (64 * 64 * 16 * 12 + 32 * 32 * 32 * 10) / 1e6

@@ -342,7 +342,9 @@ attn_wgrad_small_kernel(const float* __restrict__ X, const float* __restrict__ A
                         float* __restrict__ dWq, float* __restrict__ dbq, float* __restrict__ dWk,
                         float* __restrict__ dbk, float* __restrict__ dWv, float* __restrict__ dbv,
                         float* __restrict__ dWo, float* __restrict__ dbo, long long T, int tokens_per_block) {
-  constexpr int D = C / 8, DV = C / 2, TT = 32;
+  // token tile: as large as the 48 KB of static shared memory allow, so the global-load latency of a tile is paid
+  // 4x less often (the tiles are not double-buffered)
+  constexpr int D = C / 8, DV = C / 2, TT = C <= 16 ? 128 : (C <= 32 ? 64 : 32);
   constexpr int LW = C + 1, RW = 2 * D + DV;          // G1: left width (X | 1), right width (dQ dK dV)
   constexpr int L2 = DV + 1, R2 = C;                  // G2: (A | 1), dY
   constexpr int N1 = LW * RW, N2 = L2 * R2, NOUT = N1 + N2;
@@ -478,8 +480,8 @@ static int attn_bwd_tail_t(const float* dY, const float* X, const float* Wq, con
     SAGAN_CUDA(cudaMemsetAsync(dbk, 0, sizeof(float) * D, st));
     SAGAN_CUDA(cudaMemsetAsync(dbv, 0, sizeof(float) * DV, st));
     SAGAN_CUDA(cudaMemsetAsync(dbo, 0, sizeof(float) * C, st));
-    const int blocks = (int)std::min<long long>(num_sms() * 2, ceil_div<long long>(T, 256));
-    const int tpb = (int)(ceil_div<long long>(ceil_div<long long>(T, blocks), 32) * 32);
+    const int blocks = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(T, 256));
+    const int tpb = (int)(ceil_div<long long>(ceil_div<long long>(T, blocks), 128) * 128);
     attn_wgrad_small_kernel<C><<<(unsigned)ceil_div<long long>(T, tpb), 256, 0, st>>>(X, A, dY, dQ, dK, dV, dWq, dbq, dWk,
                                                                                     dbk, dWv, dbv, dWo, dbo, T, tpb);
     SAGAN_LAUNCH_CHECK();

@@ -43,6 +43,34 @@ bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, long long
   }
 }
 
+// Folds part[nparts][2][C] into (sum, sumsq) per channel in fp64, in a FIXED order (deterministic), using the whole
+// CTA: thread t takes channel t % cpt and every (BN_THREADS / cpt)-th partial, then the slices are folded in order.
+// (A single thread per channel walking all partials serialised ~600 dependent L2 loads in EVERY CTA: 40-60 us.)
+__device__ __forceinline__ void bn_fold_partials(const float* __restrict__ part, int nparts, int C, int c0, double* red,
+                                                 double& s_out, double& q_out, bool& owner, int& c_out) {
+  const int cpt = min(C, BN_THREADS);
+  const int sl = BN_THREADS / cpt;
+  const int c_lane = threadIdx.x % cpt, slice = threadIdx.x / cpt;
+  const int c = c0 + c_lane;
+  double s = 0.0, q = 0.0;
+  if (c < C && slice < sl)
+    for (int p = slice; p < nparts; p += sl) {
+      s += (double)part[((size_t)p * 2 + 0) * C + c];
+      q += (double)part[((size_t)p * 2 + 1) * C + c];
+    }
+  red[threadIdx.x] = s;
+  red[BN_THREADS + threadIdx.x] = q;
+  __syncthreads();
+  owner = (slice == 0 && c < C);
+  if (owner)
+    for (int j = 1; j < sl; ++j) {
+      s += red[j * cpt + c_lane];
+      q += red[BN_THREADS + j * cpt + c_lane];
+    }
+  __syncthreads();
+  s_out = s; q_out = q; c_out = c;
+}
+
 __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ y, const float* __restrict__ part, int nparts, float* __restrict__ save_mean,
@@ -51,12 +79,13 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
   extern __shared__ float sm[];   // scale[C], shift[C]
   float* scale = sm;
   float* shift = sm + C;
-  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-    double s = 0.0, q = 0.0;
-    for (int p = 0; p < nparts; ++p) {
-      s += (double)part[((size_t)p * 2 + 0) * C + c];
-      q += (double)part[((size_t)p * 2 + 1) * C + c];
-    }
+  __shared__ double red[2 * BN_THREADS];
+  for (int c0 = 0; c0 < C; c0 += min(C, BN_THREADS)) {
+    double s, q;
+    bool owner;
+    int c;
+    bn_fold_partials(part, nparts, C, c0, red, s, q, owner, c);
+    if (!owner) continue;
     const double mean = s / (double)rows;
     double var = q / (double)rows - mean * mean;   // biased variance (Keras training mode)
     if (var < 0.0) var = 0.0;
@@ -136,12 +165,13 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
   float* kc = sm + 2 * C;    // dgamma / M
   float* kmu = sm + 3 * C;
   float* kis = sm + 4 * C;
-  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-    double s = 0.0, q = 0.0;
-    for (int p = 0; p < nparts; ++p) {
-      s += (double)part[((size_t)p * 2 + 0) * C + c];
-      q += (double)part[((size_t)p * 2 + 1) * C + c];
-    }
+  __shared__ double red[2 * BN_THREADS];
+  for (int c0 = 0; c0 < C; c0 += min(C, BN_THREADS)) {
+    double s, q;
+    bool owner;
+    int c;
+    bn_fold_partials(part, nparts, C, c0, red, s, q, owner, c);
+    if (!owner) continue;
     if (blockIdx.x == 0) {
       dbeta[c] = (float)s;
       dgamma[c] = (float)q;

@@ -34,6 +34,8 @@ struct ConvTcP {
   int act;
   float slope;
   int m_per_split;      // WGRAD: pixels per blockIdx.z
+  int k_splits;         // FWD / DGRAD: split-K factor (blockIdx.z = class * k_splits + split); > 1 => atomic accumulation
+                        //              into a zeroed output, bias / activation applied afterwards by conv_tc_finish_kernel
   // FWD epilogue variants used by the large-C attention block (attn_tc_big.cu):
   const float* res;         // out = res + (*res_scale) * (acc + bias)   (gamma residual, layers.py:120)
   const float* res_scale;
@@ -83,16 +85,22 @@ conv_tc_kernel(const ConvTcP p) {
   int Mg, Ng, k_begin, k_end;            // rows, cols, reduction range
   int rh = 0, rw = 0, hi_first = 0, wi_first = 0, Hc = 1, Wc = 1, ntw = 1;   // DGRAD class geometry
   if (MODE == TC_FWD) {
-    Mg = g.M; Ng = g.Cout; k_begin = 0; k_end = g.K;
+    Mg = g.M; Ng = g.Cout;
+    const int kper = (((g.K + p.k_splits - 1) / p.k_splits) + 63) / 64 * 64;
+    k_begin = (int)blockIdx.z * kper; k_end = min(g.K, k_begin + kper);
   } else if (MODE == TC_DGRAD) {
-    rh = blockIdx.z / g.S; rw = blockIdx.z - rh * g.S;
+    const int cls = blockIdx.z / p.k_splits, split = blockIdx.z - cls * p.k_splits;
+    rh = cls / g.S; rw = cls - rh * g.S;
     hi_first = ((rh - g.PT) % g.S + g.S) % g.S;
     wi_first = ((rw - g.PL) % g.S + g.S) % g.S;
     Hc = hi_first < g.H ? (g.H - hi_first + g.S - 1) / g.S : 0;
     Wc = wi_first < g.W ? (g.W - wi_first + g.S - 1) / g.S : 0;
     const int nth = rh < g.KH ? (g.KH - rh + g.S - 1) / g.S : 0;
     ntw = rw < g.KW ? (g.KW - rw + g.S - 1) / g.S : 0;
-    Mg = g.B * Hc * Wc; Ng = g.Cin; k_begin = 0; k_end = nth * ntw * g.Cout;
+    Mg = g.B * Hc * Wc; Ng = g.Cin;
+    const int Kc = nth * ntw * g.Cout;
+    const int kper = (((Kc + p.k_splits - 1) / p.k_splits) + 63) / 64 * 64;
+    k_begin = split * kper; k_end = min(Kc, k_begin + kper);
   } else {
     Mg = g.K + (p.dbias ? 1 : 0); Ng = g.Cout;
     k_begin = blockIdx.z * p.m_per_split; k_end = min(g.M, k_begin + p.m_per_split);
@@ -331,6 +339,10 @@ conv_tc_kernel(const ConvTcP p) {
                   orow[nb + e] = fmaf(res_gm, __uint_as_float(r[e]) + (p.bias ? p.bias[nb + e] : 0.f),
                                       p.res[(size_t)m * g.Cout + nb + e]);
             }
+          } else if (MODE != TC_WGRAD && p.k_splits > 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (nb + e < Ng) atomicAdd(orow + nb + e, __uint_as_float(r[e]));
           } else if (MODE == TC_WGRAD) {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
@@ -396,10 +408,36 @@ bool conv_tc_fwd_ok(const CG& g, const float* x, const float* w) { return g.Cin 
 bool conv_tc_dgrad_ok(const CG& g, const float* dy, const float* w) { return g.Cout % 8 == 0 && g.Cin % 4 == 0 && al16(dy) && al16(w); }
 bool conv_tc_wgrad_ok(const CG& g, const float* x, const float* dy) { return g.Cin % 8 == 0 && al16(x) && al16(dy); }
 
+// y = act(y + bias) after a split-K accumulation
+__global__ void conv_tc_finish_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n, int C, int act,
+                                      float slope) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = ct_act(y[i] + (bias ? bias[(int)(i % C)] : 0.f), act, slope);
+}
+
+// Layers with few output pixels (the 4x4 / 8x8 maps: 8-16 CTAs walking 16-32 K blocks each) are latency-bound on the
+// producers' gather; splitting K over more CTAs fills the machine.  Returns 1 when splitting does not pay.
+static int pick_k_splits(int ctas, int K) {
+  const int nkb = ceil_div(K, 64);
+  if (ctas * 2 > num_sms() || nkb < 8) return 1;
+  return std::max(1, std::min(nkb / 4, num_sms() / ctas));
+}
+
 int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope,
                 cudaStream_t st) {
-  ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
-  return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
+  ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  const int gx = ceil_div(g.M, 128);
+  p.k_splits = pick_k_splits(gx * ceil_div(g.Cout, 128), g.K);
+  if (p.k_splits == 1) return dispatch_nt<TC_FWD>(p, g.Cout, gx, 1, st);
+  const long long n = (long long)g.M * g.Cout;
+  SAGAN_CUDA(cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), st));
+  int rc = dispatch_nt<TC_FWD>(p, g.Cout, gx, p.k_splits, st);
+  if (rc) return rc;
+  if (bias || act != SAGAN_ACT_NONE) {
+    conv_tc_finish_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, st>>>(y, bias, n, g.Cout, act, slope);
+    SAGAN_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 static CG gemm_geom(long long M, int K, int N) {
@@ -413,7 +451,7 @@ static CG gemm_geom(long long M, int K, int N) {
 int gemm_tc_qkv(const float* x, const float* wcat, const float* bcat, __nv_bfloat16* q, __nv_bfloat16* k,
                 __nv_bfloat16* v, long long M, int K, int d, int dv, float q_scale, cudaStream_t st) {
   const CG g = gemm_geom(M, K, 2 * d + dv);
-  ConvTcP p{x, wcat, bcat, nullptr, nullptr, g, 0, 0.f, 0, nullptr, nullptr, q, k, v, d, dv, q_scale};
+  ConvTcP p{x, wcat, bcat, nullptr, nullptr, g, 0, 0.f, 0, 1, nullptr, nullptr, q, k, v, d, dv, q_scale};
   return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
 }
 
@@ -421,14 +459,18 @@ int gemm_tc_qkv(const float* x, const float* wcat, const float* bcat, __nv_bfloa
 int gemm_tc_residual(const float* x, const float* w, const float* bias, const float* res, const float* res_scale, float* y,
                      long long M, int K, int N, cudaStream_t st) {
   const CG g = gemm_geom(M, K, N);
-  ConvTcP p{x, w, bias, y, nullptr, g, 0, 0.f, 0, res, res_scale, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  ConvTcP p{x, w, bias, y, nullptr, g, 0, 0.f, 0, 1, res, res_scale, nullptr, nullptr, nullptr, 0, 0, 0.f};
   return dispatch_nt<TC_FWD>(p, g.Cout, ceil_div(g.M, 128), 1, st);
 }
 
 int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st) {
-  ConvTcP p{dy, w, nullptr, dx, nullptr, g, 0, 0.f, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  ConvTcP p{dy, w, nullptr, dx, nullptr, g, 0, 0.f, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   const int Hc = ceil_div(g.H, g.S), Wc = ceil_div(g.W, g.S);
-  return dispatch_nt<TC_DGRAD>(p, g.Cin, ceil_div(g.B * Hc * Wc, 128), g.S * g.S, st);
+  const int gx = ceil_div(g.B * Hc * Wc, 128), classes = g.S * g.S;
+  const int Kc = ceil_div(g.KH, g.S) * ceil_div(g.KW, g.S) * g.Cout;      // reduction length of the largest class
+  p.k_splits = pick_k_splits(gx * ceil_div(g.Cin, 128) * classes, Kc);
+  if (p.k_splits > 1) SAGAN_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.B * g.H * g.W * g.Cin * sizeof(float), st));
+  return dispatch_nt<TC_DGRAD>(p, g.Cin, gx, classes * p.k_splits, st);
 }
 
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st) {
@@ -437,7 +479,7 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, cons
   int splits = std::max(1, std::min(ceil_div(g.M, 256), ceil_div(num_sms() * 2, tiles)));
   int mps = ceil_div(ceil_div(g.M, splits), 64) * 64;
   splits = ceil_div(g.M, mps);
-  ConvTcP p{x, dy, nullptr, dw, dbias, g, 0, 0.f, mps, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  ConvTcP p{x, dy, nullptr, dw, dbias, g, 0, 0.f, mps, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   return dispatch_nt<TC_WGRAD>(p, g.Cout, ceil_div(Mg, 128), splits, st);
 }
 
