@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -247,7 +247,8 @@ def run_ours(args, rank, world, local_rank):
     snn.set_default_math_mode(math_mode)
     cfg = dict(CHURCH64)
     B = cfg["batch_size"]
-    tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=126227 // (B * world), seed=0)   # LSUN church: 126 227 images
+    tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=126227 // (B * world), seed=0,   # LSUN church: 126 227 images
+                 dp_mode=args.dp)
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
     host_batches = [torch.tensor(rng.uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
     dev_batches = [b.to(dev) for b in host_batches]
@@ -282,11 +283,11 @@ def run_ours(args, rank, world, local_rank):
         return float(ms) * 1e-3
 
     # ---- value: inputs resident in HBM, whole-step CUDA graph
-    for s in range(args.warmup):
-        tr.graph_step(dev_batches[s % 4])
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # sampled from the warm-up on: the GPU is under the same load throughout
+    for s in range(args.warmup):
+        tr.graph_step(dev_batches[s % 4])
     sec = timed(lambda s: tr.graph_step(dev_batches[s % 4]), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * args.steps / sec
@@ -300,6 +301,10 @@ def run_ours(args, rank, world, local_rank):
     sec_e2e = timed(e2e_step, args.steps)
     e2e = B * world * args.steps / sec_e2e
     losses = tr.losses()
+    if tr.peer_G is not None:      # a replica that never reached an exchange barrier raises here
+        tr.peer_G.check()
+        tr.peer_D.check()
+    dp_mode = tr.dp_mode
 
     # every collective is behind us: tear the communicator down on ALL ranks together (a rank that exits while
     # another still holds captured NCCL work can hang in the teardown), then rank 0 alone finishes the report
@@ -330,6 +335,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32" if math_mode == MATH_FP32_STRICT else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                    "math_mode": args.math, "cuda_graph": True,
+                   "dp_exchange": {"p2p": "fused NVLink peer-memory gradient sum + Adam kernel (csrc/dp.cu)",
+                                   "nccl": "NCCL all-reduce + Adam", "none": "single replica"}[dp_mode],
                    "l2": f"no explicit flush: a step touches ~{act_mb:.0f} MB of saved activations (> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": sec_e2e / args.steps * 1e3,
@@ -352,6 +359,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="bf16_tc", choices=["fp32_strict", "bf16_tc"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="data-parallel gradient exchange (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

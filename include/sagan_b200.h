@@ -182,6 +182,32 @@ int sagan_hinge_g(const float* d_fake, long long n, float scale, float* loss_sum
 int sagan_adam_step(float* param, const float* grad, float* m, float* v, long long n,
                     const float* hyper, float grad_scale, sagan_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange fused with Keras Adam over NVLink peer memory.  Replaces the
+ * replica gradient SUM that MirroredStrategy performs inside optimizer.apply_gradients
+ * (sagan/main.py:190,205) plus the Adam update that follows it (main.py:119-120, beta_1 = 0).
+ * `peers` holds, for each of the `world` replicas, the PEER-MAPPED device addresses (as seen from the
+ * calling replica) of its flat gradient bucket, its flat parameter buffer (both `n` floats, n a
+ * multiple of 4 * world) and its flag pad (sagan_dp_flag_bytes() bytes, zero-initialised once).
+ * Replica `rank` sums slice `rank` of all gradient buckets (fixed order), updates that slice with its
+ * shard `v_shard` [n / world] of the second-moment state and writes the new weights into every
+ * replica's parameter buffer.  Two inter-replica barriers (flags in peer memory) bracket the exchange;
+ * the call is asynchronous on `stream`; all replicas must issue it in the same order.  `epoch` is a
+ * device counter owned by the caller (zero-initialised, one per peers set); `status[0]` becomes 1 if a
+ * peer never arrived (the kernel gives up instead of hanging).  hyper = {lr_t, b1, b2, eps} as for
+ * sagan_adam_step.
+ * ------------------------------------------------------------------------------------------ */
+#define SAGAN_DP_MAX_WORLD 8
+typedef struct sagan_dp_peers {
+  const void* grads[SAGAN_DP_MAX_WORLD];
+  void* params[SAGAN_DP_MAX_WORLD];
+  void* flags[SAGAN_DP_MAX_WORLD];
+} sagan_dp_peers;
+int sagan_dp_max_world(void);
+size_t sagan_dp_flag_bytes(void);
+int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
+                      const float* hyper, unsigned int* epoch, unsigned int* status, sagan_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

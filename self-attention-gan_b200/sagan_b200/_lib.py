@@ -31,6 +31,10 @@ class ConvGeom(C.Structure):
                 ("pad_l", C.c_int32)]
 
 
+class DpPeers(C.Structure):
+    _fields_ = [("grads", C.c_void_p * 8), ("params", C.c_void_p * 8), ("flags", C.c_void_p * 8)]
+
+
 _P, _I, _F, _LL, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 
 # every symbol include/sagan_b200.h declares: name -> (restype, argtypes)
@@ -58,6 +62,9 @@ SIGNATURES = {
     "sagan_hinge_d": (_I, [_P, _P, _LL, _F, _P, _P, _P, _P]),
     "sagan_hinge_g": (_I, [_P, _LL, _F, _P, _P, _P]),
     "sagan_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _F, _P]),
+    "sagan_dp_max_world": (_I, []),
+    "sagan_dp_flag_bytes": (_SZ, []),
+    "sagan_dp_sum_adam": (_I, [C.POINTER(DpPeers), _I, _I, _LL, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -17,6 +17,14 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_TANH
 
 LRELU = 0.1
 
+# allocator of the flat parameter / gradient buffers: fn(numel, device) -> zeroed 1-D fp32 tensor.  The data-parallel
+# trainer swaps in a symmetric-memory allocator so that peers can address the buffers over NVLink (parallel.PeerAdam).
+_FLAT_ALLOC = [None]
+
+
+def set_flat_allocator(fn):
+    _FLAT_ALLOC[0] = fn
+
 
 class GBlock(torch.nn.Module):
     """generator.py:7-12: SN(Conv2DTranspose(c,4,2,'same',no bias)) -> BN -> LeakyReLU(0.1)."""
@@ -58,8 +66,9 @@ class Network(torch.nn.Module):
         pad = lambda k: (k + 63) // 64 * 64
         total = sum(pad(p.numel()) for p in params)
         dev = params[0].device
-        self.flat_params = torch.zeros(total, device=dev)
-        self.flat_grads = torch.zeros(total, device=dev)
+        alloc = _FLAT_ALLOC[0] or (lambda n, d: torch.zeros(n, device=d))
+        self.flat_params = alloc(total, dev)
+        self.flat_grads = alloc(total, dev)
         self.param_slices = []
         off = 0
         for p in params:

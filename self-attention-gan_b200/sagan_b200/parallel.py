@@ -52,3 +52,68 @@ class ReplicaGradientSum:
         if self.world > 1:
             dist.all_reduce(loss_sums, op=dist.ReduceOp.SUM, group=self.pg)
         return loss_sums
+
+
+class PeerAdam:
+    """Replica gradient sum FUSED with Keras Adam over NVLink peer memory (csrc/dp.cu, sagan_dp_sum_adam): replica r
+    reduces slice r of every replica's gradient bucket, updates it with its shard of the second-moment state and
+    writes the new weights into every replica's parameter buffer.  One kernel per network per update, no NCCL on the
+    data path.  The network's flat buffers must be symmetric-memory allocations (see `symmetric_allocator`)."""
+
+    def __init__(self, net, opt, dp):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.net, self.opt, self.dp = net, opt, dp
+        lib = _lib.load()
+        if dp.world > lib.sagan_dp_max_world():
+            raise _lib.SaganError(f"PeerAdam supports at most {lib.sagan_dp_max_world()} replicas, got {dp.world}")
+        dev = net.flat_params.device
+        n = net.flat_params.numel()
+        if n % (4 * dp.world):
+            raise _lib.SaganError(f"flat bucket length {n} is not a multiple of 4 * world")
+        group = dp.pg if dp.pg is not None else dist.group.WORLD
+        self.flags = symm.empty(lib.sagan_dp_flag_bytes() // 4, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        hp = symm.rendezvous(net.flat_params, group)
+        hg = symm.rendezvous(net.flat_grads, group)
+        hf = symm.rendezvous(self.flags, group)
+        if int(hp.buffer_ptrs[dp.rank]) != net.flat_params.data_ptr() or int(hg.buffer_ptrs[dp.rank]) != net.flat_grads.data_ptr():
+            raise _lib.SaganError("symmetric-memory buffer pointer does not match the tensor (storage offset?)")
+        self.peers = _lib.DpPeers()
+        for q in range(dp.world):
+            self.peers.grads[q] = int(hg.buffer_ptrs[q])
+            self.peers.params[q] = int(hp.buffer_ptrs[q])
+            self.peers.flags[q] = int(hf.buffer_ptrs[q])
+        self._handles = (hp, hg, hf)
+        self.n = n
+        self.v_shard = torch.zeros(n // dp.world, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._C = C
+        torch.cuda.synchronize()
+        dist.barrier(group=dp.pg)          # every replica's flag pad is zeroed before the first kernel signals
+
+    def step(self):
+        from . import _lib
+        _lib.check(_lib.load().sagan_dp_sum_adam(self._C.byref(self.peers), self.dp.rank, self.dp.world, self.n,
+                                                 self.v_shard.data_ptr(), self.opt.hyper.data_ptr(),
+                                                 self.epoch.data_ptr(), self.status.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "sagan_dp_sum_adam")
+
+    def check(self):
+        """Raises if a peer never arrived at a barrier (synchronises)."""
+        if int(self.status.item()) != 0:
+            from . import _lib
+            raise _lib.SaganError("sagan_dp_sum_adam: a replica did not reach the exchange barrier (timed out)")
+
+
+def symmetric_allocator():
+    """Allocator for nets.set_flat_allocator: zeroed symmetric-memory buffers (peer-addressable over NVLink)."""
+    import torch.distributed._symmetric_memory as symm
+
+    def alloc(n, device):
+        t = symm.empty(n, dtype=torch.float32, device=device)
+        t.zero_()
+        return t
+    return alloc

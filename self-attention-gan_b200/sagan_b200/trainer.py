@@ -18,7 +18,7 @@ import torch
 from . import functional as F
 from . import nets
 from ._lib import MATH_FP32_STRICT  # noqa: F401
-from .parallel import ReplicaGradientSum
+from .parallel import PeerAdam, ReplicaGradientSum, symmetric_allocator
 
 ADAM_B1, ADAM_B2, ADAM_EPS = 0.0, 0.999, 1e-7      # main.py:119-120 (Keras defaults, beta_1 = 0)
 
@@ -49,9 +49,10 @@ class FlatAdam:
 
 
 class Trainer:
-    def __init__(self, config, global_batch_size=None, steps_per_epoch=1000, process_group=None, seed=0):
+    def __init__(self, config, global_batch_size=None, steps_per_epoch=1000, process_group=None, seed=0, dp_mode="p2p"):
         """config: the reference's dict (example_configs/*.py).  process_group: torch.distributed group for the
-        data-parallel gradient sum (None = single replica)."""
+        data-parallel gradient sum (None = single replica / default group).  dp_mode: "p2p" = the fused NVLink
+        peer-memory exchange + Adam kernel (parallel.PeerAdam), "nccl" = NCCL all-reduce followed by Adam."""
         self.config = dict(config)
         cfg = self.config
         self.B = cfg["batch_size"]
@@ -61,6 +62,9 @@ class Trainer:
         self.global_batch = global_batch_size or self.dp.global_batch(self.B)
         self.device = torch.device("cuda", torch.cuda.current_device())
         torch.manual_seed(seed)
+        self.dp_mode = dp_mode if self.world > 1 else "none"
+        if self.dp_mode == "p2p":
+            nets.set_flat_allocator(symmetric_allocator())
         self.G = nets.get_generator(cfg)
         self.D = nets.get_discriminator(cfg)
         with torch.no_grad():   # build pass (Keras `model.build`, main.py:134-135)
@@ -73,6 +77,11 @@ class Trainer:
         ur = cfg.get("update_ratio", 1)
         self.opt_G = FlatAdam(self.G, cfg["lr_g"], steps_per_epoch, cfg["decay_rate"])          # main.py:111-114
         self.opt_D = FlatAdam(self.D, cfg["lr_d"], steps_per_epoch * ur, cfg["decay_rate"])     # main.py:115-118
+        nets.set_flat_allocator(None)
+        self.peer_G = self.peer_D = None
+        if self.dp_mode == "p2p":
+            self.peer_G = PeerAdam(self.G, self.opt_G, self.dp)
+            self.peer_D = PeerAdam(self.D, self.opt_D, self.dp)
         self.loss_sums = torch.zeros(2, device=self.device)     # [sum L_D (over update_ratio), sum L_G]
         self.graph = None
         self._static = {}
@@ -90,8 +99,11 @@ class Trainer:
         d_fake = D([fake, fake_labels], training=True)                      # main.py:182
         g_real, g_fake = F.hinge_d_grads(d_real, d_fake, self.global_batch, self.loss_sums[0:1])   # main.py:183-184
         torch.autograd.backward([d_real, d_fake], [g_real, g_fake])         # main.py:188-189
-        self._allreduce(D.flat_grads)                                       # main.py:190 (replica SUM)
-        self.opt_D.apply()
+        if self.peer_D is not None:
+            self.peer_D.step()                                              # main.py:190: replica SUM + Adam, one kernel
+        else:
+            self._allreduce(D.flat_grads)                                   # main.py:190 (replica SUM)
+            self.opt_D.apply()
 
     def _g_phase(self, noise, fake_labels):
         G, D = self.G, self.D
@@ -106,8 +118,11 @@ class Trainer:
         finally:
             for p in D.parameters():
                 p.requires_grad_(True)
-        self._allreduce(G.flat_grads)                                       # main.py:205 (replica SUM)
-        self.opt_G.apply()
+        if self.peer_G is not None:
+            self.peer_G.step()                                              # main.py:205
+        else:
+            self._allreduce(G.flat_grads)                                   # main.py:205 (replica SUM)
+            self.opt_G.apply()
 
     def _step_body(self, images, labels, noises_d, noise_g, fake_labels_d, fake_labels_g):
         cfg = self.config
