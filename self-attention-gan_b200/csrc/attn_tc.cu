@@ -33,7 +33,9 @@ using namespace tc;
 constexpr float TC_LOG2E = 1.4426950408889634f;
 constexpr float TC_LN2 = 0.6931471805599453f;
 constexpr int TC_THREADS = 192;
-constexpr int QK_COLS = 64;   // Q / K rows are padded to 64 bf16 = one 128-byte swizzle span
+// Q / K rows: 16 bf16 (32 B, SWIZZLE_32B tiles) when the split logits fit one MMA K step (C <= 32: 3 d <= 12),
+// otherwise 64 bf16 (128 B, SWIZZLE_128B)
+__host__ __device__ constexpr int qk_cols(int C) { return C <= 32 ? 16 : 64; }
 
 // ------------------------------------------------------------------------------------ host: tensor maps
 PFN_encodeTiled get_encode_tiled() {
@@ -49,7 +51,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                      uint32_t box_rows, uint32_t box_cols) {
+                      uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_err("cuTensorMapEncodeTiled is not available from this driver");
@@ -60,7 +62,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_err("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu stride=%llu box=%ux%u)", (int)r,
@@ -120,8 +123,8 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
     q[j] = a_hi; q[D + j] = a - a_hi; q[2 * D + j] = a_hi;
     k[j] = k_hi; k[D + j] = k_hi;     k[2 * D + j] = kk - k_hi;
   }
-  uint4* qd = reinterpret_cast<uint4*>(Qb + tp * QK_COLS);
-  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * QK_COLS);
+  uint4* qd = reinterpret_cast<uint4*>(Qb + tp * qk_cols(C));
+  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * qk_cols(C));
 #pragma unroll
   for (int g = 0; g < KQ / 8; ++g) {
     qd[g] = make_uint4(pack_bf16x2(q[g * 8 + 0], q[g * 8 + 1]), pack_bf16x2(q[g * 8 + 2], q[g * 8 + 3]),
@@ -150,8 +153,9 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
 // ------------------------------------------------------------------------------------ flash forward
 template <int DVP, int NS, int NP, int CEPI>
 struct FwdSmem {
-  static constexpr int Q_BYTES = 128 * 128;
-  static constexpr int K_BYTES = 128 * 128;
+  static constexpr int QKB = qk_cols(CEPI) * 2;       // bytes per Q / K row
+  static constexpr int Q_BYTES = 128 * QKB;
+  static constexpr int K_BYTES = 128 * QKB;
   static constexpr int V_BYTES = 2 * DVP * 128;      // two 64-key sub-tiles of [DVP rows][128 B]
   static constexpr int P_BYTES = 2 * 128 * 128;      // two 64-key sub-tiles of [128 rows][128 B]
   static constexpr int OFF_Q = 0;
@@ -229,12 +233,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, DVP);
-      const uint64_t descQ = make_desc_sw128(smem_u32(sQ));
+      const uint64_t descQ = L::QKB == 32 ? make_desc_sw32(smem_u32(sQ)) : make_desc_sw128(smem_u32(sQ));
       auto issue_qk = [&](int j) {
         const int s = j & 1;
         mbar_wait(barKV + s, (j >> 1) & 1);
         tc_fence_after();
-        const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
+        const uint64_t descK = L::QKB == 32 ? make_desc_sw32(smem_u32(sK + s * L::K_BYTES)) : make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
         const uint32_t d = tmem_base + (uint32_t)((j % NS) * 128);
         for (int ks = 0; ks < kq_steps; ++ks) mma_bf16_ss(d, descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
         mma_commit(barS + (j % NS));
@@ -421,8 +425,8 @@ static TcLayout tc_layout(int B, int N, int C) {
   const size_t T = (size_t)B * t.Npad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
-  t.off_q = take(T * QK_COLS * 2);
-  t.off_k = take(T * QK_COLS * 2);
+  t.off_q = take(T * qk_cols(C) * 2);
+  t.off_k = take(T * qk_cols(C) * 2);
   t.off_v = take((size_t)B * t.DVP * t.Npad * 2);
   t.total = o + 1024;
   return t;
@@ -480,8 +484,9 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
   SAGAN_LAUNCH_CHECK();
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tq, Qb, (uint64_t)Tp, QK_COLS, QK_COLS * 2, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tp, QK_COLS, QK_COLS * 2, 128))) return rc;
+  const int qkc = qk_cols(C);
+  if ((rc = make_tmap_bf16_2d(&tq, Qb, (uint64_t)Tp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Npad, (uint64_t)t.Npad * 2, (uint32_t)t.DVP))) return rc;
   const int dv = C / 2;
   switch (C) {

@@ -103,6 +103,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major operand in the 32-byte-swizzle canonical layout: rows of 32 B (16 bf16 = exactly one MMA K step), groups of
+// 8 rows = 256 B atoms (what TMA SWIZZLE_32B writes).  Used for the logit operands at d <= 5, where a 128-byte row
+// would be 75 % padding that every CTA re-reads from L2.  Layout type 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // Same tile read as an MN-major operand (M/N contiguous): the tile is [K rows][64 MN elements = 128 B] per sub-tile,
 // 8 K-rows = 1024 B swizzle atom.  LBO = byte distance between 64-element MN atoms, SBO = between 8-row K groups.
 __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -213,6 +225,6 @@ PFN_encodeTiled get_encode_tiled();
 
 // 2D bf16 tensor [rows][cols] (cols contiguous), box [box_rows][64 cols = 128 B], SWIZZLE_128B
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                      uint32_t box_rows, uint32_t box_cols = 64);
+                      uint32_t box_rows, uint32_t box_cols = 64, int swizzle_bytes = 128);
 
 }  // namespace sagan
