@@ -50,8 +50,15 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   constexpr bool SPLIT_DA = DV <= 16;                // dA^T rows [hi | lo] for the dV GEMM
   constexpr int DVP = SPLIT_DA ? (2 * DV < 16 ? 16 : 2 * DV) : DV;
   constexpr int KQ = ((3 * D + 15) / 16) * 16;
-  constexpr int KV = SPLIT3 ? ((3 * DV + 15) / 16) * 16 : 2 * DV;
+  // FOLD (C <= 32): the per-query shift M_i of the logits, the mask of padded keys and the row term D_i are folded
+  // into spare K columns of the two score-shaped MMAs, which then deliver S - M_i and dP - D_i directly:
+  //   Q row gets [-M_hi, -16384, -M_lo] against K row [1, key padded ? 1 : 0, 1]     (all bf16-exact)
+  //   dA row gets [-D_hi, -D_lo]        against V row [1, 1]
+  // -> one exp2 and one multiply per score are left on the CUDA cores (no subtractions, no mask select, no row vectors)
+  constexpr bool FOLD = SPLIT3;
+  constexpr int KV = SPLIT3 ? ((3 * DV + 2 + 15) / 16) * 16 : 2 * DV;
   static_assert(KV <= TB_COLS, "dP operand row must fit one 128-byte swizzle span");
+  static_assert(!FOLD || 3 * D + 3 <= KQ, "no spare logit columns for the folded shift");
   __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
   __shared__ __align__(16) float sWo[DV * C];
   for (int i = threadIdx.x; i < C * D; i += 128) { sWq[i] = Wq[i]; sWk[i] = Wk[i]; }
@@ -72,6 +79,8 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
     dy[c] = g.x; dy[c + 1] = g.y; dy[c + 2] = g.z; dy[c + 3] = g.w;
   }
+  const float l2 = valid ? lse[t] * TB_LOG2E : 0.f;
+  const float Mi = ceilf(l2);
   // ---- theta / phi: split-bf16 rows for the logits, plain hi/lo transposed rows for the dK / dQ GEMMs
   float q[KQ], k[KQ];
 #pragma unroll
@@ -97,6 +106,13 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     q[j] = a_hi; q[D + j] = as - a_hi; q[2 * D + j] = a_hi;
     k[j] = k_hi; k[D + j] = k_hi;      k[2 * D + j] = kk - k_hi;
   }
+  if (FOLD) {
+    const float mq = valid ? Mi : 16384.f;
+    const float m_hi = __bfloat162float(__float2bfloat16_rn(mq));
+    q[3 * D] = -m_hi;          k[3 * D] = 1.f;
+    q[3 * D + 1] = -16384.f;   k[3 * D + 1] = valid ? 0.f : 1.f;
+    q[3 * D + 2] = -(mq - m_hi); k[3 * D + 2] = 1.f;
+  }
 #pragma unroll
   for (int j = D; j < 8; ++j) {      // rows [hi (0..7) | lo (8..15)]: unused rows are zero
     Qt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
@@ -114,8 +130,6 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
                        pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
   }
   // ---- g (values) and dA' = f gamma dY Wo^T, D' = dA' . A, with f = 2^(M - lse') the normaliser of P' (see top)
-  const float l2 = valid ? lse[t] * TB_LOG2E : 0.f;
-  const float Mi = ceilf(l2);
   const float gm = *gamma * exp2f(Mi - l2);
   float v[KV], da[KV];
 #pragma unroll
@@ -149,6 +163,11 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     // transposed dA rows for dV = P^T dA: [hi | lo] when they fit
     dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(g);
     if (SPLIT_DA) dAt[((long long)b * DVP + DV + j) * Npad + n] = __float2bfloat16_rn(g - gh);
+  }
+  if (FOLD) {
+    const float d_hi = __bfloat162float(__float2bfloat16_rn(dd));
+    v[3 * DV] = 1.f;      da[3 * DV] = -d_hi;
+    v[3 * DV + 1] = 1.f;  da[3 * DV + 1] = -(dd - d_hi);
   }
   uint4* vd = reinterpret_cast<uint4*>(Vb + tp * TB_COLS);
   uint4* ad = reinterpret_cast<uint4*>(dAb + tp * TB_COLS);
@@ -382,24 +401,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t pp[16], hi[16], lo[16];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8);
-        const float4 l1 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8 + 4);
-        const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8);
-        const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8 + 4);
-        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const float ds_[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ds_[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (!SPLIT_DA) {
+          const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8);
+          const float4 l1 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8 + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8 + 4);
+          ls[0] = l0.x; ls[1] = l0.y; ls[2] = l0.z; ls[3] = l0.w; ls[4] = l1.x; ls[5] = l1.y; ls[6] = l1.z; ls[7] = l1.w;
+          ds_[0] = d0.x; ds_[1] = d0.y; ds_[2] = d0.z; ds_[3] = d0.w; ds_[4] = d1.x; ds_[5] = d1.y; ds_[6] = d1.z; ds_[7] = d1.w;
+        }
         float p[8], g_[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
-          p[e] = key_ok ? pe : 0.f;
+          if (SPLIT_DA) {   // folded operands: the MMA delivered S - M_i (padded keys at -16384)
+            p[e] = ex2_approx(__uint_as_float(rs[g * 8 + e]));
+          } else {
+            const float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
+            p[e] = key_ok ? pe : 0.f;
+          }
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t pk = pack_bf16x2(p[2 * e], p[2 * e + 1]);   // P' = bf16(exp2(S - M)): the weights the forward used
           pp[g * 4 + e] = pk;
-          g_[2 * e] = __uint_as_float(pk << 16) * (__uint_as_float(rp[g * 8 + 2 * e]) - ds_[2 * e]);
-          g_[2 * e + 1] = __uint_as_float(pk & 0xffff0000u) * (__uint_as_float(rp[g * 8 + 2 * e + 1]) - ds_[2 * e + 1]);
+          const float dp0 = __uint_as_float(rp[g * 8 + 2 * e]), dp1 = __uint_as_float(rp[g * 8 + 2 * e + 1]);
+          g_[2 * e] = __uint_as_float(pk << 16) * (SPLIT_DA ? dp0 : dp0 - ds_[2 * e]);            // folded: dP - D_i
+          g_[2 * e + 1] = __uint_as_float(pk & 0xffff0000u) * (SPLIT_DA ? dp1 : dp1 - ds_[2 * e + 1]);
         }
         // dS^T = hi + lo (two bf16 terms): sum_j dS_ij = 0, so the theta / phi gradients cancel and need the extra bits
 #pragma unroll
@@ -501,7 +528,7 @@ static TbLayout tb_layout(int B, int N, int C) {
   t.Npad = (N + 127) / 128 * 128;
   t.DVP = C == 16 ? 16 : 32;                              // C <= 32: [dA_hi | dA_lo] rows; C = 64: dA rows unsplit
   t.kq_steps = (3 * d + 15) / 16;
-  t.kv_steps = dv <= 16 ? (3 * dv + 15) / 16 : (2 * dv) / 16;   // split-bf16 dP contraction (see the prep kernel)
+  t.kv_steps = dv <= 16 ? (3 * dv + 2 + 15) / 16 : (2 * dv) / 16;   // split-bf16 dP contraction + folded D columns
   const size_t T = (size_t)B * t.Npad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
