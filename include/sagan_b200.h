@@ -96,6 +96,22 @@ int sagan_sn_backward(const float* dW_bar, const float* W_bar, const float* u, c
                       const float* sigma, float factor, float* dW, int rows, int cols,
                       void* ws, size_t ws_bytes, sagan_stream_t stream);
 
+/* The same for up to 16 kernels (all spectrally-normalised kernels of one network) in two launches.
+ * accumulate != 0: dW += ... (gradient buckets that collect several backward passes, sagan/main.py:181-189).
+ * ws: >= 16 * 64 floats. */
+typedef struct sagan_sn_bwd_desc {
+  const float* dW_bar;
+  const float* W_bar;
+  const float* u;
+  const float* v;
+  const float* sigma;
+  float* dW;
+  float factor;      /* 0 = none */
+  int32_t rows, cols;
+} sagan_sn_bwd_desc;
+int sagan_sn_backward_multi(const sagan_sn_bwd_desc* descs_host, int n, int accumulate, void* ws, size_t ws_bytes,
+                            sagan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Self-attention block.  Replaces Attention_Layer.call, layers.py:93-120 (paper form):
  *   theta = X Wq + bq, phi = X Wk + bk, g = X Wv + bv, P = softmax(theta phi^T), A = P g,

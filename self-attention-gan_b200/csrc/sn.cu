@@ -445,9 +445,90 @@ sn_bwd_apply_kernel(const float* __restrict__ dWbar, const float* __restrict__ u
   }
 }
 
+// ---- multi-tensor backward: every spectrally-normalised kernel of a network in two launches
+constexpr int SNB_MAX_MATS = 16;
+constexpr int SNB_PARTS = 64;            // partial sums per matrix
+struct SnBwdTab {
+  const float* dWbar[SNB_MAX_MATS];
+  const float* Wbar[SNB_MAX_MATS];
+  const float* u[SNB_MAX_MATS];
+  const float* v[SNB_MAX_MATS];
+  const float* sigma[SNB_MAX_MATS];
+  float* dW[SNB_MAX_MATS];
+  float factor[SNB_MAX_MATS];
+  int R[SNB_MAX_MATS], K[SNB_MAX_MATS];
+  int n;
+};
+
+// part[m][SNB_PARTS]: fixed-order partial sums of sum(dWbar * Wbar); grid (SNB_PARTS, n)
+__global__ void __launch_bounds__(SNB_THREADS)
+sn_bwd_dot_multi_kernel(const SnBwdTab t, float* __restrict__ part) {
+  __shared__ float red[32];
+  const int m = blockIdx.y;
+  const long long n = (long long)t.R[m] * t.K[m];
+  const float* a = t.dWbar[m];
+  const float* b = t.Wbar[m];
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * SNB_THREADS;
+  for (long long i = (long long)blockIdx.x * SNB_THREADS + threadIdx.x; i < n; i += stride) acc = fmaf(a[i], b[i], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[m * SNB_PARTS + blockIdx.x] = acc;
+}
+
+// dW (+)= (dWbar - c u v^T / factor) / sigma; grid (blocks, n)
+__global__ void __launch_bounds__(SNB_THREADS)
+sn_bwd_apply_multi_kernel(const SnBwdTab t, const float* __restrict__ part, int accumulate) {
+  __shared__ float red[32];
+  const int m = blockIdx.y;
+  float c = 0.f;
+  for (int i = threadIdx.x; i < SNB_PARTS; i += SNB_THREADS) c += part[m * SNB_PARTS + i];
+  c = block_sum(c, red);
+  const float sg = *t.sigma[m];
+  const float cf = (t.factor[m] != 0.f) ? c / t.factor[m] : c;
+  const int K = t.K[m];
+  const long long n = (long long)t.R[m] * K;
+  const float* dWbar = t.dWbar[m];
+  const float* u = t.u[m];
+  const float* v = t.v[m];
+  float* dW = t.dW[m];
+  const long long stride = (long long)gridDim.x * SNB_THREADS;
+  for (long long i = (long long)blockIdx.x * SNB_THREADS + threadIdx.x; i < n; i += stride) {
+    const int r = (int)(i / K), k = (int)(i - (long long)r * K);
+    const float g = (dWbar[i] - cf * u[r] * v[k]) / sg;
+    dW[i] = accumulate ? dW[i] + g : g;
+  }
+}
+
 }  // namespace sagan
 
 using namespace sagan;
+
+extern "C" int sagan_sn_backward_multi(const sagan_sn_bwd_desc* d, int n, int accumulate, void* ws, size_t ws_bytes,
+                                       sagan_stream_t stream) {
+  SAGAN_REQUIRE(d && ws, "sagan_sn_backward_multi: null pointer");
+  SAGAN_REQUIRE(n >= 1 && n <= SNB_MAX_MATS, "sagan_sn_backward_multi: n=%d outside [1,%d]", n, SNB_MAX_MATS);
+  if (ws_bytes < (size_t)SNB_MAX_MATS * SNB_PARTS * sizeof(float)) {
+    set_err("sagan_sn_backward_multi: workspace %zu < %zu bytes", ws_bytes, (size_t)SNB_MAX_MATS * SNB_PARTS * sizeof(float));
+    return SAGAN_EWORKSPACE;
+  }
+  SnBwdTab t{};
+  t.n = n;
+  long long biggest = 0;
+  for (int i = 0; i < n; ++i) {
+    SAGAN_REQUIRE(d[i].dW_bar && d[i].W_bar && d[i].u && d[i].v && d[i].sigma && d[i].dW && d[i].rows >= 1 && d[i].cols >= 1,
+                  "sagan_sn_backward_multi: bad descriptor %d", i);
+    t.dWbar[i] = d[i].dW_bar; t.Wbar[i] = d[i].W_bar; t.u[i] = d[i].u; t.v[i] = d[i].v; t.sigma[i] = d[i].sigma;
+    t.dW[i] = d[i].dW; t.factor[i] = d[i].factor; t.R[i] = d[i].rows; t.K[i] = d[i].cols;
+    biggest = std::max(biggest, (long long)d[i].rows * d[i].cols);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  sn_bwd_dot_multi_kernel<<<dim3(SNB_PARTS, n), SNB_THREADS, 0, st>>>(t, (float*)ws);
+  SAGAN_LAUNCH_CHECK();
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(64, ceil_div<long long>(biggest, SNB_THREADS * 4)));
+  sn_bwd_apply_multi_kernel<<<dim3(blocks, n), SNB_THREADS, 0, st>>>(t, (const float*)ws, accumulate);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
 
 struct sagan_sn_plan {
   int n = 0;

@@ -31,6 +31,12 @@ class ConvGeom(C.Structure):
                 ("pad_l", C.c_int32)]
 
 
+class SnBwdDesc(C.Structure):
+    _fields_ = [("dW_bar", C.c_void_p), ("W_bar", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("sigma", C.c_void_p), ("dW", C.c_void_p), ("factor", C.c_float), ("rows", C.c_int32),
+                ("cols", C.c_int32)]
+
+
 class DpPeers(C.Structure):
     _fields_ = [("grads", C.c_void_p * 8), ("params", C.c_void_p * 8), ("flags", C.c_void_p * 8)]
 
@@ -49,6 +55,7 @@ SIGNATURES = {
     "sagan_sn_plan_phase_times": (_I, [_P, C.POINTER(C.c_float)]),
     "sagan_sn_backward_workspace_bytes": (_SZ, [_LL]),
     "sagan_sn_backward": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _P, _SZ, _P]),
+    "sagan_sn_backward_multi": (_I, [C.POINTER(SnBwdDesc), _I, _I, _P, _SZ, _P]),
     "sagan_attn_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "sagan_attn_fwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P, _SZ, _P]),
     "sagan_attn_bwd": (_I, [_P] * 23 + [_I, _I, _I, _I, _P, _SZ, _P]),

@@ -287,7 +287,7 @@ class SpectralNormGroup:
                                        C.byref(plan)), "sagan_sn_plan_create")
         self.plan = plan
         self.algorithmic_bytes = int(lib.sagan_sn_plan_algorithmic_bytes(plan))
-        self._bws = torch.empty(lib.sagan_sn_backward_workspace_bytes(0) // 4, device=dev, dtype=torch.float32)
+        self._bws = torch.empty(max(lib.sagan_sn_backward_workspace_bytes(0) // 4, 16 * 64), device=dev, dtype=torch.float32)
 
     def __del__(self):
         try:
@@ -351,20 +351,33 @@ class _SnGroupFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *dwbars):
+        """All kernels of the group in two launches (sagan_sn_backward_multi).  A kernel whose `.grad` is already
+        allocated (the networks' flat gradient bucket) is ACCUMULATED in place and autograd gets None for it, which
+        removes one elementwise add launch per kernel."""
         lib = _lib.load()
         g, snap = ctx.group, ctx.holder.t
-        grads = []
-        for i, dwb in enumerate(dwbars):
-            if dwb is None or not ctx.needs_input_grad[2 + i]:
-                grads.append(None)
-                continue
-            wbar, u, v, sigma = g.views(snap, i)
-            R, K = g.shapes[i]
-            dwb = dwb.contiguous()
-            dW = torch.empty_like(dwb)
-            check(lib.sagan_sn_backward(_ptr(dwb), _ptr(wbar), _ptr(u), _ptr(v), _ptr(sigma), g.factors[i], _ptr(dW),
-                                        R, K, _ptr(g._bws), g._bws.numel() * 4, _stream()), "sagan_sn_backward")
-            grads.append(dW)
+        todo = [i for i, dwb in enumerate(dwbars) if dwb is not None and ctx.needs_input_grad[2 + i]]
+        grads = [None] * len(dwbars)
+        keep = []
+        for mode in (1, 0):                       # 1: accumulate into existing .grad, 0: fresh output tensors
+            sel = [i for i in todo if (g.weights[i].grad is not None) == bool(mode)]
+            for a in range(0, len(sel), 16):
+                chunk = sel[a:a + 16]
+                descs = (_lib.SnBwdDesc * len(chunk))()
+                for j, i in enumerate(chunk):
+                    wbar, u, v, sigma = g.views(snap, i)
+                    R, K = g.shapes[i]
+                    dwb = dwbars[i].contiguous()
+                    keep.append(dwb)
+                    if mode:
+                        out = g.weights[i].grad
+                    else:
+                        out = torch.empty_like(dwb)
+                        grads[i] = out
+                    descs[j] = _lib.SnBwdDesc(_ptr(dwb), _ptr(wbar), _ptr(u), _ptr(v), _ptr(sigma), _ptr(out),
+                                              g.factors[i], R, K)
+                check(lib.sagan_sn_backward_multi(descs, len(chunk), mode, _ptr(g._bws), g._bws.numel() * 4, _stream()),
+                      "sagan_sn_backward_multi")
         return (None, None, *grads)
 
 

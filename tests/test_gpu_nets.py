@@ -162,15 +162,15 @@ def test_forward_and_gradients_bf16_tc_mode():
         snn.set_default_math_mode(MATH_FP32_STRICT)
     img, nd, ng = mg.step_inputs(cfg, 0)
     t64 = lambda a: torch.tensor(a, dtype=torch.float64)
-    dgr, dl = orc.d_grads(t64(img), t64(nd))
-    # the oracle's G phase must see the same D state as ours: evaluate it before any update (no optimiser step here)
-    ggr, gl = orc.g_grads(t64(ng))
-    # forward outputs of each network on its own: generated images, logits on real images
+    # forward outputs of each network on its own (generated images, logits on real images), from the INITIAL
+    # spectral-norm state on both sides
     from oracle import nets as onets
     with torch.no_grad():
         ref_img = onets.generator_forward(orc.G, dict(orc.G_sn), t64(nd), cfg, None, True, None)
         ref_logit = onets.discriminator_forward(orc.D, dict(orc.D_sn), t64(img), cfg, None, True)
-    import copy
+    dgr, dl = orc.d_grads(t64(img), t64(nd))
+    # the oracle's G phase must see the same D state as ours: evaluate it before any update (no optimiser step here)
+    ggr, gl = orc.g_grads(t64(ng))
     snap = (tr.G.sn_group.out.clone(), tr.D.sn_group.out.clone())
     with torch.no_grad():
         got_img = tr.G([cu(nd), None], training=True)
