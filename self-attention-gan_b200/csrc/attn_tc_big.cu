@@ -18,8 +18,13 @@
 //              next logits under the softmax of the current tile (two S buffers in TMEM); O += P_j V_j
 // TMEM: S0 [0,128) S1 [128,256) O [256, 256+dv) -> all 512 columns at dv = 256, one CTA per SM.
 // The O rescale is lazy (row max grows by > 2^32), so O stays in TMEM across key tiles.
+//
+// Measured per 128-key tile at dv = 256 (clock64 timeline, round 1): softmax thread ~3200 cycles (wait S 990, exp 1430,
+// P store 430), PV issue + completion ~1900 against a 1024-cycle MMA floor.  The SS-mode PV MMA reads P (4 KB) and V (8 KB)
+// from shared memory for every K step (96 B/clk) while TMA writes the next 80 KB tile and the softmax warps store P: the
+// kernel is shared-memory-bandwidth bound.  Next steps: P as the TMEM A operand (no P store / read), a 3-deep K ring
+// (S ready earlier), cluster multicast of K / V.
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -58,7 +63,7 @@ template <int DV>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, float* __restrict__ lse, float* __restrict__ A_saved,
-                    int N, int kq_steps, int dbg) {
+                    int N, int kq_steps) {
   using L = BigSmem<DV>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,7 +123,7 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(barKV + s, (j >> 1) & 1);
         tc_fence_after();
         const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
-        for (int ks = 0; ks < ((dbg & 4) ? 0 : kq_steps); ++ks)
+        for (int ks = 0; ks < kq_steps; ++ks)
           mma_bf16_ss(tmem_base + (uint32_t)(s * 128), descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
         mma_commit(barS + s);
       };
@@ -135,12 +140,6 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step
           const uint64_t a = descP + (uint64_t)((ks >> 2) * ((128 * 128) >> 4) + (ks & 3) * 2);
-          if (dbg & 2) continue;   // TIMING EXPERIMENT: no PV MMAs
-          if (dbg & 1) {   // TIMING EXPERIMENT ONLY (wrong results): same bytes read as a K-major B operand
-            const uint64_t bk = make_desc_sw128(vbase) + (uint64_t)((ks >> 2) * ((DV * 128) >> 4) + (ks & 3) * 2);
-            mma_bf16_ss(tmem_base + L::OCOL, a, bk, make_idesc_bf16(128, DV, 0, 0), (j > 0) || (ks > 0));
-            continue;
-          }
           const uint64_t bb = make_desc_sw128_mn(vbase + ks * 2048, 128 * 128, 1024);
           mma_bf16_ss(tmem_base + L::OCOL, a, bb, IDESC_O, (j > 0) || (ks > 0));
         }
@@ -198,11 +197,6 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ---- P = exp2(S - m) (logits are in log2 units: Q carries log2 e), packed to bf16 in registers
       uint32_t pk[64];
       float l0 = 0.f, l1 = 0.f;
-      if (dbg & 8) {   // TIMING EXPERIMENT: no exponentials
-#pragma unroll
-        for (int i = 0; i < 64; ++i) pk[i] = r[2 * i] ^ r[2 * i + 1];
-        l0 = 1.f;
-      } else
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const float p0 = ex2_approx(__uint_as_float(r[2 * i]) - m_used);
@@ -303,8 +297,7 @@ static int launch_big(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  static const int dbg = getenv("SAGAN_BIG_DEBUG") ? atoi(getenv("SAGAN_BIG_DEBUG")) : 0;
-  kern<<<dim3(N / 128, B), BG_THREADS, L::TOTAL, st>>>(tq, tk, tv, lse, A, N, kq_steps, dbg);
+  kern<<<dim3(N / 128, B), BG_THREADS, L::TOTAL, st>>>(tq, tk, tv, lse, A, N, kq_steps);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
