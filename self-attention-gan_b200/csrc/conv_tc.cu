@@ -1,4 +1,5 @@
-// Implicit-GEMM convolution on the 5th-gen tensor cores (BF16_TC math mode): forward, backward-data
+// Implicit-GEMM convolution on the 5th-gen tensor cores (BF16_TC math mode; FWD / DGRAD run kind::tf32 on the fp32
+// operands, WGRAD kind::f16 on bf16-converted operands -- see the TF32 note at the kernel): forward, backward-data
 // (= Conv2DTranspose forward) and backward-filter of the spectrally-normalised Conv2D / Conv2DTranspose /
 // Dense layers (/root/reference/sagan/models/generator.py:8-9,25,36, discriminator.py:8,35).
 //
@@ -57,20 +58,39 @@ __device__ __forceinline__ void st_chunk(uint8_t* dst, const float4& a, const fl
       make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
-template <int MODE, int NT>
+template <int MODE, int NT, bool TF32>
 struct ConvTcSmem {
   static constexpr int A_BYTES = 128 * 128;                                              // 16 KB either major
-  static constexpr int B_BYTES = MODE == TC_DGRAD ? NT * 128 : 8192 * ((NT + 63) / 64);  // K-major rows / MN-major sub-tiles
+  static constexpr int B_BYTES = (MODE == TC_DGRAD || TF32) ? NT * 128 : 8192 * ((NT + 63) / 64);  // K-major rows / MN-major sub-tiles
   static constexpr int STAGE = A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES);
   static constexpr int OFF_BAR = CT_STAGES * STAGE;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;
   static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
 };
 
-template <int MODE, int NT>
+// TF32 (FWD / DGRAD only): the operands stay fp32 in shared memory and the MMA is kind::tf32 (10 mantissa bits instead
+// of bf16's 7, K = 8 per instruction), K blocks of 32 elements, both operands K-major (FWD gathers the HWIO kernel
+// transposed).  Five bf16-operand layers in a row cost 6e-3 on G(z); tf32 keeps the model inside the 2e-3 tier at the
+// same shared-memory footprint, and the producers copy instead of converting.
+__host__ __device__ constexpr uint32_t make_idesc_tf32_conv(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss_conv(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+template <int MODE, int NT, bool TF32>
 __global__ void __launch_bounds__(CT_THREADS, 2)
 conv_tc_kernel(const ConvTcP p) {
-  using L = ConvTcSmem<MODE, NT>;
+  static_assert(!(TF32 && MODE == TC_WGRAD), "the tf32 variant covers FWD and DGRAD");
+  constexpr int KB = TF32 ? 32 : 64;      // K elements per block (128 bytes per row either way)
+  constexpr int CE = TF32 ? 4 : 8;        // elements per 16-byte chunk
+  using L = ConvTcSmem<MODE, NT, TF32>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -107,7 +127,7 @@ conv_tc_kernel(const ConvTcP p) {
   }
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
   if (m0 >= Mg || k_begin >= k_end) return;      // uniform per CTA (before any barrier / TMEM use)
-  const int nkb = (k_end - k_begin + 63) / 64;
+  const int nkb = (k_end - k_begin + KB - 1) / KB;
 
   if (tid == 0) {
     for (int i = 0; i < CT_STAGES; ++i) { mbar_init(full + i, 256); mbar_init(empty + i, 1); }
@@ -123,7 +143,8 @@ conv_tc_kernel(const ConvTcP p) {
   if (warp == 8) {
     // ================================================================ MMA issuer
     if (elect_one_sync()) {
-      constexpr uint32_t IDESC = make_idesc_bf16(128, NT, MODE == TC_WGRAD ? 1 : 0, MODE == TC_DGRAD ? 0 : 1);
+      constexpr uint32_t IDESC = TF32 ? make_idesc_tf32_conv(128, NT)
+                                      : make_idesc_bf16(128, NT, MODE == TC_WGRAD ? 1 : 0, MODE == TC_DGRAD ? 0 : 1);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % CT_STAGES;
         mbar_wait(full + s, (kb / CT_STAGES) & 1);
@@ -131,6 +152,11 @@ conv_tc_kernel(const ConvTcP p) {
         const uint32_t aA = smem_u32(smem + s * L::STAGE), aB = aA + L::A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
+          if (TF32) {     // 8 tf32 = 32 bytes of K per instruction, both operands K-major SW128
+            mma_tf32_ss_conv(tmem_base, make_desc_sw128(aA) + (uint64_t)(ks * 2), make_desc_sw128(aB) + (uint64_t)(ks * 2),
+                             IDESC, (kb > 0) || (ks > 0));
+            continue;
+          }
           uint64_t da, db;
           if (MODE == TC_WGRAD) da = make_desc_sw128_mn(aA + ks * 2048, 8192, 1024);
           else da = make_desc_sw128(aA) + (uint64_t)(ks * 2);
@@ -180,10 +206,10 @@ conv_tc_kernel(const ConvTcP p) {
       if (kb >= CT_STAGES) mbar_wait(empty + s, ((kb / CT_STAGES) - 1) & 1);
       uint8_t* sA = smem + s * L::STAGE;
       uint8_t* sB = sA + L::A_BYTES;
-      const int kbase = k_begin + kb * 64;
+      const int kbase = k_begin + kb * KB;
       // ------------------------------------------------ A tile
       if (MODE == TC_FWD || MODE == TC_DGRAD) {
-        const int k0 = kbase + a_chunk * 8;
+        const int k0 = kbase + a_chunk * CE;
         const int cch = MODE == TC_FWD ? g.Cin : g.Cout;          // channels per tap
         const int tap = k0 / cch, c0 = k0 - tap * cch;
         int dh, dw;
@@ -197,17 +223,20 @@ conv_tc_kernel(const ConvTcP p) {
               const int hi = a_h0[j] + dh, wi = a_w0[j] + dw;
               if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
                 const float* src = p.a_src + ((size_t)(a_base[j] * g.H + hi) * g.W + wi) * g.Cin + c0;
-                v0 = ld4(src); v1 = ld4(src + 4);
+                v0 = ld4(src);
+                if (!TF32) v1 = ld4(src + 4);
               }
             } else {
               const int ho = a_h0[j] - dh, wo = a_w0[j] - dw;
               if (ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo) {
                 const float* src = p.a_src + ((size_t)(a_base[j] * g.Ho + ho) * g.Wo + wo) * g.Cout + c0;
-                v0 = ld4(src); v1 = ld4(src + 4);
+                v0 = ld4(src);
+                if (!TF32) v1 = ld4(src + 4);
               }
             }
           }
-          st_chunk(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk), v0, v1);
+          if (TF32) *reinterpret_cast<float4*>(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk)) = v0;
+          else st_chunk(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk), v0, v1);
         }
       } else {
 #pragma unroll
@@ -232,21 +261,40 @@ conv_tc_kernel(const ConvTcP p) {
         }
       }
       // ------------------------------------------------ B tile
-      if (MODE == TC_DGRAD) {
+      if (TF32 && MODE == TC_FWD) {
+        // K-major rows n (NT), 8 chunks of 4 k: the HWIO kernel w[k][n] gathered transposed (4 strided scalar loads;
+        // the kernel is small and L2-resident)
+        constexpr int NCH = NT * 8;
+        for (int c = tid; c < NCH; c += 256) {
+          const int n = c >> 3, ch = c & 7;
+          const int k0 = kbase + ch * 4;
+          float4 v0 = z4;
+          if (n0 + n < Ng) {
+            const float* src = p.b_src + (size_t)k0 * g.Cout + n0 + n;
+            if (k0 + 0 < k_end) v0.x = src[0];
+            if (k0 + 1 < k_end) v0.y = src[g.Cout];
+            if (k0 + 2 < k_end) v0.z = src[2 * (size_t)g.Cout];
+            if (k0 + 3 < k_end) v0.w = src[3 * (size_t)g.Cout];
+          }
+          *reinterpret_cast<float4*>(sB + sw128_offset(n, ch)) = v0;
+        }
+      } else if (MODE == TC_DGRAD) {
         // K-major rows n (NT), 8 chunks of k: source w[(tap * Cin + n) * Cout + co0 ..]
         constexpr int NCH = NT * 8;
         for (int c = tid; c < NCH; c += 256) {
           const int n = c >> 3, ch = c & 7;
-          const int k0 = kbase + ch * 8;
+          const int k0 = kbase + ch * CE;
           float4 v0 = z4, v1 = z4;
           if (n0 + n < Ng && k0 < k_end) {
             const int tap = k0 / g.Cout, co0 = k0 - tap * g.Cout;
             const int th = tap / ntw, tw = tap - th * ntw;
             const int kh = rh + th * g.S, kw = rw + tw * g.S;
             const float* src = p.b_src + ((size_t)(kh * g.KW + kw) * g.Cin + n0 + n) * g.Cout + co0;
-            v0 = ld4(src); v1 = ld4(src + 4);
+            v0 = ld4(src);
+            if (!TF32) v1 = ld4(src + 4);
           }
-          st_chunk(sB + sw128_offset(n, ch), v0, v1);
+          if (TF32) *reinterpret_cast<float4*>(sB + sw128_offset(n, ch)) = v0;
+          else st_chunk(sB + sw128_offset(n, ch), v0, v1);
         }
       } else {
         // MN-major: 64 reduction rows, NT/8 chunks of n: source rows are contiguous in n (w[k][:] or dy[m][:])
@@ -379,10 +427,10 @@ conv_tc_kernel(const ConvTcP p) {
   }
 }
 
-template <int MODE, int NT>
+template <int MODE, int NT, bool TF32>
 static int launch_conv_tc(const ConvTcP& p, dim3 grid, cudaStream_t st) {
-  using L = ConvTcSmem<MODE, NT>;
-  auto kern = conv_tc_kernel<MODE, NT>;
+  using L = ConvTcSmem<MODE, NT, TF32>;
+  auto kern = conv_tc_kernel<MODE, NT, TF32>;
   static bool configured = false;
   if (!configured) {
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -393,12 +441,12 @@ static int launch_conv_tc(const ConvTcP& p, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-template <int MODE>
+template <int MODE, bool TF32 = false>
 static int dispatch_nt(const ConvTcP& p, int Ng, int gx, int gz, cudaStream_t st) {
-  if (Ng <= 16) return launch_conv_tc<MODE, 16>(p, dim3(gx, 1, gz), st);
-  if (Ng <= 32) return launch_conv_tc<MODE, 32>(p, dim3(gx, 1, gz), st);
-  if (Ng <= 64) return launch_conv_tc<MODE, 64>(p, dim3(gx, 1, gz), st);
-  return launch_conv_tc<MODE, 128>(p, dim3(gx, ceil_div(Ng, 128), gz), st);
+  if (Ng <= 16) return launch_conv_tc<MODE, 16, TF32>(p, dim3(gx, 1, gz), st);
+  if (Ng <= 32) return launch_conv_tc<MODE, 32, TF32>(p, dim3(gx, 1, gz), st);
+  if (Ng <= 64) return launch_conv_tc<MODE, 64, TF32>(p, dim3(gx, 1, gz), st);
+  return launch_conv_tc<MODE, 128, TF32>(p, dim3(gx, ceil_div(Ng, 128), gz), st);
 }
 
 static inline bool al16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
@@ -428,10 +476,10 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, con
   ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   const int gx = ceil_div(g.M, 128);
   p.k_splits = pick_k_splits(gx * ceil_div(g.Cout, 128), g.K);
-  if (p.k_splits == 1) return dispatch_nt<TC_FWD>(p, g.Cout, gx, 1, st);
+  if (p.k_splits == 1) return dispatch_nt<TC_FWD, true>(p, g.Cout, gx, 1, st);
   const long long n = (long long)g.M * g.Cout;
   SAGAN_CUDA(cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), st));
-  int rc = dispatch_nt<TC_FWD>(p, g.Cout, gx, p.k_splits, st);
+  int rc = dispatch_nt<TC_FWD, true>(p, g.Cout, gx, p.k_splits, st);
   if (rc) return rc;
   if (bias || act != SAGAN_ACT_NONE) {
     conv_tc_finish_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, st>>>(y, bias, n, g.Cout, act, slope);
@@ -470,7 +518,7 @@ int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaS
   const int Kc = ceil_div(g.KH, g.S) * ceil_div(g.KW, g.S) * g.Cout;      // reduction length of the largest class
   p.k_splits = pick_k_splits(gx * ceil_div(g.Cin, 128) * classes, Kc);
   if (p.k_splits > 1) SAGAN_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.B * g.H * g.W * g.Cin * sizeof(float), st));
-  return dispatch_nt<TC_DGRAD>(p, g.Cin, gx, classes * p.k_splits, st);
+  return dispatch_nt<TC_DGRAD, true>(p, g.Cin, gx, classes * p.k_splits, st);
 }
 
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st) {
