@@ -25,6 +25,7 @@
 // kernel is shared-memory-bandwidth bound.  Next steps: P as the TMEM A operand (no P store / read), a 3-deep K ring
 // (S ready earlier), cluster multicast of K / V.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -41,164 +42,217 @@ int gemm_tf32_residual(const float* x, const float* wt, const float* bias, const
 
 constexpr float BG_LOG2E = 1.4426950408889634f;
 constexpr float BG_LN2 = 0.6931471805599453f;
-constexpr int BG_THREADS = 192;
+#ifdef SAGAN_TIMELINE
+__device__ unsigned long long g_big_tl[32];
+#define TL_DECL unsigned long long tl_t0 = clock64(), tl_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TL_MARK(i) do { const unsigned long long t_ = clock64(); tl_acc[i] += t_ - tl_t0; tl_t0 = t_; } while (0)
+#define TL_DUMP(base, n) do { if (blockIdx.x == 0 && blockIdx.y == 0) for (int i_ = 0; i_ < (n); ++i_) g_big_tl[(base) + i_] = tl_acc[i_]; } while (0)
+#else
+#define TL_DECL
+#define TL_MARK(i)
+#define TL_DUMP(base, n)
+#endif
+constexpr int BG_THREADS = 320;   // 8 softmax warps + TMA producer warp + MMA issuer warp
 
-template <int DV>
+// NCTA = 2: a CTA pair (cluster of two adjacent 128-query tiles) runs every MMA with cta_group::2 (M = 256); each CTA
+// loads only HALF of every K tile (64 keys) and of every V tile (dv/2 value columns), which halves the L2 -> SM traffic
+// per FLOP and the shared-memory footprint per stage (4 stages instead of 2).
+template <int DV, int NCTA>
 struct BigSmem {
   static constexpr int Q_BYTES = 128 * 128;
-  static constexpr int K_BYTES = 128 * 128;
-  static constexpr int V_BYTES = (DV / 64) * 128 * 128;   // DV/64 slabs of [128 keys][64 values = 128 B]
-  static constexpr int P_BYTES = 2 * 128 * 128;           // two 64-key sub-tiles of [128 queries][128 B]
-  static constexpr int NP = DV <= 128 ? 2 : 1;            // P buffers
+  static constexpr int K_BYTES = (128 / NCTA) * 128;               // this CTA's keys of the tile, rows of 64 bf16
+  static constexpr int V_SLABS = DV / 64 / NCTA;                   // this CTA's slabs of [128 keys][64 values = 128 B]
+  static constexpr int V_BYTES = V_SLABS * 128 * 128;
+  static constexpr int NS = 2 * NCTA;                              // K / V stages
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
-  static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
-  static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
+  static constexpr int OFF_V = OFF_K + NS * K_BYTES;
+  static constexpr int OFF_X = OFF_V + NS * V_BYTES;               // row-max / row-sum exchange between the two halves
+  static constexpr int OFF_BAR = OFF_X + 2 * 2 * 128 * 4;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
   static constexpr int OCOL = 256;
+  static constexpr uint32_t STAGE_TX = NCTA * (K_BYTES + V_BYTES); // bytes landing per stage over the whole pair
+  static_assert(V_SLABS >= 1, "a CTA pair needs dv >= 128");
 };
 
-template <int DV>
+// CTA (or CTA pair) = one 128-query (256-query) tile of one sample, 10 warps per CTA:
+//   warps 0-3 / 4-7  softmax halves: thread <-> TMEM lane <-> query row, key columns [0,64) / [64,128) of the tile.  The
+//              half row is pulled into registers with tcgen05.ld, the row max is exchanged with the other half through
+//              shared memory, and P = bf16(exp2(S - m)) goes BACK INTO TMEM over the logits it came from (tcgen05.st,
+//              two keys per 32-bit column): the PV MMA takes P as its TMEM A operand, so P never touches shared memory
+//   warp 8     TMA producer (K tile + V slabs per stage; V in its natural [token][dv] layout = MN-major B operand)
+//   warp 9     MMA issuer (leader CTA only): S_{j+1} = Q K_{j+1}^T is issued BEFORE the wait for P_j (two S buffers),
+//              then O += P_j V_j.  The tensor pipe executes in issue order, which is what makes the aliasing safe:
+//              S_{j+2} overwrites buffer j & 1 only after PV_j has read P_j from it.
+// TMEM: S0/P0 [0,128)  S1/P1 [128,256)  O [256, 256+dv).  The O rescale is lazy (row max grows by > 2^32).
+template <int DV, int NCTA>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, float* __restrict__ lse, float* __restrict__ A_saved,
                     int N, int kq_steps) {
-  using L = BigSmem<DV>;
+  using L = BigSmem<DV, NCTA>;
   extern __shared__ uint8_t smem_raw[];
+  // dynamic shared memory starts at the same window offset in both CTAs of a pair, so the aligned layout matches too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem + L::OFF_Q;
   uint8_t* sK = smem + L::OFF_K;
   uint8_t* sV = smem + L::OFF_V;
-  uint8_t* sP = smem + L::OFF_P;
+  float* sX = reinterpret_cast<float*>(smem + L::OFF_X);   // [2 buffers][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* barQ = bars + 0;
-  uint64_t* barKV = bars + 1;   // [2] K / V stage full (TMA)
-  uint64_t* barS = bars + 3;    // [2] S buffer ready (MMA commit)
-  uint64_t* barPV = bars + 5;   // [2] PV_j done: K / V stage and P buffer free, O up to date
-  uint64_t* barP = bars + 7;    // [2] 128 arrivals each: P_j is in shared memory (and S_j has been read); two
-                                //     barriers so that a warp running one tile ahead cannot complete tile j's phase
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* barQ = bars + 0;             // leader: Q tiles of the pair landed
+  uint64_t* barFull = bars + 1;          // [NS] leader: K / V stage landed in both CTAs
+  uint64_t* barEmpty = barFull + L::NS;  // [NS] every CTA: PV of the stage's tile done -> stage free
+  uint64_t* barS = barEmpty + L::NS;     // [2]  every CTA: S buffer ready
+  uint64_t* barP = barS + 2;             // [2]  leader: 8 * NCTA warp arrivals: P_j is in TMEM (and S_j has been read)
+  uint64_t* barO = barP + 2;             //      every CTA: one phase per key tile: PV_j done, O up to date
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(barO + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = NCTA == 1 ? 0u : cluster_ctarank();
+  const bool leader = rank == 0;
   const int b = blockIdx.y, qt = blockIdx.x;
   const int nt = N / 128;
 
   if (threadIdx.x == 0) {
     mbar_init(barQ, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(barKV + i, 1); mbar_init(barS + i, 1); mbar_init(barPV + i, 1); }
-    mbar_init(barP, 128); mbar_init(barP + 1, 128);
+    for (int i = 0; i < L::NS; ++i) { mbar_init(barFull + i, 1); mbar_init(barEmpty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(barS + i, 1); mbar_init(barP + i, 8 * NCTA); }
+    mbar_init(barO, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(tmem_ptr, 512);
+  if (warp == 9) tmem_alloc_g<NCTA>(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
-    // ================================================================ TMA producer
+  if (warp == 8) {
+    // ================================================================ TMA producer (both CTAs: own halves)
     if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-      mbar_expect_tx(barQ, L::Q_BYTES);
-      tma_load_2d(sQ, &tmQ, barQ, 0, b * N + qt * 128);
+      if (leader) mbar_expect_tx(barQ, NCTA * L::Q_BYTES);
+      tma_load_2d_g<NCTA>(sQ, &tmQ, barQ, 0, b * N + qt * 128);
       for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait(barPV + s, ((j - 2) >> 1) & 1);
-        mbar_expect_tx(barKV + s, L::K_BYTES + L::V_BYTES);
-        tma_load_2d(sK + s * L::K_BYTES, &tmK, barKV + s, 0, b * N + j * 128);
+        const int s = j % L::NS;
+        if (j >= L::NS) mbar_wait(barEmpty + s, ((j / L::NS) - 1) & 1);
+        if (leader) mbar_expect_tx(barFull + s, L::STAGE_TX);
+        tma_load_2d_g<NCTA>(sK + s * L::K_BYTES, &tmK, barFull + s, 0, b * N + j * 128 + (int)rank * (128 / NCTA));
 #pragma unroll
-        for (int sl = 0; sl < DV / 64; ++sl)
-          tma_load_2d(sV + s * L::V_BYTES + sl * (128 * 128), &tmV, barKV + s, sl * 64, b * N + j * 128);
+        for (int sl = 0; sl < L::V_SLABS; ++sl)
+          tma_load_2d_g<NCTA>(sV + s * L::V_BYTES + sl * (128 * 128), &tmV, barFull + s,
+                              ((int)rank * L::V_SLABS + sl) * 64, b * N + j * 128);
       }
     }
-  } else if (warp == 5) {
-    // ================================================================ MMA issuer
-    if (elect_one_sync()) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
-      constexpr uint32_t IDESC_O = make_idesc_bf16(128, DV, 0, /*b_mn_major=*/1);
+  } else if (warp == 9) {
+    // ================================================================ MMA issuer (leader CTA)
+    if (leader && elect_one_sync()) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128 * NCTA, 128);
+      constexpr uint32_t IDESC_O = make_idesc_bf16(128 * NCTA, DV, 0, /*b_mn_major=*/1);
       const uint64_t descQ = make_desc_sw128(smem_u32(sQ));
+      TL_DECL;
       auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(barKV + s, (j >> 1) & 1);
+        const int s = j % L::NS;
+        TL_MARK(0);
+        mbar_wait(barFull + s, (j / L::NS) & 1);
+        TL_MARK(1);
         tc_fence_after();
         const uint64_t descK = make_desc_sw128(smem_u32(sK + s * L::K_BYTES));
         for (int ks = 0; ks < kq_steps; ++ks)
-          mma_bf16_ss(tmem_base + (uint32_t)(s * 128), descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-        mma_commit(barS + s);
+          mma_bf16_ss_g<NCTA>(tmem_base + (uint32_t)((j & 1) * 128), descQ + (uint64_t)(ks * 2), descK + (uint64_t)(ks * 2),
+                              IDESC_S, ks > 0);
+        mma_commit_g<NCTA>(barS + (j & 1));
       };
       mbar_wait(barQ, 0);
       issue_qk(0);
       for (int j = 0; j < nt; ++j) {
-        // S buffer (j+1)&1 held S_{j-1}: every softmax thread read it before arriving on barP for tile j-1
         if (j + 1 < nt) issue_qk(j + 1);
+        TL_MARK(0);
         mbar_wait(barP + (j & 1), (j >> 1) & 1);
+        TL_MARK(2);
         tc_fence_after();
-        const int s = j & 1, pb = j % L::NP;
-        const uint64_t descP = make_desc_sw128(smem_u32(sP + pb * L::P_BYTES));
+        const int s = j % L::NS;
+        const uint32_t pbase = tmem_base + (uint32_t)((j & 1) * 128);
         const uint32_t vbase = smem_u32(sV + s * L::V_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step
-          const uint64_t a = descP + (uint64_t)((ks >> 2) * ((128 * 128) >> 4) + (ks & 3) * 2);
+        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step; P of keys [64 h, 64 h + 64) sits at columns 64 h + [0, 32)
+          const uint32_t a = pbase + (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8);
           const uint64_t bb = make_desc_sw128_mn(vbase + ks * 2048, 128 * 128, 1024);
-          mma_bf16_ss(tmem_base + L::OCOL, a, bb, IDESC_O, (j > 0) || (ks > 0));
+          mma_bf16_ts_g<NCTA>(tmem_base + L::OCOL, a, bb, IDESC_O, (j > 0) || (ks > 0));
         }
-        mma_commit(barPV + s);
+        mma_commit_g<NCTA>(barEmpty + s);
+        mma_commit_g<NCTA>(barO);
+#ifdef SAGAN_TIMELINE_PV
+        TL_MARK(0);
+        mbar_wait(barO, j & 1);
+        TL_MARK(3);
+#endif
       }
+      TL_MARK(0);
+      TL_DUMP(16, 4);
     }
   } else {
     // ================================================================ softmax warps
-    const int row = threadIdx.x;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int h = warp >> 2;                      // key-column half
+    const int row = threadIdx.x & 127;
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     float m_used = -INFINITY, l = 0.f;
+    TL_DECL;
 
     for (int j = 0; j < nt; ++j) {
+      TL_MARK(0);
       mbar_wait(barS + (j & 1), (j >> 1) & 1);
+      TL_MARK(1);
       tc_fence_after();
-      const uint32_t t_s = t_row + (uint32_t)((j & 1) * 128);
-      uint32_t r[128];
+      const uint32_t t_s = t_row + (uint32_t)((j & 1) * 128 + h * 64);
+      uint32_t r[64];
       tmem_ld32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
       tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-      tmem_ld32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
-      tmem_ld32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
       tmem_wait_ld();
+      TL_MARK(2);
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(r[i]));
         mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // both halves of a row must use the same shift: exchange the partial maxima (double-buffered, one barrier a tile)
+      float* xb = sX + (j & 1) * 256;
+      xb[h * 128 + row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xb[(h ^ 1) * 128 + row]);
+      TL_MARK(3);
       // ---- lazy rescale of the running accumulators
       // threshold 2^32: P and the fp32 accumulators share the 8-bit exponent range, so a stale max costs no precision;
       // the rescale (which has to wait for the tensor core and touch all of O) then only ever runs in the first tiles
       const bool need = mx > m_used + 32.0f;
       if (__any_sync(0xffffffffu, need)) {
         if (j > 0) {
-          mbar_wait(barPV + ((j - 1) & 1), ((j - 1) >> 1) & 1);     // every PV issued so far has completed
+          mbar_wait(barO, (j - 1) & 1);                    // every PV issued so far has completed
           tc_fence_after();
           const float scale = need ? exp2f(m_used - mx) : 1.0f;
           l *= scale;
 #pragma unroll
-          for (int c = 0; c < DV / 32; ++c) {
+          for (int c = 0; c < DV / 64; ++c) {                // this half's share of the O columns
             uint32_t o[32];
-            tmem_ld32(t_row + L::OCOL + c * 32, o);
+            tmem_ld32(t_row + L::OCOL + h * (DV / 2) + c * 32, o);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
-            tmem_st32(t_row + L::OCOL + c * 32, o);
+            tmem_st32(t_row + L::OCOL + h * (DV / 2) + c * 32, o);
           }
-          tmem_wait_st();
         }
         if (need) m_used = mx;
       }
-      // ---- P = exp2(S - m) (logits are in log2 units: Q carries log2 e), packed to bf16 in registers
-      uint32_t pk[64];
+      TL_MARK(4);
+      // ---- P = exp2(S - m) (logits are in log2 units: Q carries log2 e), packed to bf16, back into TMEM over S
+      uint32_t pk[32];
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 32; ++i) {
         const float p0 = ex2_approx(__uint_as_float(r[2 * i]) - m_used);
         const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) - m_used);
         l0 += p0;
@@ -206,42 +260,46 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         pk[i] = pack_bf16x2(p0, p1);
       }
       l += l0 + l1;
-      // ---- P buffer free?  (PV_{j-NP} has finished reading it) -- the exponentials above ran under that MMA
-      const int pb = j % L::NP;
-      if (j >= L::NP) mbar_wait(barPV + ((j - L::NP) & 1), ((j - L::NP) >> 1) & 1);
-      uint8_t* sPj = sP + pb * L::P_BYTES;
-#pragma unroll
-      for (int g = 0; g < 16; ++g)   // key columns [8g, 8g+8): sub-tile g/8, 16-byte chunk g%8
-        *reinterpret_cast<uint4*>(sPj + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7)) =
-            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
+      TL_MARK(5);
+      tmem_st32(t_s, pk);
+      tmem_wait_st();
+      TL_MARK(7);
       tc_fence_before();             // orders this thread's tcgen05.ld / st before the arrive
-      mbar_arrive(barP + (j & 1));
+      __syncwarp();
+      if (elect_one_sync()) mbar_arrive_leader(barP + (j & 1));
+      TL_MARK(6);
     }
+    if (threadIdx.x == 0) TL_DUMP(0, 8);
+    if (threadIdx.x == 128) TL_DUMP(8, 8);
 
     // ---- epilogue: A = O / l (fp32, saved for the backward and read by the output-conv GEMM), lse
-    mbar_wait(barPV + ((nt - 1) & 1), ((nt - 1) >> 1) & 1);
+    mbar_wait(barO, (nt - 1) & 1);
     tc_fence_after();
+    float* xb = sX + (nt & 1) * 256;
+    xb[h * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xb[(h ^ 1) * 128 + row];
     const long long grow = (long long)b * N + qt * 128 + row;
     const float inv = 1.0f / l;
 #pragma unroll
-    for (int c = 0; c < DV / 32; ++c) {
+    for (int c = 0; c < DV / 64; ++c) {
       uint32_t o[32];
-      tmem_ld32(t_row + L::OCOL + c * 32, o);
+      tmem_ld32(t_row + L::OCOL + h * (DV / 2) + c * 32, o);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; i += 4)
-        st4(A_saved + grow * DV + c * 32 + i,
+        st4(A_saved + grow * DV + h * (DV / 2) + c * 32 + i,
             make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
                         __uint_as_float(o[i + 3]) * inv));
     }
-    lse[grow] = (m_used + log2f(l)) * BG_LN2;
+    if (h == 0) lse[grow] = (m_used + log2f(l)) * BG_LN2;
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if constexpr (NCTA == 2) cluster_sync_all();     // no CTA of the pair retires while the other may still signal it
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_g<NCTA>(tmem_base, 512);
   }
 }
 
@@ -284,20 +342,38 @@ static BigLayout big_layout(int B, int N, int C) {
   return t;
 }
 
+#ifdef SAGAN_TIMELINE
+extern "C" int sagan_debug_big_timeline(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_big_tl, sizeof(g_big_tl));
+}
+#endif
+
 bool attn_tc_big_supported(int N, int C) { return (C == 128 || C == 256 || C == 512) && N % 128 == 0; }
 size_t attn_tc_big_workspace_bytes(int B, int N, int C) { return big_layout(B, N, C).total; }
 
-template <int DV>
+template <int DV, int NCTA>
 static int launch_big(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, float* lse, float* A, int B,
                       int N, int kq_steps, cudaStream_t st) {
-  using L = BigSmem<DV>;
-  auto kern = attn_fwd_big_kernel<DV>;
+  using L = BigSmem<DV, NCTA>;
+  auto kern = attn_fwd_big_kernel<DV, NCTA>;
   static bool configured = false;
   if (!configured) {
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<dim3(N / 128, B), BG_THREADS, L::TOTAL, st>>>(tq, tk, tv, lse, A, N, kq_steps);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(N / 128, B);
+  cfg.blockDim = dim3(BG_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SAGAN_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, lse, A, N, kq_steps));
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -334,13 +410,16 @@ int attn_tc_big_fwd(const float* X, const float* Wq, const float* bq, const floa
   if (rc) return rc;
   CUtensorMap tq, tk, tv;
   if ((rc = make_tmap_bf16_2d(&tq, Qb, (uint64_t)T, 64, 128, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)T, 64, 128, 128))) return rc;
+  // CTA pairs (cta_group::2) whenever a pair has two whole query tiles and each CTA at least one 64-value slab of V
+  static const bool force_single = getenv("SAGAN_ATTN_BIG_SINGLE_CTA") != nullptr;   // diagnostics only
+  const bool pair = dv >= 128 && (N / 128) % 2 == 0 && !force_single;
+  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)T, 64, 128, pair ? 64 : 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, Vb, (uint64_t)T, (uint64_t)dv, (uint64_t)dv * 2, 128, 64))) return rc;
   const int kq = d / 16;
   switch (dv) {
-    case 64: rc = launch_big<64>(tq, tk, tv, lse, A, B, N, kq, st); break;
-    case 128: rc = launch_big<128>(tq, tk, tv, lse, A, B, N, kq, st); break;
-    default: rc = launch_big<256>(tq, tk, tv, lse, A, B, N, kq, st); break;
+    case 64: rc = launch_big<64, 1>(tq, tk, tv, lse, A, B, N, kq, st); break;
+    case 128: rc = pair ? launch_big<128, 2>(tq, tk, tv, lse, A, B, N, kq, st) : launch_big<128, 1>(tq, tk, tv, lse, A, B, N, kq, st); break;
+    default: rc = pair ? launch_big<256, 2>(tq, tk, tv, lse, A, B, N, kq, st) : launch_big<256, 1>(tq, tk, tv, lse, A, B, N, kq, st); break;
   }
   if (rc) return rc;
   return gemm_tf32_residual(A, WoT, bo, X, gamma, Y, T, dv, C, st);

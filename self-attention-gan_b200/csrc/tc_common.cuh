@@ -193,6 +193,100 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// ------------------------------------------------------------------ CTA pairs (cta_group::2) and clusters
+// A pair of CTAs (cluster ranks 2p, 2p+1) runs ONE tcgen05.mma over both SMs: M = 256 (128 rows per CTA, each in its own
+// TMEM), and each CTA supplies half of the B operand's N extent from its own shared memory, so the pair reads every
+// B tile from L2 once instead of twice.  Only the even ("leader") CTA issues the MMAs; barrier addresses with the
+// peer bit (bit 24 of the shared::cluster window) cleared name the leader's copy of a barrier.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (a no-op redirection outside a cluster / in the leader itself)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+template <int NCTA>
+__device__ __forceinline__ void tmem_alloc_g(uint32_t* smem_out, uint32_t ncols) {
+  if constexpr (NCTA == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int NCTA>
+__device__ __forceinline__ void tmem_dealloc_g(uint32_t taddr, uint32_t ncols) {
+  if constexpr (NCTA == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER's barrier (each CTA of the pair loads its own half)
+template <int NCTA>
+__device__ __forceinline__ void tma_load_2d_g(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (NCTA == 1) {
+    tma_load_2d(smem_dst, m, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+// D[tmem] (+)= A[smem] * B[smem]^T over the CTA pair (M = 256) or one CTA
+template <int NCTA>
+__device__ __forceinline__ void mma_bf16_ss_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  if constexpr (NCTA == 1) {
+    mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+  }
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is a K-major bf16 tile in TMEM (lane = row, two K elements per 32-bit column)
+template <int NCTA>
+__device__ __forceinline__ void mma_bf16_ts_g(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  if constexpr (NCTA == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+  }
+}
+// completion of all MMAs issued so far -> one arrival on `bar` in EVERY CTA of the pair
+template <int NCTA>
+__device__ __forceinline__ void mma_commit_g(uint64_t* bar) {
+  if constexpr (NCTA == 1) {
+    mma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

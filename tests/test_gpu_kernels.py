@@ -374,7 +374,8 @@ def test_attention_tc_vs_strict_full_size(F, shape):
 
 
 # ---------------------------------------------------------------------------------------- attention, large C (sweep regime)
-@pytest.mark.parametrize("shape", [(2, 256, 128), (2, 384, 256), (1, 512, 512), (1, 128, 512)])
+@pytest.mark.parametrize("shape", [(2, 256, 128), (2, 384, 256), (1, 512, 512), (1, 128, 512), (2, 512, 256), (1, 1024, 512),
+                                   (2, 2048, 256)])
 def test_attention_tc_large_c_forward(F, shape):
     """BASELINE.json configs[4] regime (C = 128..512: d = 16..64, dv = 64..256): projection GEMM -> flash forward ->
     output-conv GEMM with the gamma residual, all on tcgen05, against the fp64 oracle.  Logits here are plain bf16
