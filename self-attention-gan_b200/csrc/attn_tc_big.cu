@@ -4,9 +4,9 @@
 //
 // Replaces Attention_Layer.call (/root/reference/layers.py:93-120) as four launches:
 //   1. gemm_tf32_qkv     X [T,C] x [Wtheta | Wphi | Wg] -> bf16 Q (pre-scaled by log2 e), K (rows of 64), V [T,dv]
-//                        (TMA-fed tcgen05 kind::tf32 GEMM, gemm_tf32.cu, projection epilogue; X is read once)
+//                        (TMA-fed tcgen05 kind::tf32 GEMM over CTA pairs, gemm_tc.cu, projection epilogue)
 //   2. attn_fwd_big      flash forward, this file
-//   3. gemm_tf32_residual Y = X + gamma (A Wo + bo)  (same GEMM core, residual epilogue)
+//   3. gemm_bf16_residual Y = X + gamma (A Wo + bo)  (same GEMM core on the bf16 copy of A, residual epilogue)
 //
 // attn_fwd_big: CTA = one 128-query tile of one sample, 6 warps:
 //   warps 0-3  softmax + epilogue: thread r <-> TMEM lane r <-> query row r; the whole S row (128 fp32) is pulled
@@ -34,11 +34,11 @@ namespace sagan {
 
 using namespace tc;
 
-// gemm_tf32.cu
+// gemm_tc.cu
 int gemm_tf32_qkv(const float* x, const float* wt, const float* bcat, __nv_bfloat16* q, __nv_bfloat16* k,
                   __nv_bfloat16* v, long long M, int K, int d, int dv, float q_scale, cudaStream_t st);
-int gemm_tf32_residual(const float* x, const float* wt, const float* bias, const float* res, const float* res_scale,
-                       float* y, long long M, int K, int N, cudaStream_t st);
+int gemm_bf16_residual(const __nv_bfloat16* a, const __nv_bfloat16* wt, const float* bias, const float* res,
+                       const float* res_scale, float* y, long long M, int K, int N, cudaStream_t st);
 
 constexpr float BG_LOG2E = 1.4426950408889634f;
 constexpr float BG_LN2 = 0.6931471805599453f;
@@ -89,7 +89,7 @@ template <int DV, int NCTA>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, float* __restrict__ lse, float* __restrict__ A_saved,
-                    int N, int kq_steps) {
+                    __nv_bfloat16* __restrict__ A_bf16, int N, int kq_steps) {
   using L = BigSmem<DV, NCTA>;
   extern __shared__ uint8_t smem_raw[];
   // dynamic shared memory starts at the same window offset in both CTAs of a pair, so the aligned layout matches too
@@ -287,10 +287,19 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld32(t_row + L::OCOL + h * (DV / 2) + c * 32, o);
       tmem_wait_ld();
 #pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * inv);
+#pragma unroll
       for (int i = 0; i < 32; i += 4)
         st4(A_saved + grow * DV + h * (DV / 2) + c * 32 + i,
-            make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
-                        __uint_as_float(o[i + 3]) * inv));
+            make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3])));
+      // bf16 copy: the A operand of the output-conv GEMM
+      uint4* ab = reinterpret_cast<uint4*>(A_bf16 + grow * DV + h * (DV / 2) + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        ab[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1])),
+                           pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3])),
+                           pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5])),
+                           pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7])));
     }
     if (h == 0) lse[grow] = (m_used + log2f(l)) * BG_LN2;
     tc_fence_before();
@@ -303,12 +312,12 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-// K-major (transposed) weight operands of the two GEMMs: Wt [2d+dv][C] = [Wq | Wk | Wv]^T, bcat, WoT [C][dv] = Wo^T
+// K-major (transposed) weight operands of the two GEMMs: Wt [2d+dv][C] = [Wq | Wk | Wv]^T (fp32), bcat, WoT [C][dv] = Wo^T (bf16)
 __global__ void attn_big_weights_kernel(const float* __restrict__ Wq, const float* __restrict__ bq,
                                         const float* __restrict__ Wk, const float* __restrict__ bk,
                                         const float* __restrict__ Wv, const float* __restrict__ bv,
                                         const float* __restrict__ Wo, float* __restrict__ Wt, float* __restrict__ bcat,
-                                        float* __restrict__ WoT, int C, int d, int dv) {
+                                        __nv_bfloat16* __restrict__ WoT, int C, int d, int dv) {
   const int NN = 2 * d + dv;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C * NN) {
@@ -317,13 +326,13 @@ __global__ void attn_big_weights_kernel(const float* __restrict__ Wq, const floa
   }
   if (i < C * dv) {
     const int c = i / dv, v = i - c * dv;
-    WoT[i] = Wo[v * C + c];
+    WoT[i] = __float2bfloat16_rn(Wo[v * C + c]);
   }
   if (i < NN) bcat[i] = i < d ? bq[i] : (i < 2 * d ? bk[i - d] : bv[i - 2 * d]);
 }
 
 struct BigLayout {
-  size_t off_w, off_b, off_wo, off_q, off_k, off_v, total;
+  size_t off_w, off_b, off_wo, off_q, off_k, off_v, off_ab, total;
 };
 
 static BigLayout big_layout(int B, int N, int C) {
@@ -334,10 +343,11 @@ static BigLayout big_layout(int B, int N, int C) {
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
   t.off_w = take((size_t)C * (2 * d + dv) * 4);
   t.off_b = take((size_t)(2 * d + dv) * 4);
-  t.off_wo = take((size_t)C * dv * 4);
+  t.off_wo = take((size_t)C * dv * 2);
   t.off_q = take(T * 64 * 2);
   t.off_k = take(T * 64 * 2);
   t.off_v = take(T * dv * 2);
+  t.off_ab = take(T * dv * 2);
   t.total = o + 1024;
   return t;
 }
@@ -352,8 +362,8 @@ bool attn_tc_big_supported(int N, int C) { return (C == 128 || C == 256 || C == 
 size_t attn_tc_big_workspace_bytes(int B, int N, int C) { return big_layout(B, N, C).total; }
 
 template <int DV, int NCTA>
-static int launch_big(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, float* lse, float* A, int B,
-                      int N, int kq_steps, cudaStream_t st) {
+static int launch_big(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, float* lse, float* A,
+                      __nv_bfloat16* Ab, int B, int N, int kq_steps, cudaStream_t st) {
   using L = BigSmem<DV, NCTA>;
   auto kern = attn_fwd_big_kernel<DV, NCTA>;
   static bool configured = false;
@@ -373,7 +383,7 @@ static int launch_big(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SAGAN_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, lse, A, N, kq_steps));
+  SAGAN_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, lse, A, Ab, N, kq_steps));
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -395,7 +405,8 @@ int attn_tc_big_fwd(const float* X, const float* Wq, const float* bq, const floa
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   float* Wt = reinterpret_cast<float*>(base + t.off_w);
   float* bcat = reinterpret_cast<float*>(base + t.off_b);
-  float* WoT = reinterpret_cast<float*>(base + t.off_wo);
+  __nv_bfloat16* WoT = reinterpret_cast<__nv_bfloat16*>(base + t.off_wo);
+  __nv_bfloat16* Ab = reinterpret_cast<__nv_bfloat16*>(base + t.off_ab);
   __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(base + t.off_q);
   __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(base + t.off_k);
   __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(base + t.off_v);
@@ -417,12 +428,12 @@ int attn_tc_big_fwd(const float* X, const float* Wq, const float* bq, const floa
   if ((rc = make_tmap_bf16_2d(&tv, Vb, (uint64_t)T, (uint64_t)dv, (uint64_t)dv * 2, 128, 64))) return rc;
   const int kq = d / 16;
   switch (dv) {
-    case 64: rc = launch_big<64, 1>(tq, tk, tv, lse, A, B, N, kq, st); break;
-    case 128: rc = pair ? launch_big<128, 2>(tq, tk, tv, lse, A, B, N, kq, st) : launch_big<128, 1>(tq, tk, tv, lse, A, B, N, kq, st); break;
-    default: rc = pair ? launch_big<256, 2>(tq, tk, tv, lse, A, B, N, kq, st) : launch_big<256, 1>(tq, tk, tv, lse, A, B, N, kq, st); break;
+    case 64: rc = launch_big<64, 1>(tq, tk, tv, lse, A, Ab, B, N, kq, st); break;
+    case 128: rc = pair ? launch_big<128, 2>(tq, tk, tv, lse, A, Ab, B, N, kq, st) : launch_big<128, 1>(tq, tk, tv, lse, A, Ab, B, N, kq, st); break;
+    default: rc = pair ? launch_big<256, 2>(tq, tk, tv, lse, A, Ab, B, N, kq, st) : launch_big<256, 1>(tq, tk, tv, lse, A, Ab, B, N, kq, st); break;
   }
   if (rc) return rc;
-  return gemm_tf32_residual(A, WoT, bo, X, gamma, Y, T, dv, C, st);
+  return gemm_bf16_residual(Ab, WoT, bo, X, gamma, Y, T, dv, C, st);
 }
 
 }  // namespace sagan
