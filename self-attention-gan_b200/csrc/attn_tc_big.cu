@@ -52,6 +52,16 @@ __device__ unsigned long long g_big_tl[32];
 #define TL_MARK(i)
 #define TL_DUMP(base, n)
 #endif
+// 2^x on the FMA pipe: round-to-nearest split x = n + f (magic-number add), cubic minimax of 2^f on [-0.5, 0.5]
+// (max relative error 7.5e-5, far below the bf16 rounding of P), n added into the exponent field
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;
+  const float f = x - (r - 12582912.0f);
+  const float p = fmaf(fmaf(fmaf(5.517132208e-02f, f, 2.426105440e-01f), f, 6.932609677e-01f), f, 9.999281168e-01f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 constexpr int BG_THREADS = 320;   // 8 softmax warps + TMA producer warp + MMA issuer warp
 
 // NCTA = 2: a CTA pair (cluster of two adjacent 128-query tiles) runs every MMA with cta_group::2 (M = 256); each CTA
@@ -210,6 +220,27 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
       tmem_wait_ld();
       TL_MARK(2);
+      // ---- P = exp2(S - m) with the shift m of the PREVIOUS tiles (logits are in log2 units: Q carries log2 e).  The
+      // shift only has to keep P inside the fp32 / bf16 exponent range, so the exponentials do not wait for this
+      // tile's row max; the max (computed alongside, exchanged with the other half of the row) is checked afterwards
+      // and only when it exceeds the shift by more than 2^32 -- in practice in the first tiles only -- are O and l
+      // rescaled (which has to wait for the tensor core and touch all of O) and this tile's P recomputed.
+      uint32_t pk[32];
+      float l0, l1;
+      auto exps = [&](float m) {
+        l0 = 0.f; l1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          // one exponential in five runs as a polynomial on the FMA pipe: the MUFU unit (16 ex2 / clk / SM) is the
+          // busiest pipe of this kernel
+          const float p0 = (i % 5 == 2) ? ex2_poly(__uint_as_float(r[2 * i]) - m) : ex2_approx(__uint_as_float(r[2 * i]) - m);
+          const float p1 = (i % 5 == 4) ? ex2_poly(__uint_as_float(r[2 * i + 1]) - m) : ex2_approx(__uint_as_float(r[2 * i + 1]) - m);
+          l0 += p0;
+          l1 += p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      };
+      if (j > 0) exps(m_used);
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
@@ -219,15 +250,13 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
       }
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      TL_MARK(5);
       // both halves of a row must use the same shift: exchange the partial maxima (double-buffered, one barrier a tile)
       float* xb = sX + (j & 1) * 256;
       xb[h * 128 + row] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, xb[(h ^ 1) * 128 + row]);
       TL_MARK(3);
-      // ---- lazy rescale of the running accumulators
-      // threshold 2^32: P and the fp32 accumulators share the 8-bit exponent range, so a stale max costs no precision;
-      // the rescale (which has to wait for the tensor core and touch all of O) then only ever runs in the first tiles
       const bool need = mx > m_used + 32.0f;
       if (__any_sync(0xffffffffu, need)) {
         if (j > 0) {
@@ -246,21 +275,10 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         if (need) m_used = mx;
-      }
-      TL_MARK(4);
-      // ---- P = exp2(S - m) (logits are in log2 units: Q carries log2 e), packed to bf16, back into TMEM over S
-      uint32_t pk[32];
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float p0 = ex2_approx(__uint_as_float(r[2 * i]) - m_used);
-        const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) - m_used);
-        l0 += p0;
-        l1 += p1;
-        pk[i] = pack_bf16x2(p0, p1);
+        if (need || j == 0) exps(m_used);                  // warp-uniform in the first tile; rare afterwards
       }
       l += l0 + l1;
-      TL_MARK(5);
+      TL_MARK(4);
       tmem_st32(t_s, pk);
       tmem_wait_st();
       TL_MARK(7);
@@ -281,25 +299,33 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     l += xb[(h ^ 1) * 128 + row];
     const long long grow = (long long)b * N + qt * 128 + row;
     const float inv = 1.0f / l;
-#pragma unroll
+    // TMEM hands each thread one ROW of O (32 columns at a time).  Every MMA of the pair has completed, so the K / V
+    // ring is dead: a per-warp transpose through it lets the warp store 4 rows x 128 contiguous bytes per instruction
+    // instead of 32 rows x 16 bytes.
+    const int lane = threadIdx.x & 31;
+    float* sT = reinterpret_cast<float*>(sK) + warp * (32 * 36);       // [32 rows][36]: conflict-free 16-byte accesses
+    const long long wrow0 = (long long)b * N + qt * 128 + (warp & 3) * 32;
+#pragma unroll 1
     for (int c = 0; c < DV / 64; ++c) {
       uint32_t o[32];
       tmem_ld32(t_row + L::OCOL + h * (DV / 2) + c * 32, o);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * inv);
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(sT + lane * 36 + q * 4) =
+            make_float4(__uint_as_float(o[4 * q]) * inv, __uint_as_float(o[4 * q + 1]) * inv,
+                        __uint_as_float(o[4 * q + 2]) * inv, __uint_as_float(o[4 * q + 3]) * inv);
+      __syncwarp();
+      const int col = h * (DV / 2) + c * 32 + (lane & 7) * 4;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        st4(A_saved + grow * DV + h * (DV / 2) + c * 32 + i,
-            make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3])));
-      // bf16 copy: the A operand of the output-conv GEMM
-      uint4* ab = reinterpret_cast<uint4*>(A_bf16 + grow * DV + h * (DV / 2) + c * 32);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        ab[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1])),
-                           pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3])),
-                           pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5])),
-                           pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7])));
+      for (int it = 0; it < 8; ++it) {          // 4 rows x (8 lanes x 4 columns) per pass
+        const int rr = it * 4 + (lane >> 3);
+        const float4 a = *reinterpret_cast<const float4*>(sT + rr * 36 + (lane & 7) * 4);
+        st4(A_saved + (wrow0 + rr) * DV + col, a);
+        // bf16 copy: the A operand of the output-conv GEMM
+        *reinterpret_cast<uint2*>(A_bf16 + (wrow0 + rr) * DV + col) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+      }
+      __syncwarp();
     }
     if (h == 0) lse[grow] = (m_used + log2f(l)) * BG_LN2;
     tc_fence_before();

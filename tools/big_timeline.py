@@ -19,7 +19,7 @@ out = (ctypes.c_ulonglong * 32)()
 lib = _lib.load()
 rc = lib.sagan_debug_big_timeline(out)
 nt = N // 128
-names = ["loop", "waitS", "ld", "max+xchg", "rescale", "exp", "arrive", "st"]
+names = ["loop", "waitS", "ld", "xchg", "check", "exp+max", "arrive", "st"]
 for base, who in ((0, "softmax h=0"), (8, "softmax h=1")):
     print(who, {n: int(out[base + i]) // nt for i, n in enumerate(names)}, "per tile")
 print("issuer", {n: int(out[16 + i]) // nt for i, n in enumerate(["issue", "waitFull", "waitP", "pv_exec"])}, "per tile")
