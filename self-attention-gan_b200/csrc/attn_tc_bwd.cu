@@ -194,26 +194,35 @@ struct BwdSmem {
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE;
   static constexpr int OFF_KT = OFF_V + TILE;
-  static constexpr int OFF_STAGE = OFF_KT + T16;
-  static constexpr int ST_Q = 0;
-  static constexpr int ST_DA = ST_Q + TILE;
-  static constexpr int ST_DAT = ST_DA + TILE;
-  static constexpr int ST_QT = ST_DAT + TDV;
-  static constexpr int ST_VEC = ST_QT + T16;             // lse2[128], D[128] fp32
-  static constexpr int STAGE = ST_VEC + 1024;
-  static constexpr int OFF_PT = OFF_STAGE + 2 * STAGE;
-  static constexpr int OFF_DST = OFF_PT + 2 * TILE;
+  // query-side operands in two rings: A = what the score-shaped MMAs read (Q_i, dA_i rows; free as soon as dP^T_i has
+  // been computed, so three stages let the loads run two tiles ahead), B = what the gradient MMAs read (dA_i^T, Q_i^T
+  // rows and the lse / D vectors; free when the gradient MMAs of the tile are done)
+  static constexpr int NA = 3, NB = 2;
+  static constexpr int OFF_A = OFF_KT + T16;
+  static constexpr int A_Q = 0, A_DA = TILE, ASTAGE = 2 * TILE;
+  static constexpr int OFF_B = OFF_A + NA * ASTAGE;
+  static constexpr int B_DAT = 0, B_QT = TDV, B_VEC = TDV + T16, BSTAGE = TDV + T16 + 1024;   // vec: lse2[128], D[128]
+  static constexpr int OFF_DST = OFF_B + NB * BSTAGE;     // dS^T hi (bf16) for the dQ MMAs
   static constexpr int OFF_DSL = OFF_DST + 2 * TILE;      // dS^T - bf16(dS^T): second bf16 term of the split
   static constexpr int OFF_BAR = OFF_DSL + 2 * TILE;
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
-  static constexpr int STAGE_TX = TILE + TILE + TDV + T16 + 1024;
-  static_assert(STAGE % 1024 == 0 && OFF_STAGE % 1024 == 0, "tiles must stay 1024-byte aligned");
-  // TMEM columns
-  // Small-N MMAs that accumulate into the SAME TMEM tile execute back to back at the full pipeline latency, so the
-  // gradient GEMMs are spread over five independent accumulators issued round-robin: dV, dK from dS_hi, dK from dS_lo,
-  // dQ from dS_hi, dQ from dS_lo (the hi / lo partial sums are added in the epilogue)
-  static constexpr int ST_COL = 0, DP_COL = 128, DV_COL = 256, DKH_COL = 320, DKL_COL = 336, DQ_COL = 352;   // DQ: 2 x [hi 16 | lo 16]
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int A_TX = 2 * TILE, B_TX = TDV + T16 + 1024;
+  static_assert(ASTAGE % 1024 == 0 && BSTAGE % 1024 == 0 && OFF_A % 1024 == 0, "tiles must stay 1024-byte aligned");
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+  // TMEM columns.  P'^T and the two bf16 terms of dS^T are the A operands of the dV / dK MMAs and live in TMEM
+  // (tcgen05.mma with A from TMEM): the thread that owns dP^T columns [32 h, 32 h + 32) of a key row overwrites them
+  // with its 32 P'^T (16 packed columns) and 32 dS^T_lo values once it holds dP^T in registers; dS^T_hi has its own
+  // columns.  Small-N MMAs that accumulate into the SAME TMEM tile execute back to back at the full pipeline latency,
+  // so the gradient GEMMs are spread over five independent accumulators issued round-robin: dV, dK from dS_hi, dK from
+  // dS_lo, dQ from dS_hi, dQ from dS_lo (the hi / lo partial sums are added in the epilogue)
+  static constexpr int ST_COL = 0, DP_COL = 128, DSH_COL = 256, DV_COL = 320, DKH_COL = 352, DKL_COL = 368,
+                       DQ_COL = 384;   // DQ: 2 x [hi 16 | lo 16]
 };
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is a K-major bf16 tile in TMEM (lane = row, two K elements per 32-bit column)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  mma_bf16_ts_g<1>(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
 
 template <int DVP, bool SPLIT_DA>
 __global__ void __launch_bounds__(TB_THREADS, 1)
@@ -229,18 +238,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sK = smem + L::OFF_K;
   uint8_t* sV = smem + L::OFF_V;
   uint8_t* sKt = smem + L::OFF_KT;
-  uint8_t* sStage = smem + L::OFF_STAGE;
-  uint8_t* sPt = smem + L::OFF_PT;
+  uint8_t* sA = smem + L::OFF_A;
+  uint8_t* sB = smem + L::OFF_B;
   uint8_t* sdSt = smem + L::OFF_DST;
   uint8_t* sdSl = smem + L::OFF_DSL;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* barKV = bars + 0;
-  uint64_t* barQ = bars + 1;    // [2] stage full
-  uint64_t* barS = bars + 3;    // S^T / dP^T ready
-  uint64_t* barG = bars + 4;    // [2] gradient MMAs of iteration i done
-  uint64_t* barSfree = bars + 6;   // 256 arrivals: S^T / dP^T of tile i are in registers
-  uint64_t* barTiles = bars + 7;   // 256 arrivals: P^T / dS^T tiles of tile i are in shared memory
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* barAfull = bars + 1;     // [3] Q_i / dA_i rows landed
+  uint64_t* barAfree = bars + 4;     // [3] S^T_i and dP^T_i computed: the A stage may be overwritten
+  uint64_t* barBfull = bars + 7;     // [2] dA_i^T / Q_i^T rows and lse / D landed
+  uint64_t* barG = bars + 9;         // [2] gradient MMAs of iteration i done (both issuers commit)
+  uint64_t* barS = bars + 11;        // S^T ready
+  uint64_t* barDP = bars + 12;       // dP^T ready
+  uint64_t* barSfree = bars + 13;    // 512 arrivals: S^T of tile i is in registers
+  uint64_t* barTiles = bars + 14;    // 512 arrivals: P'^T / dS^T of tile i are in TMEM and shared memory
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, kt = blockIdx.x;
@@ -248,9 +260,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (threadIdx.x == 0) {
     mbar_init(barKV, 1);
-    mbar_init(barQ, 1); mbar_init(barQ + 1, 1);
+    for (int i = 0; i < L::NA; ++i) { mbar_init(barAfull + i, 1); mbar_init(barAfree + i, 1); }
+    for (int i = 0; i < L::NB; ++i) { mbar_init(barBfull + i, 1); mbar_init(barG + i, 2); }
     mbar_init(barS, 1);
-    mbar_init(barG, 2); mbar_init(barG + 1, 2);     // both issuer warps commit
+    mbar_init(barDP, 1);
     mbar_init(barSfree, TB_CWARPS * 32); mbar_init(barTiles, TB_CWARPS * 32);
     mbar_fence_init();
   }
@@ -270,19 +283,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sV, &tmV, barKV, 0, b * Npad + kt * 128);
       tma_load_2d(sKt, &tmKt, barKV, kt * 128, b * 16);
       tma_load_2d(sKt + 16 * 128, &tmKt, barKV, kt * 128 + 64, b * 16);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        uint8_t* st = sStage + s * L::STAGE;
-        if (i >= 2) mbar_wait(barG + s, ((i - 2) >> 1) & 1);     // every MMA of iteration i-2 has completed
-        mbar_expect_tx(barQ + s, L::STAGE_TX);
-        tma_load_2d(st + L::ST_Q, &tmQ, barQ + s, 0, b * Npad + i * 128);
-        tma_load_2d(st + L::ST_DA, &tmdA, barQ + s, 0, b * Npad + i * 128);
-        tma_load_2d(st + L::ST_DAT, &tmdAt, barQ + s, i * 128, b * DVP);
-        tma_load_2d(st + L::ST_DAT + DVP * 128, &tmdAt, barQ + s, i * 128 + 64, b * DVP);
-        tma_load_2d(st + L::ST_QT, &tmQt, barQ + s, i * 128, b * 16);
-        tma_load_2d(st + L::ST_QT + 16 * 128, &tmQt, barQ + s, i * 128 + 64, b * 16);
-        bulk_load_1d(st + L::ST_VEC, lse2 + (size_t)b * Npad + i * 128, 512, barQ + s);
-        bulk_load_1d(st + L::ST_VEC + 512, Dd + (size_t)b * Npad + i * 128, 512, barQ + s);
+      // the two rings are refilled by polling, whichever stage frees first (no assumption on their relative order)
+      int ia = 0, ib = 0;
+      while (ia < nq || ib < nq) {
+        if (ia < nq) {
+          const int s = ia % L::NA;
+          if (ia < L::NA || mbar_try_wait(barAfree + s, ((ia / L::NA) - 1) & 1)) {
+            uint8_t* st = sA + s * L::ASTAGE;
+            mbar_expect_tx(barAfull + s, L::A_TX);
+            tma_load_2d(st + L::A_Q, &tmQ, barAfull + s, 0, b * Npad + ia * 128);
+            tma_load_2d(st + L::A_DA, &tmdA, barAfull + s, 0, b * Npad + ia * 128);
+            ++ia;
+          }
+        }
+        if (ib < nq) {
+          const int s = ib % L::NB;
+          if (ib < L::NB || mbar_try_wait(barG + s, ((ib / L::NB) - 1) & 1)) {
+            uint8_t* st = sB + s * L::BSTAGE;
+            mbar_expect_tx(barBfull + s, L::B_TX);
+            tma_load_2d(st + L::B_DAT, &tmdAt, barBfull + s, ib * 128, b * DVP);
+            tma_load_2d(st + L::B_DAT + DVP * 128, &tmdAt, barBfull + s, ib * 128 + 64, b * DVP);
+            tma_load_2d(st + L::B_QT, &tmQt, barBfull + s, ib * 128, b * 16);
+            tma_load_2d(st + L::B_QT + 16 * 128, &tmQt, barBfull + s, ib * 128 + 64, b * 16);
+            bulk_load_1d(st + L::B_VEC, lse2 + (size_t)b * Npad + ib * 128, 512, barBfull + s);
+            bulk_load_1d(st + L::B_VEC + 512, Dd + (size_t)b * Npad + ib * 128, 512, barBfull + s);
+            ++ib;
+          }
+        }
       }
     }
   } else if (warp == TB_CWARPS + 1) {
@@ -291,49 +318,57 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
       constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
-      auto issue_sdp = [&](int i) {     // S^T = K Q_i^T, dP^T = V dA_i^T
-        const int s = i & 1;
-        uint8_t* st = sStage + s * L::STAGE;
-        const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dQ_ = make_desc_sw128(smem_u32(st + L::ST_Q));
-        const uint64_t dV_ = make_desc_sw128(smem_u32(sV)), dA_ = make_desc_sw128(smem_u32(st + L::ST_DA));
+      const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dV_ = make_desc_sw128(smem_u32(sV));
+      auto issue_s = [&](int i) {       // S^T = K Q_i^T
+        const uint64_t dQ_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q));
         for (int ks = 0; ks < kq_steps; ++ks)
           mma_bf16_ss(tmem_base + L::ST_COL, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-        for (int ks = 0; ks < kv_steps; ++ks)
-          mma_bf16_ss(tmem_base + L::DP_COL, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
         mma_commit(barS);
       };
-      auto issue_grads = [&](int i) {   // dV += P^T dA_i ; dK += dS^T Q_i ; dQ_i = dS K
-        const int s = i & 1;
-        uint8_t* st = sStage + s * L::STAGE;
-        const uint64_t dPt = make_desc_sw128(smem_u32(sPt)), dSt = make_desc_sw128(smem_u32(sdSt));
-        const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::ST_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::ST_QT));
-        const uint64_t dSl = make_desc_sw128(smem_u32(sdSl));
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // 16 queries per step; three independent accumulators (dQ: second issuer warp)
-          const uint64_t a_off = (uint64_t)((ks >> 2) * (L::TILE >> 4) + (ks & 3) * 2);
-          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-          const bool acc = (i > 0) || (ks > 0);
-          mma_bf16_ss(tmem_base + L::DV_COL, dPt + a_off, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
-                      IDESC_DV, acc);
-          mma_bf16_ss(tmem_base + L::DKH_COL, dSt + a_off, dQt_ + b16, IDESC_DK, acc);
-          mma_bf16_ss(tmem_base + L::DKL_COL, dSl + a_off, dQt_ + b16, IDESC_DK, acc);
-        }
-        mma_commit(barG + s);
+      auto issue_dp = [&](int i) {      // dP^T = V dA_i^T ; afterwards the A stage is free
+        const uint64_t dA_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_DA));
+        for (int ks = 0; ks < kv_steps; ++ks)
+          mma_bf16_ss(tmem_base + L::DP_COL, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barDP);
+        mma_commit(barAfree + (i % L::NA));
       };
       mbar_wait(barKV, 0);
-      mbar_wait(barQ, 0);
+      mbar_wait(barAfull, 0);
       tc_fence_after();
-      issue_sdp(0);
+      issue_s(0);
+      issue_dp(0);
       for (int i = 0; i < nq; ++i) {
         if (i + 1 < nq) {
-          mbar_wait(barQ + ((i + 1) & 1), ((i + 1) >> 1) & 1);
-          mbar_wait(barSfree, i & 1);            // every compute thread holds S^T_i / dP^T_i in registers
+          mbar_wait(barAfull + ((i + 1) % L::NA), ((i + 1) / L::NA) & 1);
+          mbar_wait(barSfree, i & 1);            // every compute thread holds S^T_i in registers
           tc_fence_after();
-          issue_sdp(i + 1);                      // runs under the exp / dS math of tile i
+          issue_s(i + 1);                        // runs under the exp / dS math of tile i
         }
-        mbar_wait(barTiles, i & 1);              // P^T_i / dS^T_i are in shared memory
+        mbar_wait(barBfull + (i & 1), (i >> 1) & 1);
+        mbar_wait(barTiles, i & 1);              // P'^T_i / dS^T_i are in TMEM (and every thread holds dP^T_i)
         tc_fence_after();
-        issue_grads(i);
+        // dV += P'^T dA_i ; dK += dS^T Q_i : A operands from TMEM, 16 queries per step.  The tensor pipe executes in
+        // issue order, so dP^T_{i+1} (issued right after the MMAs that read the aliased P'^T / dS^T_lo columns) cannot
+        // overwrite them early; the dS^T_hi MMAs follow it.
+        const uint8_t* st = sB + (i & 1) * L::BSTAGE;
+        const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::B_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::B_QT));
+        const bool acc0 = i > 0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_pt = tmem_base + L::DP_COL + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
+          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+          mma_bf16_ts(tmem_base + L::DV_COL, a_pt, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2), IDESC_DV,
+                      acc0 || (ks > 0));
+          mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
+        }
+        if (i + 1 < nq) issue_dp(i + 1);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_hi = tmem_base + L::DSH_COL + (uint32_t)(ks * 8);
+          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+          mma_bf16_ts(tmem_base + L::DKH_COL, a_hi, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
+        }
+        mma_commit(barG + (i & 1));
       }
     }
   } else if (warp == TB_CWARPS + 2) {
@@ -386,75 +421,93 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     for (int i = 0; i < nq; ++i) {
       const int s = i & 1;
-      const float* vec = reinterpret_cast<const float*>(sStage + s * L::STAGE + L::ST_VEC);
-      mbar_wait(barQ + s, (i >> 1) & 1);      // lse2 / D of this query tile have landed
       mbar_wait(barS, i & 1);
       tc_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld32(t_row + L::ST_COL + h * 32, rs);
-      tmem_ld32(t_row + L::DP_COL + h * 32, rp);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(barSfree);                                  // this thread's S^T / dP^T are in registers
-      // ---- all of this tile's math goes to registers first: it overlaps the gradient MMAs of tile i-1, which still
-      //      read the single-buffered P^T / dS^T tiles; only the stores below have to wait for them
-      uint32_t pp[16], hi[16], lo[16];
+      uint32_t pp[16];
+      float pf[32];       // P' (bf16-rounded, as fp32) -- the weights the forward used
+      {
+        uint32_t rs[32];
+        tmem_ld32(t_row + L::ST_COL + h * 32, rs);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(barSfree);                                  // this thread's S^T is in registers
+        if (SPLIT_DA) {   // folded operands: the MMA delivered S - M_i (padded keys at -16384)
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ds_[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (!SPLIT_DA) {
-          const float4 l0 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8);
-          const float4 l1 = *reinterpret_cast<const float4*>(vec + h * 32 + g * 8 + 4);
-          const float4 d0 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8);
-          const float4 d1 = *reinterpret_cast<const float4*>(vec + 128 + h * 32 + g * 8 + 4);
-          ls[0] = l0.x; ls[1] = l0.y; ls[2] = l0.z; ls[3] = l0.w; ls[4] = l1.x; ls[5] = l1.y; ls[6] = l1.z; ls[7] = l1.w;
-          ds_[0] = d0.x; ds_[1] = d0.y; ds_[2] = d0.z; ds_[3] = d0.w; ds_[4] = d1.x; ds_[5] = d1.y; ds_[6] = d1.z; ds_[7] = d1.w;
-        }
-        float p[8], g_[8];
+          for (int e = 0; e < 16; ++e) {
+            const uint32_t pk = pack_bf16x2(ex2_approx(__uint_as_float(rs[2 * e])), ex2_approx(__uint_as_float(rs[2 * e + 1])));
+            pp[e] = pk;
+            pf[2 * e] = __uint_as_float(pk << 16);
+            pf[2 * e + 1] = __uint_as_float(pk & 0xffff0000u);
+          }
+        } else {
+          mbar_wait(barBfull + s, (i >> 1) & 1);                // lse2 / D of this query tile have landed
+          const float* vec = reinterpret_cast<const float*>(sB + s * L::BSTAGE + L::B_VEC) + h * 32;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (SPLIT_DA) {   // folded operands: the MMA delivered S - M_i (padded keys at -16384)
-            p[e] = ex2_approx(__uint_as_float(rs[g * 8 + e]));
-          } else {
-            const float pe = ex2_approx(__uint_as_float(rs[g * 8 + e]) - ls[e]);
-            p[e] = key_ok ? pe : 0.f;
+          for (int e = 0; e < 16; ++e) {
+            const float2 ls = *reinterpret_cast<const float2*>(vec + 2 * e);
+            const float p0 = key_ok ? ex2_approx(__uint_as_float(rs[2 * e]) - ls.x) : 0.f;
+            const float p1 = key_ok ? ex2_approx(__uint_as_float(rs[2 * e + 1]) - ls.y) : 0.f;
+            const uint32_t pk = pack_bf16x2(p0, p1);
+            pp[e] = pk;
+            pf[2 * e] = __uint_as_float(pk << 16);
+            pf[2 * e + 1] = __uint_as_float(pk & 0xffff0000u);
           }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t pk = pack_bf16x2(p[2 * e], p[2 * e + 1]);   // P' = bf16(exp2(S - M)): the weights the forward used
-          pp[g * 4 + e] = pk;
-          const float dp0 = __uint_as_float(rp[g * 8 + 2 * e]), dp1 = __uint_as_float(rp[g * 8 + 2 * e + 1]);
-          g_[2 * e] = __uint_as_float(pk << 16) * (SPLIT_DA ? dp0 : dp0 - ds_[2 * e]);            // folded: dP - D_i
-          g_[2 * e + 1] = __uint_as_float(pk & 0xffff0000u) * (SPLIT_DA ? dp1 : dp1 - ds_[2 * e + 1]);
-        }
-        // dS^T = hi + lo (two bf16 terms): sum_j dS_ij = 0, so the theta / phi gradients cancel and need the extra bits
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t hk = pack_bf16x2(g_[2 * e], g_[2 * e + 1]);
-          hi[g * 4 + e] = hk;
-          lo[g * 4 + e] = pack_bf16x2(g_[2 * e] - __uint_as_float(hk << 16), g_[2 * e + 1] - __uint_as_float(hk & 0xffff0000u));
-        }
       }
-      if (i >= 1) {
-        mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);   // P^T / dS^T buffers free, dQ_{i-1} complete
+      // ---- dS^T = P' (dP - D) = hi + lo (two bf16 terms): sum_j dS_ij = 0, so the theta / phi gradients cancel and
+      //      need the extra bits
+      uint32_t hi[16], lo[16];
+      {
+        mbar_wait(barDP, i & 1);
         tc_fence_after();
-        flush_dq(i - 1);
+        uint32_t rp[32];
+        tmem_ld32(t_row + L::DP_COL + h * 32, rp);
+        tmem_wait_ld();
+        const float* dvec = reinterpret_cast<const float*>(sB + s * L::BSTAGE + L::B_VEC) + 128 + h * 32;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float g0, g1;
+          if (SPLIT_DA) {          // folded: the MMA delivered dP - D_i
+            g0 = pf[2 * e] * __uint_as_float(rp[2 * e]);
+            g1 = pf[2 * e + 1] * __uint_as_float(rp[2 * e + 1]);
+          } else {
+            const float2 dd = *reinterpret_cast<const float2*>(dvec + 2 * e);
+            g0 = pf[2 * e] * (__uint_as_float(rp[2 * e]) - dd.x);
+            g1 = pf[2 * e + 1] * (__uint_as_float(rp[2 * e + 1]) - dd.y);
+          }
+          const uint32_t hk = pack_bf16x2(g0, g1);
+          hi[e] = hk;
+          lo[e] = pack_bf16x2(g0 - __uint_as_float(hk << 16), g1 - __uint_as_float(hk & 0xffff0000u));
+        }
       }
+      // ---- A operands of the dV / dK MMAs -> TMEM.  P'^T and dS^T_lo go over this thread's own dP^T columns, which
+      //      it has just loaded: dP^T_i complete implies that the MMAs of tile i-1 that read those columns (issued
+      //      before it) are complete.  dS^T_hi (read by MMAs issued after dP^T_i) and the shared-memory dS^T tiles of
+      //      the dQ MMAs wait for ALL gradient MMAs of tile i-1.
+      tmem_st16(t_row + L::DP_COL + h * 32, pp);
+      tmem_st16(t_row + L::DP_COL + h * 32 + 16, lo);
+      if (i >= 1) {
+        mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st16(t_row + L::DSH_COL + h * 16, hi);
       // query columns [32 h, 32 h + 32): 64-query sub-tile h >> 1, 16-byte chunks (h & 1) * 4 + g
-      uint8_t* pt = sPt + (h >> 1) * L::TILE;
       uint8_t* dst = sdSt + (h >> 1) * L::TILE;
       uint8_t* dsl = sdSl + (h >> 1) * L::TILE;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint32_t off = sw128_offset(krow, (h & 1) * 4 + g);
-        *reinterpret_cast<uint4*>(pt + off) = make_uint4(pp[g * 4], pp[g * 4 + 1], pp[g * 4 + 2], pp[g * 4 + 3]);
         *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
         *reinterpret_cast<uint4*>(dsl + off) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
       }
+      tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(barTiles);                                  // this thread's part of P^T / dS^T is written
+      mbar_arrive(barTiles);                                  // this thread's part of P'^T / dS^T is written
+      if (i >= 1) {                                           // off the critical path: dQ_{i-1} -> global memory
+        tc_fence_after();
+        flush_dq(i - 1);
+      }
     }
     // ---- epilogue
     mbar_wait(barG + ((nq - 1) & 1), ((nq - 1) >> 1) & 1);
