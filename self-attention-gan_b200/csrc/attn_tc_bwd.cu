@@ -247,12 +247,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* barAfull = bars + 1;     // [3] Q_i / dA_i rows landed
   uint64_t* barAfree = bars + 4;     // [3] S^T_i and dP^T_i computed: the A stage may be overwritten
   uint64_t* barBfull = bars + 7;     // [2] dA_i^T / Q_i^T rows and lse / D landed
-  uint64_t* barG = bars + 9;         // [2] gradient MMAs of iteration i done (both issuers commit)
-  uint64_t* barS = bars + 11;        // S^T ready
-  uint64_t* barDP = bars + 12;       // dP^T ready
-  uint64_t* barSfree = bars + 13;    // 512 arrivals: S^T of tile i is in registers
-  uint64_t* barTiles = bars + 14;    // 512 arrivals: P'^T / dS^T of tile i are in TMEM and shared memory
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* barBfree = bars + 9;     // [2] dV / dK MMAs of tile i done: the B stage may be overwritten
+  uint64_t* barQd = bars + 11;       // [2] dQ_i computed: the shared-memory dS^T tiles are free, dQ_i may be flushed
+  // The 16 compute warps work as two HALVES (query columns [0,64) / [64,128) of the tile, 8 warps each) with their own
+  // barrier chains.  All warps of one chain run the phases MUFU (exp2) -> ALU (dS, bf16 splits) -> LSU (stores) in
+  // lockstep; two chains served alternately by the MMA issuer settle out of phase, so the three pipes overlap.
+  uint64_t* barS = bars + 13;        // [half] S^T columns of the half ready
+  uint64_t* barDP = bars + 15;       // [half] dP^T columns ready
+  uint64_t* barSfree = bars + 17;    // [half] 256 arrivals: S^T of tile i is in registers
+  uint64_t* barTiles = bars + 19;    // [half] 256 arrivals: P'^T / dS^T of tile i are in TMEM and shared memory
+  uint64_t* barGh = bars + 21;       // [half] dK-from-dS_hi MMAs of tile i done: the dS^T_hi columns may be overwritten
+  uint64_t* barDone = bars + 23;     // both issuers: every MMA of the CTA has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, kt = blockIdx.x;
@@ -261,10 +267,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(barKV, 1);
     for (int i = 0; i < L::NA; ++i) { mbar_init(barAfull + i, 1); mbar_init(barAfree + i, 1); }
-    for (int i = 0; i < L::NB; ++i) { mbar_init(barBfull + i, 1); mbar_init(barG + i, 2); }
-    mbar_init(barS, 1);
-    mbar_init(barDP, 1);
-    mbar_init(barSfree, TB_CWARPS * 32); mbar_init(barTiles, TB_CWARPS * 32);
+    for (int i = 0; i < L::NB; ++i) { mbar_init(barBfull + i, 1); mbar_init(barBfree + i, 1); mbar_init(barQd + i, 1); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(barS + x, 1); mbar_init(barDP + x, 1); mbar_init(barGh + x, 1);
+      mbar_init(barSfree + x, TB_CWARPS * 16); mbar_init(barTiles + x, TB_CWARPS * 16);
+    }
+    mbar_init(barDone, 2);
     mbar_fence_init();
   }
   if (warp == TB_CWARPS) tmem_alloc(tmem_ptr, 512);
@@ -298,7 +306,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         if (ib < nq) {
           const int s = ib % L::NB;
-          if (ib < L::NB || mbar_try_wait(barG + s, ((ib / L::NB) - 1) & 1)) {
+          if (ib < L::NB || mbar_try_wait(barBfree + s, ((ib / L::NB) - 1) & 1)) {
             uint8_t* st = sB + s * L::BSTAGE;
             mbar_expect_tx(barBfull + s, L::B_TX);
             tma_load_2d(st + L::B_DAT, &tmdAt, barBfull + s, ib * 128, b * DVP);
@@ -315,61 +323,72 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == TB_CWARPS + 1) {
     // ================================================================ MMA issuer
     if (elect_one_sync()) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 64);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
       constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
       const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dV_ = make_desc_sw128(smem_u32(sV));
-      auto issue_s = [&](int i) {       // S^T = K Q_i^T
-        const uint64_t dQ_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q));
+      auto issue_s = [&](int i, int x) {       // S^T[:, 64 x .. 64 x + 64) = K Q_i^T (64 query rows of the stage)
+        const uint64_t dQ_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q + x * (64 * 128)));
         for (int ks = 0; ks < kq_steps; ++ks)
-          mma_bf16_ss(tmem_base + L::ST_COL, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-        mma_commit(barS);
+          mma_bf16_ss(tmem_base + L::ST_COL + x * 64, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barS + x);
       };
-      auto issue_dp = [&](int i) {      // dP^T = V dA_i^T ; afterwards the A stage is free
-        const uint64_t dA_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_DA));
+      auto issue_dp = [&](int i, int x) {      // dP^T[:, 64 x .. 64 x + 64) = V dA_i^T
+        const uint64_t dA_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_DA + x * (64 * 128)));
         for (int ks = 0; ks < kv_steps; ++ks)
-          mma_bf16_ss(tmem_base + L::DP_COL, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-        mma_commit(barDP);
-        mma_commit(barAfree + (i % L::NA));
+          mma_bf16_ss(tmem_base + L::DP_COL + x * 64, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barDP + x);
+        if (x == 1) mma_commit(barAfree + (i % L::NA));     // last reader of the A stage
       };
       mbar_wait(barKV, 0);
       mbar_wait(barAfull, 0);
       tc_fence_after();
-      issue_s(0);
-      issue_dp(0);
+      issue_s(0, 0);
+      issue_dp(0, 0);
+      mbar_wait(barSfree, 0);                  // start the second half a little later: the two chains should not run
+      tc_fence_after();                        // their MUFU / ALU / LSU phases at the same time
+      issue_s(0, 1);
+      issue_dp(0, 1);
       for (int i = 0; i < nq; ++i) {
-        if (i + 1 < nq) {
-          mbar_wait(barAfull + ((i + 1) % L::NA), ((i + 1) / L::NA) & 1);
-          mbar_wait(barSfree, i & 1);            // every compute thread holds S^T_i in registers
-          tc_fence_after();
-          issue_s(i + 1);                        // runs under the exp / dS math of tile i
-        }
-        mbar_wait(barBfull + (i & 1), (i >> 1) & 1);
-        mbar_wait(barTiles, i & 1);              // P'^T_i / dS^T_i are in TMEM (and every thread holds dP^T_i)
-        tc_fence_after();
-        // dV += P'^T dA_i ; dK += dS^T Q_i : A operands from TMEM, 16 queries per step.  The tensor pipe executes in
-        // issue order, so dP^T_{i+1} (issued right after the MMAs that read the aliased P'^T / dS^T_lo columns) cannot
-        // overwrite them early; the dS^T_hi MMAs follow it.
         const uint8_t* st = sB + (i & 1) * L::BSTAGE;
         const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::B_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::B_QT));
         const bool acc0 = i > 0;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t a_pt = tmem_base + L::DP_COL + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
-          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-          mma_bf16_ts(tmem_base + L::DV_COL, a_pt, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2), IDESC_DV,
-                      acc0 || (ks > 0));
-          mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
-        }
-        if (i + 1 < nq) issue_dp(i + 1);
+        for (int x = 0; x < 2; ++x) {
+          if (i + 1 < nq) {
+            if (x == 0) mbar_wait(barAfull + ((i + 1) % L::NA), ((i + 1) / L::NA) & 1);
+            mbar_wait(barSfree + x, i & 1);          // every compute thread of the half holds S^T_i in registers
+            tc_fence_after();
+            issue_s(i + 1, x);                       // runs under the exp / dS math of tile i
+          }
+          if (x == 0) mbar_wait(barBfull + (i & 1), (i >> 1) & 1);
+          mbar_wait(barTiles + x, i & 1);            // P'^T_i / dS^T_i are in TMEM (and every thread holds dP^T_i)
+          tc_fence_after();
+          // dV += P'^T dA_i ; dK += dS^T Q_i : A operands from TMEM, 16 queries per step.  The tensor pipe executes in
+          // issue order, so dP^T_{i+1} (issued right after the MMAs that read the aliased P'^T / dS^T_lo columns)
+          // cannot overwrite them early; the dS^T_hi MMAs follow it.
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t a_hi = tmem_base + L::DSH_COL + (uint32_t)(ks * 8);
-          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-          mma_bf16_ts(tmem_base + L::DKH_COL, a_hi, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = x * 4 + k4;
+            const uint32_t a_pt = tmem_base + L::DP_COL + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
+            const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+            mma_bf16_ts(tmem_base + L::DV_COL, a_pt, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
+                        IDESC_DV, acc0 || (ks > 0));
+            mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
+          }
+          if (i + 1 < nq) issue_dp(i + 1, x);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = x * 4 + k4;
+            const uint32_t a_hi = tmem_base + L::DSH_COL + (uint32_t)(ks * 8);
+            const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+            mma_bf16_ts(tmem_base + L::DKH_COL, a_hi, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
+          }
+          mma_commit(barGh + x);
+          if (x == 1) mma_commit(barBfree + (i & 1));
         }
-        mma_commit(barG + (i & 1));
       }
+      mma_commit(barDone);
     }
   } else if (warp == TB_CWARPS + 2) {
     // ================================================================ second MMA issuer: dQ_i = dS_i K_j
@@ -380,6 +399,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(barKV, 0);
       for (int i = 0; i < nq; ++i) {
         mbar_wait(barTiles, i & 1);
+        mbar_wait(barTiles + 1, i & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {   // K = 16 keys per step: the dS^T tiles read MN-major (M = queries contiguous)
@@ -389,15 +409,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(smem_u32(sdSl) + ks * 16 * 128, L::TILE, 1024),
                       dKt_ + b16, IDESC_DQ, ks > 0);
         }
-        mma_commit(barG + (i & 1));
+        mma_commit(barQd + (i & 1));
       }
+      mma_commit(barDone);
     }
   } else {
     // ================================================================ compute warps
     // thread <-> key row krow (TMEM lane) x 32 of the tile's 128 query columns: warp w owns lane quarter w & 3 and
     // query columns [32 h, 32 h + 32), h = w >> 2.  Four warps per scheduler hide the MUFU / LDS latencies of the chain
     // exp2 -> bf16 -> (dP - D) -> split, which two warps per scheduler could not (measured 0.4 IPC).
-    const int qd = warp & 3, h = warp >> 2;
+    const int qd = warp & 3, h = warp >> 2, x = h >> 1;
     const int krow = qd * 32 + lane;                                // key row inside the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
     const bool key_ok = kt * 128 + krow < N;
@@ -421,7 +442,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     for (int i = 0; i < nq; ++i) {
       const int s = i & 1;
-      mbar_wait(barS, i & 1);
+      mbar_wait(barS + x, i & 1);
       tc_fence_after();
       uint32_t pp[16];
       float pf[32];       // P' (bf16-rounded, as fp32) -- the weights the forward used
@@ -430,7 +451,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(t_row + L::ST_COL + h * 32, rs);
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(barSfree);                                  // this thread's S^T is in registers
+        mbar_arrive(barSfree + x);                              // this thread's S^T is in registers
         if (SPLIT_DA) {   // folded operands: the MMA delivered S - M_i (padded keys at -16384)
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -458,7 +479,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       //      need the extra bits
       uint32_t hi[16], lo[16];
       {
-        mbar_wait(barDP, i & 1);
+        mbar_wait(barDP + x, i & 1);
         tc_fence_after();
         uint32_t rp[32];
         tmem_ld32(t_row + L::DP_COL + h * 32, rp);
@@ -482,15 +503,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       // ---- A operands of the dV / dK MMAs -> TMEM.  P'^T and dS^T_lo go over this thread's own dP^T columns, which
       //      it has just loaded: dP^T_i complete implies that the MMAs of tile i-1 that read those columns (issued
-      //      before it) are complete.  dS^T_hi (read by MMAs issued after dP^T_i) and the shared-memory dS^T tiles of
-      //      the dQ MMAs wait for ALL gradient MMAs of tile i-1.
+      //      before it) are complete.  dS^T_hi waits for the MMAs issued after dP^T_i, the shared-memory dS^T tiles
+      //      for the dQ MMAs of tile i-1.
       tmem_st16(t_row + L::DP_COL + h * 32, pp);
       tmem_st16(t_row + L::DP_COL + h * 32 + 16, lo);
       if (i >= 1) {
-        mbar_wait(barG + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+        mbar_wait(barGh + x, (i - 1) & 1);
         tc_fence_after();
       }
       tmem_st16(t_row + L::DSH_COL + h * 16, hi);
+      if (i >= 1) {
+        mbar_wait(barQd + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+        tc_fence_after();
+      }
       // query columns [32 h, 32 h + 32): 64-query sub-tile h >> 1, 16-byte chunks (h & 1) * 4 + g
       uint8_t* dst = sdSt + (h >> 1) * L::TILE;
       uint8_t* dsl = sdSl + (h >> 1) * L::TILE;
@@ -503,14 +528,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(barTiles);                                  // this thread's part of P'^T / dS^T is written
+      mbar_arrive(barTiles + x);                              // this thread's part of P'^T / dS^T is written
       if (i >= 1) {                                           // off the critical path: dQ_{i-1} -> global memory
         tc_fence_after();
         flush_dq(i - 1);
       }
     }
     // ---- epilogue
-    mbar_wait(barG + ((nq - 1) & 1), ((nq - 1) >> 1) & 1);
+    mbar_wait(barDone, 0);
     tc_fence_after();
     flush_dq(nq - 1);
     if (h == 0) {
