@@ -195,7 +195,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* barS = bars + 3;    // [2]
   uint64_t* barPV = bars + 5;   // [2]
   uint64_t* barP = bars + 7;    // [2] 128 arrivals each: P_j is in shared memory (and S_j has been read)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* barSfree = bars + 9;   // 128 arrivals: S_j is in registers (single S buffer: QK_{j+1} may overwrite it)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, qt = blockIdx.x;
@@ -205,6 +206,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(barQ, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(barKV + i, 1); mbar_init(barS + i, 1); mbar_init(barPV + i, 1); }
     mbar_init(barP, 128); mbar_init(barP + 1, 128);
+    mbar_init(barSfree, 128);
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(tmem_ptr, L::TMEM_COLS);
@@ -259,9 +261,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       issue_qk(0);
       for (int j = 0; j < nt; ++j) {
         if (NS == 2 && j + 1 < nt) issue_qk(j + 1);   // second S buffer: runs under softmax_j
-        mbar_wait(barP + (j & 1), (j >> 1) & 1);      // P_j written, S_j consumed by every softmax thread
+        if (NS == 1 && j + 1 < nt) {                  // single S buffer: free as soon as every softmax thread holds S_j in
+          mbar_wait(barSfree, j & 1);                 // registers; QK_{j+1} then runs under the exponentials of tile j
+          tc_fence_after();
+          issue_qk(j + 1);
+        }
+        mbar_wait(barP + (j & 1), (j >> 1) & 1);      // P_j written
         tc_fence_after();
-        if (NS == 1 && j + 1 < nt) issue_qk(j + 1);   // S is free again; QK_{j+1} queues ahead of PV_j
         issue_pv(j);
       }
     }
@@ -294,6 +300,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
       tmem_ld32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
       tmem_wait_ld();
+      if (NS == 1) {
+        tc_fence_before();
+        mbar_arrive(barSfree);
+      }
       if (kvalid < 128) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
@@ -490,8 +500,8 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
   if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Npad, (uint64_t)t.Npad * 2, (uint32_t)t.DVP))) return rc;
   const int dv = C / 2;
   switch (C) {
-    case 16: return launch_fwd<32, 1, 1, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 32: return launch_fwd<48, 1, 1, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 16: return launch_fwd<32, 1, 2, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 32: return launch_fwd<48, 1, 2, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
     case 64: return launch_fwd<80, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
   }
   return SAGAN_EUNSUPPORTED;

@@ -23,5 +23,4 @@ nt = (N + 127) // 128
 names = ["misc", "waitS", "ldS", "exp", "waitDP", "ldDP", "dSmath", "waitG", "store+arrive", "flush_dq"]
 for base, who in ((0, "compute w0"),):
     print(who, {n: int(out[base + i]) // nt for i, n in enumerate(names)}, "per tile")
-print("issuer1", {n: int(out[16 + i]) // nt for i, n in enumerate(["issue", "waitA", "waitSfree", "waitTiles", "waitB"])}, "per tile")
-#print("issuer2", {n: int(out[24 + i]) // nt for i, n in enumerate(["issue", "waitTiles"])}, "per tile")
+#
