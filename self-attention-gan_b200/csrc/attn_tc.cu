@@ -32,7 +32,7 @@ using namespace tc;
 
 constexpr float TC_LOG2E = 1.4426950408889634f;
 constexpr float TC_LN2 = 0.6931471805599453f;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // 8 softmax warps (two key-column halves per query row) + TMA producer + MMA issuer
 // Q / K rows: 16 bf16 (32 B, SWIZZLE_32B tiles) when the split logits fit one MMA K step (C <= 32: 3 d <= 12),
 // otherwise 64 bf16 (128 B, SWIZZLE_128B)
 __host__ __device__ constexpr int qk_cols(int C) { return C <= 32 ? 16 : 64; }
@@ -164,7 +164,8 @@ struct FwdSmem {
   static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
   static constexpr int OFF_W = OFF_P + NP * P_BYTES;         // fp32 Wo [dv][C] + bo [C] for the fused epilogue
   static constexpr int W_BYTES = (((CEPI / 2) * CEPI + CEPI) * 4 + 127) / 128 * 128;
-  static constexpr int OFF_BAR = OFF_W + W_BYTES;
+  static constexpr int OFF_X = OFF_W + W_BYTES;               // row-max exchange between the two column halves
+  static constexpr int OFF_BAR = OFF_X + 2 * 2 * 128 * 4;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;          // + alignment slack
   // O is spread over NACC accumulators (key steps ks % NACC): small-N MMAs that accumulate into the SAME TMEM tile run
   // back to back at the full pipeline latency, independent accumulators pipeline; they are summed in the epilogue
@@ -189,13 +190,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = smem + L::OFF_V;
   uint8_t* sP = smem + L::OFF_P;
   float* sW = reinterpret_cast<float*>(smem + L::OFF_W);
+  float* sX = reinterpret_cast<float*>(smem + L::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* barQ = bars + 0;
   uint64_t* barKV = bars + 1;   // [2]
   uint64_t* barS = bars + 3;    // [2]
   uint64_t* barPV = bars + 5;   // [2]
-  uint64_t* barP = bars + 7;    // [2] 128 arrivals each: P_j is in shared memory (and S_j has been read)
-  uint64_t* barSfree = bars + 9;   // 128 arrivals: S_j is in registers (single S buffer: QK_{j+1} may overwrite it)
+  uint64_t* barP = bars + 7;    // [2] 256 arrivals each: P_j is in shared memory (and S_j has been read)
+  uint64_t* barSfree = bars + 9;   // 256 arrivals: S_j is in registers (single S buffer: QK_{j+1} may overwrite it)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,17 +207,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(barQ, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(barKV + i, 1); mbar_init(barS + i, 1); mbar_init(barPV + i, 1); }
-    mbar_init(barP, 128); mbar_init(barP + 1, 128);
-    mbar_init(barSfree, 128);
+    mbar_init(barP, 256); mbar_init(barP + 1, 256);
+    mbar_init(barSfree, 256);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+  if (warp == 8) tmem_alloc(tmem_ptr, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================================================================ TMA producer
     if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -230,7 +232,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_2d(sV + s * L::V_BYTES + DVP * 128, &tmV, barKV + s, j * 128 + 64, b * DVP);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================================================================ MMA issuer (one elected thread)
     if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
@@ -273,14 +275,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ================================================================ softmax warps
-    const int row = threadIdx.x;                                   // query row inside the tile == TMEM lane
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // thread <-> query row (TMEM lane) x one HALF of the tile's 128 key columns: warps w and w + 4 share the lane
+    // quarter w & 3.  Eight softmax warps per CTA (four per scheduler with the co-resident CTA) keep the MUFU pipe fed
+    // where four left the schedulers idle three cycles out of four.
+    const int h = warp >> 2;
+    const int row = threadIdx.x & 127;                             // query row inside the tile == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
     if (CEPI > 0) {
       const int nW = dv * CEPI;
-      for (int e = threadIdx.x; e < nW; e += 128) sW[e] = Wo[e];
-      for (int e = threadIdx.x; e < CEPI; e += 128) sW[nW + e] = bo[e];
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the epilogue of every softmax thread reads all of sW
+      for (int e = threadIdx.x; e < nW; e += 256) sW[e] = Wo[e];
+      for (int e = threadIdx.x; e < CEPI; e += 256) sW[nW + e] = bo[e];
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the epilogue of every softmax thread reads all of sW
     }
 
     float m_used = -INFINITY;      // integer-valued (log2 units) once set: see "consistent rounding" above
@@ -294,11 +300,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
       // ---- the whole S row (128 fp32) comes to registers with ONE exposed TMEM round trip
       //      (logits are already in log2 units: Q carries log2(e))
-      uint32_t r[128];
-      tmem_ld32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-      tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-      tmem_ld32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
-      tmem_ld32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+      uint32_t r[64];
+      tmem_ld32(t_s + h * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(t_s + h * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
       tmem_wait_ld();
       if (NS == 1) {
         tc_fence_before();
@@ -306,18 +310,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (kvalid < 128) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= kvalid) r[i] = 0xff800000u;   // -inf: masked keys of the ragged last tile
+        for (int i = 0; i < 64; ++i)
+          if (h * 64 + i >= kvalid) r[i] = 0xff800000u;   // -inf: masked keys of the ragged last tile
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(r[i]));
         mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // both halves of a row must use the same shift: exchange the partial maxima (double-buffered, one barrier a tile)
+      {
+        float* xb = sX + (j & 1) * 256;
+        xb[h * 128 + row] = mx;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        mx = fmaxf(mx, xb[(h ^ 1) * 128 + row]);
+      }
       // ---- lazy rescale of the running accumulators
       const bool need = mx > m_used + 32.0f;   // P and the fp32 accumulators share the exponent range: a stale max costs no precision
       if (__any_sync(0xffffffffu, need)) {
@@ -325,14 +336,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_wait(barPV + ((j - 1) & 1), ((j - 1) >> 1) & 1);       // every PV issued so far has completed
           tc_fence_after();
           const float scale = need ? exp2f(m_used - ceilf(mx)) : 1.0f;   // exact power of two
+          static_assert((L::NACC * DVP / 16) % 2 == 0, "the two halves share the O columns evenly");
 #pragma unroll
-          for (int c = 0; c < L::NACC * DVP / 16; ++c) {
+          for (int c = 0; c < L::NACC * DVP / 32; ++c) {     // this half's share of the O columns
+            const uint32_t col = L::OCOL + (h * (L::NACC * DVP / 32) + c) * 16;
             uint32_t o[16];
-            tmem_ld16(t_row + L::OCOL + c * 16, o);
+            tmem_ld16(t_row + col, o);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
-            tmem_st16(t_row + L::OCOL + c * 16, o);
+            tmem_st16(t_row + col, o);
           }
           tmem_wait_st();
         }
@@ -344,7 +357,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint8_t* sPj = sP + pb * L::P_BYTES;
       // ---- P' = bf16(exp2(S - m)), swizzled store (16 B = 8 keys per store); the row sum comes out of the PV MMA
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
+      for (int g = 0; g < 8; ++g) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -352,9 +365,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float p1 = ex2_approx(__uint_as_float(r[g * 8 + 2 * i + 1]) - m_used);
           pk[i] = pack_bf16x2(p0, p1);
         }
-        // key columns [8g, 8g+8): sub-tile g/8, 16-byte chunk g%8
-        *reinterpret_cast<uint4*>(sPj + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7)) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        // key columns 64 h + [8g, 8g+8): 64-key sub-tile h, 16-byte chunk g
+        *reinterpret_cast<uint4*>(sPj + h * (128 * 128) + sw128_offset(row, g)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();      // st.shared of P -> visible to the tensor core (async proxy)
       tc_fence_before();             // orders this thread's tcgen05.ld / st before the arrive
@@ -390,12 +402,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int v = 0; v < DV; ++v) a[v] = (a[v] + a[DV + v]) * inv;
       if (valid) {
+        if (h == 0) {
 #pragma unroll
-        for (int v = 0; v < DV; v += 4) st4(A_saved + grow * DV + v, make_float4(a[v], a[v + 1], a[v + 2], a[v + 3]));
-        lse[grow] = (m_used + log2f(l)) * TC_LN2;
+          for (int v = 0; v < DV; v += 4) st4(A_saved + grow * DV + v, make_float4(a[v], a[v + 1], a[v + 2], a[v + 3]));
+          lse[grow] = (m_used + log2f(l)) * TC_LN2;
+        }
         const float gm = *gamma;
 #pragma unroll
-        for (int c = 0; c < C; c += 4) {
+        for (int cc = 0; cc < C / 2; cc += 4) {              // each half of the row's threads writes half of the channels
+          const int c = h * (C / 2) + cc;
           float o[4] = {sW[DV * C + c], sW[DV * C + c + 1], sW[DV * C + c + 2], sW[DV * C + c + 3]};
 #pragma unroll
           for (int v = 0; v < DV; ++v) {
@@ -412,7 +427,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, L::TMEM_COLS);
   }

@@ -208,6 +208,7 @@ conv_tc_kernel(const ConvTcP p) {
       uint8_t* sB = sA + L::A_BYTES;
       const int kbase = k_begin + kb * KB;
       // ------------------------------------------------ A tile
+      float4 va0[4], va1[4];
       if (MODE == TC_FWD || MODE == TC_DGRAD) {
         const int k0 = kbase + a_chunk * CE;
         const int cch = MODE == TC_FWD ? g.Cin : g.Cout;          // channels per tap
@@ -215,35 +216,35 @@ conv_tc_kernel(const ConvTcP p) {
         int dh, dw;
         if (MODE == TC_FWD) { dh = tap / g.KW; dw = tap - dh * g.KW; }
         else { dh = tap / ntw; dw = tap - dh * ntw; }
+        // all global loads of the block are issued before the first shared-memory store: the gather is latency-bound
+        // (L2 round trips), so the loads of a thread must be in flight together
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float4 v0 = z4, v1 = z4;
+          va0[j] = z4; va1[j] = z4;
           if (a_base[j] >= 0 && k0 < k_end) {
             if (MODE == TC_FWD) {
               const int hi = a_h0[j] + dh, wi = a_w0[j] + dw;
               if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
                 const float* src = p.a_src + ((size_t)(a_base[j] * g.H + hi) * g.W + wi) * g.Cin + c0;
-                v0 = ld4(src);
-                if (!TF32) v1 = ld4(src + 4);
+                va0[j] = ld4(src);
+                if (!TF32) va1[j] = ld4(src + 4);
               }
             } else {
               const int ho = a_h0[j] - dh, wo = a_w0[j] - dw;
               if (ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo) {
                 const float* src = p.a_src + ((size_t)(a_base[j] * g.Ho + ho) * g.Wo + wo) * g.Cout + c0;
-                v0 = ld4(src);
-                if (!TF32) v1 = ld4(src + 4);
+                va0[j] = ld4(src);
+                if (!TF32) va1[j] = ld4(src + 4);
               }
             }
           }
-          if (TF32) *reinterpret_cast<float4*>(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk)) = v0;
-          else st_chunk(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk), v0, v1);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int mr = (tid >> 4) + 16 * j;          // pixel row inside the 64-pixel block
           const int m = kbase + mr;
-          float4 v0 = z4, v1 = z4;
+          va0[j] = z4; va1[j] = z4;
           if (m < k_end) {
             if (wg_kind == 0) {
               const int b = m / (g.Ho * g.Wo), rem = m - b * (g.Ho * g.Wo);
@@ -251,71 +252,114 @@ conv_tc_kernel(const ConvTcP p) {
               const int hi = ho * g.S - g.PT + wg_kh, wi = wo * g.S - g.PL + wg_kw;
               if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
                 const float* src = p.a_src + ((size_t)(b * g.H + hi) * g.W + wi) * g.Cin + wg_ci;
-                v0 = ld4(src); v1 = ld4(src + 4);
+                va0[j] = ld4(src); va1[j] = ld4(src + 4);
               }
             } else if (wg_kind == 1) {
-              v0.x = 1.0f;                              // ones column -> bias gradient row
+              va0[j].x = 1.0f;                          // ones column -> bias gradient row
             }
           }
-          st_chunk(sA + (a_chunk >> 3) * 8192 + sw128_offset(mr, a_chunk & 7), v0, v1);
         }
       }
+      auto store_a = [&]() {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (MODE == TC_WGRAD) {
+            st_chunk(sA + (a_chunk >> 3) * 8192 + sw128_offset((tid >> 4) + 16 * j, a_chunk & 7), va0[j], va1[j]);
+          } else if (TF32) {
+            *reinterpret_cast<float4*>(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk)) = va0[j];
+          } else {
+            st_chunk(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk), va0[j], va1[j]);
+          }
+        }
+      };
       // ------------------------------------------------ B tile
       if (TF32 && MODE == TC_FWD) {
         // K-major rows n (NT), 8 chunks of 4 k: the HWIO kernel w[k][n] gathered transposed (4 strided scalar loads;
         // the kernel is small and L2-resident)
         constexpr int NCH = NT * 8;
-        for (int c = tid; c < NCH; c += 256) {
+        constexpr int NIT = (NCH + 255) / 256;
+        float4 vb[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = tid + it * 256;
           const int n = c >> 3, ch = c & 7;
           const int k0 = kbase + ch * 4;
-          float4 v0 = z4;
-          if (n0 + n < Ng) {
+          vb[it] = z4;
+          if (c < NCH && n0 + n < Ng) {
             const float* src = p.b_src + (size_t)k0 * g.Cout + n0 + n;
-            if (k0 + 0 < k_end) v0.x = src[0];
-            if (k0 + 1 < k_end) v0.y = src[g.Cout];
-            if (k0 + 2 < k_end) v0.z = src[2 * (size_t)g.Cout];
-            if (k0 + 3 < k_end) v0.w = src[3 * (size_t)g.Cout];
+            if (k0 + 0 < k_end) vb[it].x = src[0];
+            if (k0 + 1 < k_end) vb[it].y = src[g.Cout];
+            if (k0 + 2 < k_end) vb[it].z = src[2 * (size_t)g.Cout];
+            if (k0 + 3 < k_end) vb[it].w = src[3 * (size_t)g.Cout];
           }
-          *reinterpret_cast<float4*>(sB + sw128_offset(n, ch)) = v0;
+        }
+        store_a();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = tid + it * 256;
+          if (c < NCH) *reinterpret_cast<float4*>(sB + sw128_offset(c >> 3, c & 7)) = vb[it];
         }
       } else if (MODE == TC_DGRAD) {
         // K-major rows n (NT), 8 chunks of k: source w[(tap * Cin + n) * Cout + co0 ..]
         constexpr int NCH = NT * 8;
-        for (int c = tid; c < NCH; c += 256) {
+        constexpr int NIT = (NCH + 255) / 256;
+        float4 vb0[NIT], vb1[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = tid + it * 256;
           const int n = c >> 3, ch = c & 7;
           const int k0 = kbase + ch * CE;
-          float4 v0 = z4, v1 = z4;
-          if (n0 + n < Ng && k0 < k_end) {
+          vb0[it] = z4; vb1[it] = z4;
+          if (c < NCH && n0 + n < Ng && k0 < k_end) {
             const int tap = k0 / g.Cout, co0 = k0 - tap * g.Cout;
             const int th = tap / ntw, tw = tap - th * ntw;
             const int kh = rh + th * g.S, kw = rw + tw * g.S;
             const float* src = p.b_src + ((size_t)(kh * g.KW + kw) * g.Cin + n0 + n) * g.Cout + co0;
-            v0 = ld4(src);
-            if (!TF32) v1 = ld4(src + 4);
+            vb0[it] = ld4(src);
+            if (!TF32) vb1[it] = ld4(src + 4);
           }
-          if (TF32) *reinterpret_cast<float4*>(sB + sw128_offset(n, ch)) = v0;
-          else st_chunk(sB + sw128_offset(n, ch), v0, v1);
+        }
+        store_a();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = tid + it * 256;
+          if (c < NCH) {
+            if (TF32) *reinterpret_cast<float4*>(sB + sw128_offset(c >> 3, c & 7)) = vb0[it];
+            else st_chunk(sB + sw128_offset(c >> 3, c & 7), vb0[it], vb1[it]);
+          }
         }
       } else {
         // MN-major: 64 reduction rows, NT/8 chunks of n: source rows are contiguous in n (w[k][:] or dy[m][:])
         constexpr int CPR = NT / 8;                    // chunks per row
         constexpr int NCH = 64 * CPR;
-        for (int c = tid; c < NCH; c += 256) {
+        constexpr int NIT = (NCH + 255) / 256;
+        float4 vb0[NIT], vb1[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = tid + it * 256;
           const int r = c / CPR, ch = c - r * CPR;
           const int kk = kbase + r, n = n0 + ch * 8;
-          float4 v0 = z4, v1 = z4;
-          if (kk < k_end && n < Ng) {
+          vb0[it] = z4; vb1[it] = z4;
+          if (c < NCH && kk < k_end && n < Ng) {
             const float* src = p.b_src + (size_t)kk * g.Cout + n;
             if ((g.Cout & 7) == 0) {
-              v0 = ld4(src); v1 = ld4(src + 4);
+              vb0[it] = ld4(src); vb1[it] = ld4(src + 4);
             } else {   // ragged channel count (the 3-channel image head): guarded scalar loads
               float t8[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) t8[e] = (n + e < Ng) ? src[e] : 0.f;
-              v0 = make_float4(t8[0], t8[1], t8[2], t8[3]); v1 = make_float4(t8[4], t8[5], t8[6], t8[7]);
+              vb0[it] = make_float4(t8[0], t8[1], t8[2], t8[3]); vb1[it] = make_float4(t8[4], t8[5], t8[6], t8[7]);
             }
           }
-          st_chunk(sB + (ch >> 3) * 8192 + sw128_offset(r, ch & 7), v0, v1);
+        }
+        store_a();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int c = tid + it * 256;
+          if (c < NCH) {
+            const int r = c / CPR, ch = c - r * CPR;
+            st_chunk(sB + (ch >> 3) * 8192 + sw128_offset(r, ch & 7), vb0[it], vb1[it]);
+          }
         }
       }
       fence_proxy_async_smem();
