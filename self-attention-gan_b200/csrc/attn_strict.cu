@@ -459,6 +459,15 @@ static int attn_fwd_strict_t(const float* X, const float* Wq, const float* bq, c
 }
 
 // common tail of the backward: dX from (dQ, dK, dV), parameter gradients as 1x1-conv wgrads
+struct ZeroTab {
+  float* p[8];
+  int n[8];
+};
+__global__ void zero8_kernel(const ZeroTab t) {
+  float* p = t.p[blockIdx.x];
+  for (int i = threadIdx.x; i < t.n[blockIdx.x]; i += blockDim.x) p[i] = 0.f;
+}
+
 template <int C>
 static int attn_bwd_tail_t(const float* dY, const float* X, const float* Wq, const float* Wk, const float* Wv,
                            const float* Wo, const float* bo, const float* gamma, const float* A, const float* dQ,
@@ -472,14 +481,13 @@ static int attn_bwd_tail_t(const float* dY, const float* X, const float* Wq, con
     SAGAN_LAUNCH_CHECK();
   }
   if (dWq) {
-    SAGAN_CUDA(cudaMemsetAsync(dWq, 0, sizeof(float) * C * D, st));
-    SAGAN_CUDA(cudaMemsetAsync(dWk, 0, sizeof(float) * C * D, st));
-    SAGAN_CUDA(cudaMemsetAsync(dWv, 0, sizeof(float) * C * DV, st));
-    SAGAN_CUDA(cudaMemsetAsync(dWo, 0, sizeof(float) * DV * C, st));
-    SAGAN_CUDA(cudaMemsetAsync(dbq, 0, sizeof(float) * D, st));
-    SAGAN_CUDA(cudaMemsetAsync(dbk, 0, sizeof(float) * D, st));
-    SAGAN_CUDA(cudaMemsetAsync(dbv, 0, sizeof(float) * DV, st));
-    SAGAN_CUDA(cudaMemsetAsync(dbo, 0, sizeof(float) * C, st));
+    // the eight caller-owned gradient buffers are accumulated atomically: one launch zeroes them all
+    ZeroTab zt;
+    float* zp[8] = {dWq, dWk, dWv, dWo, dbq, dbk, dbv, dbo};
+    const int zn[8] = {C * D, C * D, C * DV, DV * C, D, D, DV, C};
+    for (int i = 0; i < 8; ++i) { zt.p[i] = zp[i]; zt.n[i] = zn[i]; }
+    zero8_kernel<<<8, 256, 0, st>>>(zt);
+    SAGAN_LAUNCH_CHECK();
     const int blocks = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(T, 256));
     const int tpb = (int)(ceil_div<long long>(ceil_div<long long>(T, blocks), 128) * 128);
     attn_wgrad_small_kernel<C><<<(unsigned)ceil_div<long long>(T, tpb), 256, 0, st>>>(X, A, dY, dQ, dK, dV, dWq, dbq, dWk,

@@ -31,7 +31,12 @@ using namespace tc;
 constexpr float TB_LOG2E = 1.4426950408889634f;
 constexpr int TB_THREADS = 608;   // 16 compute warps + TMA producer warp + 2 MMA issuer warps
 constexpr int TB_CWARPS = 16;
-constexpr int TB_COLS = 64;   // bf16 row length of the K-major operand buffers (128 B)
+constexpr int TB_COLS = 64;   // widest bf16 row of the K-major operand buffers (128 B)
+// Row lengths of the score-MMA operands: exactly the K extent the MMAs read (16 / 32 / 64 bf16 = 32 / 64 / 128 bytes,
+// loaded in the matching TMA swizzle mode).  Every CTA re-reads all query tiles of its sample, so padded rows would be
+// L2 -> SM traffic and shared memory spent on zeros.
+__host__ __device__ constexpr int tb_kq(int C) { return ((3 * (C / 8) + 15) / 16) * 16; }
+__host__ __device__ constexpr int tb_kv(int C) { return C <= 32 ? ((3 * (C / 2) + 2 + 15) / 16) * 16 : C; }
 
 // ------------------------------------------------------------------------------------ prep (small C)
 // one thread per PADDED token; recomputes theta/phi/g from X and forms dA = gamma dY Wo^T, D = dA . A
@@ -58,6 +63,7 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   constexpr bool FOLD = SPLIT3;
   constexpr int KV = SPLIT3 ? ((3 * DV + 2 + 15) / 16) * 16 : 2 * DV;
   static_assert(KV <= TB_COLS, "dP operand row must fit one 128-byte swizzle span");
+  static_assert(KQ == tb_kq(C) && KV == tb_kv(C), "row lengths shared with the main kernel");
   static_assert(!FOLD || 3 * D + 3 <= KQ, "no spare logit columns for the folded shift");
   __shared__ float sWq[C * D], sWk[C * D], sWv[C * DV], sbq[D], sbk[D], sbv[DV];
   __shared__ __align__(16) float sWo[DV * C];
@@ -120,8 +126,8 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     Kt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
     Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(0.f);
   }
-  uint4* qd = reinterpret_cast<uint4*>(Qb + tp * TB_COLS);
-  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * TB_COLS);
+  uint4* qd = reinterpret_cast<uint4*>(Qb + tp * KQ);
+  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * KQ);
 #pragma unroll
   for (int g = 0; g < KQ / 8; ++g) {
     qd[g] = make_uint4(pack_bf16x2(q[g * 8 + 0], q[g * 8 + 1]), pack_bf16x2(q[g * 8 + 2], q[g * 8 + 3]),
@@ -169,8 +175,8 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     v[3 * DV] = 1.f;      da[3 * DV] = -d_hi;
     v[3 * DV + 1] = 1.f;  da[3 * DV + 1] = -(dd - d_hi);
   }
-  uint4* vd = reinterpret_cast<uint4*>(Vb + tp * TB_COLS);
-  uint4* ad = reinterpret_cast<uint4*>(dAb + tp * TB_COLS);
+  uint4* vd = reinterpret_cast<uint4*>(Vb + tp * KV);
+  uint4* ad = reinterpret_cast<uint4*>(dAb + tp * KV);
 #pragma unroll
   for (int g = 0; g < KV / 8; ++g) {
     vd[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
@@ -186,27 +192,30 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------ main
-template <int DVP>
+template <int DVP, int QKB, int VAB, int NDS>
 struct BwdSmem {
   static constexpr int TILE = 128 * 128;                 // [128 rows][128 B]
   static constexpr int T16 = 2 * 16 * 128;               // two 64-column sub-tiles of [16 rows][128 B]
   static constexpr int TDV = 2 * DVP * 128;
+  static constexpr int QK_TILE = 128 * QKB;              // Q / K rows of QKB bytes
+  static constexpr int VA_TILE = 128 * VAB;              // V / dA rows of VAB bytes
   static constexpr int OFF_K = 0;
-  static constexpr int OFF_V = OFF_K + TILE;
-  static constexpr int OFF_KT = OFF_V + TILE;
+  static constexpr int OFF_V = OFF_K + QK_TILE;
+  static constexpr int OFF_KT = OFF_V + VA_TILE;
   // query-side operands in two rings: A = what the score-shaped MMAs read (Q_i, dA_i rows; free as soon as dP^T_i has
   // been computed, so three stages let the loads run two tiles ahead), B = what the gradient MMAs read (dA_i^T, Q_i^T
   // rows and the lse / D vectors; free when the gradient MMAs of the tile are done)
   static constexpr int NA = 3, NB = 2;
   static constexpr int OFF_A = OFF_KT + T16;
-  static constexpr int A_Q = 0, A_DA = TILE, ASTAGE = 2 * TILE;
+  static constexpr int A_Q = 0, A_DA = QK_TILE, ASTAGE = QK_TILE + VA_TILE;
   static constexpr int OFF_B = OFF_A + NA * ASTAGE;
   static constexpr int B_DAT = 0, B_QT = TDV, B_VEC = TDV + T16, BSTAGE = TDV + T16 + 1024;   // vec: lse2[128], D[128]
-  static constexpr int OFF_DST = OFF_B + NB * BSTAGE;     // dS^T hi (bf16) for the dQ MMAs
-  static constexpr int OFF_DSL = OFF_DST + 2 * TILE;      // dS^T - bf16(dS^T): second bf16 term of the split
-  static constexpr int OFF_BAR = OFF_DSL + 2 * TILE;
+  // dS^T tiles for the dQ MMAs (bf16 hi / lo terms), NDS buffers: with two, the stores of tile i do not wait for dQ_{i-1}
+  static constexpr int DS_BUF = 4 * TILE;                 // [hi: 2 sub-tiles | lo: 2 sub-tiles]
+  static constexpr int OFF_DS = OFF_B + NB * BSTAGE;
+  static constexpr int OFF_BAR = OFF_DS + NDS * DS_BUF;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
-  static constexpr int A_TX = 2 * TILE, B_TX = TDV + T16 + 1024;
+  static constexpr int A_TX = QK_TILE + VA_TILE, B_TX = TDV + T16 + 1024;
   static_assert(ASTAGE % 1024 == 0 && BSTAGE % 1024 == 0 && OFF_A % 1024 == 0, "tiles must stay 1024-byte aligned");
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
   // TMEM columns.  P'^T and the two bf16 terms of dS^T are the A operands of the dV / dK MMAs and live in TMEM
@@ -224,7 +233,7 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
   mma_bf16_ts_g<1>(d_tmem, a_tmem, b_desc, idesc, accumulate);
 }
 
-template <int DVP, bool SPLIT_DA>
+template <int DVP, bool SPLIT_DA, int QKB, int VAB, int NDS>
 __global__ void __launch_bounds__(TB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdA,
@@ -232,7 +241,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmKt, const float* __restrict__ lse2,
                    const float* __restrict__ Dd, float* __restrict__ dQ, float* __restrict__ dK,
                    float* __restrict__ dV, int N, int Npad, int d, int dv, int kq_steps, int kv_steps) {
-  using L = BwdSmem<DVP>;
+  using L = BwdSmem<DVP, QKB, VAB, NDS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem + L::OFF_K;
@@ -240,8 +249,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sKt = smem + L::OFF_KT;
   uint8_t* sA = smem + L::OFF_A;
   uint8_t* sB = smem + L::OFF_B;
-  uint8_t* sdSt = smem + L::OFF_DST;
-  uint8_t* sdSl = smem + L::OFF_DSL;
+  uint8_t* sDS = smem + L::OFF_DS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* barKV = bars + 0;
   uint64_t* barAfull = bars + 1;     // [3] Q_i / dA_i rows landed
@@ -286,7 +294,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdA);
       tma_prefetch_desc(&tmdAt); tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt);
-      mbar_expect_tx(barKV, 2 * L::TILE + L::T16);
+      mbar_expect_tx(barKV, L::QK_TILE + L::VA_TILE + L::T16);
       tma_load_2d(sK, &tmK, barKV, 0, b * Npad + kt * 128);
       tma_load_2d(sV, &tmV, barKV, 0, b * Npad + kt * 128);
       tma_load_2d(sKt, &tmKt, barKV, kt * 128, b * 16);
@@ -326,15 +334,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 64);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
       constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
-      const uint64_t dK_ = make_desc_sw128(smem_u32(sK)), dV_ = make_desc_sw128(smem_u32(sV));
+      const uint64_t dK_ = make_desc_rows<QKB>(smem_u32(sK)), dV_ = make_desc_rows<VAB>(smem_u32(sV));
       auto issue_s = [&](int i, int x) {       // S^T[:, 64 x .. 64 x + 64) = K Q_i^T (64 query rows of the stage)
-        const uint64_t dQ_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q + x * (64 * 128)));
+        const uint64_t dQ_ = make_desc_rows<QKB>(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q + x * (64 * QKB)));
         for (int ks = 0; ks < kq_steps; ++ks)
           mma_bf16_ss(tmem_base + L::ST_COL + x * 64, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
         mma_commit(barS + x);
       };
       auto issue_dp = [&](int i, int x) {      // dP^T[:, 64 x .. 64 x + 64) = V dA_i^T
-        const uint64_t dA_ = make_desc_sw128(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_DA + x * (64 * 128)));
+        const uint64_t dA_ = make_desc_rows<VAB>(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_DA + x * (64 * VAB)));
         for (int ks = 0; ks < kv_steps; ++ks)
           mma_bf16_ss(tmem_base + L::DP_COL + x * 64, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
         mma_commit(barDP + x);
@@ -404,9 +412,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {   // K = 16 keys per step: the dS^T tiles read MN-major (M = queries contiguous)
           const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(smem_u32(sdSt) + ks * 16 * 128, L::TILE, 1024),
+          const uint32_t ds = smem_u32(sDS + (i % NDS) * L::DS_BUF);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(ds + ks * 16 * 128, L::TILE, 1024),
                       dKt_ + b16, IDESC_DQ, ks > 0);
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(smem_u32(sdSl) + ks * 16 * 128, L::TILE, 1024),
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(ds + 2 * L::TILE + ks * 16 * 128, L::TILE, 1024),
                       dKt_ + b16, IDESC_DQ, ks > 0);
         }
         mma_commit(barQd + (i & 1));
@@ -512,13 +521,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
       }
       tmem_st16(t_row + L::DSH_COL + h * 16, hi);
-      if (i >= 1) {
-        mbar_wait(barQd + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+      if (i >= NDS) {                                         // this dS^T buffer was last read by the dQ MMAs of tile i - NDS
+        mbar_wait(barQd + ((i - NDS) & 1), ((i - NDS) >> 1) & 1);
         tc_fence_after();
       }
       // query columns [32 h, 32 h + 32): 64-query sub-tile h >> 1, 16-byte chunks (h & 1) * 4 + g
-      uint8_t* dst = sdSt + (h >> 1) * L::TILE;
-      uint8_t* dsl = sdSl + (h >> 1) * L::TILE;
+      uint8_t* dst = sDS + (i % NDS) * L::DS_BUF + (h >> 1) * L::TILE;
+      uint8_t* dsl = dst + 2 * L::TILE;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint32_t off = sw128_offset(krow, (h & 1) * 4 + g);
@@ -530,6 +539,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(barTiles + x);                              // this thread's part of P'^T / dS^T is written
       if (i >= 1) {                                           // off the critical path: dQ_{i-1} -> global memory
+        if (NDS > 1) mbar_wait(barQd + ((i - 1) & 1), ((i - 1) >> 1) & 1);
         tc_fence_after();
         flush_dq(i - 1);
       }
@@ -610,10 +620,10 @@ static TbLayout tb_layout(int B, int N, int C) {
   const size_t T = (size_t)B * t.Npad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
-  t.off_q = take(T * TB_COLS * 2);
-  t.off_k = take(T * TB_COLS * 2);
-  t.off_v = take(T * TB_COLS * 2);
-  t.off_da = take(T * TB_COLS * 2);
+  t.off_q = take(T * tb_kq(C) * 2);
+  t.off_k = take(T * tb_kq(C) * 2);
+  t.off_v = take(T * tb_kv(C) * 2);
+  t.off_da = take(T * tb_kv(C) * 2);
   t.off_dat = take((size_t)B * t.DVP * t.Npad * 2);
   t.off_qt = take((size_t)B * 16 * t.Npad * 2);
   t.off_kt = take((size_t)B * 16 * t.Npad * 2);
@@ -639,11 +649,11 @@ static int run_prep(const float* X, const float* dY, const float* A, const float
   return 0;
 }
 
-template <int DVP, bool SPLIT_DA>
+template <int DVP, bool SPLIT_DA, int QKB, int VAB, int NDS>
 static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, float* dQ, float* dK, float* dV, int B,
                       int N, int Npad, int d, int dv, int kq, int kv, cudaStream_t st) {
-  using L = BwdSmem<DVP>;
-  auto kern = attn_bwd_tc_kernel<DVP, SPLIT_DA>;
+  using L = BwdSmem<DVP, QKB, VAB, NDS>;
+  auto kern = attn_bwd_tc_kernel<DVP, SPLIT_DA, QKB, VAB, NDS>;
   static bool configured = false;
   if (!configured) {
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -679,19 +689,20 @@ int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const floa
   if (rc) return rc;
   const uint64_t Tp = (uint64_t)B * t.Npad;
   CUtensorMap m[7];
-  if ((rc = make_tmap_bf16_2d(&m[0], base + t.off_q, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&m[1], base + t.off_k, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&m[2], base + t.off_v, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&m[3], base + t.off_da, Tp, TB_COLS, TB_COLS * 2, 128))) return rc;
+  const uint32_t kq = (uint32_t)tb_kq(C), kv = (uint32_t)tb_kv(C);
+  if ((rc = make_tmap_bf16_2d(&m[0], base + t.off_q, Tp, kq, kq * 2, 128, kq, (int)kq * 2))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[1], base + t.off_k, Tp, kq, kq * 2, 128, kq, (int)kq * 2))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[2], base + t.off_v, Tp, kv, kv * 2, 128, kv, (int)kv * 2))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[3], base + t.off_da, Tp, kv, kv * 2, 128, kv, (int)kv * 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&m[4], base + t.off_dat, (uint64_t)B * t.DVP, t.Npad, (uint64_t)t.Npad * 2, t.DVP))) return rc;
   if ((rc = make_tmap_bf16_2d(&m[5], base + t.off_qt, (uint64_t)B * 16, t.Npad, (uint64_t)t.Npad * 2, 16))) return rc;
   if ((rc = make_tmap_bf16_2d(&m[6], base + t.off_kt, (uint64_t)B * 16, t.Npad, (uint64_t)t.Npad * 2, 16))) return rc;
   const float* lse2 = (const float*)(base + t.off_lse);
   const float* Dd = (const float*)(base + t.off_dd);
   const int d = C / 8, dv = C / 2;
-  if (C == 16) return launch_bwd<16, true>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
-  if (C == 32) return launch_bwd<32, true>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
-  return launch_bwd<32, false>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  if (C == 16) return launch_bwd<16, true, 32, 64, 2>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  if (C == 32) return launch_bwd<32, true, 32, 128, 1>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  return launch_bwd<32, false, 64, 128, 1>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
 }
 
 }  // namespace sagan

@@ -115,6 +115,23 @@ __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
   d |= (uint64_t)6 << 61;
   return d;
 }
+// K-major operand in the 64-byte-swizzle canonical layout: rows of 64 B (32 bf16 = two MMA K steps), groups of 8 rows =
+// 512 B atoms (what TMA SWIZZLE_64B writes).  Layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// K-major operand whose rows are RB bytes (32 / 64 / 128) in the matching swizzle mode
+template <int RB>
+__device__ __forceinline__ uint64_t make_desc_rows(uint32_t smem_addr) {
+  static_assert(RB == 32 || RB == 64 || RB == 128, "row bytes");
+  return RB == 32 ? make_desc_sw32(smem_addr) : (RB == 64 ? make_desc_sw64(smem_addr) : make_desc_sw128(smem_addr));
+}
 // Same tile read as an MN-major operand (M/N contiguous): the tile is [K rows][64 MN elements = 128 B] per sub-tile,
 // 8 K-rows = 1024 B swizzle atom.  LBO = byte distance between 64-element MN atoms, SBO = between 8-row K groups.
 __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
