@@ -302,6 +302,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // the two rings are refilled by polling, whichever stage frees first (no assumption on their relative order)
       int ia = 0, ib = 0;
       while (ia < nq || ib < nq) {
+        const int before = ia + ib;
         if (ia < nq) {
           const int s = ia % L::NA;
           if (ia < L::NA || mbar_try_wait(barAfree + s, ((ia / L::NA) - 1) & 1)) {
@@ -326,6 +327,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ++ib;
           }
         }
+        if (ia + ib == before) __nanosleep(256);      // nothing freed: do not hog the scheduler's issue slots
       }
     }
   } else if (warp == TB_CWARPS + 1) {
