@@ -373,6 +373,15 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     args.warmup = max(args.warmup, 3)
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner at N > 1) are sent to
+    # stderr while the run is in progress; the report itself goes to the saved descriptor
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved_stdout, "w", buffering=1)
+    if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1; the CPU baseline leg is an N = 1 measurement
+        args.cpu_baseline = False
     run_ours(args, rank, world, local_rank)
     if world > 1:
         sys.stdout.flush()
