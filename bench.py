@@ -248,7 +248,7 @@ def run_ours(args, rank, world, local_rank):
     cfg = dict(CHURCH64)
     B = cfg["batch_size"]
     tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=126227 // (B * world), seed=0,   # LSUN church: 126 227 images
-                 dp_mode=args.dp)
+                 dp_mode=args.dp, overlap_streams=args.overlap)
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
     host_batches = [torch.tensor(rng.uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
     dev_batches = [b.to(dev) for b in host_batches]
@@ -360,6 +360,8 @@ def main():
     ap.add_argument("--math", default="bf16_tc", choices=["fp32_strict", "bf16_tc"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="data-parallel gradient exchange (N > 1)")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
+                    help="single-stream step (default: G(z) and D(real) of the D phase run as two graph branches)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

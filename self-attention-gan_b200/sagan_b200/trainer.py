@@ -49,7 +49,8 @@ class FlatAdam:
 
 
 class Trainer:
-    def __init__(self, config, global_batch_size=None, steps_per_epoch=1000, process_group=None, seed=0, dp_mode="p2p"):
+    def __init__(self, config, global_batch_size=None, steps_per_epoch=1000, process_group=None, seed=0, dp_mode="p2p",
+                 overlap_streams=True):
         """config: the reference's dict (example_configs/*.py).  process_group: torch.distributed group for the
         data-parallel gradient sum (None = single replica / default group).  dp_mode: "p2p" = the fused NVLink
         peer-memory exchange + Adam kernel (parallel.PeerAdam), "nccl" = NCCL all-reduce followed by Adam."""
@@ -83,6 +84,12 @@ class Trainer:
             self.peer_G = PeerAdam(self.G, self.opt_G, self.dp)
             self.peer_D = PeerAdam(self.D, self.opt_D, self.dp)
         self.loss_sums = torch.zeros(2, device=self.device)     # [sum L_D (over update_ratio), sum L_G]
+        self.overlap_streams = overlap_streams
+        self._side = torch.cuda.Stream(device=self.device) if overlap_streams else None
+        self._side2 = torch.cuda.Stream(device=self.device) if overlap_streams else None
+        self._ev_g = torch.cuda.Event() if overlap_streams else None
+        if overlap_streams and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # intentional: see _d_phase
         self.graph = None
         self._static = {}
 
@@ -92,10 +99,24 @@ class Trainer:
 
     def _d_phase(self, images, labels, noise, fake_labels):
         G, D = self.G, self.D
-        with torch.no_grad():                                               # main.py:178 (outside the tape)
-            fake = G([noise, fake_labels], training=True)
         D.zero_grad_flat()
-        d_real = D([images, labels], training=True)                         # main.py:181
+        if self.overlap_streams:
+            # G(z) (no tape) and D(real) are independent: two branches of the step graph.  Most of their conv / BN /
+            # spectral-norm launches fill a fraction of the 148 SMs, so the branches overlap; autograd replays the
+            # D(real) branch of the backward on the side stream as well.  Same operations in the same per-network order.
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                d_real = D([images, labels], training=True)                 # main.py:181
+            with torch.no_grad():                                           # main.py:178 (outside the tape)
+                fake = G([noise, fake_labels], training=True)
+            self._ev_g.record(main)                                         # G is free for the G phase's forward
+            main.wait_stream(self._side)
+            d_real.record_stream(main)
+        else:
+            with torch.no_grad():                                           # main.py:178 (outside the tape)
+                fake = G([noise, fake_labels], training=True)
+            d_real = D([images, labels], training=True)                     # main.py:181
         d_fake = D([fake, fake_labels], training=True)                      # main.py:182
         g_real, g_fake = F.hinge_d_grads(d_real, d_fake, self.global_batch, self.loss_sums[0:1])   # main.py:183-184
         torch.autograd.backward([d_real, d_fake], [g_real, g_fake])         # main.py:188-189
@@ -111,7 +132,18 @@ class Trainer:
         for p in D.parameters():
             p.requires_grad_(False)                                         # main.py:203-204: grads wrt G only
         try:
-            fake = G([noise, fake_labels], training=True)                   # main.py:198
+            if self.overlap_streams:
+                # G(z') of the G phase depends on nothing the D phase still has to do (D's update only matters for
+                # D(G(z')) below): it starts as soon as the D phase's own G(z) is done and runs as a second branch
+                # under D(fake), the D backward and D's Adam / gradient exchange
+                main = torch.cuda.current_stream()
+                self._side2.wait_event(self._ev_g)
+                with torch.cuda.stream(self._side2):
+                    fake = G([noise, fake_labels], training=True)           # main.py:198
+                main.wait_stream(self._side2)
+                fake.record_stream(main)
+            else:
+                fake = G([noise, fake_labels], training=True)               # main.py:198
             d_fake = D([fake, fake_labels], training=True)                  # main.py:199
             g = F.hinge_g_grads(d_fake, self.global_batch, self.loss_sums[1:2])   # main.py:200-201
             d_fake.backward(g)
@@ -128,13 +160,18 @@ class Trainer:
         cfg = self.config
         ur = cfg.get("update_ratio", 1)
         self.loss_sums.zero_()
+        # all noise / label draws first, in the reference's order (main.py:176-177,194-195): the G phase's forward runs
+        # as a branch that starts before the D phase is over, so its inputs must exist by then
+        draws = []
         for i in range(ur):                                                 # main.py:175
             nz = noises_d[i] if noises_d is not None else torch.randn(self.B, cfg["z_dim"], device=self.device)
             fl = fake_labels_d[i] if fake_labels_d is not None else self._rand_labels()
+            draws.append((nz, fl))
+        nz_g = noise_g if noise_g is not None else torch.randn(self.B, cfg["z_dim"], device=self.device)
+        fl_g = fake_labels_g if fake_labels_g is not None else self._rand_labels()
+        for nz, fl in draws:
             self._d_phase(images, labels, nz, fl)
-        nz = noise_g if noise_g is not None else torch.randn(self.B, cfg["z_dim"], device=self.device)
-        fl = fake_labels_g if fake_labels_g is not None else self._rand_labels()
-        self._g_phase(nz, fl)
+        self._g_phase(nz_g, fl_g)
 
     def _rand_labels(self):
         cfg = self.config
