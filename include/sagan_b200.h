@@ -120,6 +120,10 @@ int sagan_sn_backward_multi(const sagan_sn_bwd_desc* descs_host, int n, int accu
  * Wv: [C, dv]; Wo: [dv, C]  (Keras [1,1,cin,cout] kernels, already spectrally normalised).
  * gamma: device scalar (`sigma`, layers.py:76-79).  Saved for backward: lse [B, N]
  * (row-wise log-sum-exp of the logits) and A [B, N, dv].  The [B,N,N] map is never written.
+ * Supported shapes: FP32_STRICT C in {8,16,32,64}, any N; BF16_TC C in {16,32,64}, any N (fused
+ * tcgen05 forward and backward) and C in {128,256,512} with N % 128 == 0 (fused forward; the
+ * backward of this regime is composed of GEMM launches and keeps the [N,N] maps of ONE sample
+ * at a time in the workspace).  Anything else returns SAGAN_EUNSUPPORTED.
  * ------------------------------------------------------------------------------------------ */
 size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode);
 int sagan_attn_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,

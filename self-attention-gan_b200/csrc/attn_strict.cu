@@ -567,12 +567,30 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
                 int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace sagan
 
+namespace sagan {
+int attn_bwd_finalize_launch(const float* Wo, const float* bo, const float* gamma, float* dWo, float* dbo, float* dgamma,
+                             int nW, int C, cudaStream_t st) {
+  attn_bwd_finalize_kernel<<<1, 256, 0, st>>>(Wo, bo, gamma, dWo, dbo, dgamma, nW, C);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// attn_big_bwd.cu
+size_t attn_big_bwd_workspace_bytes(int B, int N, int C);
+int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                    const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma, const float* A,
+                    float* dX, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo,
+                    float* dbo, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+bool attn_tc_big_supported(int N, int C);
+}  // namespace sagan
+
 extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode) {
   if (B <= 0 || N <= 0 || C <= 0) return 0;
   const long long T = (long long)B * N;
   const size_t strict = (size_t)(T * (2 * C + 1) + 64) * sizeof(float);
   if (math_mode == SAGAN_MATH_BF16_TC) {
-    if (C > 64) return attn_tc_workspace_bytes(B, N, C);                      // forward only (large-C path)
+    if (C > 64)   // large-C path: fused forward, composed backward (attn_big_bwd.cu)
+      return std::max(attn_tc_workspace_bytes(B, N, C), attn_big_bwd_workspace_bytes(B, N, C) + 256);
     const size_t small = (size_t)(T * (C / 4 + C / 2) + 64) * sizeof(float);   // dQ, dK, dV
     return std::max(strict, std::max(attn_tc_workspace_bytes(B, N, C), small + attn_tc_bwd_workspace_bytes(B, N, C)));
   }
@@ -635,8 +653,12 @@ extern "C" int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, 
     SAGAN_ATTN_DISPATCH(attn_bwd_tc_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk, dbk,
                         dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, ws_bytes, st);
   }
+  if (math_mode == SAGAN_MATH_BF16_TC && attn_tc_big_supported(N, C))
+    return attn_tc_big_bwd(dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, A_saved, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo,
+                           dbo, dgamma, B, N, C, ws, ws_bytes, st);
   SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
                       dbk, dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, st);
-  set_err("sagan_attn_bwd: supports C in {8,16,32,64} (C=%d); the large-C tensor-core path is forward-only so far", C);
+  set_err("sagan_attn_bwd: supports C in {8,16,32,64} (FP32_STRICT, BF16_TC) and {128,256,512} with N %% 128 == 0 "
+          "(BF16_TC); got C=%d N=%d", C, N);
   return SAGAN_EUNSUPPORTED;
 }

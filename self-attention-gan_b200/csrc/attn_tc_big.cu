@@ -291,6 +291,11 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (threadIdx.x == 128) TL_DUMP(8, 8);
 
     // ---- epilogue: A = O / l (fp32, saved for the backward and read by the output-conv GEMM), lse
+    // barO completes one phase per key tile and a parity wait can only tell the current phase from the one before:
+    // having read S_{nt-1}, this thread knows that PV_{nt-3} is complete (the pipe runs in issue order), no more --
+    // so it waits for PV_{nt-2} first; asking for the last phase directly could alias with phase nt-3 and return
+    // while two PV MMAs are still in flight (seen as a wrong A on a cold first launch).
+    if (nt >= 2) mbar_wait(barO, (nt - 2) & 1);
     mbar_wait(barO, (nt - 1) & 1);
     tc_fence_after();
     float* xb = sX + (nt & 1) * 256;

@@ -86,8 +86,6 @@ class Trainer:
         self.loss_sums = torch.zeros(2, device=self.device)     # [sum L_D (over update_ratio), sum L_G]
         self.overlap_streams = overlap_streams
         self._side = torch.cuda.Stream(device=self.device) if overlap_streams else None
-        self._side2 = torch.cuda.Stream(device=self.device) if overlap_streams else None
-        self._ev_g = torch.cuda.Event() if overlap_streams else None
         if overlap_streams and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # intentional: see _d_phase
         self.graph = None
@@ -102,17 +100,17 @@ class Trainer:
         D.zero_grad_flat()
         if self.overlap_streams:
             # G(z) (no tape) and D(real) are independent: two branches of the step graph.  Most of their conv / BN /
-            # spectral-norm launches fill a fraction of the 148 SMs, so the branches overlap; autograd replays the
-            # D(real) branch of the backward on the side stream as well.  Same operations in the same per-network order.
+            # spectral-norm launches fill a fraction of the 148 SMs, so the branches overlap.  The GENERATOR forwards go
+            # to the side stream: every D call stays on the main stream, because the two D calls of this phase
+            # accumulate their spectral-norm weight gradients in place into the same flat bucket and must not run
+            # their backward nodes concurrently (autograd replays a node on the stream of its forward).
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                d_real = D([images, labels], training=True)                 # main.py:181
-            with torch.no_grad():                                           # main.py:178 (outside the tape)
+            with torch.cuda.stream(self._side), torch.no_grad():                # main.py:178 (outside the tape)
                 fake = G([noise, fake_labels], training=True)
-            self._ev_g.record(main)                                         # G is free for the G phase's forward
+            d_real = D([images, labels], training=True)                     # main.py:181
             main.wait_stream(self._side)
-            d_real.record_stream(main)
+            fake.record_stream(main)
         else:
             with torch.no_grad():                                           # main.py:178 (outside the tape)
                 fake = G([noise, fake_labels], training=True)
@@ -134,13 +132,14 @@ class Trainer:
         try:
             if self.overlap_streams:
                 # G(z') of the G phase depends on nothing the D phase still has to do (D's update only matters for
-                # D(G(z')) below): it starts as soon as the D phase's own G(z) is done and runs as a second branch
-                # under D(fake), the D backward and D's Adam / gradient exchange
+                # D(G(z')) below): it follows the D phase's own G(z) on the side stream (spectral-norm u and the
+                # BatchNorm moving statistics persist from call to call, so the two forwards stay ordered) and runs under
+                # D(fake), the D backward and D's Adam / gradient exchange.  Its backward nodes run on the side stream
+                # too; the engine orders them after the D backward-data nodes that feed them.
                 main = torch.cuda.current_stream()
-                self._side2.wait_event(self._ev_g)
-                with torch.cuda.stream(self._side2):
+                with torch.cuda.stream(self._side):
                     fake = G([noise, fake_labels], training=True)           # main.py:198
-                main.wait_stream(self._side2)
+                main.wait_stream(self._side)
                 fake.record_stream(main)
             else:
                 fake = G([noise, fake_labels], training=True)               # main.py:198

@@ -349,26 +349,30 @@ def test_cuda_graph_step_equals_eager_step():
 
 
 def test_overlapped_step_equals_single_stream_step():
-    """The step with G(z) / D(real) and the G phase's forward running as side-stream branches (Trainer
-    overlap_streams=True, the default and what bench.py times) computes what the single-stream step computes:
-    same injected noise, three steps, losses and weights compared (fp32 mode; the only difference left is the
-    order of the atomic partial sums of the weight-gradient kernels)."""
+    """The step whose generator forwards run as a side-stream branch (Trainer overlap_streams=True, the default and
+    what bench.py times) computes what the single-stream step computes: same injected noise, the losses of three
+    steps and the weights after them.  The first step's losses see identical weights (agreement to rounding); after
+    that the two runs differ by the order of the atomic partial sums in the weight-gradient kernels, which Adam with
+    beta_1 = 0 turns into +-lr steps on parameters whose gradient is rounding noise (loss-trajectory
+    parity), hence the looser bounds.  Repeated to give a stream race more than one chance to show."""
     from sagan_b200.trainer import Trainer
     cfg = dict(mg.TEST_CFG)
-    a = Trainer(cfg, seed=5, overlap_streams=True)
-    b = Trainer(cfg, seed=5, overlap_streams=False)
-    b.G.flat_params.copy_(a.G.flat_params); b.D.flat_params.copy_(a.D.flat_params)
-    b.G.sn_group.out.copy_(a.G.sn_group.out); b.D.sn_group.out.copy_(a.D.sn_group.out)
-    g = torch.Generator(device="cuda").manual_seed(11)
     B = cfg["batch_size"]
-    for step in range(3):
-        img = torch.rand(B, cfg["img_size"], cfg["img_size"], 3, device="cuda", generator=g) * 2 - 1
-        nd = [torch.randn(B, cfg["z_dim"], device="cuda", generator=g)]
-        ng = torch.randn(B, cfg["z_dim"], device="cuda", generator=g)
-        a.train_step(img, noises_d=nd, noise_g=ng)
-        b.train_step(img, noises_d=nd, noise_g=ng)
-        la, lb = a.losses(), b.losses()
-        assert abs(la["D_loss"] - lb["D_loss"]) < 1e-4 and abs(la["G_loss"] - lb["G_loss"]) < 1e-4, (step, la, lb)
-    for pa, pb in ((a.G.flat_params, b.G.flat_params), (a.D.flat_params, b.D.flat_params)):
-        rel = float((pa - pb).norm() / pb.norm())
-        assert rel < 1e-4, rel
+    for rep in range(3):
+        a = Trainer(cfg, seed=5, overlap_streams=True)
+        b = Trainer(cfg, seed=5, overlap_streams=False)
+        b.G.flat_params.copy_(a.G.flat_params); b.D.flat_params.copy_(a.D.flat_params)
+        b.G.sn_group.out.copy_(a.G.sn_group.out); b.D.sn_group.out.copy_(a.D.sn_group.out)
+        g = torch.Generator(device="cuda").manual_seed(11 + rep)
+        for step in range(3):
+            img = torch.rand(B, cfg["img_size"], cfg["img_size"], 3, device="cuda", generator=g) * 2 - 1
+            nd = [torch.randn(B, cfg["z_dim"], device="cuda", generator=g)]
+            ng = torch.randn(B, cfg["z_dim"], device="cuda", generator=g)
+            a.train_step(img, noises_d=nd, noise_g=ng)
+            b.train_step(img, noises_d=nd, noise_g=ng)
+            la, lb = a.losses(), b.losses()
+            tol = 1e-5 if step == 0 else 2e-3
+            assert abs(la["D_loss"] - lb["D_loss"]) < tol and abs(la["G_loss"] - lb["G_loss"]) < tol, (rep, step, la, lb)
+        for pa, pb in ((a.G.flat_params, b.G.flat_params), (a.D.flat_params, b.D.flat_params)):
+            rel = float((pa - pb).norm() / pb.norm())
+            assert rel < 2e-3, (rep, rel)

@@ -69,7 +69,7 @@ def main():
         fl_f = 2 * B * N * C * (2 * d + dv) + 2 * B * N * N * (d + dv) + 2 * B * N * dv * C
         out.update(shape=[B, N, C], math=a.math, fwd_ms=t_f[0] * 1e3, fwd_min_ms=t_f[1] * 1e3,
                    fwd_tflops=fl_f / t_f[0] / 1e12, fwd_exps_per_s=B * N * N / t_f[0])
-        if a.bwd and C <= 64:
+        if a.bwd:
             y = F.attention(x, *w, mode)
             t_b = timed(lambda: torch.autograd.grad(y, [x] + w, dy, retain_graph=True), a.iters, flush)
             fl_b = 2 * B * N * N * (3 * d + 2 * dv) + 2 * (2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C)
