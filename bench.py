@@ -335,6 +335,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32" if math_mode == MATH_FP32_STRICT else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
                    "math_mode": args.math, "cuda_graph": True,
+                   "step_graph": ("two branches: generator forwards on a side stream" if args.overlap
+                                  else "single stream (--no-overlap)"),
                    "dp_exchange": {"p2p": "fused NVLink peer-memory gradient sum + Adam kernel (csrc/dp.cu)",
                                    "nccl": "NCCL all-reduce + Adam", "none": "single replica"}[dp_mode],
                    "l2": f"no explicit flush: a step touches ~{act_mb:.0f} MB of saved activations (> 126 MB L2)"},
