@@ -75,3 +75,23 @@ def test_product_has_no_cpu_fallback_and_does_not_import_the_oracle():
     if not torch.cuda.is_available():
         with pytest.raises(Exception, match="no CPU fallback|CUDA"):
             layers.Dense(4)(torch.zeros(2, 3))
+
+
+def test_workspace_queries_and_argument_checks_need_no_gpu(lib_path):
+    """Size queries and argument validation are host code: they answer (and refuse) without a device."""
+    from sagan_b200 import _lib
+    lib = _lib.load()
+    TC, FP = _lib.MATH_BF16_TC, _lib.MATH_FP32_STRICT
+    assert lib.sagan_attn_workspace_bytes(0, 128, 16, TC) == 0 and lib.sagan_attn_workspace_bytes(2, 0, 16, FP) == 0
+    # every supported shape gets a workspace, growing with the batch
+    for mode, C in ((FP, 8), (FP, 64), (TC, 16), (TC, 32), (TC, 64), (TC, 128), (TC, 256), (TC, 512)):
+        a, b = lib.sagan_attn_workspace_bytes(2, 1024, C, mode), lib.sagan_attn_workspace_bytes(4, 1024, C, mode)
+        assert 0 < a < b, (mode, C, a, b)
+    # the large-C backward keeps three [N, N] fp32 maps of one sample plus a [B N, C] scratch in the workspace
+    N, C, B = 4096, 512, 16
+    assert lib.sagan_attn_workspace_bytes(B, N, C, TC) >= 4 * (3 * N * N + B * N * C)
+    assert lib.sagan_bn_workspace_bytes(16) > 0
+    # null pointers are refused with a message, no launch
+    rc = lib.sagan_attn_fwd(None, None, None, None, None, None, None, None, None, None, None, None, None,
+                            2, 128, 16, TC, None, 0, None)
+    assert rc == -1 and b"null pointer" in lib.sagan_last_error()
