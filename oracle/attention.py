@@ -91,3 +91,78 @@ def make_inputs(B, N, C, seed=0, gamma=0.37, dtype=np.float64):
     X = rng.standard_normal((B, N, C)).astype(dtype)
     dY = rng.standard_normal((B, N, C)).astype(dtype)
     return X, dY, w
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Down-sampled keys / values: what /root/reference/layers.py:96,100,113 reaches for -- the SAGAN
+# paper's memory-saving variant max-pools phi and g over 2x2 windows before the attention map, so a query attends to
+# N/4 keys.  The reference writes MaxPool2D(2, 1) (pool 2, stride 1: ill-formed); the well-formed
+# reading fixed here is pool 2 / stride 2 / 'valid' on the [H, W] grid.  Not built in CUDA yet: this is the oracle the
+# kernels of that row will be tested against.
+def _pool2x2(t, hw):
+    """t [B, H*W, c] -> pooled [B, (H/2)*(W/2), c] and the flat argmax index [B, (H/2)*(W/2), c] into H*W."""
+    H, W = hw
+    B, N, c = t.shape
+    assert N == H * W and H % 2 == 0 and W % 2 == 0
+    v = t.reshape(B, H // 2, 2, W // 2, 2, c).transpose(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 4, c)
+    k = v.argmax(axis=3)                                   # first maximum wins, as in TF / cuDNN
+    pooled = np.take_along_axis(v, k[:, :, :, None, :], axis=3)[:, :, :, 0, :]
+    hh = np.arange(H // 2)[None, :, None, None] * 2 + k // 2
+    ww = np.arange(W // 2)[None, None, :, None] * 2 + k % 2
+    idx = hh * W + ww
+    return pooled.reshape(B, -1, c), idx.reshape(B, -1, c)
+
+
+def forward_pooled(X, Wphi, bphi, Wtheta, btheta, Wg, bg, Wo, bo, gamma, hw, return_cache=False):
+    """As `forward`, with keys phi and values g max-pooled 2x2 / stride 2 over the [H, W] = hw grid."""
+    phi = X @ Wphi + bphi
+    theta = X @ Wtheta + btheta
+    g = X @ Wg + bg
+    phi_p, iphi = _pool2x2(phi, hw)
+    g_p, ig = _pool2x2(g, hw)
+    S = theta @ np.swapaxes(phi_p, 1, 2)                   # [B, N, N/4]
+    S = S - S.max(axis=-1, keepdims=True)
+    E = np.exp(S)
+    P = E / E.sum(axis=-1, keepdims=True)
+    A = P @ g_p
+    O = A @ Wo + bo
+    Y = X + gamma * O
+    if return_cache:
+        return Y, dict(phi=phi, theta=theta, g=g, phi_p=phi_p, g_p=g_p, iphi=iphi, ig=ig, P=P, A=A, O=O)
+    return Y
+
+
+def backward_pooled(dY, X, Wphi, bphi, Wtheta, btheta, Wg, bg, Wo, bo, gamma, hw):
+    """Analytic gradients of `forward_pooled`: the pooled-key / pooled-value gradients are scattered to the argmax
+    positions (everything else as in `backward`)."""
+    Y, c = forward_pooled(X, Wphi, bphi, Wtheta, btheta, Wg, bg, Wo, bo, gamma, hw, return_cache=True)
+    theta, phi_p, g_p, P, A, O = c["theta"], c["phi_p"], c["g_p"], c["P"], c["A"], c["O"]
+    B, N, C = X.shape
+    dgamma = np.sum(dY * O)
+    dO = gamma * dY
+    dWo = np.einsum("bnv,bnc->vc", A, dO)
+    dbo = dO.sum(axis=(0, 1))
+    dA = dO @ Wo.T
+    dg_p = np.swapaxes(P, 1, 2) @ dA
+    dP = dA @ np.swapaxes(g_p, 1, 2)
+    dS = P * (dP - np.sum(dP * P, axis=-1, keepdims=True))
+    dtheta = dS @ phi_p
+    dphi_p = np.swapaxes(dS, 1, 2) @ theta
+
+    def scatter(dp, idx, width):
+        out = np.zeros((B, N, width), dtype=dp.dtype)
+        bb = np.arange(B)[:, None, None]
+        cc = np.arange(width)[None, None, :]
+        np.add.at(out, (bb, idx, cc), dp)
+        return out
+
+    dphi = scatter(dphi_p, c["iphi"], phi_p.shape[-1])
+    dg = scatter(dg_p, c["ig"], g_p.shape[-1])
+    Xf = X.reshape(-1, C)
+    return dict(
+        dX=dY + dtheta @ Wtheta.T + dphi @ Wphi.T + dg @ Wg.T,
+        dWphi=Xf.T @ dphi.reshape(-1, dphi.shape[-1]), dbphi=dphi.sum(axis=(0, 1)),
+        dWtheta=Xf.T @ dtheta.reshape(-1, dtheta.shape[-1]), dbtheta=dtheta.sum(axis=(0, 1)),
+        dWg=Xf.T @ dg.reshape(-1, dg.shape[-1]), dbg=dg.sum(axis=(0, 1)),
+        dWo=dWo, dbo=dbo, dgamma=dgamma,
+    )

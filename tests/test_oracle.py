@@ -154,3 +154,38 @@ def test_hinge_losses():
     a, b = torch.tensor([0.5, 2.0, -1.0]), torch.tensor([-2.0, 0.0, 3.0])
     assert torch.equal(train.hinge_loss_d(a, b), torch.tensor([0.5, 1.0, 6.0]))
     assert torch.equal(train.hinge_loss_g(b), -b)
+
+
+def test_pooled_attention_oracle_matches_torch_autograd():
+    """Down-sampled keys / values (oracle only so far): the numpy forward / analytic backward
+    against torch autograd of the same graph built from max_pool2d, in fp64."""
+    import torch
+    import torch.nn.functional as TF
+    B, H, W, C = 2, 8, 6, 16
+    X, dY, w = attention.make_inputs(B, H * W, C, seed=5, gamma=0.6, dtype=np.float64)
+    Y = attention.forward_pooled(X, **w, hw=(H, W))
+    g = attention.backward_pooled(dY, X, **w, hw=(H, W))
+    t = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True) for k, v in w.items()}
+    x = torch.tensor(X, requires_grad=True)
+
+    def pool(z):       # [B, N, c] -> [B, N/4, c]
+        c = z.shape[-1]
+        z4 = z.reshape(B, H, W, c).permute(0, 3, 1, 2)
+        return TF.max_pool2d(z4, 2, 2).permute(0, 2, 3, 1).reshape(B, -1, c)
+
+    phi = pool(x @ t["Wphi"] + t["bphi"])
+    theta = x @ t["Wtheta"] + t["btheta"]
+    gg = pool(x @ t["Wg"] + t["bg"])
+    P = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
+    y = x + t["gamma"] * ((P @ gg) @ t["Wo"] + t["bo"])
+    assert P.shape == (B, H * W, H * W // 4)
+    np.testing.assert_allclose(Y, y.detach().numpy(), rtol=1e-12, atol=1e-12)
+    y.backward(torch.tensor(dY))
+    np.testing.assert_allclose(g["dX"], x.grad.numpy(), rtol=1e-10, atol=1e-12)
+    for k in attention.WEIGHT_NAMES:
+        np.testing.assert_allclose(g["d" + k], t[k].grad.numpy(), rtol=1e-9, atol=1e-11, err_msg=k)
+    # with one key per 2x2 window the block must differ from the un-pooled one (it is not a no-op) ...
+    assert np.abs(Y - attention.forward(X, **w)).max() > 1e-3
+    # ... and reduce to it when every window holds four identical tokens
+    Xr = np.repeat(np.repeat(X.reshape(B, H, W, C)[:, ::2, ::2], 2, axis=1), 2, axis=2).reshape(B, H * W, C)
+    np.testing.assert_allclose(attention.forward_pooled(Xr, **w, hw=(H, W)), attention.forward(Xr, **w), rtol=1e-10, atol=1e-12)
