@@ -53,6 +53,13 @@ const char* sagan_last_error(void);
 /* number of kernels this library has launched in this process (all threads); bench.py's gpu_launches */
 unsigned long long sagan_launch_count(void);
 
+/* Process-wide switch (0 / 1; anything else only queries; returns the value in force; default 0).  With 1 no
+ * ACTIVATION is accumulated with floating-point atomics (the conv kernels stop splitting their reduction over CTAs
+ * for layers with few output pixels), so every forward pass -- and with it every LeakyReLU mask -- is bit-reproducible
+ * from run to run.  Weight-gradient reductions keep their atomics (summation-order noise of ~1e-7, no mask involved).
+ * Costs a few percent on small batches; used by the graph-vs-eager parity test. */
+int sagan_deterministic_forward(int set);
+
 /* ------------------------------------------------------------------------------------------
  * Spectral normalisation.  Replaces SpectralNormalization.update_uv, layers.py:50-68
  * (l2normalize layers.py:4-5).  W is the wrapped layer's kernel viewed as the RAW row-major
@@ -79,7 +86,6 @@ typedef struct sagan_sn_plan sagan_sn_plan; /* opaque: device descriptor table +
  * workspace) -- call outside the step loop.  `descs_host` is copied. */
 int sagan_sn_plan_create(const sagan_sn_desc* descs_host, int n, int device, sagan_sn_plan** plan_out);
 int sagan_sn_plan_run(sagan_sn_plan* plan, sagan_stream_t stream);
-/* Same plan, but only the matrices listed (indices into the plan) take part */
 int sagan_sn_plan_destroy(sagan_sn_plan* plan);
 /* Diagnostics: device-side durations (ms, %globaltimer) of the five phases of the plan's most recent run
  * [u W partials, s + ||s||, v W^T partials, t + ||t||, u / sigma / W_bar].  Synchronises the device. */
@@ -161,6 +167,15 @@ int sagan_conv2d_dgrad(const float* dy, const float* w, float* dx, const sagan_c
 int sagan_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias,
                        const sagan_conv_geom* g, int math_mode, sagan_stream_t stream);
 
+/* Operand precision of the tensor-core conv kernels (process-wide; BF16_TC math mode only):
+ *   SAGAN_CONV_TC_SPLIT_BF16 (default)  every operand as hi + lo bf16 tiles, three MMAs per K step (hi*hi + hi*lo +
+ *                                       lo*hi): fp32-grade products, forward / backward-data / backward-filter alike
+ *   SAGAN_CONV_TC_TF32                  round-1 arithmetic: kind::tf32 forward / backward-data, plain bf16 backward-filter
+ * Pass one of the two to select it; anything else (e.g. -1) only queries.  Returns the precision in force. */
+#define SAGAN_CONV_TC_TF32 1
+#define SAGAN_CONV_TC_SPLIT_BF16 2
+int sagan_conv_tc_precision(int set);
+
 /* dz = dy * act'(y) from the activation OUTPUT y (LeakyReLU: y>0 ? 1 : slope; tanh: 1 - y^2). */
 int sagan_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, float slope,
                   sagan_stream_t stream);
@@ -201,6 +216,13 @@ int sagan_hinge_g(const float* d_fake, long long n, float scale, float* loss_sum
  * ------------------------------------------------------------------------------------------ */
 int sagan_adam_step(float* param, const float* grad, float* m, float* v, long long n,
                     const float* hyper, float grad_scale, sagan_stream_t stream);
+/* Learning-rate schedule + Adam bias correction of sagan/main.py:111-120 evaluated on the device:
+ *   lr   = lr0 * decay_rate ^ (iterations / decay_steps)          ExponentialDecay(..., staircase=True)
+ *   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t),  t = iterations + 1   (Keras Adam)
+ * writes hyper = {lr_t, b1, b2, eps} and increments the DEVICE counter `iterations` (optimizer.iterations).
+ * One launch per apply_gradients; a captured CUDA graph that contains it follows the schedule on replay. */
+int sagan_adam_schedule(float* hyper, long long* iterations, double lr0, double decay_rate,
+                        long long decay_steps, double b1, double b2, double eps, sagan_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange fused with Keras Adam over NVLink peer memory.  Replaces the
@@ -223,8 +245,11 @@ typedef struct sagan_dp_peers {
   void* params[SAGAN_DP_MAX_WORLD];
   void* flags[SAGAN_DP_MAX_WORLD];
 } sagan_dp_peers;
+/* A replica that waits longer than the timeout (default 30 s) for a peer raises status[0], skips its update and
+ * returns; the caller must poll `status` (Trainer.losses() does) -- the replicas have diverged at that point. */
 int sagan_dp_max_world(void);
 size_t sagan_dp_flag_bytes(void);
+int sagan_dp_set_timeout_ms(long long ms);
 int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
                       const float* hyper, unsigned int* epoch, unsigned int* status, sagan_stream_t stream);
 

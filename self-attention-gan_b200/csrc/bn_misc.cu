@@ -250,6 +250,22 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// Keras ExponentialDecay(staircase) + Adam bias correction evaluated ON THE DEVICE from a device-resident step counter
+// (sagan/main.py:111-120): one thread, double precision.  Runs right before each Adam application inside the step
+// (graph), so a replayed CUDA graph follows the schedule without any per-step host -> device traffic.
+__global__ void adam_schedule_kernel(float* __restrict__ hyper, long long* __restrict__ iterations, double lr0,
+                                     double decay_rate, long long decay_steps, double b1, double b2, double eps) {
+  const long long it = *iterations;
+  const double lr = lr0 * pow(decay_rate, (double)(it / decay_steps));        // staircase=True
+  const double t = (double)(it + 1);
+  const double corr = sqrt(1.0 - pow(b2, t)) / (1.0 - (b1 > 0.0 ? pow(b1, t) : 0.0));
+  hyper[0] = (float)(lr * corr);
+  hyper[1] = (float)b1;
+  hyper[2] = (float)b2;
+  hyper[3] = (float)eps;
+  *iterations = it + 1;                                                        // optimizer.iterations
+}
+
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace sagan
@@ -337,6 +353,15 @@ extern "C" int sagan_adam_step(float* param, const float* grad, float* m, float*
   SAGAN_REQUIRE(param && grad && v && hyper && n > 0, "sagan_adam_step: bad argument");
   const int blocks = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(n, 256));
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, hyper, grad_scale);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_adam_schedule(float* hyper, long long* iterations, double lr0, double decay_rate,
+                                   long long decay_steps, double b1, double b2, double eps, sagan_stream_t stream) {
+  SAGAN_REQUIRE(hyper && iterations && decay_steps > 0 && lr0 > 0 && b2 > 0 && b2 < 1 && b1 >= 0 && b1 < 1,
+                "sagan_adam_schedule: bad argument");
+  adam_schedule_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, iterations, lr0, decay_rate, decay_steps, b1, b2, eps);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }

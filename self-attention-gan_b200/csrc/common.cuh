@@ -14,6 +14,7 @@ namespace sagan {
 char* err_buf();
 void set_err(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+extern std::atomic<int> g_deterministic_forward;   // sagan_deterministic_forward(): no atomically-accumulated activations
 
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 

@@ -23,6 +23,8 @@ bool conv_tc_wgrad_ok(const CG& g, const float* x, const float* dy);
 int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope, cudaStream_t st);
 int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st);
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st);
+int conv_tc_get_precision();
+void conv_tc_set_precision(int p);
 
 constexpr int CV_THREADS = 256;
 constexpr int CV_BK = 16;
@@ -591,6 +593,11 @@ extern "C" int sagan_conv2d_wgrad(const float* x, const float* dy, float* dw, fl
     SAGAN_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int sagan_conv_tc_precision(int set) {
+  if (set == SAGAN_CONV_TC_SPLIT_BF16 || set == SAGAN_CONV_TC_TF32) conv_tc_set_precision(set);
+  return conv_tc_get_precision();
 }
 
 extern "C" int sagan_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, float slope,

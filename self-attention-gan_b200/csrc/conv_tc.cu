@@ -12,7 +12,14 @@
 //   WGRAD  D[kk][n] = sum_m A[m][kk] dY[m][n]   both operands MN-major (the same im2col rows, dY rows); split over
 //          pixel ranges with fp32 atomics; an extra im2col column of ones yields the bias gradient for free
 //
-// CTA tile 128 x NT (NT in {16,32,64,128}), K blocks of 64, 3-stage shared-memory ring.
+// Operand precision (template PREC): 0 = plain bf16, 1 = tf32 on the fp32 operands, 2 = SPLIT bf16: every operand is
+// carried as hi + lo bf16 tiles (x = hi + lo to 16 mantissa bits) and each K step issues the three MMAs
+// hi*hi + hi*lo + lo*hi -- fp32-grade products (dropped term 2^-16) at the shared-memory footprint of the fp32 / tf32
+// tiles and 0.75x the tensor time of tf32.  PREC 2 is what BF16_TC mode uses (sagan_conv_tc_set_precision): with it
+// the conv / deconv / dense layers no longer move LeakyReLU pre-activations across zero, which is what kept the
+// model-level gradients of the tensor-core mode out of the 2e-3 tier.
+//
+// CTA tile 128 x NT (NT in {16,32,64,128}), K blocks of 64, 2- or 3-stage shared-memory ring.
 // 9 warps: 0-7 producers + epilogue, warp 8 = MMA issuer / TMEM owner.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -23,7 +30,7 @@ using namespace tc;
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 constexpr int CT_THREADS = 288;
-constexpr int CT_STAGES = 3;
+enum { PREC_BF16 = 0, PREC_TF32 = 1, PREC_SPLIT = 2 };
 
 struct ConvTcP {
   const float* a_src;   // FWD: x     DGRAD: dy    WGRAD: x
@@ -58,12 +65,27 @@ __device__ __forceinline__ void st_chunk(uint8_t* dst, const float4& a, const fl
       make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
-template <int MODE, int NT, bool TF32>
+__device__ __forceinline__ void st_chunk_split(uint8_t* dst_hi, uint8_t* dst_lo, const float4& a, const float4& b) {
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) lo[e] = v[e] - __bfloat162float(__float2bfloat16_rn(v[e]));
+  *reinterpret_cast<uint4*>(dst_hi) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(dst_lo) =
+      make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+}
+
+template <int MODE, int NT, int PREC>
 struct ConvTcSmem {
+  static constexpr bool TF32 = PREC == PREC_TF32, SPLIT = PREC == PREC_SPLIT;
   static constexpr int A_BYTES = 128 * 128;                                              // 16 KB either major
-  static constexpr int B_BYTES = (MODE == TC_DGRAD || TF32) ? NT * 128 : 8192 * ((NT + 63) / 64);  // K-major rows / MN-major sub-tiles
-  static constexpr int STAGE = A_BYTES + (B_BYTES < 1024 ? 1024 : B_BYTES);
-  static constexpr int OFF_BAR = CT_STAGES * STAGE;
+  static constexpr int B_RAW = (MODE == TC_DGRAD || TF32) ? NT * 128 : 8192 * ((NT + 63) / 64);  // K-major rows / MN-major sub-tiles
+  static constexpr int B_BYTES = B_RAW < 1024 ? 1024 : B_RAW;
+  static constexpr int STAGE = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);    // SPLIT: [A_hi | B_hi | A_lo | B_lo]
+  static constexpr int LO_OFF = A_BYTES + B_BYTES;                       // SPLIT: offset of the lo tiles inside a stage
+  static constexpr int STAGES = SPLIT ? 2 : 3;
+  static constexpr int OFF_BAR = STAGES * STAGE;
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;
   static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
 };
@@ -84,13 +106,15 @@ __device__ __forceinline__ void mma_tf32_ss_conv(uint32_t d_tmem, uint64_t a_des
       : "memory");
 }
 
-template <int MODE, int NT, bool TF32>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+template <int MODE, int NT, int PREC>
+__global__ void __launch_bounds__(CT_THREADS, (PREC == PREC_SPLIT && NT > 64) ? 1 : 2)
 conv_tc_kernel(const ConvTcP p) {
+  constexpr bool TF32 = PREC == PREC_TF32, SPLIT = PREC == PREC_SPLIT;
   static_assert(!(TF32 && MODE == TC_WGRAD), "the tf32 variant covers FWD and DGRAD");
   constexpr int KB = TF32 ? 32 : 64;      // K elements per block (128 bytes per row either way)
   constexpr int CE = TF32 ? 4 : 8;        // elements per 16-byte chunk
-  using L = ConvTcSmem<MODE, NT, TF32>;
+  using L = ConvTcSmem<MODE, NT, PREC>;
+  constexpr int CT_STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -157,12 +181,18 @@ conv_tc_kernel(const ConvTcP p) {
                              IDESC, (kb > 0) || (ks > 0));
             continue;
           }
-          uint64_t da, db;
-          if (MODE == TC_WGRAD) da = make_desc_sw128_mn(aA + ks * 2048, 8192, 1024);
-          else da = make_desc_sw128(aA) + (uint64_t)(ks * 2);
-          if (MODE == TC_DGRAD) db = make_desc_sw128(aB) + (uint64_t)(ks * 2);
-          else db = make_desc_sw128_mn(aB + ks * 2048, 8192, 1024);
+          auto desc_a = [&](uint32_t a) {
+            return MODE == TC_WGRAD ? make_desc_sw128_mn(a + ks * 2048, 8192, 1024) : make_desc_sw128(a) + (uint64_t)(ks * 2);
+          };
+          auto desc_b = [&](uint32_t b) {
+            return MODE == TC_DGRAD ? make_desc_sw128(b) + (uint64_t)(ks * 2) : make_desc_sw128_mn(b + ks * 2048, 8192, 1024);
+          };
+          const uint64_t da = desc_a(aA), db = desc_b(aB);
           mma_bf16_ss(tmem_base, da, db, IDESC, (kb > 0) || (ks > 0));
+          if (SPLIT) {      // + hi * lo + lo * hi (the lo * lo term is below 2^-16 of the product)
+            mma_bf16_ss(tmem_base, da, desc_b(aB + L::LO_OFF), IDESC, true);
+            mma_bf16_ss(tmem_base, desc_a(aA + L::LO_OFF), db, IDESC, true);
+          }
         }
         mma_commit(empty + s);
       }
@@ -263,13 +293,12 @@ conv_tc_kernel(const ConvTcP p) {
       auto store_a = [&]() {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (MODE == TC_WGRAD) {
-            st_chunk(sA + (a_chunk >> 3) * 8192 + sw128_offset((tid >> 4) + 16 * j, a_chunk & 7), va0[j], va1[j]);
-          } else if (TF32) {
-            *reinterpret_cast<float4*>(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk)) = va0[j];
-          } else {
-            st_chunk(sA + sw128_offset((tid >> 3) + 32 * j, a_chunk), va0[j], va1[j]);
-          }
+          uint8_t* dst;
+          if (MODE == TC_WGRAD) dst = sA + (a_chunk >> 3) * 8192 + sw128_offset((tid >> 4) + 16 * j, a_chunk & 7);
+          else dst = sA + sw128_offset((tid >> 3) + 32 * j, a_chunk);
+          if (TF32) *reinterpret_cast<float4*>(dst) = va0[j];
+          else if (SPLIT) st_chunk_split(dst, dst + L::LO_OFF, va0[j], va1[j]);
+          else st_chunk(dst, va0[j], va1[j]);
         }
       };
       // ------------------------------------------------ B tile
@@ -324,8 +353,10 @@ conv_tc_kernel(const ConvTcP p) {
         for (int it = 0; it < NIT; ++it) {
           const int c = tid + it * 256;
           if (c < NCH) {
-            if (TF32) *reinterpret_cast<float4*>(sB + sw128_offset(c >> 3, c & 7)) = vb0[it];
-            else st_chunk(sB + sw128_offset(c >> 3, c & 7), vb0[it], vb1[it]);
+            uint8_t* dst = sB + sw128_offset(c >> 3, c & 7);
+            if (TF32) *reinterpret_cast<float4*>(dst) = vb0[it];
+            else if (SPLIT) st_chunk_split(dst, dst + L::LO_OFF, vb0[it], vb1[it]);
+            else st_chunk(dst, vb0[it], vb1[it]);
           }
         }
       } else {
@@ -358,7 +389,9 @@ conv_tc_kernel(const ConvTcP p) {
           const int c = tid + it * 256;
           if (c < NCH) {
             const int r = c / CPR, ch = c - r * CPR;
-            st_chunk(sB + (ch >> 3) * 8192 + sw128_offset(r, ch & 7), vb0[it], vb1[it]);
+            uint8_t* dst = sB + (ch >> 3) * 8192 + sw128_offset(r, ch & 7);
+            if (SPLIT) st_chunk_split(dst, dst + L::LO_OFF, vb0[it], vb1[it]);
+            else st_chunk(dst, vb0[it], vb1[it]);
           }
         }
       }
@@ -471,10 +504,10 @@ conv_tc_kernel(const ConvTcP p) {
   }
 }
 
-template <int MODE, int NT, bool TF32>
+template <int MODE, int NT, int PREC>
 static int launch_conv_tc(const ConvTcP& p, dim3 grid, cudaStream_t st) {
-  using L = ConvTcSmem<MODE, NT, TF32>;
-  auto kern = conv_tc_kernel<MODE, NT, TF32>;
+  using L = ConvTcSmem<MODE, NT, PREC>;
+  auto kern = conv_tc_kernel<MODE, NT, PREC>;
   static bool configured = false;
   if (!configured) {
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -485,13 +518,18 @@ static int launch_conv_tc(const ConvTcP& p, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
-template <int MODE, bool TF32 = false>
+template <int MODE, int PREC = PREC_BF16>
 static int dispatch_nt(const ConvTcP& p, int Ng, int gx, int gz, cudaStream_t st) {
-  if (Ng <= 16) return launch_conv_tc<MODE, 16, TF32>(p, dim3(gx, 1, gz), st);
-  if (Ng <= 32) return launch_conv_tc<MODE, 32, TF32>(p, dim3(gx, 1, gz), st);
-  if (Ng <= 64) return launch_conv_tc<MODE, 64, TF32>(p, dim3(gx, 1, gz), st);
-  return launch_conv_tc<MODE, 128, TF32>(p, dim3(gx, ceil_div(Ng, 128), gz), st);
+  if (Ng <= 16) return launch_conv_tc<MODE, 16, PREC>(p, dim3(gx, 1, gz), st);
+  if (Ng <= 32) return launch_conv_tc<MODE, 32, PREC>(p, dim3(gx, 1, gz), st);
+  if (Ng <= 64) return launch_conv_tc<MODE, 64, PREC>(p, dim3(gx, 1, gz), st);
+  return launch_conv_tc<MODE, 128, PREC>(p, dim3(gx, ceil_div(Ng, 128), gz), st);
 }
+
+// 2 (default): split-bf16 everywhere; 1: round-1 arithmetic (tf32 forward / backward-data, plain bf16 backward-filter)
+static std::atomic<int> g_conv_prec{PREC_SPLIT};
+int conv_tc_get_precision() { return g_conv_prec.load(); }
+void conv_tc_set_precision(int p) { g_conv_prec.store(p == PREC_TF32 ? PREC_TF32 : PREC_SPLIT); }
 
 static inline bool al16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
 
@@ -510,6 +548,7 @@ __global__ void conv_tc_finish_kernel(float* __restrict__ y, const float* __rest
 // Layers with few output pixels (the 4x4 / 8x8 maps: 8-16 CTAs walking 16-32 K blocks each) are latency-bound on the
 // producers' gather; splitting K over more CTAs fills the machine.  Returns 1 when splitting does not pay.
 static int pick_k_splits(int ctas, int K) {
+  if (g_deterministic_forward.load()) return 1;      // split-K accumulates with fp32 atomics: run-to-run rounding noise
   const int nkb = ceil_div(K, 64);
   if (ctas * 2 > num_sms() || nkb < 8) return 1;
   return std::max(1, std::min(nkb / 4, num_sms() / ctas));
@@ -520,10 +559,13 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, con
   ConvTcP p{x, w, bias, y, nullptr, g, act, slope, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   const int gx = ceil_div(g.M, 128);
   p.k_splits = pick_k_splits(gx * ceil_div(g.Cout, 128), g.K);
-  if (p.k_splits == 1) return dispatch_nt<TC_FWD, true>(p, g.Cout, gx, 1, st);
+  const bool split = g_conv_prec.load() == PREC_SPLIT;
+  if (p.k_splits == 1)
+    return split ? dispatch_nt<TC_FWD, PREC_SPLIT>(p, g.Cout, gx, 1, st) : dispatch_nt<TC_FWD, PREC_TF32>(p, g.Cout, gx, 1, st);
   const long long n = (long long)g.M * g.Cout;
   SAGAN_CUDA(cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), st));
-  int rc = dispatch_nt<TC_FWD, true>(p, g.Cout, gx, p.k_splits, st);
+  int rc = split ? dispatch_nt<TC_FWD, PREC_SPLIT>(p, g.Cout, gx, p.k_splits, st)
+                 : dispatch_nt<TC_FWD, PREC_TF32>(p, g.Cout, gx, p.k_splits, st);
   if (rc) return rc;
   if (bias || act != SAGAN_ACT_NONE) {
     conv_tc_finish_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, st>>>(y, bias, n, g.Cout, act, slope);
@@ -562,7 +604,8 @@ int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaS
   const int Kc = ceil_div(g.KH, g.S) * ceil_div(g.KW, g.S) * g.Cout;      // reduction length of the largest class
   p.k_splits = pick_k_splits(gx * ceil_div(g.Cin, 128) * classes, Kc);
   if (p.k_splits > 1) SAGAN_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.B * g.H * g.W * g.Cin * sizeof(float), st));
-  return dispatch_nt<TC_DGRAD, true>(p, g.Cin, gx, classes * p.k_splits, st);
+  if (g_conv_prec.load() == PREC_SPLIT) return dispatch_nt<TC_DGRAD, PREC_SPLIT>(p, g.Cin, gx, classes * p.k_splits, st);
+  return dispatch_nt<TC_DGRAD, PREC_TF32>(p, g.Cin, gx, classes * p.k_splits, st);
 }
 
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st) {
@@ -572,6 +615,7 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, cons
   int mps = ceil_div(ceil_div(g.M, splits), 64) * 64;
   splits = ceil_div(g.M, mps);
   ConvTcP p{x, dy, nullptr, dw, dbias, g, 0, 0.f, mps, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  if (g_conv_prec.load() == PREC_SPLIT) return dispatch_nt<TC_WGRAD, PREC_SPLIT>(p, g.Cout, ceil_div(Mg, 128), splits, st);
   return dispatch_nt<TC_WGRAD>(p, g.Cout, ceil_div(Mg, 128), splits, st);
 }
 

@@ -15,14 +15,16 @@
 // Per replica and update 2 (W-1)/W x bucket bytes cross NVLink (G: 4.9 MB, D: 0.7 MB at church64) instead of an
 // all-reduce followed by a full-bucket Adam on every replica.  The buffers are symmetric-memory allocations
 // (torch.distributed._symmetric_memory) whose peer-mapped addresses the host passes in `sagan_dp_peers`.
-// Every spin loop is bounded: on a lost peer the kernel raises `status[0]` and returns instead of hanging the GPU.
+// Every wait is bounded by a wall-clock timeout (sagan_dp_set_timeout_ms, default 30 s): on a lost peer the kernel
+// raises `status[0]`, skips the update and still completes its barrier bookkeeping instead of hanging the GPU.
 #include "common.cuh"
 
 namespace sagan {
 
 constexpr int DP_MAX_WORLD = 8;
 constexpr int DP_THREADS = 256;
-constexpr long long DP_SPIN_LIMIT = 1ll << 26;   // ~ seconds
+// how long a replica waits for its peers at a barrier before it gives up (wall clock, %globaltimer); host-settable
+static std::atomic<long long> g_dp_timeout_ns{30ll * 1000 * 1000 * 1000};
 
 struct DpPeers {
   const float* grads[DP_MAX_WORLD];
@@ -43,8 +45,14 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // late it is scheduled, and a captured CUDA graph replays with fresh epochs
 __global__ void dp_bump_epoch_kernel(unsigned int* epoch) { *epoch += 1u; }
 
+__device__ __forceinline__ unsigned long long dp_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ bool dp_barrier(const DpPeers& pr, int rank, int world, int row, unsigned int epoch,
-                                           unsigned int* status, bool signal) {
+                                           unsigned int* status, bool signal, long long timeout_ns) {
   __syncthreads();
   if (signal && threadIdx.x < world) {
     __threadfence_system();
@@ -55,10 +63,11 @@ __device__ __forceinline__ bool dp_barrier(const DpPeers& pr, int rank, int worl
   __syncthreads();
   if (threadIdx.x < world) {
     const unsigned int* mine = pr.flags[rank] + row * DP_MAX_WORLD + threadIdx.x;
-    long long spins = 0;
+    const unsigned long long t0 = dp_now_ns();
+    unsigned int spins = 0;
     // epochs only grow; signed distance handles wrap-around
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (++spins > DP_SPIN_LIMIT) {
+      if ((++spins & 1023u) == 0 && (long long)(dp_now_ns() - t0) > timeout_ns) {
         ok = 0;
         atomicExch(status, 1u);
         break;
@@ -71,17 +80,20 @@ __device__ __forceinline__ bool dp_barrier(const DpPeers& pr, int rank, int worl
 
 __global__ void __launch_bounds__(DP_THREADS)
 dp_sum_adam_kernel(const DpPeers pr, int rank, int world, long long n, float* __restrict__ v_shard,
-                   const float* __restrict__ hyper, const unsigned int* __restrict__ epoch_ptr, unsigned int* status) {
+                   const float* __restrict__ hyper, const unsigned int* __restrict__ epoch_ptr, unsigned int* status,
+                   long long timeout_ns) {
   const unsigned int epoch = *epoch_ptr;
-  // barrier A: only CTA 0 signals, every CTA waits on the local flags
-  if (!dp_barrier(pr, rank, world, 0, epoch, status, blockIdx.x == 0)) return;
+  // barrier A: only CTA 0 signals, every CTA waits on the local flags.  A CTA whose wait timed out (status raised)
+  // skips the update but still takes part in the CTA count and barrier B below, so the counter never goes stale and
+  // the peers are not made to wait for a signal that would never come.
+  const bool arrived = dp_barrier(pr, rank, world, 0, epoch, status, blockIdx.x == 0, timeout_ns);
 
   const float lr_t = hyper[0], b2 = hyper[2], eps = hyper[3];     // beta_1 = 0 (sagan/main.py:119-120): m == g
   const long long per = n / world;                                 // n is a multiple of 4 * world (host pads)
   const long long base = (long long)rank * per;
   const long long n4 = per / 4;
   const long long stride = (long long)gridDim.x * DP_THREADS;
-  for (long long i = (long long)blockIdx.x * DP_THREADS + threadIdx.x; i < n4; i += stride) {
+  for (long long i = (long long)blockIdx.x * DP_THREADS + threadIdx.x; arrived && i < n4; i += stride) {
     const long long e = base + i * 4;
     float4 g = ld4(pr.grads[0] + e);
     for (int q = 1; q < world; ++q) {
@@ -112,7 +124,7 @@ dp_sum_adam_kernel(const DpPeers pr, int rank, int world, long long n, float* __
   // slice has landed in this replica's parameter buffer and every replica has stopped reading this replica's gradients
   if (last) {
     __threadfence_system();
-    dp_barrier(pr, rank, world, 1, epoch, status, true);
+    dp_barrier(pr, rank, world, 1, epoch, status, true, timeout_ns);
   }
 }
 
@@ -122,6 +134,12 @@ using namespace sagan;
 
 extern "C" int sagan_dp_max_world(void) { return DP_MAX_WORLD; }
 extern "C" size_t sagan_dp_flag_bytes(void) { return 4 * DP_MAX_WORLD * sizeof(unsigned int); }
+
+extern "C" int sagan_dp_set_timeout_ms(long long ms) {
+  SAGAN_REQUIRE(ms > 0, "sagan_dp_set_timeout_ms: timeout must be positive");
+  g_dp_timeout_ns.store(ms * 1000000ll);
+  return 0;
+}
 
 extern "C" int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
                                  const float* hyper, unsigned int* epoch, unsigned int* status,
@@ -142,7 +160,8 @@ extern "C" int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int worl
   SAGAN_LAUNCH_CHECK();
   const long long n4 = n / world / 4;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(num_sms(), ceil_div<long long>(n4, DP_THREADS)));
-  dp_sum_adam_kernel<<<blocks, DP_THREADS, 0, st>>>(pr, rank, world, n, v_shard, hyper, epoch, status);
+  dp_sum_adam_kernel<<<blocks, DP_THREADS, 0, st>>>(pr, rank, world, n, v_shard, hyper, epoch, status,
+                                                       g_dp_timeout_ns.load());
   SAGAN_LAUNCH_CHECK();
   return 0;
 }

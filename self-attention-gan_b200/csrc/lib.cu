@@ -6,6 +6,7 @@
 namespace sagan {
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_deterministic_forward{0};
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -24,3 +25,7 @@ void set_err(const char* fmt, ...) {
 extern "C" int sagan_abi_version(void) { return SAGAN_B200_ABI_VERSION; }
 extern "C" const char* sagan_last_error(void) { return sagan::err_buf(); }
 extern "C" unsigned long long sagan_launch_count(void) { return sagan::g_launches.load(); }
+extern "C" int sagan_deterministic_forward(int set) {
+  if (set == 0 || set == 1) sagan::g_deterministic_forward.store(set);
+  return sagan::g_deterministic_forward.load();
+}

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsagan_b200.so")
 MATH_FP32_STRICT = 0
 MATH_BF16_TC = 1
 ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+CONV_TC_TF32, CONV_TC_SPLIT_BF16 = 1, 2
 
 
 class SaganError(RuntimeError):
@@ -48,6 +49,7 @@ SIGNATURES = {
     "sagan_abi_version": (_I, []),
     "sagan_last_error": (C.c_char_p, []),
     "sagan_launch_count": (C.c_ulonglong, []),
+    "sagan_deterministic_forward": (_I, [_I]),
     "sagan_sn_plan_create": (_I, [C.POINTER(SnDesc), _I, _I, C.POINTER(_P)]),
     "sagan_sn_plan_run": (_I, [_P, _P]),
     "sagan_sn_plan_destroy": (_I, [_P]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "sagan_conv2d_fwd": (_I, [_P, _P, _P, _P, C.POINTER(ConvGeom), _I, _F, _I, _P]),
     "sagan_conv2d_dgrad": (_I, [_P, _P, _P, C.POINTER(ConvGeom), _I, _P]),
     "sagan_conv2d_wgrad": (_I, [_P, _P, _P, _P, C.POINTER(ConvGeom), _I, _P]),
+    "sagan_conv_tc_precision": (_I, [_I]),
     "sagan_act_bwd": (_I, [_P, _P, _P, _LL, _I, _F, _P]),
     "sagan_bn_workspace_bytes": (_SZ, [_I]),
     "sagan_bn_lrelu_fwd": (_I, [_P] * 8 + [_LL, _I, _F, _F, _F, _P, _SZ, _P]),
@@ -69,7 +72,9 @@ SIGNATURES = {
     "sagan_hinge_d": (_I, [_P, _P, _LL, _F, _P, _P, _P, _P]),
     "sagan_hinge_g": (_I, [_P, _LL, _F, _P, _P, _P]),
     "sagan_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _F, _P]),
+    "sagan_adam_schedule": (_I, [_P, _P, C.c_double, C.c_double, _LL, C.c_double, C.c_double, C.c_double, _P]),
     "sagan_dp_max_world": (_I, []),
+    "sagan_dp_set_timeout_ms": (_I, [_LL]),
     "sagan_dp_flag_bytes": (_SZ, []),
     "sagan_dp_sum_adam": (_I, [C.POINTER(DpPeers), _I, _I, _LL, _P, _P, _P, _P, _P]),
 }

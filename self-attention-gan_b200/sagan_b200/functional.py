@@ -406,3 +406,13 @@ def adam_step(param, grad, v, hyper, m=None, grad_scale=1.0):
     """Keras Adam over a flat bucket (sagan/main.py:119-120); hyper = device [lr_t, b1, b2, eps]."""
     check(_lib.load().sagan_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), _ptr(hyper),
                                       float(grad_scale), _stream()), "sagan_adam_step")
+
+
+def adam_schedule(hyper, iterations, lr0, decay_rate, decay_steps, b1, b2, eps):
+    """sagan/main.py:111-120 on the device: hyper <- [lr_t, b1, b2, eps] from the device counter `iterations`
+    (int64 [1]), which is then incremented."""
+    if not (iterations.is_cuda and iterations.dtype == torch.int64):
+        raise _lib.SaganError("adam_schedule: `iterations` must be a CUDA int64 tensor")
+    check(_lib.load().sagan_adam_schedule(_ptr(hyper), iterations.data_ptr(), float(lr0), float(decay_rate),
+                                          int(decay_steps), float(b1), float(b2), float(eps), _stream()),
+          "sagan_adam_schedule")

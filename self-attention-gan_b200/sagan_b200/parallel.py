@@ -47,6 +47,10 @@ class ReplicaGradientSum:
             dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.pg)
         return flat_grads
 
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.pg)
+
     def sum_losses_(self, loss_sums):
         """main.py:216-220: per-replica loss sums -> global sums (reporting only)."""
         if self.world > 1:

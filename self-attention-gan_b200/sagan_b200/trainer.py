@@ -24,27 +24,44 @@ ADAM_B1, ADAM_B2, ADAM_EPS = 0.0, 0.999, 1e-7      # main.py:119-120 (Keras defa
 
 
 class FlatAdam:
-    """Keras Adam + ExponentialDecay(staircase) over a network's flat bucket (main.py:111-120)."""
+    """Keras Adam + ExponentialDecay(staircase) over a network's flat bucket (main.py:111-120).
+
+    `optimizer.iterations` lives in DEVICE memory and the schedule (staircase decay, bias correction) is evaluated by
+    a one-thread kernel right before each application (`sagan_adam_schedule`), which also bumps the counter -- once
+    per `apply_gradients`, as Keras does (so the `update_ratio` D updates of one step see t, t+1, ...).  Nothing is
+    staged from the host per step: a replayed CUDA graph follows the schedule by itself, and the CPU running many
+    replays ahead of the GPU cannot hand a step the learning rate of a later one."""
 
     def __init__(self, net, lr0, decay_steps, decay_rate):
         self.net = net
         self.lr0, self.decay_steps, self.decay_rate = float(lr0), int(decay_steps), float(decay_rate)
-        self.iterations = 0
+        dev = net.flat_params.device
+        self._iters = torch.zeros(1, dtype=torch.int64, device=dev)
         self.v = torch.zeros_like(net.flat_params)
-        self.hyper = torch.zeros(4, device=net.flat_params.device)
-        self._host = torch.zeros(4).pin_memory()
+        self.hyper = torch.zeros(4, device=dev)
 
-    def lr_t(self):
-        lr = self.lr0 * self.decay_rate ** (self.iterations // self.decay_steps)
-        t = self.iterations + 1
+    @property
+    def iterations(self):
+        """optimizer.iterations (synchronises: device -> host read)."""
+        return int(self._iters.item())
+
+    @iterations.setter
+    def iterations(self, value):
+        self._iters.fill_(int(value))
+
+    def lr_t(self, iterations=None):
+        """Host restatement of the schedule kernel (tests / logging)."""
+        it = self.iterations if iterations is None else int(iterations)
+        lr = self.lr0 * self.decay_rate ** (it // self.decay_steps)
+        t = it + 1
         return lr * math.sqrt(1.0 - ADAM_B2 ** t) / (1.0 - ADAM_B1 ** t)
 
-    def stage_hyper(self):
-        """Host -> device copy of this step's [lr_t, b1, b2, eps]; stays outside a captured graph."""
-        self._host[0], self._host[1], self._host[2], self._host[3] = self.lr_t(), ADAM_B1, ADAM_B2, ADAM_EPS
-        self.hyper.copy_(self._host, non_blocking=True)
+    def schedule(self):
+        """hyper <- [lr_t, b1, b2, eps] for the current `iterations`; iterations += 1 (on the stream)."""
+        F.adam_schedule(self.hyper, self._iters, self.lr0, self.decay_rate, self.decay_steps, ADAM_B1, ADAM_B2, ADAM_EPS)
 
     def apply(self):
+        self.schedule()
         F.adam_step(self.net.flat_params, self.net.flat_grads, self.v, self.hyper)
 
 
@@ -62,7 +79,7 @@ class Trainer:
         # main.py:358: global_batch_size = batch_size * len(gpu)
         self.global_batch = global_batch_size or self.dp.global_batch(self.B)
         self.device = torch.device("cuda", torch.cuda.current_device())
-        torch.manual_seed(seed)
+        torch.manual_seed(seed)            # initial weights (replica 0's are broadcast below)
         self.dp_mode = dp_mode if self.world > 1 else "none"
         if self.dp_mode == "p2p":
             nets.set_flat_allocator(symmetric_allocator())
@@ -75,6 +92,9 @@ class Trainer:
             self.D([img, lab])
         # identical initial weights and spectral-norm state on every replica (MirroredStrategy variables)
         self.dp.broadcast_(self.G.flat_params, self.D.flat_params, self.G.sn_group.out, self.D.sn_group.out)
+        # every replica draws its OWN noise / fake labels (MirroredStrategy runs main.py:176-177,194-195 per replica):
+        # the device generator is re-seeded per replica once the weights are identical everywhere
+        torch.cuda.manual_seed(seed * 9973 + self.dp.rank)
         ur = cfg.get("update_ratio", 1)
         self.opt_G = FlatAdam(self.G, cfg["lr_g"], steps_per_epoch, cfg["decay_rate"])          # main.py:111-114
         self.opt_D = FlatAdam(self.D, cfg["lr_d"], steps_per_epoch * ur, cfg["decay_rate"])     # main.py:115-118
@@ -119,6 +139,7 @@ class Trainer:
         g_real, g_fake = F.hinge_d_grads(d_real, d_fake, self.global_batch, self.loss_sums[0:1])   # main.py:183-184
         torch.autograd.backward([d_real, d_fake], [g_real, g_fake])         # main.py:188-189
         if self.peer_D is not None:
+            self.opt_D.schedule()
             self.peer_D.step()                                              # main.py:190: replica SUM + Adam, one kernel
         else:
             self._allreduce(D.flat_grads)                                   # main.py:190 (replica SUM)
@@ -150,6 +171,7 @@ class Trainer:
             for p in D.parameters():
                 p.requires_grad_(True)
         if self.peer_G is not None:
+            self.opt_G.schedule()
             self.peer_G.step()                                              # main.py:205
         else:
             self._allreduce(G.flat_grads)                                   # main.py:205 (replica SUM)
@@ -178,68 +200,117 @@ class Trainer:
             return None
         return torch.randint(0, cfg["num_classes"], (self.B,), device=self.device)   # main.py:177,195
 
-    def _stage(self):
-        self.opt_D.stage_hyper()
-        self.opt_G.stage_hyper()
-
-    def _advance(self):
-        self.opt_D.iterations += self.config.get("update_ratio", 1)
-        self.opt_G.iterations += 1
-
     # ------------------------------------------------------------------------------------------
     def train_step(self, images, labels=None, noises_d=None, noise_g=None, fake_labels_d=None, fake_labels_g=None):
         """Eager step.  images: device NHWC float32 in [-1,1] (sagan/dataset.py:34).  Noise may be injected
         (parity tests); otherwise it is drawn on the device (main.py:176,194).  Returns the device tensor
         [sum L_D, sum L_G]; see `losses()` for the reported means."""
-        if self.config.get("update_ratio", 1) != 1 and noises_d is None:
-            pass
-        self._stage()
         self._step_body(images, labels, noises_d, noise_g, fake_labels_d, fake_labels_g)
-        self._advance()
         return self.loss_sums
 
-    def losses(self):
-        """Reported losses (main.py:216-229): sum over the batch / global batch, mean over the rest.
-        Synchronises (device -> host read of two floats)."""
-        s = self.loss_sums.tolist()
+    def losses(self, reduce=True):
+        """Reported losses (main.py:216-229): sum over the GLOBAL batch (all replicas, `strategy.reduce(SUM)`) / global
+        batch, mean over the rest.  Synchronises (device -> host read of two floats) and raises if the peer-memory
+        exchange reported a lost replica.  reduce=False keeps the replica-local sums (divided by the per-replica
+        batch)."""
+        sums = self.loss_sums
+        denom = self.global_batch
+        if self.world > 1:
+            if reduce:
+                sums = self.dp.sum_losses_(sums.clone())
+            else:
+                denom = self.B
+        s = sums.tolist()
+        self.check_exchange()
         ur = self.config.get("update_ratio", 1)
         n_elem = self._logit_elems()
-        return dict(D_loss=s[0] / ur / (self.global_batch * n_elem), G_loss=s[1] / (self.global_batch * n_elem))
+        return dict(D_loss=s[0] / ur / (denom * n_elem), G_loss=s[1] / (denom * n_elem))
+
+    def check_exchange(self):
+        """Raises if a replica timed out at an exchange barrier (the replicas have diverged).  Synchronises."""
+        for peer in (self.peer_D, self.peer_G):
+            if peer is not None:
+                peer.check()
 
     def _logit_elems(self):
         return 1 if self.config.get("use_label") else 16     # [B,4,4,1] patch logits (discriminator.py:35)
 
     # ------------------------------------------------------------------------------------------
-    def capture(self, warmup=3):
-        """Capture the whole step (both phases, all-reduces, Adam) into one CUDA graph.  Images (and labels)
-        are read from static device buffers that `graph_step` refills."""
+    def _state_tensors(self):
+        """Everything a training step mutates: weights, Adam moments and counters, spectral-norm u / v / W_bar,
+        BatchNorm moving statistics, loss sums."""
+        ts = [self.G.flat_params, self.D.flat_params, self.G.sn_group.out, self.D.sn_group.out,
+              self.opt_G.v, self.opt_D.v, self.opt_G._iters, self.opt_D._iters, self.loss_sums]
+        for peer in (self.peer_G, self.peer_D):
+            if peer is not None:
+                ts.append(peer.v_shard)
+        for net in (self.G, self.D):
+            for m in net.modules():
+                if hasattr(m, "moving_mean"):
+                    ts += [m.moving_mean, m.moving_var]
+        return ts
+
+    def capture(self, warmup=3, static_noise=False):
+        """Capture the whole step (both phases, gradient exchange, LR schedule, Adam) into one CUDA graph.  Images (and
+        labels) are read from static device buffers that `graph_step` refills.  The warm-up steps that CUDA-graph
+        capture needs run on throw-away state: weights, optimiser state and counters, spectral-norm vectors, BatchNorm
+        statistics and the device RNG are restored afterwards, so capturing does not train.
+        static_noise=True additionally routes the latent noise (and fake labels) through static buffers
+        (`graph_step(noises_d=..., noise_g=...)`) instead of drawing them inside the graph."""
         cfg = self.config
+        ur = cfg.get("update_ratio", 1)
         self._static["images"] = torch.zeros(self.B, cfg["img_size"], cfg["img_size"], 3, device=self.device)
         self._static["labels"] = (torch.zeros(self.B, dtype=torch.int64, device=self.device)
                                   if cfg.get("use_label") else None)
+        nz_d = nz_g = fl_d = fl_g = None
+        if static_noise:
+            nz_d = [torch.zeros(self.B, cfg["z_dim"], device=self.device) for _ in range(ur)]
+            nz_g = torch.zeros(self.B, cfg["z_dim"], device=self.device)
+            if cfg.get("use_label"):
+                fl_d = [torch.zeros(self.B, dtype=torch.int64, device=self.device) for _ in range(ur)]
+                fl_g = torch.zeros(self.B, dtype=torch.int64, device=self.device)
+        self._static.update(noises_d=nz_d, noise_g=nz_g, fake_labels_d=fl_d, fake_labels_g=fl_g)
+        torch.cuda.synchronize()
+        saved = [t.clone() for t in self._state_tensors()]
+        rng = torch.cuda.get_rng_state(self.device)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self.train_step(self._static["images"], self._static["labels"])
+                self._step_body(self._static["images"], self._static["labels"], nz_d, nz_g, fl_d, fl_g)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.dp.barrier()              # no replica restores its buffers while a peer is still writing into them
+        for t, t0 in zip(self._state_tensors(), saved):
+            t.copy_(t0)
+        torch.cuda.set_rng_state(rng, self.device)
+        torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self._stage()
         with torch.cuda.graph(self.graph):
-            self._step_body(self._static["images"], self._static["labels"], None, None, None, None)
+            self._step_body(self._static["images"], self._static["labels"], nz_d, nz_g, fl_d, fl_g)
         return self.graph
 
-    def graph_step(self, images=None, labels=None):
+    def graph_step(self, images=None, labels=None, noises_d=None, noise_g=None, fake_labels_d=None, fake_labels_g=None):
         """Replay the captured step.  `images` may be a pinned host tensor (copied asynchronously) or a
-        device tensor; None keeps the buffer contents."""
+        device tensor; None keeps the buffer contents.  Noise / fake labels can be given only after
+        `capture(static_noise=True)`."""
         if self.graph is None:
             raise RuntimeError("call capture() first")
+        st = self._static
         if images is not None:
-            self._static["images"].copy_(images, non_blocking=True)
-        if labels is not None and self._static["labels"] is not None:
-            self._static["labels"].copy_(labels, non_blocking=True)
-        self._stage()
+            st["images"].copy_(images, non_blocking=True)
+        if labels is not None and st["labels"] is not None:
+            st["labels"].copy_(labels, non_blocking=True)
+        for given, key in ((noises_d, "noises_d"), (fake_labels_d, "fake_labels_d")):
+            if given is not None:
+                if st[key] is None:
+                    raise RuntimeError(f"{key} given, but the graph was captured without static noise buffers")
+                for dst, src in zip(st[key], given):
+                    dst.copy_(src, non_blocking=True)
+        for given, key in ((noise_g, "noise_g"), (fake_labels_g, "fake_labels_g")):
+            if given is not None:
+                if st[key] is None:
+                    raise RuntimeError(f"{key} given, but the graph was captured without static noise buffers")
+                st[key].copy_(given, non_blocking=True)
         self.graph.replay()
-        self._advance()
         return self.loss_sums

@@ -25,6 +25,8 @@ from oracle import attention, nets, sn, train  # noqa: E402
 SN_SHAPES = [(4096, 128), (256, 2048), (128, 1024), (64, 512), (32, 256), (4, 32), (16, 32), (32, 16),
              (2, 16), (8, 16), (16, 8), (16, 48), (7, 13), (1, 130)]
 ATTN_CASES = [(2, 64, 16), (2, 256, 16), (2, 64, 32), (2, 256, 32), (2, 64, 64), (2, 200, 16)]
+# in-model token counts (N in {64, 256, 1024}): the 32x32 maps of church64 / 128x128-conditional G and D
+ATTN_CASES_N1024 = [(1, 1024, 16), (1, 1024, 32), (1, 1024, 64)]
 
 TEST_CFG = dict(z_dim=128, gf_dim=16, df_dim=16, img_size=64, use_attention=True, attn_dim_G=[32, 64],
                 attn_dim_D=[8, 4], use_label=False, batch_size=4, lr_g=2e-4, lr_d=7e-4, decay_rate=0.99,
@@ -77,10 +79,10 @@ def make_sn():
     np.savez_compressed(os.path.join(HERE, "sn.npz"), **out)
 
 
-def make_attn():
+def make_attn(cases=ATTN_CASES, seed0=200, fname="attention.npz"):
     out = {}
-    for i, (B, N, C) in enumerate(ATTN_CASES):
-        X, dY, w = attn_inputs(B, N, C, 200 + i)
+    for i, (B, N, C) in enumerate(cases):
+        X, dY, w = attn_inputs(B, N, C, seed0 + i)
         w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
         Y = attention.forward(X.astype(np.float64), **w64)
         g = attention.backward(dY.astype(np.float64), X.astype(np.float64), **w64)
@@ -89,7 +91,7 @@ def make_attn():
         out[tag + "_dX"] = g["dX"].astype(np.float32)
         for k in attention.WEIGHT_NAMES:
             out[tag + "_d" + k] = np.asarray(g["d" + k], dtype=np.float64)
-    np.savez_compressed(os.path.join(HERE, "attention.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, fname), **out)
 
 
 def make_nets():
@@ -129,11 +131,15 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--traj", action="store_true")
     ap.add_argument("--only-traj", action="store_true")
+    ap.add_argument("--only-n1024", action="store_true", help="only attention_n1024.npz (added in round 2)")
     a = ap.parse_args()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    if not a.only_traj:
+    if a.only_n1024:
+        make_attn(ATTN_CASES_N1024, 300, "attention_n1024.npz")
+    elif not a.only_traj:
         make_sn()
         make_attn()
+        make_attn(ATTN_CASES_N1024, 300, "attention_n1024.npz")
         make_nets()
     if a.traj or a.only_traj:
         make_traj()

@@ -350,11 +350,63 @@ def test_attention_tc_vs_golden(F, case):
     # parameter gradients: the cancellation-prone operands of the backward GEMMs (V, dA in dP = dA g^T; dS in the
     # theta / phi gradients) are carried as split bf16 pairs, so only the bf16 rounding of P itself is left for
     # C <= 32.  C = 64 (dv = 32): the 3-term split of dP does not fit the 64-column operand row, V stays rounded.
-    tol_w = TC_TOL if C <= 32 else 6e-3
+    tol_w = TC_TOL if C <= 32 else 4e-3
     for k, e in errs.items():
         # d gamma = sum(dY * O) is ONE scalar summed over zero-mean terms (this test's dY is independent of O), so its
         # relative error is a ratio of two random-walk sums: loose bound
         assert e < (1e-2 if k == "gamma" else tol_w), (k, e)
+
+
+def _check_attn_grads(tag, mode_name, y, dx, gw, X, dY, Y_ref, g_ref, tol, tol_w, tol_att):
+    errs = {k: rel_l2(gw[k], g_ref["d" + k]) for k in oattn.WEIGHT_NAMES if k != "bphi"}
+    e_y, e_att, e_dx = rel_l2(y, Y_ref), rel_l2(y - X, Y_ref - X), rel_l2(dx, g_ref["dX"])
+    e_dxa = rel_l2(dx - dY, g_ref["dX"] - dY)
+    print(tag, mode_name, "Y %.2e Y-X %.2e dX %.2e dX-dY %.2e" % (e_y, e_att, e_dx, e_dxa),
+          {k: "%.1e" % v for k, v in errs.items()})
+    assert e_y < tol and e_dx < tol, (tag, mode_name, e_y, e_dx)
+    assert e_att < tol_att and e_dxa < tol_att, (tag, mode_name, e_att, e_dxa)
+    for k, e in errs.items():
+        # d gamma is ONE scalar summed over zero-mean terms (dY independent of O): ratio of two random-walk sums
+        assert e < (5 * tol_w if k == "gamma" else tol_w), (tag, mode_name, k, e)
+    assert np.abs(gw["bphi"]).max() < 1e-2 * np.abs(gw["btheta"]).max() + 1e-7     # exactly zero in exact arithmetic
+
+
+@pytest.mark.parametrize("case", list(enumerate(mg.ATTN_CASES_N1024)))
+@pytest.mark.parametrize("mode_name", ["strict", "tc"])
+def test_attention_fwd_bwd_vs_golden_n1024(F, case, mode_name):
+    """In-model token count N = 1024 (the 32x32 maps), C in {16, 32, 64}: forward AND all gradients of
+    the fused kernels against the committed fp64 golden vectors, in both math modes (BASELINE.json tolerances:
+    1e-5 strict, 2e-3 tensor cores; the strict gradients sum ~1e3 fp32 terms per output: 2e-5)."""
+    i, (B, N, C) = case
+    gold = np.load(os.path.join(GOLD, "attention_n1024.npz"))
+    X, dY, w = mg.attn_inputs(B, N, C, 300 + i)
+    tag = f"B{B}_N{N}_C{C}"
+    g_ref = {"dX": gold[tag + "_dX"], **{"d" + k: gold[tag + "_d" + k] for k in oattn.WEIGHT_NAMES}}
+    mode = F.MATH_FP32_STRICT if mode_name == "strict" else F.MATH_BF16_TC
+    y, dx, gw = _run_attn(F, X, dY, w, mode)
+    if mode_name == "strict":
+        _check_attn_grads(tag, mode_name, y, dx, gw, X, dY, gold[tag + "_Y"], g_ref, STRICT_TOL, 3e-5, 5e-5)
+    else:
+        # C = 64 (dv = 32): the 3-term split of the dP contraction does not fit the 64-column operand row, V stays
+        # bf16-rounded there -> parameter-gradient tier 4e-3 (measured 2.2e-3 on the kernels, 3.7e-3 on btheta)
+        _check_attn_grads(tag, mode_name, y, dx, gw, X, dY, gold[tag + "_Y"], g_ref, TC_TOL, TC_TOL if C <= 32 else 4e-3, 1e-2)
+
+
+@pytest.mark.parametrize("mode_name", ["strict", "tc"])
+def test_attention_fwd_bwd_vs_oracle_n4096(F, mode_name):
+    """church64_attn G attention at the 64x64 map (N = 4096, C = 16 -- the step's dominant kernel) against the fp64
+    oracle evaluated here (one sample: the materialised [N, N] maps are 128 MiB each in fp64)."""
+    B, N, C = 1, 4096, 16
+    X, dY, w = oattn.make_inputs(B, N, C, seed=404, gamma=0.37, dtype=np.float32)
+    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    Y_ref = oattn.forward(X.astype(np.float64), **w64)
+    g_ref = oattn.backward(dY.astype(np.float64), X.astype(np.float64), **w64)
+    mode = F.MATH_FP32_STRICT if mode_name == "strict" else F.MATH_BF16_TC
+    y, dx, gw = _run_attn(F, X, dY, w, mode)
+    if mode_name == "strict":
+        _check_attn_grads("B1_N4096_C16", mode_name, y, dx, gw, X, dY, Y_ref, g_ref, STRICT_TOL, 5e-5, 1e-4)
+    else:
+        _check_attn_grads("B1_N4096_C16", mode_name, y, dx, gw, X, dY, Y_ref, g_ref, TC_TOL, TC_TOL, 1e-2)
 
 
 @pytest.mark.parametrize("shape", [(4, 4096, 16), (4, 1024, 32), (2, 1024, 64), (3, 1000, 16)])
@@ -452,17 +504,27 @@ def tf32r(a, mode):
     return (bits & ~0x1FFF).view(torch.float32).to(torch.float64)
 
 
-@pytest.mark.parametrize("case", TC_CONV_CASES)
-def test_conv2d_tc(F, case):
-    """tcgen05 implicit-GEMM conv: forward / backward-data run kind::tf32 on the fp32 operands, backward-filter
-    kind::f16 on bf16-converted operands, fp32 accumulation in TMEM.
+@pytest.fixture(params=["split_bf16", "tf32"])
+def conv_prec(request):
+    """Operand precision of the tensor-core conv kernels (sagan_conv_tc_precision): split-bf16 is the default of
+    BF16_TC mode, tf32 (+ plain bf16 backward-filter) the round-1 arithmetic kept for comparison."""
+    from sagan_b200 import _lib
+    lib = _lib.load()
+    lib.sagan_conv_tc_precision(_lib.CONV_TC_SPLIT_BF16 if request.param == "split_bf16" else _lib.CONV_TC_TF32)
+    yield request.param
+    lib.sagan_conv_tc_precision(_lib.CONV_TC_SPLIT_BF16)
 
-    (1) Exactness of the kernels: against fp64 torch evaluated on the SAME rounded operands the only difference is
-    fp32 accumulation order -> 2e-5 (tf32: whichever of truncation / round-to-nearest the tensor core applies).
-    (2) Against the un-rounded fp64 reference the forward is inside the tf32 tier (the tensor core TRUNCATES fp32 to
-    tf32: relative operand error < 2^-10, measured 8e-4 on y; bf16 operands gave 2.3e-3).  Gradients are not compared
-    un-rounded through LeakyReLU: a rounding-sized perturbation of y flips the sign of the few outputs nearest zero
-    and each flip changes dz by 0.9 dy -- a property of reduced-precision operands, not of the kernel."""
+
+SPLIT_TOL = 5e-5     # split-bf16 products carry 16 mantissa bits (dropped lo*lo term 2^-16): fp32-grade results
+
+
+@pytest.mark.parametrize("case", TC_CONV_CASES)
+def test_conv2d_tc_split_vs_fp64(F, case):
+    """Default BF16_TC conv arithmetic (split-bf16, three MMAs per K step): forward, backward-data, backward-filter and
+    bias gradient of Conv2D + LeakyReLU against UN-ROUNDED fp64 (the kernel's own activation mask is used for the
+    reference gradient: a pre-activation within 1e-5 of zero may legitimately land on either side)."""
+    from sagan_b200 import _lib
+    assert _lib.load().sagan_conv_tc_precision(-1) == _lib.CONV_TC_SPLIT_BF16
     B, H, W, Cin, Cout, k, s = case
     rng = np.random.Generator(np.random.PCG64(41))
     x = rng.standard_normal((B, H, W, Cin))
@@ -473,6 +535,45 @@ def test_conv2d_tc(F, case):
     dy = rng.standard_normal(tuple(y.shape))
     y.backward(cu(dy))
     torch.cuda.synchronize()
+    yk = y.detach().cpu().double()
+    dz = torch.tensor(dy) * torch.where(yk > 0, 1.0, 0.1)
+    tx, tw, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, b))
+    z = onets.conv2d_same(tx, tw, tb, s)
+    z.backward(dz)
+    errs = (rel_l2(yk.numpy(), torch.nn.functional.leaky_relu(z, 0.1).detach().numpy()),
+            rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()), rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()),
+            rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()))
+    print(case, "split-bf16 vs fp64: y %.2e dx %.2e dw %.2e db %.2e" % errs)
+    assert max(errs) < SPLIT_TOL
+
+
+@pytest.mark.parametrize("case", TC_CONV_CASES)
+def test_conv2d_tc(F, case):
+    """Round-1 arithmetic (sagan_conv_tc_precision = TF32), kept selectable.
+    tcgen05 implicit-GEMM conv: forward / backward-data run kind::tf32 on the fp32 operands, backward-filter
+    kind::f16 on bf16-converted operands, fp32 accumulation in TMEM.
+
+    (1) Exactness of the kernels: against fp64 torch evaluated on the SAME rounded operands the only difference is
+    fp32 accumulation order -> 2e-5 (tf32: whichever of truncation / round-to-nearest the tensor core applies).
+    (2) Against the un-rounded fp64 reference the forward is inside the tf32 tier (the tensor core TRUNCATES fp32 to
+    tf32: relative operand error < 2^-10, measured 8e-4 on y; bf16 operands gave 2.3e-3).  Gradients are not compared
+    un-rounded through LeakyReLU: a rounding-sized perturbation of y flips the sign of the few outputs nearest zero
+    and each flip changes dz by 0.9 dy -- a property of reduced-precision operands, not of the kernel."""
+    from sagan_b200 import _lib
+    B, H, W, Cin, Cout, k, s = case
+    rng = np.random.Generator(np.random.PCG64(41))
+    x = rng.standard_normal((B, H, W, Cin))
+    w = rng.standard_normal((k, k, Cin, Cout)) * 0.1
+    b = rng.standard_normal(Cout) * 0.1
+    gx, gw, gb = (cu(a).requires_grad_(True) for a in (x, w, b))
+    _lib.load().sagan_conv_tc_precision(_lib.CONV_TC_TF32)
+    try:
+        y = F.conv2d(gx, gw, gb, s, "same", F.ACT_LRELU, 0.1, F.MATH_BF16_TC)
+        dy = rng.standard_normal(tuple(y.shape))
+        y.backward(cu(dy))
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().sagan_conv_tc_precision(_lib.CONV_TC_SPLIT_BF16)
     yk = y.detach().cpu().double()
     tb = torch.tensor(b, dtype=torch.float64)
     dz = torch.tensor(dy) * torch.where(yk > 0, 1.0, 0.1)        # the kernel's own activation mask
@@ -499,7 +600,7 @@ def test_conv2d_tc(F, case):
 
 
 @pytest.mark.parametrize("case", TC_CONV_CASES[:4])
-def test_conv2d_tc_linear_vs_fp64(F, case):
+def test_conv2d_tc_linear_vs_fp64(F, case, conv_prec):
     """No activation (so no mask flips): fwd / dgrad / wgrad / dbias against un-rounded fp64 inside the BF16_TC tier."""
     B, H, W, Cin, Cout, k, s = case
     rng = np.random.Generator(np.random.PCG64(42))
@@ -516,13 +617,13 @@ def test_conv2d_tc_linear_vs_fp64(F, case):
     torch.cuda.synchronize()
     errs = (rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()), rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()),
             rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()), rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()))
-    print(case, "y %.2e dx %.2e dw %.2e db %.2e" % errs)
-    assert max(errs) < 2 * TC_TOL
+    print(case, conv_prec, "y %.2e dx %.2e dw %.2e db %.2e" % errs)
+    assert max(errs) < (SPLIT_TOL if conv_prec == "split_bf16" else 2 * TC_TOL)
 
 
 @pytest.mark.parametrize("case", [(2, 4, 4, 256, 128, 4, 2), (2, 16, 16, 64, 32, 4, 2), (2, 32, 32, 32, 16, 4, 2),
                                   (2, 5, 6, 8, 16, 3, 2)])
-def test_conv2d_transpose_tc(F, case):
+def test_conv2d_transpose_tc(F, case, conv_prec):
     B, H, W, Cin, Cout, k, s = case
     rng = np.random.Generator(np.random.PCG64(43))
     x = rng.standard_normal((B, H, W, Cin))
@@ -537,11 +638,11 @@ def test_conv2d_transpose_tc(F, case):
     torch.cuda.synchronize()
     errs = (rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()), rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()),
             rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()))
-    print(case, "y %.2e dx %.2e dw %.2e" % errs)
-    assert max(errs) < 5e-3
+    print(case, conv_prec, "y %.2e dx %.2e dw %.2e" % errs)
+    assert max(errs) < (SPLIT_TOL if conv_prec == "split_bf16" else 5e-3)
 
 
-def test_dense_tc(F):
+def test_dense_tc(F, conv_prec):
     rng = np.random.Generator(np.random.PCG64(44))
     x, w, b = rng.standard_normal((64, 128)), rng.standard_normal((128, 4096)) * 0.05, rng.standard_normal(4096)
     tx, tw, tb = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, b))
@@ -554,5 +655,5 @@ def test_dense_tc(F):
     torch.cuda.synchronize()
     errs = (rel_l2(y.detach().cpu().numpy(), ref.detach().numpy()), rel_l2(gx.grad.cpu().numpy(), tx.grad.numpy()),
             rel_l2(gw.grad.cpu().numpy(), tw.grad.numpy()), rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()))
-    print("dense y %.2e dx %.2e dw %.2e db %.2e" % errs)
-    assert max(errs) < 5e-3
+    print("dense", conv_prec, "y %.2e dx %.2e dw %.2e db %.2e" % errs)
+    assert max(errs) < (SPLIT_TOL if conv_prec == "split_bf16" else 5e-3)

@@ -29,12 +29,30 @@ def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
 
 
-def make_pair(cfg, attn_sigma, bias_scale, dtype=torch.float64, steps_per_epoch=1000):
-    """Oracle trainer and GPU trainer holding identical weights and spectral-norm state."""
+MODES = ["fp32_strict", "bf16_tc"]
+
+
+def _math(mode_name):
+    from sagan_b200 import MATH_BF16_TC, MATH_FP32_STRICT
+    return {"fp32_strict": MATH_FP32_STRICT, "bf16_tc": MATH_BF16_TC}[mode_name]
+
+
+def make_trainer(cfg, mode_name="fp32_strict", **kw):
+    """GPU trainer whose layers run in the given math mode (bf16_tc is the mode bench.py times)."""
+    from sagan_b200 import nn as snn
     from sagan_b200.trainer import Trainer
+    snn.set_default_math_mode(_math(mode_name))
+    try:
+        return Trainer(cfg, **kw)
+    finally:
+        snn.set_default_math_mode(_math("fp32_strict"))
+
+
+def make_pair(cfg, attn_sigma, bias_scale, dtype=torch.float64, steps_per_epoch=1000, mode_name="fp32_strict"):
+    """Oracle trainer and GPU trainer holding identical weights and spectral-norm state."""
     orc = otrain.OracleTrainer(cfg, dtype, seed=0, attn_sigma=attn_sigma, bias_scale=bias_scale,
                                global_batch_size=cfg["batch_size"], steps_per_epoch=steps_per_epoch)
-    tr = Trainer(cfg, global_batch_size=cfg["batch_size"], steps_per_epoch=steps_per_epoch)
+    tr = make_trainer(cfg, mode_name, global_batch_size=cfg["batch_size"], steps_per_epoch=steps_per_epoch)
     tr.G.load_keras_weights({k: v.numpy() for k, v in orc.G.items()},
                             {k: v.numpy() for k, v in orc.G_sn.items() if k.endswith(".u")})
     tr.D.load_keras_weights({k: v.numpy() for k, v in orc.D.items()},
@@ -154,14 +172,8 @@ def test_forward_and_gradients_bf16_tc_mode():
     Parameter gradients are reported and bounded, not held to 2e-3: a forward error of 1e-3 moves ~0.1 % of the
     LeakyReLU(0.1) inputs across zero, each flip changes dz by 0.9 dy, i.e. ~3 % rel-L2 per layer on the gradient --
     a property of ANY reduced-precision forward through this topology (the FP32_STRICT test above holds 1e-4)."""
-    from sagan_b200 import nn as snn
-    from sagan_b200 import MATH_BF16_TC, MATH_FP32_STRICT
     cfg = dict(mg.TEST_CFG)
-    snn.set_default_math_mode(MATH_BF16_TC)
-    try:
-        orc, tr = make_pair(cfg, attn_sigma=0.37, bias_scale=0.05)
-    finally:
-        snn.set_default_math_mode(MATH_FP32_STRICT)
+    orc, tr = make_pair(cfg, attn_sigma=0.37, bias_scale=0.05, mode_name="bf16_tc")
     img, nd, ng = mg.step_inputs(cfg, 0)
     t64 = lambda a: torch.tensor(a, dtype=torch.float64)
     # forward outputs of each network on its own (generated images, logits on real images), from the INITIAL
@@ -182,8 +194,8 @@ def test_forward_and_gradients_bf16_tc_mode():
     le_d, le_g = _phase_grads(tr, cfg, img, nd, ng)
     e_d, e_g = rel_l2(le_d, dl.numpy()), rel_l2(le_g, gl.numpy())
     print("BF16_TC forward: G(z) %.2e  D(x) %.2e | loss elems: D %.2e G %.2e" % (e_img, e_logit, e_d, e_g))
-    assert e_img < 2e-3 and e_logit < 2e-3 and e_d < 2e-3
-    assert e_g < 2e-3          # -D(G(z)): both networks composed
+    assert e_img < 2e-4 and e_logit < 2e-4 and e_d < 2e-4
+    assert e_g < 2e-4          # -D(G(z)): both networks composed
     errs = {}
     for net, ref in ((tr.D, dgr), (tr.G, ggr)):
         for k, p in net.named_parameters_by_oracle_name():
@@ -193,7 +205,10 @@ def test_forward_and_gradients_bf16_tc_mode():
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
     print("BF16_TC worst per-parameter gradient rel-L2:", [(k, "%.2e" % v) for k, v in worst])
     print("BF16_TC median per-parameter gradient rel-L2: %.2e" % float(np.median(list(errs.values()))))
-    assert max(errs.values()) < 1.5e-1 and float(np.median(list(errs.values()))) < 5e-2
+    # round 1 (tf32 conv forward): worst 1.5e-1, median 5e-2.  With split-bf16 convs the forward is fp32-grade (G(z) 2e-5,
+    # D(x) 8e-6), a handful of LeakyReLU flips remain (each flip among the n pre-activations of a layer costs
+    # 0.9 / sqrt(n) on everything upstream): measured worst 1.0e-2, median 2.9e-3
+    assert max(errs.values()) < 3e-2 and float(np.median(list(errs.values()))) < 8e-3
 
 
 def test_conditional_128_forward_and_gradients():
@@ -225,20 +240,33 @@ def test_conditional_128_forward_and_gradients():
     print("128x128 conditional: worst per-parameter gradient rel-L2 %.2e" % worst)
 
 
-def test_train_steps_match_oracle_fp32():
-    """5 full steps (both Adam updates, LR schedule) against the fp32 oracle: losses and weights."""
+@pytest.mark.parametrize("mode_name", MODES)
+def test_train_steps_match_oracle_fp32(mode_name):
+    """5 full steps (both Adam updates, LR schedule evaluated on the device) against the fp32 oracle: losses and
+    weights, in both math modes (bf16_tc is what bench.py times)."""
     cfg = dict(mg.TEST_CFG)
-    orc, tr = make_pair(cfg, attn_sigma=0.2, bias_scale=0.02, dtype=torch.float32, steps_per_epoch=2)
+    orc, tr = make_pair(cfg, attn_sigma=0.2, bias_scale=0.02, dtype=torch.float32, steps_per_epoch=2, mode_name=mode_name)
     for s in range(5):
         img, nd, ng = mg.step_inputs(cfg, s)
         ref = orc.train_step(torch.tensor(img), [torch.tensor(nd)], torch.tensor(ng))
         tr.train_step(cu(img), None, [cu(nd)], cu(ng))
         got = tr.losses()
-        assert abs(got["D_loss"] - ref["D_loss"]) < 1e-3 and abs(got["G_loss"] - ref["G_loss"]) < 1e-3, (s, got, ref)
-    for k, p in tr.G.named_parameters_by_oracle_name():
-        assert rel_l2(p.detach().cpu().numpy(), orc.G[k].numpy()) < 2e-3, k
-    for k, p in tr.D.named_parameters_by_oracle_name():
-        assert rel_l2(p.detach().cpu().numpy(), orc.D[k].numpy()) < 2e-3, k
+        # free-running: the reduced-precision mode follows the fp32 oracle to 1e-3 for the first two steps; after that
+        # Adam(beta_1 = 0) has amplified the 1e-3-level attention-gradient differences (the teacher-forced 100-step test
+        # below holds 1e-3 at EVERY step)
+        tol = 1e-3 if (mode_name == "fp32_strict" or s < 2) else 2e-2
+        assert abs(got["D_loss"] - ref["D_loss"]) < tol and abs(got["G_loss"] - ref["G_loss"]) < tol, (s, got, ref)
+    assert tr.opt_G.iterations == 5 == orc.opt_G.iterations and tr.opt_D.iterations == 5
+    assert abs(float(tr.opt_D.hyper[0]) - tr.opt_D.lr_t(4)) < 1e-6 * tr.opt_D.lr_t(4)    # staircase: 0.99^(4 // 2)
+    worst = 0.0
+    for net, ref_params in ((tr.G, orc.G), (tr.D, orc.D)):
+        for k, p in net.named_parameters_by_oracle_name():
+            e = rel_l2(p.detach().cpu().numpy(), ref_params[k].numpy())
+            worst = max(worst, e)
+            # Adam(beta_1 = 0) turns the sign of a rounding-sized gradient into a +-lr step: the tiny attention biases
+            # / gamma can sit at a few lr after 5 steps in the reduced-precision mode
+            assert e < (2e-3 if mode_name == "fp32_strict" else (2e-2 if p.numel() > 64 else 2e-1)), (k, e)
+    print(mode_name, "worst weight rel-L2 after 5 steps: %.2e" % worst)
 
 
 def _sync_from_oracle(tr, orc):
@@ -256,7 +284,8 @@ def _sync_from_oracle(tr, orc):
         opt.iterations = oopt.iterations
 
 
-def test_loss_trajectory_100_steps_teacher_forced():
+@pytest.mark.parametrize("mode_name", MODES)
+def test_loss_trajectory_100_steps_teacher_forced(mode_name):
     """Per-step G and D hinge losses within 1e-3 of the oracle's over 100 training steps (BASELINE.json tolerance).
 
     The comparison is made ALONG the oracle's trajectory: before every step the GPU trainer receives the oracle's
@@ -264,9 +293,10 @@ def test_loss_trajectory_100_steps_teacher_forced():
     noise, and the reported losses must agree.  A free-running comparison cannot hold this tolerance for ANY two
     fp32 implementations at this configuration: Adam with beta_1 = 0 is a sign-like update in its first steps, and
     the fp32 oracle run with 1 thread instead of 8 (summation order only) already differs from itself by 1.5e-3 at
-    step 5 and by O(1) at step 30 ("Loss-trajectory parity"); see the free-running test below."""
+    step 5 and by O(1) at step 30 ("Loss-trajectory parity"); see the free-running test below.
+    Runs in both math modes: bf16_tc is the mode bench.py times."""
     cfg = dict(mg.TEST_CFG)
-    orc, tr = make_pair(cfg, attn_sigma=0.0, bias_scale=0.0, dtype=torch.float32, steps_per_epoch=40)
+    orc, tr = make_pair(cfg, attn_sigma=0.0, bias_scale=0.0, dtype=torch.float32, steps_per_epoch=40, mode_name=mode_name)
     worst = worst_w = 0.0
     worst_k = None
     for s in range(100):
@@ -289,11 +319,12 @@ def test_loss_trajectory_100_steps_teacher_forced():
                     e_w = rel_l2(p_.detach().cpu().numpy(), ref_params[k].numpy())
                     if e_w > worst_w:
                         worst_w, worst_k = e_w, (s, k)
-    print("worst |loss - oracle| over 100 teacher-forced steps: %.2e; worst post-step weight rel-L2: %.2e at %s" % (worst, worst_w, worst_k))
+    print(mode_name, "worst |loss - oracle| over 100 teacher-forced steps: %.2e; worst post-step weight rel-L2: %.2e at %s" % (worst, worst_w, worst_k))
     assert worst_w < 2e-3
 
 
-def test_loss_trajectory_free_running_vs_golden():
+@pytest.mark.parametrize("mode_name", MODES)
+def test_loss_trajectory_free_running_vs_golden(mode_name):
     """Free-running (no state sync) against the committed golden trajectory: the first steps, before fp32
     summation-order noise is amplified, stay within 1e-3; afterwards the losses must stay finite and in range."""
     path = os.path.join(GOLD, "trajectory.npz")
@@ -301,7 +332,7 @@ def test_loss_trajectory_free_running_vs_golden():
         pytest.skip("trajectory.npz not generated (python tests/golden/make_golden.py --traj)")
     gold = np.load(path)
     cfg = dict(mg.TEST_CFG)
-    orc, tr = make_pair(cfg, attn_sigma=0.0, bias_scale=0.0, dtype=torch.float32, steps_per_epoch=40)
+    orc, tr = make_pair(cfg, attn_sigma=0.0, bias_scale=0.0, dtype=torch.float32, steps_per_epoch=40, mode_name=mode_name)
     devs = []
     for s in range(20):
         img, nd, ng = mg.step_inputs(cfg, s)
@@ -309,58 +340,118 @@ def test_loss_trajectory_free_running_vs_golden():
         got = tr.losses()
         devs.append(max(abs(got["D_loss"] - gold["D_loss"][s]), abs(got["G_loss"] - gold["G_loss"][s])))
         assert np.isfinite(got["D_loss"]) and np.isfinite(got["G_loss"])
-    print("free-running |loss - golden| per step:", ["%.1e" % d for d in devs])
+    print(mode_name, "free-running |loss - golden| per step:", ["%.1e" % d for d in devs])
     assert max(devs[:3]) < 1e-3
 
 
-def test_cuda_graph_step_equals_eager_step():
-    """The captured whole-step graph reproduces the eager step (same weights after the same inputs)."""
-    from sagan_b200.trainer import Trainer
+def _bn_buffers(tr):
+    return [t for m in tr.G.modules() if hasattr(m, "moving_mean") for t in (m.moving_mean, m.moving_var)]
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+def test_cuda_graph_step_equals_eager_step(mode_name):
+    """The captured whole-step graph (what bench.py times) IS the eager step: two trainers built from the same seed,
+    one captured (`capture(static_noise=True)`: latent noise read from static buffers), fed the same images and noise.
+    Capturing must not train (its warm-up runs on throw-away state).
+
+    What "equal" can mean: the weight-gradient kernels accumulate fp32 partial sums with atomics, so two EAGER runs
+    already differ in the last bits (measured 2e-6 rel-L2 on a gradient bucket).  After D's Adam update those bits can
+    (i) turn a rounding-sized gradient into a +-lr step (beta_1 = 0: sign-like first steps) and (ii) once in a few
+    runs move ONE LeakyReLU pre-activation of D's last 4x4 map across zero, which changes every upstream G-phase
+    gradient by ~0.9 / sqrt(8192) = 1e-2 (tools/det2.py reproduces both between two eager trainers).  Hence:
+
+      part 1 (real learning rates, one step): losses, D-phase gradient bucket, Adam second moments, schedule output,
+             step counters, spectral-norm state and BatchNorm statistics agree to summation-order noise; the weights
+             are identical except for (i): |delta| <= 2 lr on < 0.1 % of the elements; the G-phase bucket within (ii);
+      part 2 (learning rates ~0, so both trainers keep the same weights; sagan_deterministic_forward(1), so no
+             activation is accumulated with atomics and no mask can flip): four consecutive steps with fresh inputs --
+             every replay of the graph reproduces the eager losses to 1e-6 and BOTH gradient buckets to 1e-5.
+    """
+    from sagan_b200 import _lib
     cfg = dict(mg.TEST_CFG)
-    torch.manual_seed(0)
-    a = Trainer(cfg, seed=3)
-    b = Trainer(cfg, seed=3)
-    b.G.flat_params.copy_(a.G.flat_params); b.D.flat_params.copy_(a.D.flat_params)
-    b.G.sn_group.out.copy_(a.G.sn_group.out); b.D.sn_group.out.copy_(a.D.sn_group.out)
-    img = cu(mg.step_inputs(cfg, 0)[0])
-    b.capture(warmup=3)
-    # bring `a` to the same state: capture() ran 3 warm-up steps with zero images and device noise, so instead
-    # compare two replays of the graph against two eager steps from a common snapshot
-    snap = [t.clone() for t in (b.G.flat_params, b.D.flat_params, b.G.sn_group.out, b.D.sn_group.out, b.opt_G.v, b.opt_D.v)]
-    a.G.flat_params.copy_(snap[0]); a.D.flat_params.copy_(snap[1])
-    a.G.sn_group.out.copy_(snap[2]); a.D.sn_group.out.copy_(snap[3])
-    a.opt_G.v.copy_(snap[4]); a.opt_D.v.copy_(snap[5])
-    a.opt_G.iterations, a.opt_D.iterations = b.opt_G.iterations, b.opt_D.iterations
-    for bn_a, bn_b in zip([m for m in a.G.modules() if hasattr(m, "moving_mean")],
-                          [m for m in b.G.modules() if hasattr(m, "moving_mean")]):
-        bn_a.moving_mean.copy_(bn_b.moving_mean); bn_a.moving_var.copy_(bn_b.moving_var)
-    # same device RNG stream for the noise drawn inside the step
-    state = torch.cuda.get_rng_state()
-    b.graph_step(img)
-    lb = b.losses()
-    torch.cuda.set_rng_state(state)
-    a.train_step(img)
-    la = a.losses()
-    # graph replays use the Philox offset registered at capture, not the live generator, so noise differs:
-    # compare statistics that do not depend on the noise draw instead -- D loss on real data dominates
-    assert np.isfinite(lb["D_loss"]) and np.isfinite(lb["G_loss"])
-    assert abs(la["D_loss"] - lb["D_loss"]) < 0.5 and abs(la["G_loss"] - lb["G_loss"]) < 0.5
-    assert torch.isfinite(b.G.flat_params).all() and torch.isfinite(b.D.flat_params).all()
+    B = cfg["batch_size"]
+    g = torch.Generator(device="cuda").manual_seed(99)
+
+    def inputs():
+        img = torch.rand(B, cfg["img_size"], cfg["img_size"], 3, device="cuda", generator=g) * 2 - 1
+        return img, [torch.randn(B, cfg["z_dim"], device="cuda", generator=g)], torch.randn(B, cfg["z_dim"], device="cuda", generator=g)
+
+    def rel(x, y):
+        return float((x - y).norm() / (y.norm() + 1e-30))
+
+    # ---- part 1
+    a = make_trainer(cfg, mode_name, seed=3, steps_per_epoch=2)
+    b = make_trainer(cfg, mode_name, seed=3, steps_per_epoch=2)
+    before = [t.clone() for t in b._state_tensors()]
+    b.capture(warmup=3, static_noise=True)
+    for t0, t1 in zip(before, b._state_tensors()):
+        assert torch.equal(t0, t1)                           # capture() left weights / optimiser / SN / BN state alone
+    for t0, t1 in zip(a._state_tensors(), b._state_tensors()):
+        assert torch.equal(t0, t1)                           # same seed -> same initial state
+    img, nd, ng = inputs()
+    a.train_step(img, noises_d=nd, noise_g=ng)
+    b.graph_step(img, noises_d=nd, noise_g=ng)
+    la, lb = a.losses(), b.losses()
+    assert abs(la["D_loss"] - lb["D_loss"]) < 1e-6 * max(1, abs(la["D_loss"])), (la, lb)
+    assert abs(la["G_loss"] - lb["G_loss"]) < 2e-5 * max(1, abs(la["G_loss"])), (la, lb)     # through the updated D
+    assert a.opt_G.iterations == b.opt_G.iterations == 1 and a.opt_D.iterations == b.opt_D.iterations == 1
+    assert torch.equal(a.opt_G.hyper, b.opt_G.hyper) and torch.equal(a.opt_D.hyper, b.opt_D.hyper)
+    assert rel(a.D.flat_grads, b.D.flat_grads) < 1e-5
+    assert rel(a.G.flat_grads, b.G.flat_grads) < 5e-2        # (ii); part 2 holds this bucket to 1e-5
+    assert rel(a.opt_D.v, b.opt_D.v) < 1e-5 and rel(a.opt_G.v, b.opt_G.v) < 1e-1
+    assert rel(a.G.sn_group.out, b.G.sn_group.out) < 1e-6 and rel(a.D.sn_group.out, b.D.sn_group.out) < 1e-5
+    for ta, tb in zip(_bn_buffers(a), _bn_buffers(b)):
+        assert torch.allclose(ta, tb, rtol=1e-5, atol=1e-7)
+    for (na, nb, lr) in ((a.G, b.G, cfg["lr_g"]), (a.D, b.D, cfg["lr_d"])):
+        diff = (na.flat_params - nb.flat_params).abs()
+        assert float(diff.max()) <= 2.001 * lr, float(diff.max())
+        if na is a.D:      # D's update follows the (agreeing) D-phase bucket; G's follows the G-phase bucket, see (ii)
+            assert float((diff > 1e-6).float().mean()) < 1e-3
+    # ---- part 2
+    frozen = dict(cfg, lr_g=1e-12, lr_d=1e-12)
+    _lib.load().sagan_deterministic_forward(1)
+    try:
+        a = make_trainer(frozen, mode_name, seed=4)
+        b = make_trainer(frozen, mode_name, seed=4)
+        b.capture(warmup=3, static_noise=True)
+        for step in range(4):
+            img, nd, ng = inputs()
+            a.train_step(img, noises_d=nd, noise_g=ng)
+            b.graph_step(img, noises_d=nd, noise_g=ng)
+            la, lb = a.losses(), b.losses()
+            assert abs(la["D_loss"] - lb["D_loss"]) < 1e-6 * max(1, abs(la["D_loss"])), (step, la, lb)
+            assert abs(la["G_loss"] - lb["G_loss"]) < 1e-6 * max(1, abs(la["G_loss"])), (step, la, lb)
+            e_d, e_g = rel(a.D.flat_grads, b.D.flat_grads), rel(a.G.flat_grads, b.G.flat_grads)
+            assert e_d < 1e-5 and e_g < 1e-5, (step, e_d, e_g)
+            assert a.opt_G.iterations == b.opt_G.iterations == step + 1
+            assert rel(a.G.sn_group.out, b.G.sn_group.out) < 1e-6 and rel(a.D.sn_group.out, b.D.sn_group.out) < 1e-6
+        assert torch.allclose(a.G.flat_params, b.G.flat_params, rtol=0, atol=1e-9)
+        assert torch.allclose(a.D.flat_params, b.D.flat_params, rtol=0, atol=1e-9)
+    finally:
+        _lib.load().sagan_deterministic_forward(0)
+    # ---- the graph draws its own noise when none is injected (bench.py's mode) and stays finite
+    c = make_trainer(cfg, mode_name, seed=3)
+    c.capture(warmup=3)
+    c.graph_step(img)
+    lc = c.losses()
+    assert np.isfinite(lc["D_loss"]) and np.isfinite(lc["G_loss"])
+    with pytest.raises(RuntimeError, match="static noise"):
+        c.graph_step(img, noise_g=ng)
 
 
-def test_overlapped_step_equals_single_stream_step():
+@pytest.mark.parametrize("mode_name", MODES)
+def test_overlapped_step_equals_single_stream_step(mode_name):
     """The step whose generator forwards run as a side-stream branch (Trainer overlap_streams=True, the default and
     what bench.py times) computes what the single-stream step computes: same injected noise, the losses of three
     steps and the weights after them.  The first step's losses see identical weights (agreement to rounding); after
     that the two runs differ by the order of the atomic partial sums in the weight-gradient kernels, which Adam with
     beta_1 = 0 turns into +-lr steps on parameters whose gradient is rounding noise (loss-trajectory
     parity), hence the looser bounds.  Repeated to give a stream race more than one chance to show."""
-    from sagan_b200.trainer import Trainer
     cfg = dict(mg.TEST_CFG)
     B = cfg["batch_size"]
     for rep in range(3):
-        a = Trainer(cfg, seed=5, overlap_streams=True)
-        b = Trainer(cfg, seed=5, overlap_streams=False)
+        a = make_trainer(cfg, mode_name, seed=5, overlap_streams=True)
+        b = make_trainer(cfg, mode_name, seed=5, overlap_streams=False)
         b.G.flat_params.copy_(a.G.flat_params); b.D.flat_params.copy_(a.D.flat_params)
         b.G.sn_group.out.copy_(a.G.sn_group.out); b.D.sn_group.out.copy_(a.D.sn_group.out)
         g = torch.Generator(device="cuda").manual_seed(11 + rep)
@@ -371,8 +462,8 @@ def test_overlapped_step_equals_single_stream_step():
             a.train_step(img, noises_d=nd, noise_g=ng)
             b.train_step(img, noises_d=nd, noise_g=ng)
             la, lb = a.losses(), b.losses()
-            tol = 1e-5 if step == 0 else 2e-3
+            tol = 1e-5 if step == 0 else (2e-3 if mode_name == "fp32_strict" else 1e-2)
             assert abs(la["D_loss"] - lb["D_loss"]) < tol and abs(la["G_loss"] - lb["G_loss"]) < tol, (rep, step, la, lb)
         for pa, pb in ((a.G.flat_params, b.G.flat_params), (a.D.flat_params, b.D.flat_params)):
             rel = float((pa - pb).norm() / pb.norm())
-            assert rel < 2e-3, (rep, rel)
+            assert rel < (2e-3 if mode_name == "fp32_strict" else 5e-3), (rep, rel)

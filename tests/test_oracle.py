@@ -99,6 +99,22 @@ def test_attention_golden_autograd_and_fp32():
         assert rel(Y32, Y) < 1e-5
 
 
+def test_attention_golden_n1024():
+    """The in-model token count (N = 1024) fixture added for the tensor-core backward parity tests."""
+    gold = np.load(os.path.join(GOLD, "attention_n1024.npz"))
+    i, (B, N, C) = 0, mg.ATTN_CASES_N1024[0]
+    X, dY, w = mg.attn_inputs(B, N, C, 300 + i)
+    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    tag = f"B{B}_N{N}_C{C}"
+    assert rel(attention.forward(X.astype(np.float64), **w64), gold[tag + "_Y"]) < 1e-6      # stored as fp32
+    g = attention.backward(dY.astype(np.float64), X.astype(np.float64), **w64)
+    assert rel(g["dX"], gold[tag + "_dX"]) < 1e-6
+    for k in attention.WEIGHT_NAMES:
+        if k != "bphi":
+            assert rel(g["d" + k], gold[tag + "_d" + k]) < 1e-12, k
+    assert {f"B{b}_N{n}_C{c}_Y" for b, n, c in mg.ATTN_CASES_N1024} <= set(gold.files)
+
+
 def test_same_padding_matches_tf_convention():
     assert nets.same_pad(64, 4, 2) == (1, 1, 32)
     assert nets.same_pad(64, 4, 1) == (1, 2, 64)     # k=4, s=1: 1 before / 2 after

@@ -34,8 +34,12 @@ def main():
             ng = torch.randn(8, 128, device=dev, generator=g)
             tr.train_step(img, None, [nd], ng)
         torch.cuda.synchronize()
-        if tr.peer_G is not None:
-            tr.peer_G.check(); tr.peer_D.check()
+        tr.check_exchange()
+        # the reported losses are the GLOBAL sums / global batch (main.py:216-220): identical on every replica
+        ls = tr.losses()
+        lt = torch.tensor([ls["D_loss"], ls["G_loss"]], device=dev, dtype=torch.float64)
+        l0 = lt.clone(); dist.broadcast(l0, 0)
+        out[f"{mode}_loss_replica_max_abs_diff"] = float((lt - l0).abs().max())
         weights[mode] = (tr.G.flat_params.clone(), tr.D.flat_params.clone())
         # identical on every replica?
         for name, w in zip("GD", weights[mode]):
@@ -44,10 +48,9 @@ def main():
             out[f"{mode}_{name}_replica_max_abs_diff"] = float((w - ref).abs().max())
         # time one exchange + update in isolation
         net, opt = tr.G, tr.opt_G
-        tr._stage()
         def upd():
             if tr.peer_G is not None:
-                tr.peer_G.step()
+                opt.schedule(); tr.peer_G.step()
             else:
                 tr._allreduce(net.flat_grads); opt.apply()
         for _ in range(5):
@@ -73,15 +76,22 @@ def main():
         tr = Trainer(cfg, seed=0, dp_mode=mode)
         gg = torch.Generator(device=dev).manual_seed(7 + rank)
         tr.G.flat_grads.copy_(torch.randn(tr.G.flat_grads.numel(), device=dev, generator=gg) * 1e-3)
-        tr._stage()
         p0 = tr.G.flat_params.clone()
         if tr.peer_G is not None:
-            tr.peer_G.step()
+            tr.opt_G.schedule(); tr.peer_G.step()
         else:
             tr._allreduce(tr.G.flat_grads); tr.opt_G.apply()
         torch.cuda.synchronize()
         res[mode] = (tr.G.flat_params - p0).clone()
         del tr
+    # every replica draws its own noise (main.py:176,194 run per replica): the device generators must differ
+    tr = Trainer(cfg, seed=0, dp_mode="nccl")
+    z = torch.randn(8, 128, device=dev)
+    z0 = z.clone(); dist.broadcast(z0, 0)
+    differs = torch.tensor([float((z - z0).abs().max() > 0)], device=dev)
+    dist.all_reduce(differs)
+    out["replicas_with_own_noise"] = int(differs.item()) + 1        # rank 0 trivially equals itself
+    del tr
     out["one_update_delta_rel_l2"] = float((res["nccl"] - res["p2p"]).norm() / res["nccl"].norm())
     out["one_update_delta_max_abs"] = float((res["nccl"] - res["p2p"]).abs().max())
     if rank == 0:
