@@ -36,9 +36,17 @@ CHURCH64 = dict(  # /root/reference/example_configs/church64_attn.py:14-27 (mode
     model="vanilla", z_dim=128, gf_dim=16, df_dim=16, lr_g=2e-4, lr_d=7e-4, decay_rate=0.99, use_attention=True,
     attn_dim_G=[32, 64], attn_dim_D=[8, 4], use_label=False, batch_size=64, loss="hinge_loss", update_ratio=1,
     img_size=64, num_classes=1)
-METRIC = "sagan_train_images_per_sec_64x64"
+# BASELINE.json configs[3]: 128x128 class-conditional SAGAN (vanilla builders with img_size 128, use_label, 1000 ImageNet
+# classes; attention lands at the 32x32 and 64x64 maps of both networks).  `--config cond128`; not the headline workload.
+COND128 = dict(CHURCH64, img_size=128, use_label=True, num_classes=1000)
+CONFIGS = {
+    "church64": (CHURCH64, "sagan_train_images_per_sec_64x64",
+                 "church64_attn train step (D update + G update), per-GPU batch 64, 64x64x3, synthetic"),
+    "cond128": (COND128, "sagan_train_images_per_sec_128x128_cond",
+                "128x128 class-conditional SAGAN train step (1000 classes, attention at 32x32 and 64x64), per-GPU batch "
+                "64, 128x128x3, synthetic"),
+}
 UNIT = "images/s"
-WORKLOAD = "church64_attn train step (D update + G update), per-GPU batch 64, 64x64x3, synthetic"
 
 
 def peaks():
@@ -92,39 +100,45 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU oracle leg
-def cpu_oracle_images_per_sec(steps, warmup, sample_batch=8, threads=None):
-    """Times the CPU oracle (oracle.train.OracleTrainer: un-fused torch-CPU fp32 restatement of the TF graph)
-    on a bounded sample: `sample_batch` images per step instead of 64."""
+def cpu_oracle_images_per_sec(cfg, steps, warmup, threads=None):
+    """Times the CPU oracle (oracle.train.OracleTrainer: un-fused torch-CPU fp32 restatement of the TF graph) on the
+    SAME workload as the GPU arm: full train steps at the full per-GPU batch; only the NUMBER of steps is bounded."""
     from oracle import train as otrain
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(threads or cores)
-    cfg = dict(CHURCH64, batch_size=sample_batch)
-    tr = otrain.OracleTrainer(cfg, torch.float32, seed=0, attn_sigma=0.0, global_batch_size=sample_batch)
+    B, S = cfg["batch_size"], cfg["img_size"]
+    tr = otrain.OracleTrainer(cfg, torch.float32, seed=0, attn_sigma=0.0, global_batch_size=B)
     rng = np.random.Generator(np.random.PCG64(1234))
-    img = torch.tensor(rng.uniform(-1, 1, (sample_batch, 64, 64, 3)).astype(np.float32))
+    img = torch.tensor(rng.uniform(-1, 1, (B, S, S, 3)).astype(np.float32))
+    lab = torch.tensor(rng.integers(0, cfg["num_classes"], B)) if cfg.get("use_label") else None
     times = []
     for s in range(warmup + steps):
-        nd = torch.tensor(rng.standard_normal((sample_batch, 128)).astype(np.float32))
-        ng = torch.tensor(rng.standard_normal((sample_batch, 128)).astype(np.float32))
+        nd = torch.tensor(rng.standard_normal((B, cfg["z_dim"])).astype(np.float32))
+        ng = torch.tensor(rng.standard_normal((B, cfg["z_dim"])).astype(np.float32))
+        fl = torch.tensor(rng.integers(0, cfg["num_classes"], B)) if cfg.get("use_label") else None
         t0 = time.perf_counter()
-        tr.train_step(img, [nd], ng)
+        tr.train_step(img, [nd], ng, lab, None if fl is None else [fl], fl)
         if s >= warmup:
             times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return dict(value=sample_batch / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"{sample_batch} of the 64 images of a step per iteration (full G+D train step, fp32, "
-                       f"{steps} timed + {warmup} warm-up iterations), oracle.train.OracleTrainer on torch-CPU"), dt
+    return dict(value=B / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"{steps} timed + {warmup} warm-up full train steps at the full batch of {B} images (fp32), "
+                       f"oracle.train.OracleTrainer on torch-CPU"), dt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    base, dt = cpu_oracle_images_per_sec(max(1, min(args.steps, 30)), max(1, min(args.warmup, 5)))
-    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    cfg, metric, workload = CONFIGS[args.config]
+    # one full-batch CPU step takes seconds: the step COUNT is bounded so the run ends within minutes, the batch is not
+    steps = max(1, min(args.steps, 8 if args.config == "church64" else 2))
+    base, dt = cpu_oracle_images_per_sec(cfg, steps, 1)
+    out = {"impl": "reference", "metric": metric, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "note": "CPU oracle (torch-CPU port of the reference TF2 graph; TensorFlow "
-                      "is not installable in this image), bounded sample per step"},
+           "config": {"workload": workload, "global_batch": cfg["batch_size"],
+                      "note": f"CPU oracle (torch-CPU port of the reference TF2 graph; TensorFlow is not installable in "
+                              f"this image); same step and batch as the GPU arm, {steps} timed steps"},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -157,12 +171,25 @@ def attn_flops(B, N, C, bwd=False):
     return 2 * B * N * N * (3 * d + 2 * dv) + 2 * (2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C)
 
 
+TRAFFIC_FILES = ("r2_traffic.json", "r1_traffic.json")
+
+
 def _traffic(name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this kernel at this
-    shape (profiles/r1_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(name)
+    shape (profiles/r*_traffic.json: NOT measured in this run -- a number taken under a profiler), or None."""
+    for f in TRAFFIC_FILES:
+        p = os.path.join(ROOT, "profiles", f)
+        if os.path.exists(p):
+            v = json.load(open(p)).get(name)
+            if v is not None:
+                return v
+    return None
+
+
+def _traffic_source():
+    for f in TRAFFIC_FILES:
+        if os.path.exists(os.path.join(ROOT, "profiles", f)):
+            return f"profiles/{f} (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same kernel and shape; not measured in this run)"
     return None
 
 
@@ -245,13 +272,18 @@ def run_ours(args, rank, world, local_rank):
     _lib.load()
     math_mode = MATH_BF16_TC if args.math == "bf16_tc" else MATH_FP32_STRICT
     snn.set_default_math_mode(math_mode)
-    cfg = dict(CHURCH64)
-    B = cfg["batch_size"]
-    tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=126227 // (B * world), seed=0,   # LSUN church: 126 227 images
+    cfg, metric, workload = CONFIGS[args.config]
+    cfg = dict(cfg, batch_size=args.batch or cfg["batch_size"])
+    B, S = cfg["batch_size"], cfg["img_size"]
+    n_records = 126227 if args.config == "church64" else 1281167           # LSUN church / ImageNet train set sizes
+    tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=n_records // (B * world), seed=0,
                  dp_mode=args.dp, overlap_streams=args.overlap)
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
-    host_batches = [torch.tensor(rng.uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
+    host_batches = [torch.tensor(rng.uniform(-1, 1, (B, S, S, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
     dev_batches = [b.to(dev) for b in host_batches]
+    use_label = bool(cfg.get("use_label"))
+    host_labels = [torch.tensor(rng.integers(0, cfg["num_classes"], B)).pin_memory() if use_label else None for _ in range(4)]
+    dev_labels = [None if l is None else l.to(dev) for l in host_labels]
 
     n0 = _lib.launch_count()
     tr.capture(warmup=max(3, args.warmup))
@@ -260,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
     launches_per_step = None
     # count by re-running one eager step (same launch sequence as the captured one)
     c0 = _lib.launch_count()
-    tr.train_step(dev_batches[0])
+    tr.train_step(dev_batches[0], dev_labels[0])
     launches_per_step = _lib.launch_count() - c0
     torch.cuda.synchronize()
 
@@ -287,24 +319,37 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()          # sampled from the warm-up on: the GPU is under the same load throughout
     for s in range(args.warmup):
-        tr.graph_step(dev_batches[s % 4])
-    sec = timed(lambda s: tr.graph_step(dev_batches[s % 4]), args.steps)
+        tr.graph_step(dev_batches[s % 4], dev_labels[s % 4])
+    sec = timed(lambda s: tr.graph_step(dev_batches[s % 4], dev_labels[s % 4]), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * args.steps / sec
 
     # ---- e2e: pinned host batch -> device each step, losses read back each step
     def e2e_step(s):
-        tr.graph_step(host_batches[s % 4])
-        tr.losses()                       # device -> host read of the two loss sums (synchronises)
+        tr.graph_step(host_batches[s % 4], host_labels[s % 4])
+        tr.losses()                       # global loss sums (all-reduced at N > 1) read back to the host (synchronises)
     for s in range(2):
         e2e_step(s)
     sec_e2e = timed(e2e_step, args.steps)
     e2e = B * world * args.steps / sec_e2e
     losses = tr.losses()
-    if tr.peer_G is not None:      # a replica that never reached an exchange barrier raises here
-        tr.peer_G.check()
-        tr.peer_D.check()
     dp_mode = tr.dp_mode
+    # replica consistency after all the steps above: every replica must hold bit-identical weights (the fused exchange
+    # sums in a fixed order and writes the same values everywhere); a replica that timed out at a barrier raises
+    dp_status, replica_diff = "single replica", 0.0
+    if world > 1:
+        try:
+            tr.check_exchange()
+            dp_status = "ok"
+        except Exception as e:      # noqa: BLE001
+            dp_status = f"FAILED: {e}"
+        worst = torch.zeros(1, device=dev)
+        for flat in (tr.G.flat_params, tr.D.flat_params):
+            ref = flat.clone()
+            torch.distributed.broadcast(ref, 0)
+            worst = torch.maximum(worst, (flat - ref).abs().max().reshape(1))
+        torch.distributed.all_reduce(worst, op=torch.distributed.ReduceOp.MAX)
+        replica_diff = float(worst)
 
     # every collective is behind us: tear the communicator down on ALL ranks together (a rank that exits while
     # another still holds captured NCCL work can hang in the teardown), then rank 0 alone finishes the report
@@ -325,16 +370,18 @@ def run_ours(args, rank, world, local_rank):
                          "binding unit: mufu_frac = exps_per_s / (148 SMs x 16 ex2/clk x 1.965 GHz).  The tensor-bound "
                          "regime is kernels.attn_fwd_C512.")
     if args.cpu_baseline:
-        cpu, _ = cpu_oracle_images_per_sec(8, 2)
+        cpu, _ = cpu_oracle_images_per_sec(dict(CONFIGS[args.config][0]), 4 if args.config == "church64" else 1, 1)
     else:
         cpu = None
-    act_mb = 4 * B * (64 * 64 * 16 * 12 + 32 * 32 * 32 * 10) / 1e6
+    act_mb = 4 * B * (S * S * 16 * 12 + (S // 2) ** 2 * 32 * 10) / 1e6
+    roofline["traffic_source"] = _traffic_source()
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if math_mode == MATH_FP32_STRICT else "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "math_mode": args.math, "cuda_graph": True,
+        "config": {"workload": workload if B == CONFIGS[args.config][0]["batch_size"] else workload + f" [per-GPU batch {B}]",
+                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "math_mode": args.math, "conv_precision": "split-bf16 (3 MMAs per K step, fp32-grade)", "cuda_graph": True,
                    "step_graph": ("two branches: generator forwards on a side stream" if args.overlap
                                   else "single stream (--no-overlap)"),
                    "dp_exchange": {"p2p": "fused NVLink peer-memory gradient sum + Adam kernel (csrc/dp.cu)",
@@ -342,7 +389,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": f"no explicit flush: a step touches ~{act_mb:.0f} MB of saved activations (> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": sec_e2e / args.steps * 1e3,
-                "h2d_bytes_per_step": int(host_batches[0].numel() * 4 + 2 * 16), "d2h_bytes_per_step": 8},
+                "h2d_bytes_per_step": int(host_batches[0].numel() * 4 + (B * 8 if use_label else 0)),
+                "d2h_bytes_per_step": 8},
+        "dp_status": dp_status, "replica_max_abs_diff": replica_diff,
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "roofline": roofline,
@@ -359,6 +408,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="church64", choices=sorted(CONFIGS),
+                    help="church64 = BASELINE.json configs[1] (headline); cond128 = configs[3], 128x128 class-conditional")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's 64)")
     ap.add_argument("--math", default="bf16_tc", choices=["fp32_strict", "bf16_tc"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="data-parallel gradient exchange (N > 1)")
