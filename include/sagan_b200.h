@@ -145,6 +145,25 @@ int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, const float
                    float* dgamma, int B, int N, int C, int math_mode, void* ws, size_t ws_bytes,
                    sagan_stream_t stream);
 
+/* Down-sampled keys / values: what layers.py:96,100,113 reaches for -- `MaxPool2D` on
+ * phi and g, so that a query attends to N/4 keys (the literal `MaxPool2D(2, 1)` + reshape is ill-formed, SURVEY.md
+ * appendix A.5; the reading built here is the SAGAN paper's: pool 2 / stride 2 / 'valid' over the [H, W] token grid,
+ * per channel, first maximum of a window wins as in TF).  Same arguments as sagan_attn_fwd / sagan_attn_bwd with the
+ * token grid given explicitly: X, Y [B, H*W, C]; H, W even; C in {8,16,32,64} (C = 8 always runs the fp32 kernels).
+ * lse [B, H*W] and A_saved [B, H*W, C/2] as before; the backward scatters the pooled-key / pooled-value gradients to
+ * the window positions that won.  Workspace: sagan_attn_pool_workspace_bytes. */
+size_t sagan_attn_pool_workspace_bytes(int B, int H, int W, int C, int math_mode);
+int sagan_attn_pool_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                        const float* Wv, const float* bv, const float* Wo, const float* bo,
+                        const float* gamma, float* Y, float* lse, float* A_saved, int B, int H, int W, int C,
+                        int math_mode, void* ws, size_t ws_bytes, sagan_stream_t stream);
+int sagan_attn_pool_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                        const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                        const float* gamma, const float* lse, const float* A_saved, float* dX, float* dWq,
+                        float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo,
+                        float* dgamma, int B, int H, int W, int C, int math_mode, void* ws, size_t ws_bytes,
+                        sagan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Conv2D (generator.py:36, discriminator.py:8,35; the 1x1 convs of layers.py:82-85; Dense as
  * the H=W=k=1 case, generator.py:25).  Geometry is explicit so TF 'same' padding asymmetry

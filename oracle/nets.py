@@ -108,8 +108,9 @@ def batchnorm_train(x, gamma, beta, stats=None, key=None):
     return (x - mean) * torch.rsqrt(var + BN_EPS) * gamma + beta
 
 
-def attention(x, p, sn_state, prefix, training=True):
-    """layers.py:93-120 (paper form).  x NHWC."""
+def attention(x, p, sn_state, prefix, training=True, downsample=False):
+    """layers.py:93-120 (paper form).  x NHWC.  downsample=True: phi and g max-pooled 2x2 / stride 2 before the
+    attention map (layers.py:100,113 in the well-formed reading of oracle.attention.forward_pooled)."""
     B, H, W, C = x.shape
     X = x.reshape(B, H * W, C)
 
@@ -117,11 +118,18 @@ def attention(x, p, sn_state, prefix, training=True):
         k = spectral_norm(p[f"{prefix}.{name}.kernel"], sn_state, f"{prefix}.{name}.u", training)
         return inp @ k.reshape(k.shape[2], k.shape[3]) + p[f"{prefix}.{name}.bias"]
 
+    def pool(t):                                           # layers.py:100,113
+        c = t.shape[-1]
+        t = torch.nn.functional.max_pool2d(t.reshape(B, H, W, c).permute(0, 3, 1, 2), 2, 2)
+        return t.permute(0, 2, 3, 1).reshape(B, (H // 2) * (W // 2), c)
+
     phi = proj("phi", X)                                   # layers.py:99
     theta = proj("theta", X)                               # layers.py:104-105
+    g = proj("g", X)                                       # layers.py:112-114
+    if downsample:
+        phi, g = pool(phi), pool(g)
     S = theta @ phi.transpose(1, 2)                        # layers.py:108
     P = torch.softmax(S, dim=-1)                           # layers.py:109
-    g = proj("g", X)                                       # layers.py:112-114
     A = P @ g                                              # layers.py:116
     O = proj("o", A)                                       # layers.py:119
     return (X + p[f"{prefix}.sigma"] * O).reshape(B, H, W, C)   # layers.py:120
@@ -256,7 +264,7 @@ def generator_forward(p, sn_state, z, cfg, labels=None, training=True, bn_stats=
         x = batchnorm_train(x, p[f"block{i}.bn.gamma"], p[f"block{i}.bn.beta"], bn_stats, f"block{i}.bn")
         x = F.leaky_relu(x, LRELU)                                             # generator.py:11
         if cfg.get("use_attention") and x.shape[1] in cfg["attn_dim_G"]:       # generator.py:33-34
-            x = attention(x, p, sn_state, f"block{i}.attn", training)
+            x = attention(x, p, sn_state, f"block{i}.attn", training, bool(cfg.get("attn_downsample")))
     x = conv2d_same(x, p["head.kernel"], None, 1)                              # generator.py:36
     return torch.tanh(x)
 
@@ -270,7 +278,7 @@ def discriminator_forward(p, sn_state, img, cfg, labels=None, training=True):
         x = conv2d_same(x, W, p[f"block{i}.conv.bias"], 2)                     # discriminator.py:8-9
         x = F.leaky_relu(x, LRELU)                                             # discriminator.py:10
         if cfg.get("use_attention") and x.shape[1] in cfg["attn_dim_G"]:       # discriminator.py:23-24
-            x = attention(x, p, sn_state, f"block{i}.attn", training)
+            x = attention(x, p, sn_state, f"block{i}.attn", training, bool(cfg.get("attn_downsample")))
     if cfg.get("use_label"):
         h = x.sum(dim=(1, 2))                                                  # discriminator.py:27
         out = h @ p["head.dense.kernel"] + p["head.dense.bias"]               # discriminator.py:28

@@ -68,6 +68,92 @@ attn_proj_kernel(const float* __restrict__ X, const float* __restrict__ Wq, cons
   }
 }
 
+// ---------------------------------------------------------------------------- down-sampled keys / values
+// SURVEY.md §8f row 2 (what /root/reference/layers.py:96,100,113 reaches for: `MaxPool2D` on phi and g): keys and values
+// are max-pooled 2x2 / stride 2 over the [H, W] token grid, per channel, so a query attends to N/4 keys.  One thread per
+// pooled position; the first maximum of a window wins (TF / cuDNN order: (0,0), (0,1), (1,0), (1,1)); its index
+// (0..3) per channel is kept for the backward scatter.
+template <int C>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_pool_kernel(const float* __restrict__ K, const float* __restrict__ V, float* __restrict__ Kp, float* __restrict__ Vp,
+                 uint8_t* __restrict__ idxK, uint8_t* __restrict__ idxV, int B, int H, int W) {
+  constexpr int D = C / 8, DV = C / 2;
+  const int Hp = H / 2, Wp = W / 2;
+  const long long p = (long long)blockIdx.x * AT_THREADS + threadIdx.x;
+  if (p >= (long long)B * Hp * Wp) return;
+  const int b = (int)(p / (Hp * Wp)), r = (int)(p - (long long)b * Hp * Wp);
+  const int ph = r / Wp, pw = r - ph * Wp;
+  const long long t0 = (long long)b * H * W + (long long)(2 * ph) * W + 2 * pw;
+  const long long tk[4] = {t0, t0 + 1, t0 + W, t0 + W + 1};
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    float best = K[tk[0] * D + c];
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float v = K[tk[k] * D + c];
+      if (v > best) { best = v; arg = k; }
+    }
+    Kp[p * D + c] = best;
+    if (idxK) idxK[p * D + c] = (uint8_t)arg;
+  }
+#pragma unroll
+  for (int c = 0; c < DV; ++c) {
+    float best = V[tk[0] * DV + c];
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float v = V[tk[k] * DV + c];
+      if (v > best) { best = v; arg = k; }
+    }
+    Vp[p * DV + c] = best;
+    if (idxV) idxV[p * DV + c] = (uint8_t)arg;
+  }
+}
+
+// backward of the pooling: the gradient of a pooled key / value channel goes to the window position that won, the
+// other three get zero.  Every token-level element is written exactly once (no zero-fill needed).
+template <int D, int DV>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_unpool_kernel(const float* __restrict__ dKp, const float* __restrict__ dVp, const uint8_t* __restrict__ idxK,
+                   const uint8_t* __restrict__ idxV, float* __restrict__ dK, float* __restrict__ dV, int B, int H, int W) {
+  const int Hp = H / 2, Wp = W / 2;
+  const long long p = (long long)blockIdx.x * AT_THREADS + threadIdx.x;
+  if (p >= (long long)B * Hp * Wp) return;
+  const int b = (int)(p / (Hp * Wp)), r = (int)(p - (long long)b * Hp * Wp);
+  const int ph = r / Wp, pw = r - ph * Wp;
+  const long long t0 = (long long)b * H * W + (long long)(2 * ph) * W + 2 * pw;
+  const long long tk[4] = {t0, t0 + 1, t0 + W, t0 + W + 1};
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const float g = dKp[p * D + c];
+    const int a = idxK[p * D + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dK[tk[k] * D + c] = (a == k) ? g : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < DV; ++c) {
+    const float g = dVp[p * DV + c];
+    const int a = idxV[p * DV + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dV[tk[k] * DV + c] = (a == k) ? g : 0.f;
+  }
+}
+
+int attn_unpool_launch(const float* dKp, const float* dVp, const uint8_t* idxK, const uint8_t* idxV, float* dK, float* dV,
+                       int B, int H, int W, int C, cudaStream_t st) {
+  const unsigned nb = (unsigned)ceil_div<long long>((long long)B * (H / 2) * (W / 2), AT_THREADS);
+  switch (C) {
+    case 8: attn_unpool_kernel<1, 4><<<nb, AT_THREADS, 0, st>>>(dKp, dVp, idxK, idxV, dK, dV, B, H, W); break;
+    case 16: attn_unpool_kernel<2, 8><<<nb, AT_THREADS, 0, st>>>(dKp, dVp, idxK, idxV, dK, dV, B, H, W); break;
+    case 32: attn_unpool_kernel<4, 16><<<nb, AT_THREADS, 0, st>>>(dKp, dVp, idxK, idxV, dK, dV, B, H, W); break;
+    case 64: attn_unpool_kernel<8, 32><<<nb, AT_THREADS, 0, st>>>(dKp, dVp, idxK, idxV, dK, dV, B, H, W); break;
+    default: set_err("attention pooling supports C in {8,16,32,64} (C=%d)", C); return SAGAN_EUNSUPPORTED;
+  }
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------- forward
 // grid (ceil(N/128), B); thread i owns query row i: q[D], o[DV], running max m (log2 units), sum l.
 template <int C>
@@ -75,8 +161,8 @@ __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_strict_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                        const float* __restrict__ X, const float* __restrict__ Wo, const float* __restrict__ bo,
                        const float* __restrict__ gamma, float* __restrict__ Y, float* __restrict__ lse,
-                       float* __restrict__ A, int N) {
-  constexpr int D = C / 8, DV = C / 2, KT = 128;
+                       float* __restrict__ A, int N, int Nk) {
+  constexpr int D = C / 8, DV = C / 2, KT = 128;       // N queries, Nk keys / values (Nk == N unless pooled)
   __shared__ __align__(16) float Ks[KT * D];
   __shared__ __align__(16) float Vs[KT * DV];
   __shared__ __align__(16) float sWo[DV * C];
@@ -96,11 +182,11 @@ attn_fwd_strict_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   for (int v = 0; v < DV; ++v) o[v] = 0.f;
   float m = -INFINITY, l = 0.f;
 
-  for (int kt = 0; kt < N; kt += KT) {
-    const int nk = min(KT, N - kt);
+  for (int kt = 0; kt < Nk; kt += KT) {
+    const int nk = min(KT, Nk - kt);
     __syncthreads();
-    const float* Kg = K + ((long long)b * N + kt) * D;
-    const float* Vg = V + ((long long)b * N + kt) * DV;
+    const float* Kg = K + ((long long)b * Nk + kt) * D;
+    const float* Vg = V + ((long long)b * Nk + kt) * DV;
     for (int e = tid; e < KT * D; e += AT_THREADS) Ks[e] = e < nk * D ? Kg[e] : 0.f;
     for (int e = tid * 4; e < KT * DV; e += AT_THREADS * 4) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -209,16 +295,16 @@ template <int C>
 __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_strict_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                        const float* __restrict__ dA, const float* __restrict__ lse, const float* __restrict__ Dd,
-                       float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV, int N) {
-  constexpr int D = C / 8, DV = C / 2, QT = 128, NW = AT_THREADS / 32;
+                       float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV, int N, int Nk) {
+  constexpr int D = C / 8, DV = C / 2, QT = 128, NW = AT_THREADS / 32;    // Nk key rows (K, V, dK, dV), N query rows
   __shared__ __align__(16) float Qs[QT * D];      // pre-scaled by log2(e)
   __shared__ __align__(16) float dAs[QT * DV];
   __shared__ float lses[QT], Dds[QT];
   __shared__ float dqs[NW][QT * D];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.y;
   const int j = blockIdx.x * AT_THREADS + tid;
-  const bool valid = j < N;
-  const long long krow = (long long)b * N + (valid ? j : 0);
+  const bool valid = j < Nk;
+  const long long krow = (long long)b * Nk + (valid ? j : 0);
   float k[D], v[DV], dk[D], dv[DV];
 #pragma unroll
   for (int d = 0; d < D; ++d) { k[d] = K[krow * D + d]; dk[d] = 0.f; }
@@ -443,7 +529,7 @@ static sagan_conv_geom geom_1x1(long long T, int cin, int cout) {
 template <int C>
 static int attn_fwd_strict_t(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
                              const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
-                             float* Y, float* lse, float* A, int B, int N, float* ws, cudaStream_t st) {
+                             float* Y, float* lse, float* A, int B, int N, int PH, int PW, float* ws, cudaStream_t st) {
   constexpr int D = C / 8, DV = C / 2;
   const long long T = (long long)B * N;
   float* Q = ws;
@@ -452,8 +538,18 @@ static int attn_fwd_strict_t(const float* X, const float* Wq, const float* bq, c
   attn_proj_kernel<C><<<(unsigned)ceil_div<long long>(T, AT_THREADS), AT_THREADS, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Q,
                                                                                             K, V, T);
   SAGAN_LAUNCH_CHECK();
+  int Nk = N;
+  if (PH > 0) {          // down-sampled keys / values: [PH, PW] token grid -> N / 4 pooled rows
+    Nk = N / 4;
+    float* Kp = V + T * DV;
+    float* Vp = Kp + (long long)B * Nk * D;
+    attn_pool_kernel<C><<<(unsigned)ceil_div<long long>((long long)B * Nk, AT_THREADS), AT_THREADS, 0, st>>>(
+        K, V, Kp, Vp, nullptr, nullptr, B, PH, PW);
+    SAGAN_LAUNCH_CHECK();
+    K = Kp; V = Vp;
+  }
   attn_fwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, X, Wo, bo, gamma, Y, lse,
-                                                                                      A, N);
+                                                                                      A, N, Nk);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
@@ -504,7 +600,7 @@ static int attn_bwd_strict_t(const float* dY, const float* X, const float* Wq, c
                              const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
                              const float* gamma, const float* lse, const float* A, float* dX, float* dWq, float* dbq,
                              float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma,
-                             int B, int N, float* ws, cudaStream_t st) {
+                             int B, int N, int PH, int PW, float* ws, cudaStream_t st) {
   constexpr int D = C / 8, DV = C / 2;
   const long long T = (long long)B * N;
   float* dQ = ws;
@@ -521,18 +617,38 @@ static int attn_bwd_strict_t(const float* dY, const float* X, const float* Wq, c
   attn_bwd_pre_kernel<C><<<tb, AT_THREADS, 0, st>>>(dY, A, Wo, gamma, dA, Dd, T);
   SAGAN_LAUNCH_CHECK();
   SAGAN_CUDA(cudaMemsetAsync(dQ, 0, (size_t)T * D * sizeof(float), st));
-  attn_bwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, dA, lse, Dd, dQ, dK, dV, N);
-  SAGAN_LAUNCH_CHECK();
+  if (PH > 0) {
+    // pooled keys / values: Kp, Vp, their gradients and the argmax codes live behind the token-level buffers
+    const int Nk = N / 4;
+    const long long Tk = (long long)B * Nk;
+    float* Kp = Dd + T;
+    float* Vp = Kp + Tk * D;
+    float* dKp = Vp + Tk * DV;
+    float* dVp = dKp + Tk * D;
+    uint8_t* idxK = reinterpret_cast<uint8_t*>(dVp + Tk * DV);
+    uint8_t* idxV = idxK + Tk * D;
+    const unsigned pb = (unsigned)ceil_div<long long>(Tk, AT_THREADS);
+    attn_pool_kernel<C><<<pb, AT_THREADS, 0, st>>>(K, V, Kp, Vp, idxK, idxV, B, PH, PW);
+    SAGAN_LAUNCH_CHECK();
+    attn_bwd_strict_kernel<C><<<dim3(ceil_div(Nk, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, Kp, Vp, dA, lse, Dd, dQ, dKp,
+                                                                                          dVp, N, Nk);
+    SAGAN_LAUNCH_CHECK();
+    int rc = attn_unpool_launch(dKp, dVp, idxK, idxV, dK, dV, B, PH, PW, C, st);
+    if (rc) return rc;
+  } else {
+    attn_bwd_strict_kernel<C><<<dim3(ceil_div(N, AT_THREADS), B), AT_THREADS, 0, st>>>(Q, K, V, dA, lse, Dd, dQ, dK, dV, N, N);
+    SAGAN_LAUNCH_CHECK();
+  }
   return attn_bwd_tail_t<C>(dY, X, Wq, Wk, Wv, Wo, bo, gamma, A, dQ, dK, dV, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo, dbo,
                             dgamma, B, N, st);
 }
 
 // implemented in attn_tc_bwd.cu
-size_t attn_tc_bwd_workspace_bytes(int B, int N, int C);
+size_t attn_tc_bwd_workspace_bytes(int B, int N, int C, bool pool);
 int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const float* lse, const float* Wq, const float* bq,
                      const float* Wk, const float* bk, const float* Wv, const float* bv, const float* Wo,
-                     const float* gamma, float* dQ, float* dK, float* dV, int B, int N, int C, void* ws, size_t ws_bytes,
-                     cudaStream_t st);
+                     const float* gamma, float* dQ, float* dK, float* dV, int B, int N, int C, int PH, int PW, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
 
 // BF16_TC backward: dQ / dK / dV on the tensor cores, then the common tail
 template <int C>
@@ -540,7 +656,7 @@ static int attn_bwd_tc_t(const float* dY, const float* X, const float* Wq, const
                          const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
                          const float* gamma, const float* lse, const float* A, float* dX, float* dWq, float* dbq,
                          float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma, int B,
-                         int N, float* ws, size_t ws_bytes, cudaStream_t st) {
+                         int N, int PH, int PW, float* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int D = C / 8, DV = C / 2;
   const long long T = (long long)B * N;
   float* dQ = ws;
@@ -548,7 +664,7 @@ static int attn_bwd_tc_t(const float* dY, const float* X, const float* Wq, const
   float* dV = dK + T * D;
   const size_t used = (size_t)(T * (2 * D + DV) + 64) * sizeof(float);
   SAGAN_CUDA(cudaMemsetAsync(dQ, 0, (size_t)T * D * sizeof(float), st));
-  int rc = attn_tc_bwd_core(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, dQ, dK, dV, B, N, C,
+  int rc = attn_tc_bwd_core(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, dQ, dK, dV, B, N, C, PH, PW,
                             reinterpret_cast<uint8_t*>(ws) + used, ws_bytes - used, st);
   if (rc) return rc;
   return attn_bwd_tail_t<C>(dY, X, Wq, Wk, Wv, Wo, bo, gamma, A, dQ, dK, dV, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo, dbo,
@@ -564,7 +680,7 @@ namespace sagan {
 size_t attn_tc_workspace_bytes(int B, int N, int C);
 int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
                 const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
-                int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+                int B, int N, int C, int PH, int PW, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace sagan
 
 namespace sagan {
@@ -584,17 +700,27 @@ int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const floa
 bool attn_tc_big_supported(int N, int C);
 }  // namespace sagan
 
-extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode) {
+static size_t attn_ws_bytes(int B, int N, int C, int math_mode, bool pool) {
   if (B <= 0 || N <= 0 || C <= 0) return 0;
   const long long T = (long long)B * N;
-  const size_t strict = (size_t)(T * (2 * C + 1) + 64) * sizeof(float);
+  // strict: dQ dK dV Q K V dA Dd (+ pooled K / V, their gradients and the argmax codes: < 2 C bytes per token)
+  const size_t strict = (size_t)(T * (2 * C + 1) + 64) * sizeof(float) + (pool ? (size_t)T * C * 2 : 0);
   if (math_mode == SAGAN_MATH_BF16_TC) {
     if (C > 64)   // large-C path: fused forward, composed backward (attn_big_bwd.cu)
       return std::max(attn_tc_workspace_bytes(B, N, C), attn_big_bwd_workspace_bytes(B, N, C) + 256);
     const size_t small = (size_t)(T * (C / 4 + C / 2) + 64) * sizeof(float);   // dQ, dK, dV
-    return std::max(strict, std::max(attn_tc_workspace_bytes(B, N, C), small + attn_tc_bwd_workspace_bytes(B, N, C)));
+    return std::max(strict, std::max(attn_tc_workspace_bytes(B, N, C), small + attn_tc_bwd_workspace_bytes(B, N, C, pool)));
   }
   return strict;
+}
+
+extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode) {
+  return attn_ws_bytes(B, N, C, math_mode, false);
+}
+
+extern "C" size_t sagan_attn_pool_workspace_bytes(int B, int H, int W, int C, int math_mode) {
+  if (H <= 0 || W <= 0) return 0;
+  return attn_ws_bytes(B, H * W, C, math_mode, true);
 }
 
 #define SAGAN_ATTN_DISPATCH(FN, ...)                      \
@@ -606,29 +732,73 @@ extern "C" size_t sagan_attn_workspace_bytes(int B, int N, int C, int math_mode)
     default: break;                                       \
   }
 
-extern "C" int sagan_attn_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
-                              const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
-                              float* Y, float* lse, float* A_saved, int B, int N, int C, int math_mode, void* ws,
-                              size_t ws_bytes, sagan_stream_t stream) {
+// PH, PW = token grid when keys / values are down-sampled (N == PH * PW), 0 otherwise
+static int attn_fwd_impl(const char* who, const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                         const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y,
+                         float* lse, float* A_saved, int B, int N, int C, int PH, int PW, int math_mode, void* ws,
+                         size_t ws_bytes, sagan_stream_t stream) {
   SAGAN_REQUIRE(X && Wq && bq && Wk && bk && Wv && bv && Wo && bo && gamma && Y && lse && A_saved && ws,
-                "sagan_attn_fwd: null pointer");
-  SAGAN_REQUIRE(B > 0 && N > 0 && C >= 8 && C % 8 == 0, "sagan_attn_fwd: need B,N > 0 and C a positive multiple of 8 (C=%d)", C);
+                "%s: null pointer", who);
+  SAGAN_REQUIRE(B > 0 && N > 0 && C >= 8 && C % 8 == 0, "%s: need B,N > 0 and C a positive multiple of 8 (C=%d)", who, C);
   SAGAN_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)A_saved | (uintptr_t)ws) & 15) == 0,
-                "sagan_attn_fwd: X, Y, A_saved, ws must be 16-byte aligned");
-  if (ws_bytes < sagan_attn_workspace_bytes(B, N, C, math_mode)) {
-    set_err("sagan_attn_fwd: workspace %zu < %zu bytes", ws_bytes, sagan_attn_workspace_bytes(B, N, C, math_mode));
+                "%s: X, Y, A_saved, ws must be 16-byte aligned", who);
+  const size_t need = attn_ws_bytes(B, N, C, math_mode, PH > 0);
+  if (ws_bytes < need) {
+    set_err("%s: workspace %zu < %zu bytes", who, ws_bytes, need);
     return SAGAN_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (math_mode == SAGAN_MATH_BF16_TC)
-    return attn_tc_fwd(X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, C, ws, ws_bytes, st);
+    return attn_tc_fwd(X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, C, PH, PW, ws, ws_bytes, st);
   if (math_mode != SAGAN_MATH_FP32_STRICT) {
-    set_err("sagan_attn_fwd: unknown math_mode %d", math_mode);
+    set_err("%s: unknown math_mode %d", who, math_mode);
     return SAGAN_EINVAL;
   }
-  SAGAN_ATTN_DISPATCH(attn_fwd_strict_t, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, (float*)ws, st);
-  set_err("sagan_attn_fwd: FP32_STRICT supports C in {8,16,32,64} (C=%d); use SAGAN_MATH_BF16_TC", C);
+  SAGAN_ATTN_DISPATCH(attn_fwd_strict_t, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, PH, PW, (float*)ws, st);
+  set_err("%s: FP32_STRICT supports C in {8,16,32,64} (C=%d); use SAGAN_MATH_BF16_TC", who, C);
   return SAGAN_EUNSUPPORTED;
+}
+
+static int attn_bwd_impl(const char* who, const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                         const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                         const float* gamma, const float* lse, const float* A_saved, float* dX, float* dWq, float* dbq,
+                         float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo, float* dgamma, int B,
+                         int N, int C, int PH, int PW, int math_mode, void* ws, size_t ws_bytes, sagan_stream_t stream) {
+  SAGAN_REQUIRE(dY && X && Wq && bq && Wk && bk && Wv && bv && Wo && bo && gamma && lse && A_saved && ws,
+                "%s: null pointer", who);
+  SAGAN_REQUIRE(B > 0 && N > 0 && C >= 8 && C % 8 == 0, "%s: need B,N > 0 and C a positive multiple of 8 (C=%d)", who, C);
+  const bool all_w = dWq && dbq && dWk && dbk && dWv && dbv && dWo && dbo && dgamma;
+  const bool no_w = !dWq && !dbq && !dWk && !dbk && !dWv && !dbv && !dWo && !dbo && !dgamma;
+  SAGAN_REQUIRE(all_w || no_w, "%s: parameter-gradient outputs must be all set or all NULL", who);
+  SAGAN_REQUIRE(dX || all_w, "%s: nothing to compute", who);
+  const size_t need = attn_ws_bytes(B, N, C, math_mode, PH > 0);
+  if (ws_bytes < need) {
+    set_err("%s: workspace %zu < %zu bytes", who, ws_bytes, need);
+    return SAGAN_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (math_mode == SAGAN_MATH_BF16_TC && (C == 16 || C == 32 || C == 64)) {
+    SAGAN_ATTN_DISPATCH(attn_bwd_tc_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk, dbk,
+                        dWv, dbv, dWo, dbo, dgamma, B, N, PH, PW, (float*)ws, ws_bytes, st);
+  }
+  if (math_mode == SAGAN_MATH_BF16_TC && PH == 0 && attn_tc_big_supported(N, C))
+    return attn_tc_big_bwd(dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, A_saved, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo,
+                           dbo, dgamma, B, N, C, ws, ws_bytes, st);
+  if (math_mode == SAGAN_MATH_FP32_STRICT || C == 8) {
+    SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
+                        dbk, dWv, dbv, dWo, dbo, dgamma, B, N, PH, PW, (float*)ws, st);
+  }
+  set_err("%s: supports C in {8,16,32,64} (FP32_STRICT, BF16_TC) and {128,256,512} with N %% 128 == 0 (BF16_TC, "
+          "un-pooled); got C=%d N=%d", who, C, N);
+  return SAGAN_EUNSUPPORTED;
+}
+
+extern "C" int sagan_attn_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                              const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
+                              float* Y, float* lse, float* A_saved, int B, int N, int C, int math_mode, void* ws,
+                              size_t ws_bytes, sagan_stream_t stream) {
+  return attn_fwd_impl("sagan_attn_fwd", X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, N, C, 0, 0, math_mode,
+                       ws, ws_bytes, stream);
 }
 
 extern "C" int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
@@ -637,28 +807,40 @@ extern "C" int sagan_attn_bwd(const float* dY, const float* X, const float* Wq, 
                               float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo,
                               float* dgamma, int B, int N, int C, int math_mode, void* ws, size_t ws_bytes,
                               sagan_stream_t stream) {
-  SAGAN_REQUIRE(dY && X && Wq && bq && Wk && bk && Wv && bv && Wo && bo && gamma && lse && A_saved && ws,
-                "sagan_attn_bwd: null pointer");
-  SAGAN_REQUIRE(B > 0 && N > 0 && C >= 8 && C % 8 == 0, "sagan_attn_bwd: need B,N > 0 and C a positive multiple of 8 (C=%d)", C);
-  const bool all_w = dWq && dbq && dWk && dbk && dWv && dbv && dWo && dbo && dgamma;
-  const bool no_w = !dWq && !dbq && !dWk && !dbk && !dWv && !dbv && !dWo && !dbo && !dgamma;
-  SAGAN_REQUIRE(all_w || no_w, "sagan_attn_bwd: parameter-gradient outputs must be all set or all NULL");
-  SAGAN_REQUIRE(dX || all_w, "sagan_attn_bwd: nothing to compute");
-  if (ws_bytes < sagan_attn_workspace_bytes(B, N, C, math_mode)) {
-    set_err("sagan_attn_bwd: workspace %zu < %zu bytes", ws_bytes, sagan_attn_workspace_bytes(B, N, C, math_mode));
-    return SAGAN_EWORKSPACE;
+  return attn_bwd_impl("sagan_attn_bwd", dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk, dbk,
+                       dWv, dbv, dWo, dbo, dgamma, B, N, C, 0, 0, math_mode, ws, ws_bytes, stream);
+}
+
+static int check_pool_grid(const char* who, int H, int W, int C) {
+  SAGAN_REQUIRE(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "%s: the token grid must be even in both directions (H=%d, W=%d)",
+                who, H, W);
+  if (!(C == 8 || C == 16 || C == 32 || C == 64)) {
+    set_err("%s: down-sampled keys / values are built for C in {8,16,32,64} (C=%d)", who, C);
+    return SAGAN_EUNSUPPORTED;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  if (math_mode == SAGAN_MATH_BF16_TC && (C == 16 || C == 32 || C == 64)) {
-    SAGAN_ATTN_DISPATCH(attn_bwd_tc_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk, dbk,
-                        dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, ws_bytes, st);
-  }
-  if (math_mode == SAGAN_MATH_BF16_TC && attn_tc_big_supported(N, C))
-    return attn_tc_big_bwd(dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, A_saved, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo,
-                           dbo, dgamma, B, N, C, ws, ws_bytes, st);
-  SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
-                      dbk, dWv, dbv, dWo, dbo, dgamma, B, N, (float*)ws, st);
-  set_err("sagan_attn_bwd: supports C in {8,16,32,64} (FP32_STRICT, BF16_TC) and {128,256,512} with N %% 128 == 0 "
-          "(BF16_TC); got C=%d N=%d", C, N);
-  return SAGAN_EUNSUPPORTED;
+  return 0;
+}
+
+extern "C" int sagan_attn_pool_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                                   const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
+                                   float* Y, float* lse, float* A_saved, int B, int H, int W, int C, int math_mode,
+                                   void* ws, size_t ws_bytes, sagan_stream_t stream) {
+  int rc = check_pool_grid("sagan_attn_pool_fwd", H, W, C);
+  if (rc) return rc;
+  if (C == 8) math_mode = SAGAN_MATH_FP32_STRICT;      // no tensor-core kernel at d = 1
+  return attn_fwd_impl("sagan_attn_pool_fwd", X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A_saved, B, H * W, C, H, W,
+                       math_mode, ws, ws_bytes, stream);
+}
+
+extern "C" int sagan_attn_pool_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk,
+                                   const float* bk, const float* Wv, const float* bv, const float* Wo, const float* bo,
+                                   const float* gamma, const float* lse, const float* A_saved, float* dX, float* dWq,
+                                   float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo, float* dbo,
+                                   float* dgamma, int B, int H, int W, int C, int math_mode, void* ws, size_t ws_bytes,
+                                   sagan_stream_t stream) {
+  int rc = check_pool_grid("sagan_attn_pool_bwd", H, W, C);
+  if (rc) return rc;
+  if (C == 8) math_mode = SAGAN_MATH_FP32_STRICT;
+  return attn_bwd_impl("sagan_attn_pool_bwd", dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
+                       dbk, dWv, dbv, dWo, dbo, dgamma, B, H * W, C, H, W, math_mode, ws, ws_bytes, stream);
 }

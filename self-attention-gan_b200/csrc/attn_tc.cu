@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "attn_pool.cuh"
 
 namespace sagan {
 
@@ -78,7 +79,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // ------------------------------------------------------------------------------------ projections (small C)
 // one thread per PADDED token: Qb[b][n][64] = bf16(log2e * (x Wq + bq)), Kb[b][n][64] = bf16(x Wk + bk),
 // Vt[b][v][n] = bf16(x Wv + bv); rows n >= N are zero (so masked keys contribute exactly 0 to P V).
-template <int C>
+// KV = false (down-sampled keys / values): only the query rows are written; K / V^T come from attn_pool_proj_tc_kernel.
+template <int C, bool KV>
 __global__ void __launch_bounds__(128)
 attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, const float* __restrict__ bq,
                     const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
@@ -131,9 +133,11 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
   for (int g = 0; g < KQ / 8; ++g) {
     qd[g] = make_uint4(pack_bf16x2(q[g * 8 + 0], q[g * 8 + 1]), pack_bf16x2(q[g * 8 + 2], q[g * 8 + 3]),
                        pack_bf16x2(q[g * 8 + 4], q[g * 8 + 5]), pack_bf16x2(q[g * 8 + 6], q[g * 8 + 7]));
-    kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
-                       pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
+    if (KV)
+      kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
+                         pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
   }
+  if (!KV) return;
   // values are split the same way (v = v_hi + v_lo, two bf16 rows of V^T), so O = P [v_hi | v_lo] carries V exactly
   // and the only bf16 rounding left in A is that of P itself
 #pragma unroll
@@ -150,6 +154,61 @@ attn_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wq, c
   Vt[((long long)b * DVP + 2 * DV) * Npad + n] = __float2bfloat16_rn(valid ? 1.0f : 0.0f);
 #pragma unroll
   for (int v = 2 * DV + 1; v < DVP; ++v) Vt[((long long)b * DVP + v) * Npad + n] = __float2bfloat16_rn(0.0f);
+}
+
+// ------------------------------------------------------------------------------------ down-sampled keys / values
+// SURVEY.md §8f row 2 (/root/reference/layers.py:96,100,113): phi and g max-pooled 2x2 / stride 2 over the [H, W] token
+// grid, per channel.  pooled_kv computes the two projections of the four tokens of one window in fp32 (the SAME fmaf
+// sequence in the forward and the backward, so both pick the same winners), the channel maxima and which window position
+// (0..3, first maximum wins) supplied each of them.
+// one thread per PADDED pooled position: Kb rows (split-bf16 layout of attn_proj_tc_kernel) and V^T columns
+template <int C>
+__global__ void __launch_bounds__(128)
+attn_pool_proj_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wk, const float* __restrict__ bk,
+                         const float* __restrict__ Wv, const float* __restrict__ bv, __nv_bfloat16* __restrict__ Kb,
+                         __nv_bfloat16* __restrict__ Vt, int B, int H, int W, int Nk, int Nkpad) {
+  constexpr int D = C / 8, DV = C / 2;
+  constexpr int DVP = ((2 * DV + 1 + 15) / 16) * 16;
+  constexpr int KQ = ((3 * D + 15) / 16) * 16;
+  __shared__ float sWk[C * D], sWv[C * DV], sbk[D], sbv[DV];
+  for (int i = threadIdx.x; i < C * D; i += 128) sWk[i] = Wk[i];
+  for (int i = threadIdx.x; i < C * DV; i += 128) sWv[i] = Wv[i];
+  for (int i = threadIdx.x; i < D; i += 128) sbk[i] = bk[i];
+  for (int i = threadIdx.x; i < DV; i += 128) sbv[i] = bv[i];
+  __syncthreads();
+  const long long tp = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (tp >= (long long)B * Nkpad) return;
+  const int b = (int)(tp / Nkpad), n = (int)(tp - (long long)b * Nkpad);
+  const bool valid = n < Nk;
+  float kk[D], vv[DV];
+  uint8_t ik[D], iv[DV];
+#pragma unroll
+  for (int j = 0; j < D; ++j) kk[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < DV; ++j) vv[j] = 0.f;
+  if (valid) pooled_kv<C>(X, sWk, sbk, sWv, sbv, b, H, W, n / (W / 2), n % (W / 2), kk, vv, ik, iv);
+  float k[KQ];
+#pragma unroll
+  for (int j = 0; j < KQ; ++j) k[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const float k_hi = __bfloat162float(__float2bfloat16_rn(kk[j]));
+    k[j] = k_hi; k[D + j] = k_hi; k[2 * D + j] = kk[j] - k_hi;
+  }
+  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * qk_cols(C));
+#pragma unroll
+  for (int g = 0; g < KQ / 8; ++g)
+    kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
+                       pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
+#pragma unroll
+  for (int v = 0; v < DV; ++v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(vv[v]);
+    Vt[((long long)b * DVP + v) * Nkpad + n] = hi;
+    Vt[((long long)b * DVP + DV + v) * Nkpad + n] = __float2bfloat16_rn(vv[v] - __bfloat162float(hi));
+  }
+  Vt[((long long)b * DVP + 2 * DV) * Nkpad + n] = __float2bfloat16_rn(valid ? 1.0f : 0.0f);
+#pragma unroll
+  for (int v = 2 * DV + 1; v < DVP; ++v) Vt[((long long)b * DVP + v) * Nkpad + n] = __float2bfloat16_rn(0.0f);
 }
 
 // ------------------------------------------------------------------------------------ flash forward
@@ -196,7 +255,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const float* __restrict__ X, const float* __restrict__ Wo,
                    const float* __restrict__ bo, const float* __restrict__ gamma, float* __restrict__ Y,
                    float* __restrict__ lse, float* __restrict__ A_saved, __nv_bfloat16* __restrict__ A_bf16, int N,
-                   int Npad, int dv, int kq_steps) {
+                   int Npad, int Nk, int Nkpad, int dv, int kq_steps) {
+  // N queries (Npad padded), Nk keys / values (Nkpad padded); Nk == N unless the keys are down-sampled
   using L = FwdSmem<DVP, NS, NP, CEPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -217,7 +277,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, qt = blockIdx.x;
-  const int nt = Npad / 128;
+  const int nt = Nkpad / 128;
 
   if (threadIdx.x == 0) {
     mbar_init(barQ, 1);
@@ -242,7 +302,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int s = j & 1;
         if (j >= 2) mbar_wait(barPV + s, ((j - 2) >> 1) & 1);   // PV_{j-2} done (=> QK_{j-2} done): stage s is free
         mbar_expect_tx(barKV + s, L::K_BYTES + L::V_BYTES);
-        tma_load_2d(sK + s * L::K_BYTES, &tmK, barKV + s, 0, b * Npad + j * 128);
+        tma_load_2d(sK + s * L::K_BYTES, &tmK, barKV + s, 0, b * Nkpad + j * 128);
         tma_load_2d(sV + s * L::V_BYTES, &tmV, barKV + s, j * 128, b * DVP);
         tma_load_2d(sV + s * L::V_BYTES + DVP * 128, &tmV, barKV + s, j * 128 + 64, b * DVP);
       }
@@ -305,13 +365,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 
     float m_used = -INFINITY;      // integer-valued (log2 units) once set: see "consistent rounding" above
-    const bool ragged = (N % 128) != 0;
+    const bool ragged = (Nk % 128) != 0;
 
     for (int j = 0; j < nt; ++j) {
       mbar_wait(barS + (j % NS), (j / NS) & 1);
       tc_fence_after();
       const uint32_t t_s = t_row + (uint32_t)((j % NS) * 128);
-      const int kvalid = (ragged && j == nt - 1) ? (N - j * 128) : 128;   // keys of this tile that exist
+      const int kvalid = (ragged && j == nt - 1) ? (Nk - j * 128) : 128;   // keys of this tile that exist
 
       // ---- the whole S row (128 fp32) comes to registers with ONE exposed TMEM round trip
       //      (logits are already in log2 units: Q carries log2(e))
@@ -453,22 +513,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct TcLayout {
-  int Npad, DVP, kq_steps;
+  int Npad, Nk, Nkpad, DVP, kq_steps;
   size_t off_q, off_k, off_v, total;
 };
 
-static TcLayout tc_layout(int B, int N, int C) {
+// Nk = number of keys / values (N, or N / 4 when they are down-sampled)
+static TcLayout tc_layout(int B, int N, int Nk, int C) {
   TcLayout t;
   const int d = C / 8, dv = C / 2;
   t.Npad = round_up(N, 128);
+  t.Nk = Nk;
+  t.Nkpad = round_up(Nk, 128);
   t.DVP = round_up(2 * dv + 1, 16);   // V^T rows [v_hi | v_lo | ones | 0 ...]
   t.kq_steps = (3 * d + 15) / 16;   // split-bf16 logits: [hi|lo|hi] x [hi|hi|lo]
-  const size_t T = (size_t)B * t.Npad;
+  const size_t T = (size_t)B * t.Npad, Tk = (size_t)B * t.Nkpad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
   t.off_q = take(T * qk_cols(C) * 2);
-  t.off_k = take(T * qk_cols(C) * 2);
-  t.off_v = take((size_t)B * t.DVP * t.Npad * 2);
+  t.off_k = take(Tk * qk_cols(C) * 2);
+  t.off_v = take((size_t)B * t.DVP * t.Nkpad * 2);
   t.total = o + 1024;
   return t;
 }
@@ -482,13 +545,13 @@ int attn_tc_big_fwd(const float* X, const float* Wq, const float* bq, const floa
 
 size_t attn_tc_workspace_bytes(int B, int N, int C) {
   if (C > 64) return attn_tc_big_workspace_bytes(B, N, C);
-  return tc_layout(B, N, C).total;
+  return tc_layout(B, N, N, C).total;      // upper bound of the down-sampled layout as well
 }
 
 template <int DVP, int NS, int NP, int CEPI>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const float* X,
                       const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
-                      __nv_bfloat16* Ab, int B, int N, int Npad, int dv, int kq_steps, cudaStream_t st) {
+                      __nv_bfloat16* Ab, int B, int N, int Npad, int Nk, int Nkpad, int dv, int kq_steps, cudaStream_t st) {
   using L = FwdSmem<DVP, NS, NP, CEPI>;
   auto kern = attn_fwd_tc_kernel<DVP, NS, NP, CEPI>;
   static bool configured = false;
@@ -496,44 +559,63 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<dim3(Npad / 128, B), TC_THREADS, L::TOTAL, st>>>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, Ab, N, Npad, dv,
-                                                          kq_steps);
+  kern<<<dim3(Npad / 128, B), TC_THREADS, L::TOTAL, st>>>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, Ab, N, Npad, Nk, Nkpad,
+                                                          dv, kq_steps);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
 
+// PH, PW > 0: keys / values max-pooled 2x2 / stride 2 over the [PH, PW] token grid (N == PH * PW), else PH = PW = 0
 int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
                 const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
-                int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (C > 64) return attn_tc_big_fwd(X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A, B, N, C, ws, ws_bytes, st);
+                int B, int N, int C, int PH, int PW, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bool pool = PH > 0;
+  if (C > 64) {
+    if (pool) {
+      set_err("sagan_attn_pool_fwd: down-sampled keys / values are built for C in {8,16,32,64} (C=%d)", C);
+      return SAGAN_EUNSUPPORTED;
+    }
+    return attn_tc_big_fwd(X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, Y, lse, A, B, N, C, ws, ws_bytes, st);
+  }
   if (!(C == 16 || C == 32 || C == 64)) {
     set_err("sagan_attn_fwd: BF16_TC supports C in {16,32,64} (small-d kernel) and {128,256,512} (C=%d)", C);
     return SAGAN_EUNSUPPORTED;
   }
-  const TcLayout t = tc_layout(B, N, C);
+  const TcLayout t = tc_layout(B, N, pool ? N / 4 : N, C);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(base + t.off_q);
   __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(base + t.off_k);
   __nv_bfloat16* Vt = reinterpret_cast<__nv_bfloat16*>(base + t.off_v);
-  const long long Tp = (long long)B * t.Npad;
-  const unsigned pb = (unsigned)ceil_div<long long>(Tp, 128);
+  const long long Tp = (long long)B * t.Npad, Tkp = (long long)B * t.Nkpad;
+  const unsigned pb = (unsigned)ceil_div<long long>(Tp, 128), pkb = (unsigned)ceil_div<long long>(Tkp, 128);
+#define SAGAN_PROJ_CASE(CC)                                                                                              \
+  case CC:                                                                                                              \
+    if (pool) {                                                                                                         \
+      attn_proj_tc_kernel<CC, false><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad);           \
+      SAGAN_LAUNCH_CHECK();                                                                                             \
+      attn_pool_proj_tc_kernel<CC><<<pkb, 128, 0, st>>>(X, Wk, bk, Wv, bv, Kb, Vt, B, PH, PW, t.Nk, t.Nkpad);            \
+    } else {                                                                                                            \
+      attn_proj_tc_kernel<CC, true><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad);            \
+    }                                                                                                                   \
+    break;
   switch (C) {
-    case 16: attn_proj_tc_kernel<16><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad); break;
-    case 32: attn_proj_tc_kernel<32><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad); break;
-    case 64: attn_proj_tc_kernel<64><<<pb, 128, 0, st>>>(X, Wq, bq, Wk, bk, Wv, bv, Qb, Kb, Vt, B, N, t.Npad); break;
+    SAGAN_PROJ_CASE(16)
+    SAGAN_PROJ_CASE(32)
+    SAGAN_PROJ_CASE(64)
   }
+#undef SAGAN_PROJ_CASE
   SAGAN_LAUNCH_CHECK();
   CUtensorMap tq, tk, tv;
   int rc;
   const int qkc = qk_cols(C);
   if ((rc = make_tmap_bf16_2d(&tq, Qb, (uint64_t)Tp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Npad, (uint64_t)t.Npad * 2, (uint32_t)t.DVP))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tkp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Nkpad, (uint64_t)t.Nkpad * 2, (uint32_t)t.DVP))) return rc;
   const int dv = C / 2;
   switch (C) {
-    case 16: return launch_fwd<32, 1, 2, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 32: return launch_fwd<48, 1, 2, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
-    case 64: return launch_fwd<80, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, dv, t.kq_steps, st);
+    case 16: return launch_fwd<32, 1, 2, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, t.Nk, t.Nkpad, dv, t.kq_steps, st);
+    case 32: return launch_fwd<48, 1, 2, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, t.Nk, t.Nkpad, dv, t.kq_steps, st);
+    case 64: return launch_fwd<80, 1, 1, 64>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, t.Nk, t.Nkpad, dv, t.kq_steps, st);
   }
   return SAGAN_EUNSUPPORTED;
 }

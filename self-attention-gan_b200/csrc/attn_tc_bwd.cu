@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "attn_pool.cuh"
 
 namespace sagan {
 
@@ -40,7 +41,8 @@ __host__ __device__ constexpr int tb_kv(int C) { return C <= 32 ? ((3 * (C / 2) 
 
 // ------------------------------------------------------------------------------------ prep (small C)
 // one thread per PADDED token; recomputes theta/phi/g from X and forms dA = gamma dY Wo^T, D = dA . A
-template <int C>
+// KSIDE = false (down-sampled keys / values): the key-side rows (Kb, Kt, Vb) come from attn_bwd_prep_pool_tc_kernel.
+template <int C, bool KSIDE>
 __global__ void __launch_bounds__(128)
 attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ dY, const float* __restrict__ A,
                         const float* __restrict__ lse, const float* __restrict__ Wq, const float* __restrict__ bq,
@@ -105,8 +107,10 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     const __nv_bfloat16 qh = __float2bfloat16_rn(a), kh = __float2bfloat16_rn(kk);
     Qt[((long long)b * 16 + j) * Npad + n] = qh;
     Qt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(qh));
-    Kt[((long long)b * 16 + j) * Npad + n] = kh;
-    Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(kk - __bfloat162float(kh));
+    if (KSIDE) {
+      Kt[((long long)b * 16 + j) * Npad + n] = kh;
+      Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(kk - __bfloat162float(kh));
+    }
     const float as = a * TB_LOG2E;
     const float a_hi = __bfloat162float(__float2bfloat16_rn(as)), k_hi = __bfloat162float(kh);
     q[j] = a_hi; q[D + j] = as - a_hi; q[2 * D + j] = a_hi;
@@ -123,8 +127,10 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   for (int j = D; j < 8; ++j) {      // rows [hi (0..7) | lo (8..15)]: unused rows are zero
     Qt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
     Qt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(0.f);
-    Kt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
-    Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+    if (KSIDE) {
+      Kt[((long long)b * 16 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+      Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(0.f);
+    }
   }
   uint4* qd = reinterpret_cast<uint4*>(Qb + tp * KQ);
   uint4* kd = reinterpret_cast<uint4*>(Kb + tp * KQ);
@@ -132,8 +138,9 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   for (int g = 0; g < KQ / 8; ++g) {
     qd[g] = make_uint4(pack_bf16x2(q[g * 8 + 0], q[g * 8 + 1]), pack_bf16x2(q[g * 8 + 2], q[g * 8 + 3]),
                        pack_bf16x2(q[g * 8 + 4], q[g * 8 + 5]), pack_bf16x2(q[g * 8 + 6], q[g * 8 + 7]));
-    kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
-                       pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
+    if (KSIDE)
+      kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
+                         pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
   }
   // ---- g (values) and dA' = f gamma dY Wo^T, D' = dA' . A, with f = 2^(M - lse') the normaliser of P' (see top)
   const float gm = *gamma * exp2f(Mi - l2);
@@ -179,8 +186,9 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   uint4* ad = reinterpret_cast<uint4*>(dAb + tp * KV);
 #pragma unroll
   for (int g = 0; g < KV / 8; ++g) {
-    vd[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+    if (KSIDE)
+      vd[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                         pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
     ad[g] = make_uint4(pack_bf16x2(da[g * 8 + 0], da[g * 8 + 1]), pack_bf16x2(da[g * 8 + 2], da[g * 8 + 3]),
                        pack_bf16x2(da[g * 8 + 4], da[g * 8 + 5]), pack_bf16x2(da[g * 8 + 6], da[g * 8 + 7]));
   }
@@ -189,6 +197,83 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   lse2[tp] = valid ? Mi : INFINITY;                  // integer shift M_i; +inf => P' = 0 for padded queries
   Dd[tp] = valid ? dd : 0.f;
   (void)dA_f32;
+}
+
+// ------------------------------------------------------------------------------------ prep, down-sampled keys / values
+// one thread per PADDED pooled position: the key-side operand rows of the main kernel (Kb with the folded shift / mask
+// columns, Kt, Vb with the folded ones columns) from the 2x2 max-pooled phi / g, plus the window position that supplied
+// each channel (for the scatter of dK / dV back to the tokens).
+template <int C>
+__global__ void __launch_bounds__(128)
+attn_bwd_prep_pool_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wk, const float* __restrict__ bk,
+                             const float* __restrict__ Wv, const float* __restrict__ bv, __nv_bfloat16* __restrict__ Kb,
+                             __nv_bfloat16* __restrict__ Vb, __nv_bfloat16* __restrict__ Kt, uint8_t* __restrict__ idxK,
+                             uint8_t* __restrict__ idxV, int B, int H, int W, int Nk, int Nkpad) {
+  constexpr int D = C / 8, DV = C / 2;
+  constexpr bool SPLIT3 = DV <= 16, FOLD = SPLIT3;
+  constexpr int KQ = ((3 * D + 15) / 16) * 16;
+  constexpr int KV = SPLIT3 ? ((3 * DV + 2 + 15) / 16) * 16 : 2 * DV;
+  static_assert(KQ == tb_kq(C) && KV == tb_kv(C), "row lengths shared with the main kernel");
+  __shared__ float sWk[C * D], sWv[C * DV], sbk[D], sbv[DV];
+  for (int i = threadIdx.x; i < C * D; i += 128) sWk[i] = Wk[i];
+  for (int i = threadIdx.x; i < C * DV; i += 128) sWv[i] = Wv[i];
+  for (int i = threadIdx.x; i < D; i += 128) sbk[i] = bk[i];
+  for (int i = threadIdx.x; i < DV; i += 128) sbv[i] = bv[i];
+  __syncthreads();
+  const long long tp = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (tp >= (long long)B * Nkpad) return;
+  const int b = (int)(tp / Nkpad), n = (int)(tp - (long long)b * Nkpad);
+  const bool valid = n < Nk;
+  float kk[D], vv[DV];
+  uint8_t ik[D], iv[DV];
+#pragma unroll
+  for (int j = 0; j < D; ++j) { kk[j] = 0.f; ik[j] = 0; }
+#pragma unroll
+  for (int j = 0; j < DV; ++j) { vv[j] = 0.f; iv[j] = 0; }
+  if (valid) {
+    pooled_kv<C>(X, sWk, sbk, sWv, sbv, b, H, W, n / (W / 2), n % (W / 2), kk, vv, ik, iv);
+    const long long p = (long long)b * Nk + n;
+#pragma unroll
+    for (int j = 0; j < D; ++j) idxK[p * D + j] = ik[j];
+#pragma unroll
+    for (int j = 0; j < DV; ++j) idxV[p * DV + j] = iv[j];
+  }
+  float k[KQ], v[KV];
+#pragma unroll
+  for (int j = 0; j < KQ; ++j) k[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < KV; ++j) v[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const __nv_bfloat16 kh = __float2bfloat16_rn(kk[j]);
+    const float k_hi = __bfloat162float(kh);
+    Kt[((long long)b * 16 + j) * Nkpad + n] = kh;
+    Kt[((long long)b * 16 + 8 + j) * Nkpad + n] = __float2bfloat16_rn(kk[j] - k_hi);
+    k[j] = k_hi; k[D + j] = k_hi; k[2 * D + j] = kk[j] - k_hi;
+  }
+#pragma unroll
+  for (int j = D; j < 8; ++j) {
+    Kt[((long long)b * 16 + j) * Nkpad + n] = __float2bfloat16_rn(0.f);
+    Kt[((long long)b * 16 + 8 + j) * Nkpad + n] = __float2bfloat16_rn(0.f);
+  }
+  if (FOLD) { k[3 * D] = 1.f; k[3 * D + 1] = valid ? 0.f : 1.f; k[3 * D + 2] = 1.f; }
+#pragma unroll
+  for (int j = 0; j < DV; ++j) {
+    const float vh = __bfloat162float(__float2bfloat16_rn(vv[j]));
+    if (SPLIT3) { v[j] = vh; v[DV + j] = vh; v[2 * DV + j] = vv[j] - vh; }
+    else { v[j] = vh; v[DV + j] = vv[j] - vh; }
+  }
+  if (FOLD) { v[3 * DV] = 1.f; v[3 * DV + 1] = 1.f; }
+  uint4* kd = reinterpret_cast<uint4*>(Kb + tp * KQ);
+#pragma unroll
+  for (int g = 0; g < KQ / 8; ++g)
+    kd[g] = make_uint4(pack_bf16x2(k[g * 8 + 0], k[g * 8 + 1]), pack_bf16x2(k[g * 8 + 2], k[g * 8 + 3]),
+                       pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
+  uint4* vd = reinterpret_cast<uint4*>(Vb + tp * KV);
+#pragma unroll
+  for (int g = 0; g < KV / 8; ++g)
+    vd[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                       pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
 }
 
 // ------------------------------------------------------------------------------------ main
@@ -240,7 +325,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmdAt, const __grid_constant__ CUtensorMap tmQt,
                    const __grid_constant__ CUtensorMap tmKt, const float* __restrict__ lse2,
                    const float* __restrict__ Dd, float* __restrict__ dQ, float* __restrict__ dK,
-                   float* __restrict__ dV, int N, int Npad, int d, int dv, int kq_steps, int kv_steps) {
+                   float* __restrict__ dV, int N, int Npad, int Nk, int Nkpad, int d, int dv, int kq_steps, int kv_steps) {
+  // N queries (Npad padded), Nk keys / values (Nkpad padded; grid.x = Nkpad / 128); Nk == N unless down-sampled
   using L = BwdSmem<DVP, QKB, VAB, NDS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -295,8 +381,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdA);
       tma_prefetch_desc(&tmdAt); tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt);
       mbar_expect_tx(barKV, L::QK_TILE + L::VA_TILE + L::T16);
-      tma_load_2d(sK, &tmK, barKV, 0, b * Npad + kt * 128);
-      tma_load_2d(sV, &tmV, barKV, 0, b * Npad + kt * 128);
+      tma_load_2d(sK, &tmK, barKV, 0, b * Nkpad + kt * 128);
+      tma_load_2d(sV, &tmV, barKV, 0, b * Nkpad + kt * 128);
       tma_load_2d(sKt, &tmKt, barKV, kt * 128, b * 16);
       tma_load_2d(sKt + 16 * 128, &tmKt, barKV, kt * 128 + 64, b * 16);
       // the two rings are refilled by polling, whichever stage frees first (no assumption on their relative order)
@@ -432,7 +518,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int qd = warp & 3, h = warp >> 2, x = h >> 1;
     const int krow = qd * 32 + lane;                                // key row inside the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const bool key_ok = kt * 128 + krow < N;
+    const bool key_ok = kt * 128 + krow < Nk;
     // dQ_i tile (TMEM lanes = queries) -> atomicAdd; the four column groups take turns so the atomics are spread evenly
     auto flush_dq = [&](int i) {
       if (h == (i & 3)) {
@@ -552,7 +638,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     flush_dq(nq - 1);
     if (h == 0) {
       const int key = kt * 128 + krow;
-      const size_t grow = (size_t)b * N + key;
+      const size_t grow = (size_t)b * Nk + key;
       if (SPLIT_DA) {
         // columns [dV from dA_hi (dv) | dV from dA_lo (dv)]
         float acc[DVP];
@@ -565,7 +651,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int e = 0; e < 16; ++e) acc[c * 16 + e] = __uint_as_float(r[e]);
         }
         constexpr int DVH = DVP / 2;   // == dv
-        if (key < N) {
+        if (key < Nk) {
 #pragma unroll
           for (int e = 0; e < DVH; e += 4)
             st4(dV + grow * DVH + e, make_float4(acc[e] + acc[DVH + e], acc[e + 1] + acc[DVH + e + 1],
@@ -577,7 +663,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           uint32_t r[16];
           tmem_ld16(t_row + L::DV_COL + c * 16, r);
           tmem_wait_ld();
-          if (key < N) {
+          if (key < Nk) {
 #pragma unroll
             for (int e = 0; e < 16; e += 4)
               if (c * 16 + e < dv)
@@ -589,7 +675,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t r[32];
       tmem_ld32(t_row + L::DKH_COL, r);                       // [from dS_hi: Q_hi (8) Q_lo (8) | from dS_lo: Q_hi Q_lo]
       tmem_wait_ld();
-      if (key < N) {
+      if (key < Nk) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           if (c < d)
@@ -608,52 +694,77 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // ------------------------------------------------------------------------------------ host
 struct TbLayout {
-  int Npad, DVP, kq_steps, kv_steps;
-  size_t off_q, off_k, off_v, off_da, off_dat, off_qt, off_kt, off_lse, off_dd, total;
+  int Npad, Nk, Nkpad, DVP, kq_steps, kv_steps;
+  size_t off_q, off_k, off_v, off_da, off_dat, off_qt, off_kt, off_lse, off_dd, off_dkp, off_dvp, off_ik, off_iv, total;
 };
 
-static TbLayout tb_layout(int B, int N, int C) {
+// Nk = number of keys / values (N, or N / 4 when they are down-sampled: then the pooled gradients and the argmax codes
+// live in the workspace as well)
+static TbLayout tb_layout(int B, int N, int Nk, int C) {
   TbLayout t;
   const int d = C / 8, dv = C / 2;
   t.Npad = (N + 127) / 128 * 128;
+  t.Nk = Nk;
+  t.Nkpad = (Nk + 127) / 128 * 128;
   t.DVP = C == 16 ? 16 : 32;                              // C <= 32: [dA_hi | dA_lo] rows; C = 64: dA rows unsplit
   t.kq_steps = (3 * d + 15) / 16;
   t.kv_steps = dv <= 16 ? (3 * dv + 2 + 15) / 16 : (2 * dv) / 16;   // split-bf16 dP contraction + folded D columns
-  const size_t T = (size_t)B * t.Npad;
+  const size_t T = (size_t)B * t.Npad, Tk = (size_t)B * t.Nkpad;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
   t.off_q = take(T * tb_kq(C) * 2);
-  t.off_k = take(T * tb_kq(C) * 2);
-  t.off_v = take(T * tb_kv(C) * 2);
+  t.off_k = take(Tk * tb_kq(C) * 2);
+  t.off_v = take(Tk * tb_kv(C) * 2);
   t.off_da = take(T * tb_kv(C) * 2);
   t.off_dat = take((size_t)B * t.DVP * t.Npad * 2);
   t.off_qt = take((size_t)B * 16 * t.Npad * 2);
-  t.off_kt = take((size_t)B * 16 * t.Npad * 2);
+  t.off_kt = take((size_t)B * 16 * t.Nkpad * 2);
   t.off_lse = take(T * 4);
   t.off_dd = take(T * 4);
+  t.off_dkp = t.off_dvp = t.off_ik = t.off_iv = 0;
+  if (Nk != N) {
+    t.off_dkp = take((size_t)B * Nk * d * 4);
+    t.off_dvp = take((size_t)B * Nk * dv * 4);
+    t.off_ik = take((size_t)B * Nk * d);
+    t.off_iv = take((size_t)B * Nk * dv);
+  }
   t.total = o + 1024;
   return t;
 }
 
-size_t attn_tc_bwd_workspace_bytes(int B, int N, int C) { return tb_layout(B, N, C).total; }
+size_t attn_tc_bwd_workspace_bytes(int B, int N, int C, bool pool) { return tb_layout(B, N, pool ? N / 4 : N, C).total; }
+
+int attn_unpool_launch(const float* dKp, const float* dVp, const uint8_t* idxK, const uint8_t* idxV, float* dK, float* dV,
+                       int B, int H, int W, int C, cudaStream_t st);      // attn_strict.cu
 
 template <int C>
 static int run_prep(const float* X, const float* dY, const float* A, const float* lse, const float* Wq, const float* bq,
                     const float* Wk, const float* bk, const float* Wv, const float* bv, const float* Wo,
-                    const float* gamma, uint8_t* base, const TbLayout& t, int B, int N, cudaStream_t st) {
+                    const float* gamma, uint8_t* base, const TbLayout& t, int B, int N, int PH, int PW, cudaStream_t st) {
   const long long Tp = (long long)B * t.Npad;
-  attn_bwd_prep_tc_kernel<C><<<(unsigned)ceil_div<long long>(Tp, 128), 128, 0, st>>>(
-      X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, (__nv_bfloat16*)(base + t.off_q), (__nv_bfloat16*)(base + t.off_k),
-      (__nv_bfloat16*)(base + t.off_v), (__nv_bfloat16*)(base + t.off_da), (__nv_bfloat16*)(base + t.off_dat),
-      (__nv_bfloat16*)(base + t.off_qt), (__nv_bfloat16*)(base + t.off_kt), (float*)(base + t.off_lse),
-      (float*)(base + t.off_dd), nullptr, B, N, t.Npad);
+  const unsigned nb = (unsigned)ceil_div<long long>(Tp, 128);
+  __nv_bfloat16 *Qb = (__nv_bfloat16*)(base + t.off_q), *Kb = (__nv_bfloat16*)(base + t.off_k),
+                *Vb = (__nv_bfloat16*)(base + t.off_v), *dAb = (__nv_bfloat16*)(base + t.off_da),
+                *dAt = (__nv_bfloat16*)(base + t.off_dat), *Qt = (__nv_bfloat16*)(base + t.off_qt),
+                *Kt = (__nv_bfloat16*)(base + t.off_kt);
+  float *lse2 = (float*)(base + t.off_lse), *Dd = (float*)(base + t.off_dd);
+  if (PH > 0) {
+    attn_bwd_prep_tc_kernel<C, false><<<nb, 128, 0, st>>>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, Qb, Kb, Vb, dAb,
+                                                          dAt, Qt, Kt, lse2, Dd, nullptr, B, N, t.Npad);
+    SAGAN_LAUNCH_CHECK();
+    attn_bwd_prep_pool_tc_kernel<C><<<(unsigned)ceil_div<long long>((long long)B * t.Nkpad, 128), 128, 0, st>>>(
+        X, Wk, bk, Wv, bv, Kb, Vb, Kt, base + t.off_ik, base + t.off_iv, B, PH, PW, t.Nk, t.Nkpad);
+  } else {
+    attn_bwd_prep_tc_kernel<C, true><<<nb, 128, 0, st>>>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, Qb, Kb, Vb, dAb,
+                                                         dAt, Qt, Kt, lse2, Dd, nullptr, B, N, t.Npad);
+  }
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
 
 template <int DVP, bool SPLIT_DA, int QKB, int VAB, int NDS>
 static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, float* dQ, float* dK, float* dV, int B,
-                      int N, int Npad, int d, int dv, int kq, int kv, cudaStream_t st) {
+                      int N, const TbLayout& t, int d, int dv, cudaStream_t st) {
   using L = BwdSmem<DVP, QKB, VAB, NDS>;
   auto kern = attn_bwd_tc_kernel<DVP, SPLIT_DA, QKB, VAB, NDS>;
   static bool configured = false;
@@ -661,22 +772,25 @@ static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, 
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<dim3(Npad / 128, B), TB_THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], lse2, Dd, dQ, dK, dV,
-                                                          N, Npad, d, dv, kq, kv);
+  kern<<<dim3(t.Nkpad / 128, B), TB_THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], lse2, Dd, dQ, dK, dV,
+                                                             N, t.Npad, t.Nk, t.Nkpad, d, dv, t.kq_steps, t.kv_steps);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
 
-// dQ / dK / dV [B,N,.] fp32 from the tensor-core kernel (dQ must be zero on entry: it is accumulated atomically)
+// dQ / dK / dV [B,N,.] fp32 from the tensor-core kernel (dQ must be zero on entry: it is accumulated atomically).
+// PH, PW > 0: keys / values were max-pooled 2x2 / stride 2 over the [PH, PW] token grid; dK / dV are still TOKEN-level
+// (the pooled gradients are scattered to the window positions that won).
 int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const float* lse, const float* Wq, const float* bq,
                      const float* Wk, const float* bk, const float* Wv, const float* bv, const float* Wo,
-                     const float* gamma, float* dQ, float* dK, float* dV, int B, int N, int C, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+                     const float* gamma, float* dQ, float* dK, float* dV, int B, int N, int C, int PH, int PW, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
   if (!(C == 16 || C == 32 || C == 64)) {
     set_err("sagan_attn_bwd: BF16_TC supports C in {16,32,64} (C=%d)", C);
     return SAGAN_EUNSUPPORTED;
   }
-  const TbLayout t = tb_layout(B, N, C);
+  const bool pool = PH > 0;
+  const TbLayout t = tb_layout(B, N, pool ? N / 4 : N, C);
   if (ws_bytes < t.total) {
     set_err("sagan_attn_bwd: tensor-core workspace %zu < %zu bytes", ws_bytes, t.total);
     return SAGAN_EWORKSPACE;
@@ -684,27 +798,31 @@ int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const floa
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   int rc = 0;
   switch (C) {
-    case 16: rc = run_prep<16>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, st); break;
-    case 32: rc = run_prep<32>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, st); break;
-    case 64: rc = run_prep<64>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, st); break;
+    case 16: rc = run_prep<16>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, PH, PW, st); break;
+    case 32: rc = run_prep<32>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, PH, PW, st); break;
+    case 64: rc = run_prep<64>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, base, t, B, N, PH, PW, st); break;
   }
   if (rc) return rc;
-  const uint64_t Tp = (uint64_t)B * t.Npad;
+  const uint64_t Tp = (uint64_t)B * t.Npad, Tkp = (uint64_t)B * t.Nkpad;
   CUtensorMap m[7];
   const uint32_t kq = (uint32_t)tb_kq(C), kv = (uint32_t)tb_kv(C);
   if ((rc = make_tmap_bf16_2d(&m[0], base + t.off_q, Tp, kq, kq * 2, 128, kq, (int)kq * 2))) return rc;
-  if ((rc = make_tmap_bf16_2d(&m[1], base + t.off_k, Tp, kq, kq * 2, 128, kq, (int)kq * 2))) return rc;
-  if ((rc = make_tmap_bf16_2d(&m[2], base + t.off_v, Tp, kv, kv * 2, 128, kv, (int)kv * 2))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[1], base + t.off_k, Tkp, kq, kq * 2, 128, kq, (int)kq * 2))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[2], base + t.off_v, Tkp, kv, kv * 2, 128, kv, (int)kv * 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&m[3], base + t.off_da, Tp, kv, kv * 2, 128, kv, (int)kv * 2))) return rc;
   if ((rc = make_tmap_bf16_2d(&m[4], base + t.off_dat, (uint64_t)B * t.DVP, t.Npad, (uint64_t)t.Npad * 2, t.DVP))) return rc;
   if ((rc = make_tmap_bf16_2d(&m[5], base + t.off_qt, (uint64_t)B * 16, t.Npad, (uint64_t)t.Npad * 2, 16))) return rc;
-  if ((rc = make_tmap_bf16_2d(&m[6], base + t.off_kt, (uint64_t)B * 16, t.Npad, (uint64_t)t.Npad * 2, 16))) return rc;
+  if ((rc = make_tmap_bf16_2d(&m[6], base + t.off_kt, (uint64_t)B * 16, t.Nkpad, (uint64_t)t.Nkpad * 2, 16))) return rc;
   const float* lse2 = (const float*)(base + t.off_lse);
   const float* Dd = (const float*)(base + t.off_dd);
   const int d = C / 8, dv = C / 2;
-  if (C == 16) return launch_bwd<16, true, 32, 64, 2>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
-  if (C == 32) return launch_bwd<32, true, 32, 128, 1>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
-  return launch_bwd<32, false, 64, 128, 1>(m, lse2, Dd, dQ, dK, dV, B, N, t.Npad, d, dv, t.kq_steps, t.kv_steps, st);
+  float* dKo = pool ? (float*)(base + t.off_dkp) : dK;
+  float* dVo = pool ? (float*)(base + t.off_dvp) : dV;
+  if (C == 16) rc = launch_bwd<16, true, 32, 64, 2>(m, lse2, Dd, dQ, dKo, dVo, B, N, t, d, dv, st);
+  else if (C == 32) rc = launch_bwd<32, true, 32, 128, 1>(m, lse2, Dd, dQ, dKo, dVo, B, N, t, d, dv, st);
+  else rc = launch_bwd<32, false, 64, 128, 1>(m, lse2, Dd, dQ, dKo, dVo, B, N, t, d, dv, st);
+  if (rc || !pool) return rc;
+  return attn_unpool_launch(dKo, dVo, base + t.off_ik, base + t.off_iv, dK, dV, B, PH, PW, C, st);
 }
 
 }  // namespace sagan

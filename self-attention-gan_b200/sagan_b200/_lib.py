@@ -61,6 +61,9 @@ SIGNATURES = {
     "sagan_attn_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "sagan_attn_fwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P, _SZ, _P]),
     "sagan_attn_bwd": (_I, [_P] * 23 + [_I, _I, _I, _I, _P, _SZ, _P]),
+    "sagan_attn_pool_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "sagan_attn_pool_fwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _I, _P, _SZ, _P]),
+    "sagan_attn_pool_bwd": (_I, [_P] * 23 + [_I, _I, _I, _I, _I, _P, _SZ, _P]),
     "sagan_conv2d_fwd": (_I, [_P, _P, _P, _P, C.POINTER(ConvGeom), _I, _F, _I, _P]),
     "sagan_conv2d_dgrad": (_I, [_P, _P, _P, C.POINTER(ConvGeom), _I, _P]),
     "sagan_conv2d_wgrad": (_I, [_P, _P, _P, _P, C.POINTER(ConvGeom), _I, _P]),

@@ -198,20 +198,28 @@ def batchnorm_lrelu(x, gamma, beta, moving_mean=None, moving_var=None, eps=1e-3,
 # ------------------------------------------------------------------------------------ attention
 class _AttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wq, bq, wk, bk, wv, bv, wo, bo, gamma, math_mode):
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, wo, bo, gamma, math_mode, grid):
+        """grid = None: every token is a key (layers.py:93-120, paper form); grid = (H, W): keys / values max-pooled
+        2x2 / stride 2 over the token grid (sagan_attn_pool_*)."""
         lib = _lib.load()
         B, N, Cc = x.shape
         dv = Cc // 2
         y = torch.empty_like(x)
         lse = torch.empty((B, N), device=x.device, dtype=torch.float32)
         a = torch.empty((B, N, dv), device=x.device, dtype=torch.float32)
-        wsb = lib.sagan_attn_workspace_bytes(B, N, Cc, math_mode)
-        ws = torch.empty((wsb + 3) // 4, device=x.device, dtype=torch.float32)
-        check(lib.sagan_attn_fwd(_ptr(x), _ptr(wq), _ptr(bq), _ptr(wk), _ptr(bk), _ptr(wv), _ptr(bv), _ptr(wo),
-                                 _ptr(bo), _ptr(gamma), _ptr(y), _ptr(lse), _ptr(a), B, N, Cc, math_mode, _ptr(ws),
-                                 wsb, _stream()), "sagan_attn_fwd")
+        ptrs = (_ptr(x), _ptr(wq), _ptr(bq), _ptr(wk), _ptr(bk), _ptr(wv), _ptr(bv), _ptr(wo), _ptr(bo), _ptr(gamma),
+                _ptr(y), _ptr(lse), _ptr(a))
+        if grid is None:
+            wsb = lib.sagan_attn_workspace_bytes(B, N, Cc, math_mode)
+            ws = torch.empty((wsb + 3) // 4, device=x.device, dtype=torch.float32)
+            check(lib.sagan_attn_fwd(*ptrs, B, N, Cc, math_mode, _ptr(ws), wsb, _stream()), "sagan_attn_fwd")
+        else:
+            H, W = grid
+            wsb = lib.sagan_attn_pool_workspace_bytes(B, H, W, Cc, math_mode)
+            ws = torch.empty((wsb + 3) // 4, device=x.device, dtype=torch.float32)
+            check(lib.sagan_attn_pool_fwd(*ptrs, B, H, W, Cc, math_mode, _ptr(ws), wsb, _stream()), "sagan_attn_pool_fwd")
         ctx.save_for_backward(x, wq, bq, wk, bk, wv, bv, wo, bo, gamma, lse, a)
-        ctx.mm = math_mode
+        ctx.mm, ctx.grid = math_mode, grid
         return y
 
     @staticmethod
@@ -227,19 +235,32 @@ class _AttnFn(torch.autograd.Function):
         else:
             gs = [None] * 9
         if dx is None and not need_w:
-            return (None,) * 11
-        wsb = lib.sagan_attn_workspace_bytes(B, N, Cc, ctx.mm)
-        ws = torch.empty((wsb + 3) // 4, device=x.device, dtype=torch.float32)
-        check(lib.sagan_attn_bwd(_ptr(dy), _ptr(x), _ptr(wq), _ptr(bq), _ptr(wk), _ptr(bk), _ptr(wv), _ptr(bv),
-                                 _ptr(wo), _ptr(bo), _ptr(gamma), _ptr(lse), _ptr(a), _ptr(dx), *[_ptr(g) for g in gs],
-                                 B, N, Cc, ctx.mm, _ptr(ws), wsb, _stream()), "sagan_attn_bwd")
-        return (dx, *gs, None)
+            return (None,) * 12
+        ptrs = (_ptr(dy), _ptr(x), _ptr(wq), _ptr(bq), _ptr(wk), _ptr(bk), _ptr(wv), _ptr(bv), _ptr(wo), _ptr(bo),
+                _ptr(gamma), _ptr(lse), _ptr(a), _ptr(dx), *[_ptr(g) for g in gs])
+        if ctx.grid is None:
+            wsb = lib.sagan_attn_workspace_bytes(B, N, Cc, ctx.mm)
+            ws = torch.empty((wsb + 3) // 4, device=x.device, dtype=torch.float32)
+            check(lib.sagan_attn_bwd(*ptrs, B, N, Cc, ctx.mm, _ptr(ws), wsb, _stream()), "sagan_attn_bwd")
+        else:
+            H, W = ctx.grid
+            wsb = lib.sagan_attn_pool_workspace_bytes(B, H, W, Cc, ctx.mm)
+            ws = torch.empty((wsb + 3) // 4, device=x.device, dtype=torch.float32)
+            check(lib.sagan_attn_pool_bwd(*ptrs, B, H, W, Cc, ctx.mm, _ptr(ws), wsb, _stream()), "sagan_attn_pool_bwd")
+        return (dx, *gs, None, None)
 
 
-def attention(x, wq, bq, wk, bk, wv, bv, wo, bo, gamma, math_mode=MATH_FP32_STRICT):
-    """x [B,N,C]; wq (theta) / wk (phi) [C,C//8]; wv (g) [C,C//2]; wo [C//2,C]; gamma 0-d tensor."""
+def attention(x, wq, bq, wk, bk, wv, bv, wo, bo, gamma, math_mode=MATH_FP32_STRICT, pool_grid=None):
+    """x [B,N,C]; wq (theta) / wk (phi) [C,C//8]; wv (g) [C,C//2]; wo [C//2,C]; gamma 0-d tensor.
+    pool_grid = (H, W) with H * W == N: keys (phi) and values (g) are max-pooled 2x2 / stride 2 over the token grid,
+    what layers.py:96,100,113 reaches for (N / 4 keys)."""
+    if pool_grid is not None:
+        H, W = int(pool_grid[0]), int(pool_grid[1])
+        if H * W != x.shape[1]:
+            raise ValueError(f"pool_grid {pool_grid} does not match {x.shape[1]} tokens")
+        pool_grid = (H, W)
     return _AttnFn.apply(x.contiguous(), wq.contiguous(), bq, wk.contiguous(), bk, wv.contiguous(), bv,
-                         wo.contiguous(), bo, gamma.reshape(1), math_mode)
+                         wo.contiguous(), bo, gamma.reshape(1), math_mode, pool_grid)
 
 
 # ------------------------------------------------------------------------------------ spectral norm

@@ -26,6 +26,13 @@ def set_flat_allocator(fn):
     _FLAT_ALLOC[0] = fn
 
 
+def _attn_pool(config):
+    """Optional config key `attn_downsample` (not in the reference's dict; default off = the oracle's fixed reading):
+    True selects the down-sampled attention layers.py:96,100,113 reaches for ("downsampled attn layer",
+    example_configs/church64_attn.py:3): keys / values max-pooled 2x2 / stride 2."""
+    return "2x2s2" if config.get("attn_downsample") else None
+
+
 class GBlock(torch.nn.Module):
     """generator.py:7-12: SN(Conv2DTranspose(c,4,2,'same',no bias)) -> BN -> LeakyReLU(0.1)."""
 
@@ -149,7 +156,7 @@ class Generator(Network):
             self.blocks.append(GBlock(gf * (2 ** p)))                                      # generator.py:32
             size *= 2
             if config.get("use_attention") and size in config["attn_dim_G"]:              # generator.py:33-34
-                self.attn[str(i)] = nn.AttentionLayer()
+                self.attn[str(i)] = nn.AttentionLayer(pool=_attn_pool(config))
         self.head = nn.Conv2D(3, 4, 1, padding="same", use_bias=False, activation="tanh")  # generator.py:36
 
     def forward(self, inputs, training=True):
@@ -207,7 +214,7 @@ class Discriminator(Network):
             size //= 2
             # discriminator.py:23 reads attn_dim_G (sic); attn_dim_D is ignored, kept for drop-in parity
             if config.get("use_attention") and size in config["attn_dim_G"]:
-                self.attn[str(i)] = nn.AttentionLayer()
+                self.attn[str(i)] = nn.AttentionLayer(pool=_attn_pool(config))
         if config.get("use_label"):
             self.head_dense = nn.Dense(1)                                                  # discriminator.py:28
             self.embedding = None

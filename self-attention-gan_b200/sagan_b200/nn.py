@@ -280,9 +280,15 @@ class Attention_Layer(Layer):
     """layers.py:71-120 (paper form).  One fused kernel:
     Y = X + sigma * ((softmax((X Wtheta + b)(X Wphi + b)^T) (X Wg + b)) Wo + bo)."""
 
-    def __init__(self, math_mode=None):
+    def __init__(self, math_mode=None, pool=None):
+        """pool=None: paper form, every token is a key (the oracle's fixed reading).
+        pool='2x2s2': phi and g are max-pooled 2x2 / stride 2 before the attention map, the down-sampling
+        layers.py:96,100,113 reaches for ("downsampled attn layer", example_configs/church64_attn.py:3)."""
         super().__init__()
         self.math_mode = _DEFAULT_MATH[0] if math_mode is None else math_mode
+        if pool not in (None, "2x2s2"):
+            raise ValueError(f"pool must be None or '2x2s2', got {pool!r}")
+        self.pool = pool
 
     def build(self, input_shape):
         b, w, h, c = [int(s) if s is not None else None for s in input_shape]
@@ -318,7 +324,8 @@ class Attention_Layer(Layer):
                         kernels[0], phi.module.bias,         # keys:    phi,   layers.py:99
                         kernels[2], g.module.bias,           # values:  g,     layers.py:112
                         kernels[3], o.module.bias,           # output conv,    layers.py:119
-                        self.sigma, self.math_mode)
+                        self.sigma, self.math_mode,
+                        (H, W) if self.pool else None)       # layers.py:100,113 (MaxPool2D on phi and g)
         return y.reshape(B, H, W, Cc)
 
 

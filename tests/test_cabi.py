@@ -60,7 +60,11 @@ def test_layer_surface_mirrors_reference():
     assert sig.parameters["name"].default == "weights" and sig.parameters["Ip"].default == 1
     with pytest.raises(ValueError, match="positive integer"):                   # layers.py:17-18
         layers.SpectralNormalization(layers.Dense(4), Ip=0)
-    assert len(inspect.signature(layers.AttentionLayer.__init__).parameters) == 2   # no-arg constructor (+ math_mode)
+    # no-arg constructor (layers.py:72); math_mode / pool are optional extras
+    assert all(p.default is not inspect.Parameter.empty
+               for n, p in inspect.signature(layers.AttentionLayer.__init__).parameters.items() if n != "self")
+    with pytest.raises(ValueError, match="pool"):
+        layers.AttentionLayer(pool="3x3")
 
 
 def test_product_has_no_cpu_fallback_and_does_not_import_the_oracle():
@@ -91,6 +95,16 @@ def test_workspace_queries_and_argument_checks_need_no_gpu(lib_path):
     N, C, B = 4096, 512, 16
     assert lib.sagan_attn_workspace_bytes(B, N, C, TC) >= 4 * (3 * N * N + B * N * C)
     assert lib.sagan_bn_workspace_bytes(16) > 0
+    # down-sampled keys / values: a workspace for every supported C; odd grids and large C are refused
+    for mode in (FP, TC):
+        for C in (8, 16, 32, 64):
+            assert 0 < lib.sagan_attn_pool_workspace_bytes(2, 32, 32, C, mode) < lib.sagan_attn_pool_workspace_bytes(4, 32, 32, C, mode)
+    rc = lib.sagan_attn_pool_fwd(None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 2, 31, 32, 16, TC, None, 0, None)
+    assert rc == -1 and b"even" in lib.sagan_last_error()
+    rc = lib.sagan_attn_pool_fwd(None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 2, 32, 32, 128, TC, None, 0, None)
+    assert rc == -2 and b"down-sampled" in lib.sagan_last_error()
     # null pointers are refused with a message, no launch
     rc = lib.sagan_attn_fwd(None, None, None, None, None, None, None, None, None, None, None, None, None,
                             2, 128, 16, TC, None, 0, None)

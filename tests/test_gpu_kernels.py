@@ -425,6 +425,79 @@ def test_attention_tc_vs_strict_full_size(F, shape):
     assert rel_l2((yt - x).cpu().numpy(), (ys - x).cpu().numpy()) < 1e-2
 
 
+# ---------------------------------------------------------------------------------------- attention, down-sampled keys / values
+POOL_CASES = [(2, 16, 16, 16), (2, 16, 16, 32), (1, 32, 32, 64), (2, 8, 8, 16), (2, 8, 16, 32), (3, 12, 10, 16), (1, 64, 64, 16)]
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+@pytest.mark.parametrize("mode_name", ["strict", "tc"])
+def test_attention_pooled_vs_oracle(F, case, mode_name):
+    """phi and g max-pooled 2x2 / stride 2 over the [H, W] token grid (what layers.py:96,100,113
+    reaches for; N / 4 keys), forward and every gradient against oracle.attention.forward_pooled / backward_pooled
+    (fp64), in both math modes.  Covers a ragged key tile (8x8 -> 16 keys), non-square and non-power-of-two grids and the
+    in-model 64x64 map (4096 queries, 1024 keys)."""
+    B, H, W, C = case
+    N = H * W
+    X, dY, w = oattn.make_inputs(B, N, C, seed=500 + C + H, gamma=0.37, dtype=np.float32)
+    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    Y_ref = oattn.forward_pooled(X.astype(np.float64), **w64, hw=(H, W))
+    g_ref = oattn.backward_pooled(dY.astype(np.float64), X.astype(np.float64), **w64, hw=(H, W))
+    mode = F.MATH_FP32_STRICT if mode_name == "strict" else F.MATH_BF16_TC
+    t = {k: cu(np.asarray(v)).requires_grad_(True) for k, v in w.items()}
+    tx = cu(X).requires_grad_(True)
+    y = F.attention(tx, t["Wtheta"], t["btheta"], t["Wphi"], t["bphi"], t["Wg"], t["bg"], t["Wo"], t["bo"], t["gamma"], mode,
+                    pool_grid=(H, W))
+    y.backward(cu(dY))
+    torch.cuda.synchronize()
+    gw = {k: v.grad.cpu().numpy() for k, v in t.items()}
+    tag = f"pooled B{B}_{H}x{W}_C{C}"
+    yk, dx = y.detach().cpu().numpy(), tx.grad.cpu().numpy()
+    # not the un-pooled block by accident
+    assert rel_l2(yk - X, oattn.forward(X.astype(np.float64), **w64) - X) > 1e-2
+    errs = {k: rel_l2(gw[k], g_ref["d" + k]) for k in oattn.WEIGHT_NAMES}
+    e_y, e_att, e_dx = rel_l2(yk, Y_ref), rel_l2(yk - X, Y_ref - X), rel_l2(dx, g_ref["dX"])
+    print(tag, mode_name, "Y %.2e Y-X %.2e dX %.2e" % (e_y, e_att, e_dx), {k: "%.1e" % v for k, v in errs.items()})
+    # d(phi bias) is exactly zero in exact arithmetic here too (max-pooling commutes with a per-channel shift of all keys,
+    # and softmax is invariant to it): the computed value is rounding noise and is only bounded
+    assert np.abs(gw["bphi"]).max() < 1e-2 * np.abs(gw["btheta"]).max() + 1e-6
+    if mode_name == "strict":
+        assert e_y < STRICT_TOL and e_dx < STRICT_TOL and e_att < 5e-5
+        for k, e in errs.items():
+            if k != "bphi":
+                assert e < 1e-4, (k, e)     # fp32 sums over up to 4096 tokens (measured <= 5e-5, d(theta bias) at 64x64)
+    else:
+        tol_w = TC_TOL if C <= 32 else 4e-3
+        assert e_y < TC_TOL and e_dx < TC_TOL and e_att < 1e-2
+        for k, e in errs.items():
+            if k == "bphi":
+                continue
+            # d gamma and d(theta bias) are sums of zero-mean terms over ALL tokens (d theta_i = sum_j dS_ij phi_j with
+            # sum_j dS_ij = 0): their relative error is a ratio of random-walk sums (measured up to 4.2e-3)
+            assert e < (5 * tol_w if k in ("gamma", "btheta") else tol_w), (k, e)
+
+
+def test_attention_layer_pool_option(F):
+    """Layer surface: AttentionLayer(pool='2x2s2') routes through sagan_attn_pool_* and differs from the un-pooled
+    layer; spectral-norm wrapped kernels, NHWC input."""
+    from sagan_b200 import nn as snn
+    torch.manual_seed(0)
+    x = torch.randn(2, 16, 16, 32, device="cuda")
+    a, b = snn.AttentionLayer(pool="2x2s2"), snn.AttentionLayer()
+    ya = a(x)
+    b(x)
+    with torch.no_grad():
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            pb.copy_(pa)
+        a.sigma.fill_(0.5); b.sigma.fill_(0.5)
+        for sa, sb in zip(a.SN_conv, b.SN_conv):
+            sb._group.u(0).copy_(sa._group.u(0))
+    ya, yb = a(x, training=False), b(x, training=False)
+    assert ya.shape == x.shape and torch.isfinite(ya).all()
+    assert float((ya - yb).norm() / (yb - x).norm()) > 1e-2
+    ya.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in a.parameters())
+
+
 # ---------------------------------------------------------------------------------------- attention, large C (sweep regime)
 @pytest.mark.parametrize("shape", [(2, 256, 128), (2, 384, 256), (1, 512, 512), (1, 128, 512), (2, 512, 256), (1, 1024, 512), (1, 256, 512),
                                    (2, 2048, 256)])

@@ -211,6 +211,34 @@ def test_forward_and_gradients_bf16_tc_mode():
     assert max(errs.values()) < 3e-2 and float(np.median(list(errs.values()))) < 8e-3
 
 
+@pytest.mark.parametrize("mode_name", MODES)
+def test_downsampled_attention_model_forward_and_gradients(mode_name):
+    """SURVEY.md §8f row 2 at model level: church64 G / D with `attn_downsample` (keys / values max-pooled 2x2 / stride 2
+    in all three attention layers) against the fp64 oracle: loss elements and every parameter gradient."""
+    cfg = dict(mg.TEST_CFG, attn_downsample=True)
+    orc, tr = make_pair(cfg, attn_sigma=0.37, bias_scale=0.05, mode_name=mode_name)
+    img, nd, ng = mg.step_inputs(cfg, 0)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    dgr, dl = orc.d_grads(t64(img), t64(nd))
+    ggr, gl = orc.g_grads(t64(ng))
+    le_d, le_g = _phase_grads(tr, cfg, img, nd, ng)
+    strict = mode_name == "fp32_strict"
+    assert rel_l2(le_d, dl.numpy()) < (1e-5 if strict else 2e-4) and rel_l2(le_g, gl.numpy()) < (1e-5 if strict else 2e-4)
+    errs = {}
+    for net, ref in ((tr.D, dgr), (tr.G, ggr)):
+        for k, p in net.named_parameters_by_oracle_name():
+            if k.endswith("phi.bias"):
+                continue
+            errs[("D." if net is tr.D else "G.") + k] = rel_l2(p.grad.cpu().numpy(), ref[k].numpy())
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print("down-sampled attention,", mode_name, "worst gradient rel-L2 %.2e at %s, median %.2e" % (
+        worst[1], worst[0], float(np.median(list(errs.values())))))
+    if strict:
+        assert worst[1] < 2e-4, worst
+    else:
+        assert worst[1] < 3e-2 and float(np.median(list(errs.values()))) < 8e-3, worst
+
+
 def test_conditional_128_forward_and_gradients():
     """BASELINE.json configs[3]: 128x128 class-conditional SAGAN (one-hot concat in G, projection head in D,
     attention at 32x32 and 64x64), B = 2, against the fp64 oracle (FP32_STRICT tier)."""
