@@ -205,7 +205,7 @@ def kernel_rooflines(pk, math_mode):
     mufu_peak = 148 * 16 * 1.965e9       # ex2 / s: 16 per clock per SM at the maximum SM clock
     out = {}
 
-    def attn_case(B, N, C, mode, bwd, iters):
+    def attn_case(B, N, C, mode, bwd, iters, pool_grid=None):
         d, dv = C // 8, C // 2
         g = torch.Generator(device="cuda").manual_seed(0)
         x = torch.randn(B, N, C, device="cuda", generator=g, requires_grad=True)
@@ -217,25 +217,33 @@ def kernel_rooflines(pk, math_mode):
             w[2] *= 1.5 ** 0.5 / d ** 0.25
         dy = torch.randn(B, N, C, device="cuda", generator=g)
         with torch.no_grad():
-            t_f = time_cuda(lambda: F.attention(x, *w, mode), iters, flush)
+            t_f = time_cuda(lambda: F.attention(x, *w, mode, pool_grid), iters, flush)
         t_b = None
         if bwd:
-            y = F.attention(x, *w, mode)
+            y = F.attention(x, *w, mode, pool_grid)
             t_b = time_cuda(lambda: torch.autograd.grad(y, [x] + w, dy, retain_graph=True), max(3, iters // 2), flush)
         return t_f, t_b
 
-    def attn_entry(name, B, N, C, t, bwd):
-        fl = attn_flops(B, N, C, bwd)
+    def attn_entry(name, B, N, C, t, bwd, Nk=None):
+        Nk = Nk or N
         d, dv = C // 8, C // 2
+        fl = attn_flops(B, N, C, bwd)
+        if Nk != N:      # down-sampled keys: the score-shaped terms scale with N * Nk, the projections stay
+            proj = 2 * B * N * C * (2 * d + dv) + 2 * B * N * dv * C
+            fl = (2 * B * N * Nk * (3 * d + 2 * dv) + 2 * proj) if bwd else (proj + 2 * B * N * Nk * (d + dv))
         return dict(bound="tensor", achieved=fl / t / 1e12, peak=pk["tc_burst"], unit="TFLOP/s",
                     frac=fl / t / 1e12 / pk["tc_burst"], traffic=_traffic(name), seconds=t,
-                    shape=f"B={B} N={N} C={C} (d={d}, dv={dv})", exps_per_s=B * N * N / t,
-                    mufu_frac=B * N * N / t / mufu_peak)
+                    shape=f"B={B} N={N} keys={Nk} C={C} (d={d}, dv={dv})", exps_per_s=B * N * Nk / t,
+                    mufu_frac=B * N * Nk / t / mufu_peak)
 
     B, N, C = 64, 4096, 16
     t_f, t_b = attn_case(B, N, C, math_mode, True, 10)
     out["attn_fwd"] = attn_entry("attn_fwd", B, N, C, t_f, False)
     out["attn_bwd"] = attn_entry("attn_bwd", B, N, C, t_b, True)
+    # the same block with down-sampled keys / values (2x2 / stride-2 max-pooled phi and g: 1024 keys), SURVEY.md §8f-2
+    t_f, t_b = attn_case(B, N, C, math_mode, True, 10, pool_grid=(64, 64))
+    out["attn_fwd_pooled"] = attn_entry("attn_fwd_pooled", B, N, C, t_f, False, Nk=N // 4)
+    out["attn_bwd_pooled"] = attn_entry("attn_bwd_pooled", B, N, C, t_b, True, Nk=N // 4)
     if math_mode == MATH_BF16_TC:
         B, N, C = 16, 4096, 512
         t_f, _ = attn_case(B, N, C, math_mode, False, 10)
@@ -273,20 +281,22 @@ def run_ours(args, rank, world, local_rank):
     math_mode = MATH_BF16_TC if args.math == "bf16_tc" else MATH_FP32_STRICT
     snn.set_default_math_mode(math_mode)
     cfg, metric, workload = CONFIGS[args.config]
-    cfg = dict(cfg, batch_size=args.batch or cfg["batch_size"])
+    cfg = dict(cfg, batch_size=args.batch or cfg["batch_size"], attn_downsample=args.attn_downsample)
     B, S = cfg["batch_size"], cfg["img_size"]
     n_records = 126227 if args.config == "church64" else 1281167           # LSUN church / ImageNet train set sizes
     tr = Trainer(cfg, global_batch_size=B * world, steps_per_epoch=n_records // (B * world), seed=0,
                  dp_mode=args.dp, overlap_streams=args.overlap)
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
-    host_batches = [torch.tensor(rng.uniform(-1, 1, (B, S, S, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
+    # the reference's input contract (sagan/dataset.py:27-40): raw uint8 HWC records, decoded as x * (2. / 255) - 1. --
+    # here on the device, as the first node of the step graph
+    host_batches = [torch.tensor(rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory() for _ in range(4)]
     dev_batches = [b.to(dev) for b in host_batches]
     use_label = bool(cfg.get("use_label"))
     host_labels = [torch.tensor(rng.integers(0, cfg["num_classes"], B)).pin_memory() if use_label else None for _ in range(4)]
     dev_labels = [None if l is None else l.to(dev) for l in host_labels]
 
     n0 = _lib.launch_count()
-    tr.capture(warmup=max(3, args.warmup))
+    tr.capture(warmup=max(3, args.warmup), uint8_input=True)
     # kernels launched while capturing == kernel nodes of this library in one replay of the step graph
     n_cap0 = _lib.launch_count()
     launches_per_step = None
@@ -378,8 +388,9 @@ def run_ours(args, rank, world, local_rank):
     out = {
         "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if math_mode == MATH_FP32_STRICT else "bf16", "data": "synthetic",
-        "config": {"workload": workload if B == CONFIGS[args.config][0]["batch_size"] else workload + f" [per-GPU batch {B}]",
+        "dtype": "f32" if math_mode == MATH_FP32_STRICT else "bf16", "data": "synthetic (uniform uint8 records)",
+        "config": {"workload": (workload if B == CONFIGS[args.config][0]["batch_size"] else workload + f" [per-GPU batch {B}]")
+                               + (" [attn_downsample: keys / values max-pooled 2x2 / stride 2]" if args.attn_downsample else ""),
                    "global_batch": B * world, "parallelism": f"dp{world}",
                    "math_mode": args.math, "conv_precision": "split-bf16 (3 MMAs per K step, fp32-grade)", "cuda_graph": True,
                    "step_graph": ("two branches: generator forwards on a side stream" if args.overlap
@@ -389,7 +400,8 @@ def run_ours(args, rank, world, local_rank):
                    "l2": f"no explicit flush: a step touches ~{act_mb:.0f} MB of saved activations (> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": sec_e2e / args.steps * 1e3,
-                "h2d_bytes_per_step": int(host_batches[0].numel() * 4 + (B * 8 if use_label else 0)),
+                "h2d_bytes_per_step": int(host_batches[0].numel() + (B * 8 if use_label else 0)),
+                "input": "raw uint8 records (sagan/dataset.py:27-40), decoded on the device inside the step graph",
                 "d2h_bytes_per_step": 8},
         "dp_status": dp_status, "replica_max_abs_diff": replica_diff,
         "gpu_launches": int(launches_per_step * args.steps),
@@ -411,6 +423,9 @@ def main():
     ap.add_argument("--config", default="church64", choices=sorted(CONFIGS),
                     help="church64 = BASELINE.json configs[1] (headline); cond128 = configs[3], 128x128 class-conditional")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's 64)")
+    ap.add_argument("--attn-downsample", action="store_true",
+                    help="down-sampled attention (keys / values max-pooled 2x2 / stride 2, layers.py:100,113); not the "
+                         "headline workload, whose attention is the oracle's un-pooled reading")
     ap.add_argument("--math", default="bf16_tc", choices=["fp32_strict", "bf16_tc"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="data-parallel gradient exchange (N > 1)")

@@ -216,6 +216,25 @@ int sagan_bn_lrelu_bwd(const float* dy, const float* x, const float* y, const fl
                        sagan_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Weight normalisation: the wrapper the `sagan/` tree actually wraps its layers with
+ * (sagan/layers.py:75-135, TF-Addons WeightNormalization under the name `SpectralNormalization`):
+ *   kernel = l2_normalize(v, all axes but the last) * g = v * rsqrt(max(sum_rows v^2, 1e-12)) * g      sagan/layers.py:124
+ * v, w, dw, dv: [rows, cols] row-major views of the Keras kernel (cols = its last, filter axis); g, dg: [cols].
+ * fwd writes w and inv_norm [cols] (kept for the backward); bwd: dot = sum_rows dw * v,
+ *   dv = g inv_norm (dw - v dot inv_norm^2),  dg = dot inv_norm.   dot_ws: [cols] scratch.
+ * The data-dependent initialisation (sagan/layers.py:159-194) is host logic over sagan_bn_lrelu_fwd's batch moments.
+ * ------------------------------------------------------------------------------------------ */
+int sagan_wn_fwd(const float* v, const float* g, float* w, float* inv_norm, int rows, int cols, sagan_stream_t stream);
+int sagan_wn_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg,
+                 float* dot_ws, int rows, int cols, sagan_stream_t stream);
+
+/* Input contract of the reference's record reader (sagan/dataset.py:27-40): a record is the raw uint8 HWC image (+ an
+ * int64 label); the reader feeds float32 NHWC `image * (2. / 255) - 1.`.  dst[i] = float(src[i]) * scale + shift as two
+ * separately rounded fp32 operations (bit-identical to the un-fused TF / numpy float32 arithmetic).  Lets a step take
+ * its batch as uint8 (4x fewer host -> device bytes) and decode it on the device. */
+int sagan_u8_to_f32(const uint8_t* src, float* dst, long long n, float scale, float shift, sagan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Hinge losses, sagan/main.py:21-27, with the scaling of main.py:184,201 folded in:
  *   D: L = relu(1 - d_real) + relu(1 + d_fake);   G: L = -d_fake
  * loss_sum[0] += sum(L) (caller zeroes it); gradients are d(scale * sum L)/d logits with

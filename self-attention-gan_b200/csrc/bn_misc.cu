@@ -266,6 +266,84 @@ __global__ void adam_schedule_kernel(float* __restrict__ hyper, long long* __res
   *iterations = it + 1;                                                        // optimizer.iterations
 }
 
+// ------------------------------------------------------------------------------------ weight normalisation
+// /root/reference/sagan/layers.py:75-135 (the TF-Addons WeightNormalization wrapper the `sagan/` tree wraps its layers
+// with): kernel = l2_normalize(v, all axes but the last) * g.  v is the [rows, cols] row-major view of the Keras kernel
+// (cols = the last, filter axis).  Two phases: per-column partial sums over row ranges (coalesced along the columns,
+// fp32 atomics into a zeroed [cols] vector), then one elementwise pass.
+constexpr int WN_COLS = 32, WN_ROWS_PER_CTA = 256;
+
+template <bool DOT>   // DOT = false: sum v^2 ; DOT = true: sum a * b
+__global__ void __launch_bounds__(256)
+wn_colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int rows, int cols) {
+  __shared__ float red[8][WN_COLS];
+  const int c = blockIdx.x * WN_COLS + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * WN_ROWS_PER_CTA, r1 = min(rows, r0 + WN_ROWS_PER_CTA);
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float x = a[(size_t)r * cols + c];
+      acc = fmaf(x, DOT ? b[(size_t)r * cols + c] : x, acc);
+    }
+  red[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// w = v * rsqrt(max(sumsq, 1e-12)) * g   (tf.nn.l2_normalize: epsilon = 1e-12 under the square root); inv_norm <- rsqrt(..)
+__global__ void __launch_bounds__(256)
+wn_apply_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ sumsq_to_inv,
+                float* __restrict__ w, long long n, int cols, const float* __restrict__ sumsq_ro) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = (int)(i % cols);
+    const float inv = rsqrtf(fmaxf(sumsq_ro[c], 1e-12f));
+    w[i] = v[i] * inv * g[c];
+  }
+  (void)sumsq_to_inv;
+}
+
+__global__ void wn_inv_kernel(float* __restrict__ sumsq, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < cols) sumsq[c] = rsqrtf(fmaxf(sumsq[c], 1e-12f));
+}
+
+// dv = g inv (dw - v dot inv^2), dg = dot inv     with dot[c] = sum_r dw[r,c] v[r,c]
+__global__ void __launch_bounds__(256)
+wn_bwd_apply_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
+                    const float* __restrict__ inv_norm, const float* __restrict__ dot, float* __restrict__ dv,
+                    float* __restrict__ dg, long long n, int cols) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = (int)(i % cols);
+    const float inv = inv_norm[c];
+    dv[i] = g[c] * inv * (dw[i] - v[i] * dot[c] * inv * inv);
+    if (i < cols) dg[i] = dot[i] * inv_norm[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------ uint8 records -> [-1, 1] floats
+// sagan/dataset.py:31-34: image = cast(decode_raw(uint8), float32) * (2. / 255) - 1.  (two separately rounded fp32 ops,
+// as the un-fused TF graph computes them: no FMA contraction, so the result is bit-identical to numpy float32)
+__global__ void __launch_bounds__(256)
+u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n, float scale, float shift) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const uchar4 u = *reinterpret_cast<const uchar4*>(src + i);
+      st4(dst + i, make_float4(__fadd_rn(__fmul_rn((float)u.x, scale), shift), __fadd_rn(__fmul_rn((float)u.y, scale), shift),
+                               __fadd_rn(__fmul_rn((float)u.z, scale), shift), __fadd_rn(__fmul_rn((float)u.w, scale), shift)));
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __fadd_rn(__fmul_rn((float)src[j], scale), shift);
+    }
+  }
+}
+
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace sagan
@@ -362,6 +440,46 @@ extern "C" int sagan_adam_schedule(float* hyper, long long* iterations, double l
   SAGAN_REQUIRE(hyper && iterations && decay_steps > 0 && lr0 > 0 && b2 > 0 && b2 < 1 && b1 >= 0 && b1 < 1,
                 "sagan_adam_schedule: bad argument");
   adam_schedule_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, iterations, lr0, decay_rate, decay_steps, b1, b2, eps);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_wn_fwd(const float* v, const float* g, float* w, float* inv_norm, int rows, int cols,
+                            sagan_stream_t stream) {
+  SAGAN_REQUIRE(v && g && w && inv_norm && rows > 0 && cols > 0, "sagan_wn_fwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAGAN_CUDA(cudaMemsetAsync(inv_norm, 0, sizeof(float) * cols, st));
+  wn_colreduce_kernel<false><<<dim3(ceil_div(cols, WN_COLS), ceil_div(rows, WN_ROWS_PER_CTA)), 256, 0, st>>>(v, nullptr, inv_norm, rows, cols);
+  SAGAN_LAUNCH_CHECK();
+  const long long n = (long long)rows * cols;
+  const int blocks = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(n, 256));
+  wn_apply_kernel<<<blocks, 256, 0, st>>>(v, g, nullptr, w, n, cols, inv_norm);
+  SAGAN_LAUNCH_CHECK();
+  wn_inv_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(inv_norm, cols);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_wn_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg,
+                            float* dot_ws, int rows, int cols, sagan_stream_t stream) {
+  SAGAN_REQUIRE(dw && v && g && inv_norm && dv && dg && dot_ws && rows > 0 && cols > 0, "sagan_wn_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAGAN_CUDA(cudaMemsetAsync(dot_ws, 0, sizeof(float) * cols, st));
+  wn_colreduce_kernel<true><<<dim3(ceil_div(cols, WN_COLS), ceil_div(rows, WN_ROWS_PER_CTA)), 256, 0, st>>>(dw, v, dot_ws, rows, cols);
+  SAGAN_LAUNCH_CHECK();
+  const long long n = (long long)rows * cols;
+  const int blocks = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(n, 256));
+  wn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dw, v, g, inv_norm, dot_ws, dv, dg, n, cols);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_u8_to_f32(const uint8_t* src, float* dst, long long n, float scale, float shift,
+                               sagan_stream_t stream) {
+  SAGAN_REQUIRE(src && dst && n > 0, "sagan_u8_to_f32: bad argument");
+  SAGAN_REQUIRE((((uintptr_t)src) & 3) == 0 && al16(dst), "sagan_u8_to_f32: src must be 4-byte, dst 16-byte aligned");
+  const int blocks = (int)std::min<long long>(num_sms() * 8, ceil_div<long long>(n, 1024));
+  u8_to_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n, scale, shift);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }

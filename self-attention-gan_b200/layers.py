@@ -16,6 +16,7 @@ from sagan_b200.nn import (  # noqa: F401
     SNConv2D,
     SNDense,
     SpectralNormalization,
+    WeightNormalization,
 )
 
 

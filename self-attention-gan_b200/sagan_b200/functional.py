@@ -437,3 +437,60 @@ def adam_schedule(hyper, iterations, lr0, decay_rate, decay_steps, b1, b2, eps):
     check(_lib.load().sagan_adam_schedule(_ptr(hyper), iterations.data_ptr(), float(lr0), float(decay_rate),
                                           int(decay_steps), float(b1), float(b2), float(eps), _stream()),
           "sagan_adam_schedule")
+
+
+# ------------------------------------------------------------------------------------ weight normalisation / records
+class _WeightNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, g):
+        lib = _lib.load()
+        cols = v.shape[-1]
+        rows = v.numel() // cols
+        w = torch.empty_like(v)
+        inv = torch.empty(cols, device=v.device, dtype=torch.float32)
+        check(lib.sagan_wn_fwd(_ptr(v), _ptr(g), _ptr(w), _ptr(inv), rows, cols, _stream()), "sagan_wn_fwd")
+        ctx.save_for_backward(v, g, inv)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        lib = _lib.load()
+        v, g, inv = ctx.saved_tensors
+        cols = v.shape[-1]
+        rows = v.numel() // cols
+        dv, dg, ws = torch.empty_like(v), torch.empty_like(g), torch.empty_like(g)
+        check(lib.sagan_wn_bwd(_ptr(dw.contiguous()), _ptr(v), _ptr(g), _ptr(inv), _ptr(dv), _ptr(dg), _ptr(ws), rows, cols,
+                               _stream()), "sagan_wn_bwd")
+        return dv, dg
+
+
+def weight_norm(v, g):
+    """sagan/layers.py:124: kernel = l2_normalize(v, all axes but the last) * g."""
+    return _WeightNormFn.apply(v.contiguous(), g.contiguous())
+
+
+def batch_moments(x, eps):
+    """Per-channel (last axis) mean and 1 / sqrt(var + eps) of x over all other axes (biased variance, tf.nn.moments)."""
+    lib = _lib.load()
+    x = x.contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    ones, zeros = torch.ones(Cc, device=x.device), torch.zeros(Cc, device=x.device)
+    y = torch.empty_like(x)
+    mean, invstd = torch.empty(Cc, device=x.device), torch.empty(Cc, device=x.device)
+    wsb = lib.sagan_bn_workspace_bytes(Cc)
+    ws = torch.empty(wsb // 4, device=x.device, dtype=torch.float32)
+    check(lib.sagan_bn_lrelu_fwd(_ptr(x), _ptr(ones), _ptr(zeros), _ptr(y), _ptr(mean), _ptr(invstd), None, None, rows, Cc,
+                                 float(eps), 0.0, 1.0, _ptr(ws), wsb, _stream()), "sagan_bn_lrelu_fwd")
+    return mean, invstd
+
+
+def decode_records(raw_u8, out=None):
+    """sagan/dataset.py:31-34: uint8 HWC records -> float32 in [-1, 1] (`x * (2. / 255) - 1.`), on the device."""
+    if not (raw_u8.is_cuda and raw_u8.dtype == torch.uint8 and raw_u8.is_contiguous()):
+        raise _lib.SaganError("decode_records expects a contiguous CUDA uint8 tensor")
+    if out is None:
+        out = torch.empty(raw_u8.shape, device=raw_u8.device, dtype=torch.float32)
+    check(_lib.load().sagan_u8_to_f32(raw_u8.data_ptr(), _ptr(out), raw_u8.numel(), 2.0 / 255, -1.0, _stream()),
+          "sagan_u8_to_f32")
+    return out

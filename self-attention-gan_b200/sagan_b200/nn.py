@@ -254,6 +254,61 @@ class SpectralNormalization(Layer):
         return self.module.call_with_kernel(x, w_bar)
 
 
+class WeightNormalization(Layer):
+    """sagan/layers.py:6-211: the weight-normalisation wrapper the `sagan/` tree ships (there under the NAME
+    `SpectralNormalization`): kernel = l2_normalize(v, all axes but the last) * g, with `v` the wrapped layer's kernel
+    and a trainable per-filter `g`.  On the first call g (and the layer's bias) are initialised from the data
+    (`data_init=True`, sagan/layers.py:159-194) or from ||v|| (sagan/layers.py:152-157)."""
+
+    def __init__(self, layer, data_init=True, **kwargs):
+        super().__init__()
+        if not isinstance(layer, Layer):
+            raise ValueError("Please initialize `WeightNormalization` layer with a `Layer` instance")
+        self.layer = layer
+        self.data_init = data_init
+        self._initialized = False
+
+    def build(self, input_shape):
+        if not self.layer.built:
+            self.layer.build(input_shape)                    # sagan/layers.py:57-58
+            self.layer.built = True
+        if getattr(self.layer, "kernel", None) is None:      # sagan/layers.py:62-64
+            raise ValueError("`WeightNormalization` must wrap a layer that contains a `kernel` for weights")
+        self.v = self.layer.kernel                           # sagan/layers.py:83
+        self.layer_depth = int(self.v.shape[-1])             # sagan/layers.py:72
+        self.g = torch.nn.Parameter(torch.ones(self.layer_depth, device=self.v.device))   # sagan/layers.py:75-82
+        self.built = True
+
+    @torch.no_grad()
+    def _initialize_weights(self, x):
+        if self.data_init:                                   # sagan/layers.py:159-194
+            act, slope = getattr(self.layer, "activation", ACT_NONE), getattr(self.layer, "leaky_slope", 0.0)
+            if hasattr(self.layer, "activation"):
+                self.layer.activation = ACT_NONE             # the naked clone has no activation (sagan/layers.py:104-105)
+            x_init = self.layer.call_with_kernel(x, self.v)
+            if hasattr(self.layer, "activation"):
+                self.layer.activation, self.layer.leaky_slope = act, slope
+            mean, scale = F.batch_moments(x_init, 1e-10)     # scale = 1 / sqrt(var + 1e-10)
+            self.g.mul_(scale)
+            if getattr(self.layer, "bias", None) is not None:
+                self.layer.bias.copy_(-mean * scale)
+        else:                                                # sagan/layers.py:152-157
+            self.g.copy_(self.v.reshape(-1, self.layer_depth).norm(dim=0))
+        self._initialized = True
+
+    def call(self, x):
+        if not self._initialized:                            # sagan/layers.py:109-121
+            self._initialize_weights(x)
+        kernel = F.weight_norm(self.v, self.g)               # sagan/layers.py:124
+        return self.layer.call_with_kernel(x, kernel)
+
+    def remove(self):
+        """sagan/layers.py:201-211: bake the normalised kernel into the wrapped layer and return it."""
+        with torch.no_grad():
+            self.layer.kernel.copy_(F.weight_norm(self.v, self.g))
+        return self.layer
+
+
 def SNConv2D(filters, kernel_size, strides=1, padding="valid", use_bias=True, activation=None, **sn_kwargs):
     """Name imported at sagan/models/discriminator.py:4 (never defined in the reference):
     spectrally-normalised Conv2D."""

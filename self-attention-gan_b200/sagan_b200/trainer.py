@@ -205,6 +205,8 @@ class Trainer:
         """Eager step.  images: device NHWC float32 in [-1,1] (sagan/dataset.py:34).  Noise may be injected
         (parity tests); otherwise it is drawn on the device (main.py:176,194).  Returns the device tensor
         [sum L_D, sum L_G]; see `losses()` for the reported means."""
+        if images.dtype == torch.uint8:          # raw records (sagan/dataset.py:31-34): decoded on the device
+            images = F.decode_records(images.contiguous())
         self._step_body(images, labels, noises_d, noise_g, fake_labels_d, fake_labels_g)
         return self.loss_sums
 
@@ -250,18 +252,22 @@ class Trainer:
                     ts += [m.moving_mean, m.moving_var]
         return ts
 
-    def capture(self, warmup=3, static_noise=False):
+    def capture(self, warmup=3, static_noise=False, uint8_input=False):
         """Capture the whole step (both phases, gradient exchange, LR schedule, Adam) into one CUDA graph.  Images (and
         labels) are read from static device buffers that `graph_step` refills.  The warm-up steps that CUDA-graph
         capture needs run on throw-away state: weights, optimiser state and counters, spectral-norm vectors, BatchNorm
         statistics and the device RNG are restored afterwards, so capturing does not train.
         static_noise=True additionally routes the latent noise (and fake labels) through static buffers
-        (`graph_step(noises_d=..., noise_g=...)`) instead of drawing them inside the graph."""
+        (`graph_step(noises_d=..., noise_g=...)`) instead of drawing them inside the graph.
+        uint8_input=True: the graph takes the batch as the reference's raw uint8 records (sagan/dataset.py:27-40) and
+        starts with the decode `x * (2. / 255) - 1.`; `graph_step` then expects uint8 images (4x fewer bytes to copy)."""
         cfg = self.config
         ur = cfg.get("update_ratio", 1)
         self._static["images"] = torch.zeros(self.B, cfg["img_size"], cfg["img_size"], 3, device=self.device)
         self._static["labels"] = (torch.zeros(self.B, dtype=torch.int64, device=self.device)
                                   if cfg.get("use_label") else None)
+        self._static["images_u8"] = (torch.full((self.B, cfg["img_size"], cfg["img_size"], 3), 128, dtype=torch.uint8,
+                                                device=self.device) if uint8_input else None)
         nz_d = nz_g = fl_d = fl_g = None
         if static_noise:
             nz_d = [torch.zeros(self.B, cfg["z_dim"], device=self.device) for _ in range(ur)]
@@ -287,6 +293,8 @@ class Trainer:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if uint8_input:
+                F.decode_records(self._static["images_u8"], out=self._static["images"])
             self._step_body(self._static["images"], self._static["labels"], nz_d, nz_g, fl_d, fl_g)
         return self.graph
 
@@ -298,7 +306,10 @@ class Trainer:
             raise RuntimeError("call capture() first")
         st = self._static
         if images is not None:
-            st["images"].copy_(images, non_blocking=True)
+            if (images.dtype == torch.uint8) != (st["images_u8"] is not None):
+                raise RuntimeError("graph_step: uint8 records need capture(uint8_input=True), float images need "
+                                   "capture(uint8_input=False)")
+            (st["images_u8"] if images.dtype == torch.uint8 else st["images"]).copy_(images, non_blocking=True)
         if labels is not None and st["labels"] is not None:
             st["labels"].copy_(labels, non_blocking=True)
         for given, key in ((noises_d, "noises_d"), (fake_labels_d, "fake_labels_d")):

@@ -467,6 +467,34 @@ def test_cuda_graph_step_equals_eager_step(mode_name):
         c.graph_step(img, noise_g=ng)
 
 
+def test_uint8_record_input_contract():
+    """SURVEY.md §8f row 4 / sagan/dataset.py:27-40: a step fed the raw uint8 records equals the step fed the decoded
+    float images (eager and captured graph), with sagan_deterministic_forward so that nothing but the input path differs."""
+    from sagan_b200 import _lib
+    from oracle import weightnorm as own
+    cfg = dict(mg.TEST_CFG, lr_g=1e-12, lr_d=1e-12)
+    B = cfg["batch_size"]
+    rng = np.random.Generator(np.random.PCG64(71))
+    raw = rng.integers(0, 256, (B, 64, 64, 3), dtype=np.uint8)
+    nd, ng = [cu(rng.standard_normal((B, 128)))], cu(rng.standard_normal((B, 128)))
+    _lib.load().sagan_deterministic_forward(1)
+    try:
+        a, b, c = (make_trainer(cfg, "bf16_tc", seed=6) for _ in range(3))
+        a.train_step(cu(own.decode_records(raw)), noises_d=nd, noise_g=ng)
+        b.train_step(torch.tensor(raw).cuda(), noises_d=nd, noise_g=ng)
+        c.capture(static_noise=True, uint8_input=True)
+        c.graph_step(torch.tensor(raw).pin_memory(), noises_d=nd, noise_g=ng)
+        la, lb, lc = a.losses(), b.losses(), c.losses()
+        for k in la:
+            assert abs(la[k] - lb[k]) < 1e-6 and abs(la[k] - lc[k]) < 1e-6, (k, la, lb, lc)
+        for t in (b, c):
+            assert float((a.D.flat_grads - t.D.flat_grads).norm() / a.D.flat_grads.norm()) < 1e-5
+        with pytest.raises(RuntimeError, match="uint8"):
+            c.graph_step(cu(own.decode_records(raw)))
+    finally:
+        _lib.load().sagan_deterministic_forward(0)
+
+
 @pytest.mark.parametrize("mode_name", MODES)
 def test_overlapped_step_equals_single_stream_step(mode_name):
     """The step whose generator forwards run as a side-stream branch (Trainer overlap_streams=True, the default and

@@ -205,3 +205,24 @@ def test_pooled_attention_oracle_matches_torch_autograd():
     # ... and reduce to it when every window holds four identical tokens
     Xr = np.repeat(np.repeat(X.reshape(B, H, W, C)[:, ::2, ::2], 2, axis=1), 2, axis=2).reshape(B, H * W, C)
     np.testing.assert_allclose(attention.forward_pooled(Xr, **w, hw=(H, W)), attention.forward(Xr, **w), rtol=1e-10, atol=1e-12)
+
+
+def test_weightnorm_oracle_gradients_and_record_decode():
+    """oracle.weightnorm (sagan/layers.py:124,152-194; sagan/dataset.py:31-34) against torch autograd / exact values."""
+    from oracle import weightnorm as own
+    rng = np.random.Generator(np.random.PCG64(5))
+    v, g, dw = rng.standard_normal((3, 3, 5, 7)), rng.uniform(0.5, 2, 7), rng.standard_normal((3, 3, 5, 7))
+    tv, tg = torch.tensor(v, requires_grad=True), torch.tensor(g, requires_grad=True)
+    w = tv / tv.pow(2).sum(dim=(0, 1, 2), keepdim=True).clamp_min(1e-12).sqrt() * tg
+    w.backward(torch.tensor(dw))
+    dv, dg = own.backward(dw, v, g)
+    assert rel(own.kernel_from_vg(v, g), w.detach().numpy()) < 1e-14
+    assert rel(dv, tv.grad.numpy()) < 1e-13 and rel(dg, tg.grad.numpy()) < 1e-13
+    assert rel(own.kernel_from_vg(v, own.init_norm(v)), v) < 1e-14            # g = ||v|| reproduces v
+    x = rng.standard_normal((4, 6, 6, 7)) * 3 + 2
+    g2, b2 = own.data_dep_init(x, np.ones(7), np.zeros(7))
+    z = x * g2 + b2
+    assert np.abs(z.mean((0, 1, 2))).max() < 1e-12 and np.abs(z.std((0, 1, 2)) - 1).max() < 1e-8
+    raw = np.arange(256, dtype=np.uint8)
+    dec = own.decode_records(raw)
+    assert dec.dtype == np.float32 and dec[0] == -1.0 and abs(dec[255] - 1.0) < 1e-6 and np.all(np.diff(dec) > 0)
