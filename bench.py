@@ -46,6 +46,11 @@ CONFIGS = {
                 "128x128 class-conditional SAGAN train step (1000 classes, attention at 32x32 and 64x64), per-GPU batch "
                 "64, 128x128x3, synthetic"),
 }
+# the reference's legacy program (/root/reference/main.py + models/): 128x128 class-conditional RESIDUAL SAGAN, attention at 32x32
+RES128 = dict(COND128, model="resnet", attn_dim_G=[32])
+CONFIGS["res128"] = (RES128, "sagan_train_images_per_sec_128x128_resnet",
+                     "128x128 class-conditional residual SAGAN train step (models/generator.py:23, models/discriminator.py:40; "
+                     "1000 classes, attention at 32x32), per-GPU batch 64, synthetic")
 UNIT = "images/s"
 
 
@@ -130,6 +135,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cfg, metric, workload = CONFIGS[args.config]
+    if args.config == "res128":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU oracle trainer restates the vanilla train step only"}))
+        return
     # one full-batch CPU step takes seconds: the step COUNT is bounded so the run ends within minutes, the batch is not
     steps = max(1, min(args.steps, 8 if args.config == "church64" else 2))
     base, dt = cpu_oracle_images_per_sec(cfg, steps, 1)
@@ -379,7 +387,7 @@ def run_ours(args, rank, world, local_rank):
                          "the in-model dims (d=2, dv=8: 20 useful FLOPs per score against one exp2) the MUFU pipe is the "
                          "binding unit: mufu_frac = exps_per_s / (148 SMs x 16 ex2/clk x 1.965 GHz).  The tensor-bound "
                          "regime is kernels.attn_fwd_C512.")
-    if args.cpu_baseline:
+    if args.cpu_baseline and args.config != "res128":      # the CPU oracle trainer restates the vanilla step only
         cpu, _ = cpu_oracle_images_per_sec(dict(CONFIGS[args.config][0]), 4 if args.config == "church64" else 1, 1)
     else:
         cpu = None
@@ -421,7 +429,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="church64", choices=sorted(CONFIGS),
-                    help="church64 = BASELINE.json configs[1] (headline); cond128 = configs[3], 128x128 class-conditional")
+                    help="church64 = BASELINE.json configs[1] (headline); cond128 = configs[3], 128x128 class-conditional; "
+                         "res128 = the legacy residual 128x128 program")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's 64)")
     ap.add_argument("--attn-downsample", action="store_true",
                     help="down-sampled attention (keys / values max-pooled 2x2 / stride 2, layers.py:100,113); not the "

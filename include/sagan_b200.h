@@ -199,6 +199,15 @@ int sagan_conv_tc_precision(int set);
 int sagan_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, float slope,
                   sagan_stream_t stream);
 
+/* Elementwise glue of the residual topologies (models/generator.py:6-21,
+ * models/discriminator.py:6-38): y[i] = act(a[i] + bias[i % C] + residual[i]); bias and residual may be NULL.
+ * Covers the stand-alone ReLU / LeakyReLU in front of a conv, the bias of a Conv2DTranspose and `layers.add`.
+ * Backward: sagan_act_bwd on y, then the gradient passes to a / residual unchanged and sagan_colsum gives d bias. */
+int sagan_ew_fwd(const float* a, const float* bias, const float* residual, float* y, long long n, int C,
+                 int act, float slope, sagan_stream_t stream);
+/* out[c] = sum_r x[r, c]  (x [rows, C]; out is overwritten) */
+int sagan_colsum(const float* x, float* out, long long rows, int C, sagan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * BatchNormalization(training) + LeakyReLU, generator.py:10-11.  x, y: [rows, C] (NHWC flattened).
  * Batch statistics are per replica (plain BatchNormalization, not SyncBN).  save_mean/save_invstd [C]

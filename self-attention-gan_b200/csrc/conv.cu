@@ -509,6 +509,23 @@ static int make_geom(const sagan_conv_geom* s, CG* g, const char* who) {
   return 0;
 }
 
+// y = act(a + b[c] (bias, may be null) + r (residual, may be null)): stand-alone ReLU / LeakyReLU (the pre-activation
+// blocks of /root/reference/models/discriminator.py:24-36), bias of a Conv2DTranspose (models/generator.py:11) and
+// `layers.add` of the residual blocks (models/generator.py:21, models/discriminator.py:17,38)
+__global__ void __launch_bounds__(256)
+ew_fwd_kernel(const float* __restrict__ a, const float* __restrict__ bias, const float* __restrict__ r,
+              float* __restrict__ y, long long n, int C, int act, float slope) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = a[i];
+    if (bias) v += bias[(int)(i % C)];
+    if (r) v += r[i];
+    if (act == SAGAN_ACT_LRELU) v = v > 0.f ? v : v * slope;
+    else if (act == SAGAN_ACT_TANH) v = tanhf(v);
+    y[i] = v;
+  }
+}
+
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace sagan
@@ -606,6 +623,25 @@ extern "C" int sagan_act_bwd(const float* y, const float* dy, float* dz, long lo
   SAGAN_REQUIRE(al16(y) && al16(dy) && al16(dz), "sagan_act_bwd: pointers must be 16-byte aligned");
   const int blocks = (int)std::min<long long>(num_sms() * 8, ceil_div<long long>(n, 1024));
   act_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, dy, dz, n, act, slope);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_ew_fwd(const float* a, const float* bias, const float* residual, float* y, long long n, int C,
+                            int act, float slope, sagan_stream_t stream) {
+  SAGAN_REQUIRE(a && y && n > 0 && (!bias || C > 0), "sagan_ew_fwd: bad argument");
+  const int blocks = (int)std::min<long long>(num_sms() * 8, ceil_div<long long>(n, 256));
+  ew_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, bias, residual, y, n, bias ? C : 1, act, slope);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_colsum(const float* x, float* out, long long rows, int C, sagan_stream_t stream) {
+  SAGAN_REQUIRE(x && out && rows > 0 && C > 0, "sagan_colsum: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAGAN_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
+  const int rows_per_block = (int)std::max<long long>(64, ceil_div<long long>(rows, num_sms() * 2));
+  colsum_kernel<<<(unsigned)ceil_div<long long>(rows, rows_per_block), 256, 0, st>>>(x, out, rows, C, rows_per_block);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -13,6 +13,9 @@ from sagan_b200.nn import (  # noqa: F401
     Conv2D,
     Conv2DTranspose,
     Dense,
+    Embedding,
+    LeakyReLU,
+    ReLU,
     SNConv2D,
     SNDense,
     SpectralNormalization,

@@ -69,6 +69,8 @@ SIGNATURES = {
     "sagan_conv2d_wgrad": (_I, [_P, _P, _P, _P, C.POINTER(ConvGeom), _I, _P]),
     "sagan_conv_tc_precision": (_I, [_I]),
     "sagan_act_bwd": (_I, [_P, _P, _P, _LL, _I, _F, _P]),
+    "sagan_ew_fwd": (_I, [_P, _P, _P, _P, _LL, _I, _I, _F, _P]),
+    "sagan_colsum": (_I, [_P, _P, _LL, _I, _P]),
     "sagan_bn_workspace_bytes": (_SZ, [_I]),
     "sagan_bn_lrelu_fwd": (_I, [_P] * 8 + [_LL, _I, _F, _F, _F, _P, _SZ, _P]),
     "sagan_bn_lrelu_bwd": (_I, [_P] * 9 + [_LL, _I, _F, _P, _SZ, _P]),

@@ -494,3 +494,49 @@ def decode_records(raw_u8, out=None):
     check(_lib.load().sagan_u8_to_f32(raw_u8.data_ptr(), _ptr(out), raw_u8.numel(), 2.0 / 255, -1.0, _stream()),
           "sagan_u8_to_f32")
     return out
+
+
+# ------------------------------------------------------------------------------------ elementwise glue (residual nets)
+class _EwFn(torch.autograd.Function):
+    """y = act(a + bias[c] + residual)."""
+
+    @staticmethod
+    def forward(ctx, a, bias, residual, act, slope):
+        lib = _lib.load()
+        y = torch.empty_like(a)
+        Cc = a.shape[-1]
+        check(lib.sagan_ew_fwd(_ptr(a), _ptr(bias), _ptr(residual), _ptr(y), a.numel(), Cc, act, slope, _stream()),
+              "sagan_ew_fwd")
+        ctx.save_for_backward(y if act != ACT_NONE else None)
+        ctx.act, ctx.slope, ctx.C = act, slope, Cc
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            check(lib.sagan_act_bwd(_ptr(y), _ptr(dy), _ptr(dz), dy.numel(), ctx.act, ctx.slope, _stream()), "sagan_act_bwd")
+            dy = dz
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            db = torch.empty(ctx.C, device=dy.device, dtype=torch.float32)
+            check(lib.sagan_colsum(_ptr(dy), _ptr(db), dy.numel() // ctx.C, ctx.C, _stream()), "sagan_colsum")
+        return dy, db, (dy if ctx.has_res else None), None, None
+
+
+def activation(x, act=ACT_LRELU, slope=0.0):
+    """Stand-alone ReLU (slope 0) / LeakyReLU / tanh."""
+    return _EwFn.apply(x.contiguous(), None, None, act, float(slope))
+
+
+def bias_add(x, bias, act=ACT_NONE, slope=0.0):
+    return _EwFn.apply(x.contiguous(), bias, None, act, float(slope))
+
+
+def add(a, b):
+    """keras `layers.add([a, b])`."""
+    return _EwFn.apply(a.contiguous(), None, b.contiguous(), ACT_NONE, 0.0)

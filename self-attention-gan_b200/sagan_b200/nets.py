@@ -267,6 +267,173 @@ class Discriminator(Network):
         return out
 
 
+# ------------------------------------------------------------------------------------------------ residual topologies
+class ResGBlock(torch.nn.Module):
+    """/root/reference/models/generator.py:6-21: BN -> ReLU -> SN(Conv2DTranspose(c,3,2,'same')) -> BN -> ReLU ->
+    SN(Conv2D(c,3,1,'same')), plus the shortcut SN(Conv2DTranspose(c,3,2,'same')) of the block INPUT."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.pre_bn = nn.BatchNormalization(leaky_slope=0.0)                                        # :7-8 (BN + ReLU fused)
+        self.deconv1 = nn.SpectralNormalization(nn.Conv2DTranspose(c, 3, 2, padding="same"))        # :11-12
+        self.mid_bn = nn.BatchNormalization(leaky_slope=0.0)                                        # :13-14
+        self.conv2 = nn.SpectralNormalization(nn.Conv2D(c, 3, 1, padding="same"))                   # :15-16
+        self.deconv_sc = nn.SpectralNormalization(nn.Conv2DTranspose(c, 3, 2, padding="same"))      # :18-19
+
+    def forward(self, x):
+        h = self.conv2(self.mid_bn(self.deconv1(self.pre_bn(x))))
+        return nn.add([self.deconv_sc(x), h])                                                       # :21
+
+
+class ResGenerator(Network):
+    """/root/reference/models/generator.py:23-43 (class-conditional; block count from img_size, 5 at 128x128)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        gf = config["gf_dim"]
+        self.power = int(np.log2(config["img_size"] / 4))
+        self.dense = nn.SpectralNormalization(nn.Dense(4 * 4 * gf * 2 ** (self.power - 1)))         # :28
+        self.blocks = torch.nn.ModuleList()
+        self.attn = torch.nn.ModuleDict()
+        size = 4
+        for i in range(self.power):
+            self.blocks.append(ResGBlock(gf * 2 ** (self.power - 1 - i)))                           # :31-37
+            size *= 2
+            if size in config.get("attn_dim_G", [32]):                                              # :34 (32x32)
+                self.attn[str(i)] = nn.Attention_Layer(pool=_attn_pool(config))
+        self.final_bn = nn.BatchNormalization(leaky_slope=0.0)                                      # :39-40
+        self.final_conv = nn.SpectralNormalization(nn.Conv2D(3, 3, 1, padding="same", activation="tanh"))   # :41-42
+
+    def forward(self, inputs, training=True):
+        z, labels = inputs
+        cfg = self.config
+        onehot = torch.nn.functional.one_hot(labels.long(), cfg["num_classes"]).to(z.dtype)         # :26
+        x = torch.cat([z, onehot], dim=1).contiguous()                                              # :27
+        if self.finalized:
+            self._normalise_all(training)
+        x = self.dense(x)
+        x = x.reshape(-1, 4, 4, x.shape[1] // 16)                                                   # :29
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            if str(i) in self.attn:
+                x = self.attn[str(i)](x)
+        out = self.final_conv(self.final_bn(x))
+        if not self.finalized:
+            self.finalize()
+        return out
+
+    def named_parameters_by_oracle_name(self):
+        out = [("dense.kernel", self.dense.module.kernel), ("dense.bias", self.dense.module.bias)]
+        for i, b in enumerate(self.blocks):
+            out += [(f"block{i}.pre.bn.gamma", b.pre_bn.gamma), (f"block{i}.pre.bn.beta", b.pre_bn.beta),
+                    (f"block{i}.deconv1.kernel", b.deconv1.module.kernel), (f"block{i}.deconv1.bias", b.deconv1.module.bias),
+                    (f"block{i}.mid.bn.gamma", b.mid_bn.gamma), (f"block{i}.mid.bn.beta", b.mid_bn.beta),
+                    (f"block{i}.conv2.kernel", b.conv2.module.kernel), (f"block{i}.conv2.bias", b.conv2.module.bias),
+                    (f"block{i}.deconv_sc.kernel", b.deconv_sc.module.kernel), (f"block{i}.deconv_sc.bias", b.deconv_sc.module.bias)]
+            if str(i) in self.attn:
+                out += _attn_names(f"block{i}.attn", self.attn[str(i)])
+        out += [("final.bn.gamma", self.final_bn.gamma), ("final.bn.beta", self.final_bn.beta),
+                ("final.conv.kernel", self.final_conv.module.kernel), ("final.conv.bias", self.final_conv.module.bias)]
+        return out
+
+    def sn_by_oracle_name(self):
+        out = [("dense.u", self.dense)]
+        for i, b in enumerate(self.blocks):
+            out += [(f"block{i}.deconv1.u", b.deconv1), (f"block{i}.conv2.u", b.conv2), (f"block{i}.deconv_sc.u", b.deconv_sc)]
+            if str(i) in self.attn:
+                out += _attn_sn(f"block{i}.attn", self.attn[str(i)])
+        out.append(("final.conv.u", self.final_conv))
+        return out
+
+
+class ResDBlock(torch.nn.Module):
+    """/root/reference/models/discriminator.py:19-38 (`first=True`: Optimized_Block, :6-17, no activation on the image)."""
+
+    def __init__(self, c, downsample=True, first=False):
+        super().__init__()
+        s = 2 if downsample else 1
+        self.first = first
+        self.relu = nn.ReLU()
+        self.conv1 = nn.SpectralNormalization(nn.Conv2D(c, 3, 1, padding="same", leaky_slope=0.0))   # conv + the ReLU that follows
+        self.conv2 = nn.SpectralNormalization(nn.Conv2D(c, 3, s, padding="same"))
+        self.conv_sc = nn.SpectralNormalization(nn.Conv2D(c, 3, s, padding="same"))
+
+    def forward(self, x):
+        a = x if self.first else self.relu(x)                                                       # :22, :32
+        return nn.add([self.conv_sc(a), self.conv2(self.conv1(a))])                                 # :17, :36
+
+
+class ResDiscriminator(Network):
+    """/root/reference/models/discriminator.py:40-57: projection discriminator with a spectrally-normalised Embedding."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        df = config["df_dim"]
+        self.power = int(np.log2(config["img_size"] / 4))
+        self.opt = ResDBlock(df, first=True)                                                        # :44
+        chans = [df * 2 ** p for p in range(1, self.power)] + [df * 2 ** (self.power - 1)]          # :45-51
+        self.blocks = torch.nn.ModuleList()
+        self.attn = torch.nn.ModuleDict()
+        size = config["img_size"] // 2
+        for i, c in enumerate(chans):
+            last = i == len(chans) - 1
+            self.blocks.append(ResDBlock(c, downsample=not last))
+            if not last:
+                size //= 2
+                if size in config.get("attn_dim_G", [32]):                                          # :46 (32x32)
+                    self.attn[str(i)] = nn.Attention_Layer(pool=_attn_pool(config))
+        self.relu = nn.ReLU()
+        self.head_dense = nn.SpectralNormalization(nn.Dense(1))                                     # :52
+        self.embedding = nn.SpectralNormalization(nn.Embedding(config["num_classes"], chans[-1]))   # :53-54
+
+    def forward(self, inputs, training=True):
+        img, labels = inputs
+        if self.finalized:
+            self._normalise_all(training)
+        x = self.opt(img)
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            if str(i) in self.attn:
+                x = self.attn[str(i)](x)
+        h = self.relu(x).sum(dim=(1, 2))                                                            # :49-50
+        out = self.head_dense(h) + torch.sum(h * self.embedding(labels), dim=1, keepdim=True)       # :52-55
+        if not self.finalized:
+            self.finalize()
+        return out
+
+    def named_parameters_by_oracle_name(self):
+        out = []
+        for nm, b in [("opt", self.opt)] + [(f"block{i}", b) for i, b in enumerate(self.blocks)]:
+            out += [(f"{nm}.conv1.kernel", b.conv1.module.kernel), (f"{nm}.conv1.bias", b.conv1.module.bias),
+                    (f"{nm}.conv2.kernel", b.conv2.module.kernel), (f"{nm}.conv2.bias", b.conv2.module.bias),
+                    (f"{nm}.conv_sc.kernel", b.conv_sc.module.kernel), (f"{nm}.conv_sc.bias", b.conv_sc.module.bias)]
+            if nm != "opt" and nm[5:] in self.attn:
+                out += _attn_names(f"{nm}.attn", self.attn[nm[5:]])
+        out += [("head.dense.kernel", self.head_dense.module.kernel), ("head.dense.bias", self.head_dense.module.bias),
+                ("head.embedding", self.embedding.module.kernel)]
+        return out
+
+    def sn_by_oracle_name(self):
+        out = []
+        for nm, b in [("opt", self.opt)] + [(f"block{i}", b) for i, b in enumerate(self.blocks)]:
+            out += [(f"{nm}.conv1.u", b.conv1), (f"{nm}.conv2.u", b.conv2), (f"{nm}.conv_sc.u", b.conv_sc)]
+            if nm != "opt" and nm[5:] in self.attn:
+                out += _attn_sn(f"{nm}.attn", self.attn[nm[5:]])
+        out += [("head.dense.u", self.head_dense), ("head.embedding.u", self.embedding)]
+        return out
+
+
+def get_res_generator(config):
+    """The residual generator of /root/reference/models/generator.py:23 on the config dict of the `sagan/` tree
+    (`model: 'resnet'`, sagan/main.py:104-107 -- disabled there with "TODO: fix resnet model")."""
+    return ResGenerator(config)
+
+
+def get_res_discriminator(config):
+    """/root/reference/models/discriminator.py:40."""
+    return ResDiscriminator(config)
+
+
 def get_generator(config):
     """generator.py:14.  Returns a callable model: model([z, labels], training=True) -> images NHWC."""
     return Generator(config)

@@ -106,9 +106,10 @@ class Conv2DTranspose(Layer):
         self.filters, self.kernel_size = int(filters), (int(ks[0]), int(ks[1]))
         self.strides = int(strides[0] if isinstance(strides, (tuple, list)) else strides)
         self.padding = padding
-        if use_bias or activation is not None:
-            raise ValueError("Conv2DTranspose: only use_bias=False, activation=None is built "
-                             "(the form used at sagan/models/generator.py:8)")
+        if activation is not None:
+            raise ValueError("Conv2DTranspose: only activation=None is built "
+                             "(the forms used at sagan/models/generator.py:8 and models/generator.py:11,18)")
+        self.use_bias = use_bias
         self.math_mode = _DEFAULT_MATH[0] if math_mode is None else math_mode
         self.kernel = self.bias = None
 
@@ -118,10 +119,13 @@ class Conv2DTranspose(Layer):
         # Keras kernel layout [kh, kw, cout, cin]
         k = _glorot_uniform((kh, kw, self.filters, cin), cin * kh * kw, self.filters * kh * kw)
         self.kernel = torch.nn.Parameter(k.to(_device()))
+        if self.use_bias:
+            self.bias = torch.nn.Parameter(torch.zeros(self.filters, device=_device()))
         self.built = True
 
     def call_with_kernel(self, x, kernel):
-        return F.conv2d_transpose(x, kernel, self.strides, self.padding, self.math_mode)
+        y = F.conv2d_transpose(x, kernel, self.strides, self.padding, self.math_mode)
+        return F.bias_add(y, self.bias) if self.bias is not None else y
 
     def call(self, x):
         return self.call_with_kernel(x, self.kernel)
@@ -321,14 +325,51 @@ def SNDense(units, use_bias=True, **sn_kwargs):
 
 
 class LeakyReLU(Layer):
-    """Stand-alone LeakyReLU(alpha); inside the builders it is fused into the producing kernel."""
+    """Stand-alone LeakyReLU(alpha) (the pre-activation blocks of models/discriminator.py:22-34); inside the vanilla
+    builders it is fused into the producing kernel instead."""
 
     def __init__(self, alpha=0.3):
         super().__init__()
         self.alpha = float(alpha)
 
     def call(self, x):
-        raise NotImplementedError("use the fused forms: Conv2D+LeakyReLU (nets.DBlock) / BatchNormalization(leaky_slope=)")
+        return F.activation(x, ACT_LRELU, self.alpha)
+
+
+class ReLU(LeakyReLU):
+    def __init__(self):
+        super().__init__(0.0)
+
+
+def add(tensors):
+    """keras `layers.add([a, b])` (models/generator.py:21, models/discriminator.py:17,38)."""
+    a, b = tensors
+    return F.add(a, b)
+
+
+class Embedding(Layer):
+    """keras Embedding(input_dim, output_dim): `kernel` = the [input_dim, output_dim] table (weights[0], what
+    SpectralNormalization normalises at models/discriminator.py:53-54); the lookup itself is a gather."""
+
+    def __init__(self, input_dim, output_dim):
+        super().__init__()
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.kernel = self.bias = None
+
+    def build(self, input_shape=None):
+        self.kernel = torch.nn.Parameter((torch.rand(self.input_dim, self.output_dim) * 0.1 - 0.05).to(_device()))
+        self.built = True
+
+    def forward(self, labels, *args, **kwargs):
+        if not self.built:
+            self.build()
+        return self.call(labels, *args, **kwargs)
+
+    def call_with_kernel(self, labels, kernel):
+        return kernel.index_select(0, labels.long())
+
+    def call(self, labels):
+        return self.call_with_kernel(labels, self.kernel)
 
 
 class Attention_Layer(Layer):

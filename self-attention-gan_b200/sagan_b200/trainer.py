@@ -83,8 +83,12 @@ class Trainer:
         self.dp_mode = dp_mode if self.world > 1 else "none"
         if self.dp_mode == "p2p":
             nets.set_flat_allocator(symmetric_allocator())
-        self.G = nets.get_generator(cfg)
-        self.D = nets.get_discriminator(cfg)
+        if cfg.get("model", "vanilla") == "resnet":      # sagan/main.py:101-107 (the branch the reference left disabled)
+            if not cfg.get("use_label"):
+                raise ValueError("the residual topologies are class-conditional (models/generator.py:25): set use_label")
+            self.G, self.D = nets.get_res_generator(cfg), nets.get_res_discriminator(cfg)
+        else:
+            self.G, self.D = nets.get_generator(cfg), nets.get_discriminator(cfg)
         with torch.no_grad():   # build pass (Keras `model.build`, main.py:134-135)
             z = torch.zeros(self.B, cfg["z_dim"], device=self.device)
             lab = torch.zeros(self.B, dtype=torch.int64, device=self.device) if cfg.get("use_label") else None

@@ -467,6 +467,136 @@ def test_cuda_graph_step_equals_eager_step(mode_name):
         c.graph_step(img, noise_g=ng)
 
 
+# ---------------------------------------------------------------------------------------- residual topologies
+RES_CFG = dict(model="resnet", z_dim=16, gf_dim=8, df_dim=8, img_size=32, num_classes=6, use_label=True, use_attention=True,
+               attn_dim_G=[16], batch_size=2, lr_g=2e-4, lr_d=7e-4, decay_rate=0.99, update_ratio=1)
+
+
+def _res_pair(cfg, mode_name, seed=0):
+    """Oracle parameters / spectral-norm state and GPU residual networks holding the same values."""
+    from oracle import resnets as ores
+    from sagan_b200 import nets as gnets
+    from sagan_b200 import nn as snn
+    gs, ds = ores.res_generator_spec(cfg), ores.res_discriminator_spec(cfg)
+    pg = onets.init_params(gs, seed, torch.float64, attn_sigma=0.3, bias_scale=0.05)
+    pd = onets.init_params(ds, seed + 100, torch.float64, attn_sigma=0.3, bias_scale=0.05)
+    sg, sd = ores.init_res_sn_state(gs, seed + 1), ores.init_res_sn_state(ds, seed + 101)
+    snn.set_default_math_mode(_math(mode_name))
+    try:
+        G, D = gnets.get_res_generator(cfg), gnets.get_res_discriminator(cfg)
+        B = cfg["batch_size"]
+        with torch.no_grad():       # build pass
+            lab = torch.zeros(B, dtype=torch.int64, device="cuda")
+            D([G([torch.zeros(B, cfg["z_dim"], device="cuda"), lab]), lab])
+    finally:
+        snn.set_default_math_mode(_math("fp32_strict"))
+    G.load_keras_weights({k: v.numpy() for k, v in pg.items()}, {k: v.numpy() for k, v in sg.items()})
+    D.load_keras_weights({k: v.numpy() for k, v in pd.items()}, {k: v.numpy() for k, v in sd.items()})
+    return (pg, sg, pd, sd), (G, D)
+
+
+def test_resnet_inventory_and_reference_shapes():
+    """The reference's own tests for these models assert output SHAPES: [B,128,128,3] (test/test_generator.py:26) and
+    [B,1] (test/test_discriminator.py:28).  Same here at the reference's size, plus the parameter inventory against the
+    oracle's restatement of models/generator.py:23-43 / models/discriminator.py:40-57."""
+    from oracle import resnets as ores
+    from sagan_b200 import nets as gnets
+    cfg = dict(RES_CFG, img_size=128, gf_dim=16, df_dim=16, z_dim=128, num_classes=10, attn_dim_G=[32])
+    G, D = gnets.get_res_generator(cfg), gnets.get_res_discriminator(cfg)
+    B = 2
+    lab = torch.tensor([3, 7], device="cuda")
+    with torch.no_grad():
+        img = G([torch.randn(B, 128, device="cuda"), lab])
+        out = D([img, lab])
+    assert tuple(img.shape) == (B, 128, 128, 3) and tuple(out.shape) == (B, 1)
+    assert float(img.abs().max()) <= 1.0
+    assert {k: tuple(v.shape) for k, v in G.named_parameters_by_oracle_name()} == dict(ores.res_generator_spec(cfg))
+    assert {k: tuple(v.shape) for k, v in D.named_parameters_by_oracle_name()} == dict(ores.res_discriminator_spec(cfg))
+    assert [k for k, _ in G.sn_by_oracle_name()] == list(ores.res_sn_keys(ores.res_generator_spec(cfg)))
+    assert [k for k, _ in D.sn_by_oracle_name()] == list(ores.res_sn_keys(ores.res_discriminator_spec(cfg)))
+    assert len(G.attn) == 1 and len(D.attn) == 1          # attention at 32x32 only (models/generator.py:34, discriminator.py:42)
+
+
+@pytest.mark.parametrize("mode_name", MODES)
+def test_resnet_forward_and_gradients_vs_oracle(mode_name):
+    """Residual G / D (3x3 SN convs, Conv2DTranspose(3,2) with bias, BN + ReLU, residual adds, attention, projection head
+    with SN Embedding) against the fp64 oracle: D(real) logits and all D gradients, D(G(z)) and all G gradients."""
+    from oracle import resnets as ores
+    cfg = dict(RES_CFG)
+    (pg, sg, pd, sd), (G, D) = _res_pair(cfg, mode_name)
+    B = cfg["batch_size"]
+    rng = np.random.Generator(np.random.PCG64(81))
+    img = rng.uniform(-1, 1, (B, 32, 32, 3))
+    z = rng.standard_normal((B, cfg["z_dim"]))
+    lab, flab = np.array([1, 4]), np.array([5, 0])
+    cot = rng.standard_normal((B, 1))
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    # ---- oracle
+    for v in pd.values():
+        v.requires_grad_(True)
+    d_real_ref = ores.res_discriminator_forward(pd, sd, t64(img), torch.tensor(lab), cfg, True)
+    dg_ref = dict(zip(pd.keys(), torch.autograd.grad((d_real_ref * t64(cot)).sum(), list(pd.values()))))
+    for v in pd.values():
+        v.requires_grad_(False)
+    for v in pg.values():
+        v.requires_grad_(True)
+    fake_ref = ores.res_generator_forward(pg, sg, t64(z), torch.tensor(flab), cfg, True, None)
+    d_fake_ref = ores.res_discriminator_forward(pd, sd, fake_ref, torch.tensor(flab), cfg, True)
+    gg_ref = dict(zip(pg.keys(), torch.autograd.grad((d_fake_ref * t64(cot)).sum(), list(pg.values()))))
+    # ---- GPU
+    D.zero_grad_flat()
+    d_real = D([cu(img), torch.tensor(lab).cuda()], training=True)
+    d_real.backward(cu(cot))
+    torch.cuda.synchronize()
+    strict = mode_name == "fp32_strict"
+    tol_f, tol_g = (1e-5, 2e-4) if strict else (2e-4, 1e-2)       # measured 1.0e-6 / 7.6e-4
+    assert rel_l2(d_real.detach().cpu().numpy(), d_real_ref.detach().numpy()) < tol_f
+    def grad_errs(tag, net, ref):
+        """Biases that feed a BatchNormalization (models/generator.py:11-13: the batch mean removes them) and the attention
+        key bias have an exactly-zero gradient: the computed value is rounding noise and is only bounded."""
+        out = {}
+        for k, p in net.named_parameters_by_oracle_name():
+            r, g = ref[k].numpy(), p.grad.cpu().numpy()
+            if np.linalg.norm(r) < 1e-9 * max(1.0, np.sqrt(r.size)):
+                assert np.linalg.norm(g) < 1e-4, (k, np.linalg.norm(g))
+                continue
+            out[tag + k] = rel_l2(g, r)
+        return out
+
+    errs = grad_errs("D.", D, dg_ref)
+    G.zero_grad_flat()
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake = G([cu(z), torch.tensor(flab).cuda()], training=True)
+    d_fake = D([fake, torch.tensor(flab).cuda()], training=True)
+    d_fake.backward(cu(cot))
+    torch.cuda.synchronize()
+    assert rel_l2(fake.detach().cpu().numpy(), fake_ref.detach().numpy()) < tol_f
+    assert rel_l2(d_fake.detach().cpu().numpy(), d_fake_ref.detach().numpy()) < tol_f
+    errs.update(grad_errs("G.", G, gg_ref))
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print("resnet", mode_name, "worst gradient rel-L2 %.2e at %s, median %.2e" % (worst[1], worst[0], float(np.median(list(errs.values())))))
+    assert worst[1] < tol_g, worst
+    for k, m in G.sn_by_oracle_name() + D.sn_by_oracle_name():
+        ref = (sg if k in sg and m in [w for _, w in G.sn_by_oracle_name()] else sd)[k]
+        assert rel_l2(m.u.cpu().numpy(), ref.numpy()) < 1e-5, k
+
+
+def test_resnet_train_step_runs_through_the_trainer():
+    """`model: 'resnet'` (the branch sagan/main.py:104-107 leaves disabled) through Trainer: eager and captured steps."""
+    tr = make_trainer(dict(RES_CFG), "bf16_tc", seed=1)
+    B = RES_CFG["batch_size"]
+    img = torch.rand(B, 32, 32, 3, device="cuda") * 2 - 1
+    lab = torch.tensor([2, 5], device="cuda")
+    tr.train_step(img, lab)
+    l0 = tr.losses()
+    tr.capture()
+    tr.graph_step(img, lab)
+    l1 = tr.losses()
+    assert all(np.isfinite(v) for v in list(l0.values()) + list(l1.values()))
+    assert tr.opt_G.iterations == 2 and tr.opt_D.iterations == 2
+
+
 def test_uint8_record_input_contract():
     """SURVEY.md §8f row 4 / sagan/dataset.py:27-40: a step fed the raw uint8 records equals the step fed the decoded
     float images (eager and captured graph), with sagan_deterministic_forward so that nothing but the input path differs."""
