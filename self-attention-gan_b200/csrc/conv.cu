@@ -25,6 +25,13 @@ int conv_tc_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaS
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, float* dbias, const CG& g, cudaStream_t st);
 int conv_tc_get_precision();
 void conv_tc_set_precision(int p);
+// direct kernels for the 3-channel image side (conv_small.cu)
+bool conv_small_ok(const CG& g, const void* a, const void* b);
+bool conv_small_fwd_ok(const CG& g, const void* a, const void* b);
+bool conv_small_wgrad_ok(const CG& g, const void* a, const void* b);
+int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope, cudaStream_t st);
+int conv_small_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st);
+int conv_small_wgrad(const float* x, const float* dy, float* dw, float* db, const CG& g, cudaStream_t st);
 
 constexpr int CV_THREADS = 256;
 constexpr int CV_BK = 16;
@@ -539,6 +546,7 @@ extern "C" int sagan_conv2d_fwd(const float* x, const float* w, const float* bia
   CG g;
   int rc = make_geom(geom, &g, "sagan_conv2d_fwd");
   if (rc) return rc;
+  if (conv_small_fwd_ok(g, x, y)) return conv_small_fwd(x, w, bias, y, g, act, slope, (cudaStream_t)stream);
   if (math_mode == SAGAN_MATH_BF16_TC && conv_tc_fwd_ok(g, x, w))
     return conv_tc_fwd(x, w, bias, y, g, act, slope, (cudaStream_t)stream);
   const int vecA = (g.Cin % 4 == 0 && al16(x)) ? 1 : 0;
@@ -566,6 +574,7 @@ extern "C" int sagan_conv2d_dgrad(const float* dy, const float* w, float* dx, co
   bool full_cover = true;
   for (int r = 0; r < g.S; ++r)
     if (r >= g.KH || r >= g.KW) full_cover = false;
+  if (conv_small_ok(g, dy, dx)) return conv_small_dgrad(dy, w, dx, g, st);      // writes every element of dx
   if (!full_cover) SAGAN_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.B * g.H * g.W * g.Cin * sizeof(float), st));
   if (math_mode == SAGAN_MATH_BF16_TC && conv_tc_dgrad_ok(g, dy, w)) return conv_tc_dgrad(dy, w, dx, g, st);
   const int vecA = (g.Cout % 4 == 0 && al16(dy)) ? 1 : 0;
@@ -590,6 +599,10 @@ extern "C" int sagan_conv2d_wgrad(const float* x, const float* dy, float* dw, fl
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SAGAN_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.K * g.Cout * sizeof(float), st));
+  if (conv_small_wgrad_ok(g, x, dy)) {
+    if (dbias) SAGAN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st));
+    return conv_small_wgrad(x, dy, dw, dbias, g, st);
+  }
   if (math_mode == SAGAN_MATH_BF16_TC && conv_tc_wgrad_ok(g, x, dy)) {
     if (dbias) SAGAN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st));
     return conv_tc_wgrad(x, dy, dw, dbias, g, st);

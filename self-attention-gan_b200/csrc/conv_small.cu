@@ -1,0 +1,257 @@
+// Direct (no GEMM view) fp32 convolution kernels for the layers whose channel count on one side is tiny:
+//   the discriminator's first layer   SN(Conv2D(df, 4, 2, 'same')) on the 3-channel image   discriminator.py:8,21-22
+//   the generator's output layer      Conv2D(3, 4, 1, 'same', tanh)                          generator.py:36
+// An implicit GEMM with K = 48 or N = 3 wastes a 128-wide tile on them and is bound by its im2col gather (every input
+// pixel re-read 16 x through L2); here one thread owns one pixel, keeps the whole small side in registers, reads its
+// 4 x 4 window straight through L1 (neighbouring threads share 12 of 16 taps) and the weights from shared memory.
+// These layers move 3 - 17 MB each, so the kernels are HBM / L1 bound, not FMA bound.  fp32 throughout: used by both
+// math modes (exact to fp32 rounding; the tensor-core kernels have nothing to gain at these shapes).
+//
+//   fwd     y[p, :] = act(sum_taps x[p @ tap, :] w[tap, :, :] + bias)        thread = output pixel
+//   dgrad   dx[q, :] = sum_{taps reaching q} dy[p(q, tap), :] w[tap, :, :]^T  thread = input pixel
+//   wgrad   dw[tap, ci, co] = sum_p x[p @ tap, ci] dy[p, co], db = sum_p dy  CTA = 256 pixels, thread = 3 outputs, atomics
+#include "common.cuh"
+
+namespace sagan {
+
+constexpr int CS_THREADS = 256;
+
+// the CIN * COUT weights of one tap: broadcast 128-bit shared-memory loads (scalar ones would make the kernels LDS-bound)
+template <int N>
+__device__ __forceinline__ void cs_load_tap(const float* wp, float (&wv)[N]) {
+  static_assert(N % 4 == 0, "tap size must be a multiple of 4 floats");
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(wp + i);
+    wv[i] = t.x; wv[i + 1] = t.y; wv[i + 2] = t.z; wv[i + 3] = t.w;
+  }
+}
+
+__device__ __forceinline__ float cs_act(float v, int act, float slope) {
+  if (act == SAGAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == SAGAN_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(CS_THREADS)
+conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ y, CG g, int act, float slope) {
+  extern __shared__ __align__(16) float sw[];        // [KH*KW*CIN][COUT] + bias[COUT]
+  const int nw = g.K * COUT;
+  for (int i = threadIdx.x; i < nw; i += CS_THREADS) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += CS_THREADS) sw[nw + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int m = blockIdx.x * CS_THREADS + threadIdx.x;
+  if (m >= g.M) return;
+  const int b = m / (g.Ho * g.Wo), rem = m - b * (g.Ho * g.Wo);
+  const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+  const int h0 = ho * g.S - g.PT, w0 = wo * g.S - g.PL;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = sw[nw + c];
+  for (int kh = 0; kh < g.KH; ++kh) {
+    const int hi = h0 + kh;
+    if (hi < 0 || hi >= g.H) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      const int wi = w0 + kw;
+      if (wi < 0 || wi >= g.W) continue;
+      const float* xp = x + ((size_t)(b * g.H + hi) * g.W + wi) * CIN;
+      const float* wp = sw + (kh * g.KW + kw) * CIN * COUT;
+      float xv[CIN];
+      if (CIN % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < CIN; c += 4) {
+          const float4 t = ld4(xp + c);
+          xv[c] = t.x; xv[c + 1] = t.y; xv[c + 2] = t.z; xv[c + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) xv[c] = __ldg(xp + c);
+      }
+      float wv[CIN * COUT];
+      cs_load_tap(wp, wv);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv[ci], wv[ci * COUT + co], acc[co]);
+    }
+  }
+  float* yp = y + (size_t)m * COUT;
+  if (COUT % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < COUT; c += 4)
+      st4(yp + c, make_float4(cs_act(acc[c], act, slope), cs_act(acc[c + 1], act, slope), cs_act(acc[c + 2], act, slope),
+                              cs_act(acc[c + 3], act, slope)));
+  } else {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) yp[c] = cs_act(acc[c], act, slope);
+  }
+}
+
+// dx[b, hi, wi, ci] = sum over (kh, kw) with (hi + PT - kh) % S == 0, ho = (hi + PT - kh) / S in range (same for w):
+//                     sum_co dy[b, ho, wo, co] w[kh, kw, ci, co]
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(CS_THREADS)
+conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, CG g) {
+  extern __shared__ __align__(16) float sw[];        // [KH*KW][CIN][COUT]
+  const int nw = g.K * COUT;
+  for (int i = threadIdx.x; i < nw; i += CS_THREADS) sw[i] = w[i];
+  __syncthreads();
+  const long long q = (long long)blockIdx.x * CS_THREADS + threadIdx.x;
+  if (q >= (long long)g.B * g.H * g.W) return;
+  const int b = (int)(q / (g.H * g.W)), rem = (int)(q - (long long)b * g.H * g.W);
+  const int hi = rem / g.W, wi = rem - hi * g.W;
+  float acc[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) acc[c] = 0.f;
+  for (int kh = 0; kh < g.KH; ++kh) {
+    const int th = hi + g.PT - kh;
+    if (th < 0 || th % g.S) continue;
+    const int ho = th / g.S;
+    if (ho >= g.Ho) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      const int tw = wi + g.PL - kw;
+      if (tw < 0 || tw % g.S) continue;
+      const int wo = tw / g.S;
+      if (wo >= g.Wo) continue;
+      const float* dp = dy + ((size_t)(b * g.Ho + ho) * g.Wo + wo) * COUT;
+      const float* wp = sw + (kh * g.KW + kw) * CIN * COUT;
+      float dv[COUT];
+      if (COUT % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < COUT; c += 4) {
+          const float4 t = ld4(dp + c);
+          dv[c] = t.x; dv[c + 1] = t.y; dv[c + 2] = t.z; dv[c + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) dv[c] = __ldg(dp + c);
+      }
+      float wv[CIN * COUT];
+      cs_load_tap(wp, wv);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[ci] = fmaf(dv[co], wv[ci * COUT + co], acc[ci]);
+    }
+  }
+  float* xp = dx + (size_t)q * CIN;
+  if (CIN % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < CIN; c += 4) st4(xp + c, make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+  } else {
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) xp[c] = acc[c];
+  }
+}
+
+// CTA = PIX consecutive output pixels, dy tile in shared memory.  Thread t owns ONE (tap, ci) row of dw -- all COUT
+// columns of it in registers -- and every NSL-th pixel of the tile: per pixel one x load (through L1) feeds COUT FMAs
+// against a broadcast dy row.  The NSL pixel slices are folded through shared memory, then one fp32 atomic per gradient
+// element and CTA (dw / db zeroed by the caller).  Requires KH * KW * CIN <= CS_THREADS.
+template <int CIN, int COUT, int PIX>
+__global__ void __launch_bounds__(CS_THREADS)
+conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                        float* __restrict__ db, CG g) {
+  __shared__ __align__(16) float sdy[PIX][COUT];
+  __shared__ int s_base[PIX], s_h0[PIX], s_w0[PIX];
+  __shared__ float red[CS_THREADS][COUT + 1];
+  const int m0 = blockIdx.x * PIX;
+  for (int i = threadIdx.x; i < PIX * COUT; i += CS_THREADS) {
+    const int p = i / COUT, c = i - p * COUT;
+    sdy[p][c] = (m0 + p < g.M) ? dy[(size_t)(m0 + p) * COUT + c] : 0.f;
+  }
+  for (int p = threadIdx.x; p < PIX; p += CS_THREADS) {
+    const int m = min(m0 + p, g.M - 1);
+    const int b = m / (g.Ho * g.Wo), rem = m - b * (g.Ho * g.Wo);
+    const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+    s_base[p] = b; s_h0[p] = ho * g.S - g.PT; s_w0[p] = wo * g.S - g.PL;
+  }
+  __syncthreads();
+  const int K = g.K;                         // rows of dw
+  const int nsl = CS_THREADS / K;            // pixel slices
+  const int kk = threadIdx.x % K, sl = threadIdx.x / K;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  if (sl < nsl) {
+    const int tap = kk / CIN, ci = kk - tap * CIN;
+    const int kh = tap / g.KW, kw = tap - kh * g.KW;
+    for (int p = sl; p < PIX; p += nsl) {
+      const int hi = s_h0[p] + kh, wi = s_w0[p] + kw;
+      if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
+        const float xv = __ldg(x + ((size_t)(s_base[p] * g.H + hi) * g.W + wi) * CIN + ci);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, sdy[p][c], acc[c]);
+      }
+    }
+  } else if (db) {
+    // the threads left over (CS_THREADS - nsl * K >= COUT is checked by the host) sum the dy columns
+    const int c = threadIdx.x - nsl * K;
+    if (c < COUT) {
+      float t = 0.f;
+      for (int p = 0; p < PIX; ++p) t += sdy[p][c];
+      atomicAdd(db + c, t);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) red[threadIdx.x][c] = acc[c];
+  __syncthreads();
+  for (int o = threadIdx.x; o < K * COUT; o += CS_THREADS) {
+    const int r = o / COUT, c = o - r * COUT;
+    float t = 0.f;
+    for (int q = 0; q < nsl; ++q) t += red[q * K + r][c];
+    atomicAdd(dw + o, t);
+  }
+}
+
+static inline bool cs_al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// which (Cin, Cout) pairs have a direct kernel: the image side of D (3 -> 16) and of G (16 -> 3)
+static int cs_pair(const CG& g) {
+  if (g.KH * g.KW > 16) return 0;
+  if (g.Cin == 3 && g.Cout == 16) return 1;
+  if (g.Cin == 16 && g.Cout == 3) return 2;
+  return 0;
+}
+
+bool conv_small_ok(const CG& g, const void* a, const void* b) { return cs_pair(g) != 0 && cs_al16(a) && cs_al16(b); }
+// forward: the 16 -> 3 output layer stays on the implicit-GEMM kernels (measured: 54 us direct against 30 us)
+bool conv_small_fwd_ok(const CG& g, const void* a, const void* b) { return cs_pair(g) == 1 && cs_al16(a) && cs_al16(b); }
+// backward-filter: only where all rows of dw fit the CTA (K <= 240 leaves >= COUT threads for the bias column sums)
+bool conv_small_wgrad_ok(const CG& g, const void* a, const void* b) {
+  return cs_pair(g) == 1 && g.K + 16 <= CS_THREADS && cs_al16(a) && cs_al16(b);
+}
+
+int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, const CG& g, int act, float slope,
+                   cudaStream_t st) {
+  const unsigned nb = (unsigned)ceil_div(g.M, CS_THREADS);
+  if (cs_pair(g) == 1)
+    conv_small_fwd_kernel<3, 16><<<nb, CS_THREADS, (g.K * 16 + 16) * sizeof(float), st>>>(x, w, bias, y, g, act, slope);
+  else
+    conv_small_fwd_kernel<16, 3><<<nb, CS_THREADS, (g.K * 3 + 3) * sizeof(float), st>>>(x, w, bias, y, g, act, slope);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_small_dgrad(const float* dy, const float* w, float* dx, const CG& g, cudaStream_t st) {
+  const unsigned nb = (unsigned)ceil_div<long long>((long long)g.B * g.H * g.W, CS_THREADS);
+  if (cs_pair(g) == 1)
+    conv_small_dgrad_kernel<3, 16><<<nb, CS_THREADS, g.K * 16 * sizeof(float), st>>>(dy, w, dx, g);
+  else
+    conv_small_dgrad_kernel<16, 3><<<nb, CS_THREADS, g.K * 3 * sizeof(float), st>>>(dy, w, dx, g);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dw (and db) must be zero on entry
+int conv_small_wgrad(const float* x, const float* dy, float* dw, float* db, const CG& g, cudaStream_t st) {
+  constexpr int PIX = 256;
+  const unsigned nb = (unsigned)ceil_div(g.M, PIX);
+  conv_small_wgrad_kernel<3, 16, PIX><<<nb, CS_THREADS, 0, st>>>(x, dy, dw, db, g);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sagan
