@@ -1,29 +1,20 @@
-// Self-attention block, BF16_TC math mode, LARGE channel counts (C = 128 / 256 / 512): BACKWARD.
+// Self-attention block, BF16_TC math mode, LARGE channel counts (C = 128 / 256 / 512): BACKWARD, host orchestration.
 //
 // The reference has no hand-written backward (tf.GradientTape differentiates /root/reference/layers.py:93-120); the
-// formulas are SURVEY.md §8a row 2.  This first large-C backward is COMPOSED, not fused: every contraction runs on the
-// tensor cores through the library's own implicit-GEMM kernels in their kind::tf32 forms (1x1 geometry, conv_tc.cu; the
-// backward-filter form rounds both operands to bf16, which costs 5e-3 on every gradient here, so the transposed
-// contractions are run as forward GEMMs on explicitly transposed operands instead), the score-shaped tensors S, P, dP,
-// dS of ONE sample at a time live in the workspace ([N, N] fp32 each), and two row kernels do the softmax and its Jacobian:
+// formulas are SURVEY.md §8a row 2.  The score-shaped part is FUSED (attn_big_fbwd.cu: two flash launches, the [N, N]
+// maps never leave the SM); around it every contraction over the channel axis runs on the tensor cores:
 //
-//   theta, phi, g = X W + b                      3 x conv fwd   (the forward's bf16 copies are not saved: recomputed)
-//   dA = gamma dY Wo^T                           conv dgrad + scale
-//   dWo', dbo' = A^T dY, colsum dY               transpose + conv fwd, column sums (gamma, dgamma: finalize kernel)
-//   per sample b:
-//     S   = theta_b phi_b^T                      conv fwd against the transposed phi_b
-//     P   = softmax_rows(S)                      row kernel (in place); self-consistent with the S computed HERE
-//     dP  = dA_b g_b^T                           conv fwd against the transposed g_b
-//     dS  = P * (dP - rowsum(P * dP))            row kernel (in place)
-//     dg_b     = P^T dA_b                        transpose + conv fwd
-//     dphi_b   = dS^T theta_b                    transpose + conv fwd
-//     dtheta_b = dS phi_b                        conv fwd (sum_j dS_ij = 0: this contraction cancels and amplifies the tf32
-//                                                truncation of dS; measured +0.6e-3 on dWtheta against an fp32 GEMM)
-//   dX = dY + dtheta Wq^T + dphi Wk^T + dg Wv^T  3 x conv dgrad + adds
-//   dWq, dbq, ... = X^T [dtheta dphi dg]          transpose of X + 3 x conv fwd (split-K over the tokens), column sums
+//   Q', K, V (bf16)     = X [Wtheta | Wphi | Wg] + b          CTA-pair tf32 GEMM, gemm_tc.cu (the forward's own launch,
+//                                                             so S is recomputed from exactly the forward's operands)
+//   dA' (bf16)          = dY Wo^T                             same GEMM (gamma is folded into the flash epilogues)
+//   D', lse2            = rowsum(dA' * A), lse log2 e         one warp per token
+//   dV, dK | dQ         flash backward, attn_big_fbwd.cu
+//   dWo', dbo', dgamma  = A^T dY, colsum dY, finalize         transpose + conv-as-GEMM, column sums
+//   dX = dY + dQ Wq^T + dK Wk^T + dV Wv^T                     3 x conv dgrad + adds
+//   dWq, dbq, ...       = X^T [dQ dK dV], column sums         transpose of X + 3 x conv-as-GEMM (split-K over the tokens)
 //
-// ~14 launches per sample: HBM-bound on the [N, N] tensors (about 14 passes of 4 N^2 bytes per sample), i.e. roughly
-// 15-20 x the fused forward.  The fused plan (two flash kernels) replaces the per-sample part.
+// Launch count is independent of the batch (round 1 ran ~14 launches PER SAMPLE over [N, N] fp32 tensors in HBM:
+// 9.6 ms at B=16, N=4096, C=512 and 21 ms at B=256, N=256, C=128).
 #include <algorithm>
 
 #include "common.cuh"
@@ -35,75 +26,49 @@ int attn_bwd_finalize_launch(const float* Wo, const float* bo, const float* gamm
 
 namespace {
 
-// [rows, cols] -> [cols, rows]
-__global__ void bb_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
-  }
+__global__ void bb_set_kernel(float* p, float v) { *p = v; }
+
+// src [R][2 d + dv] -> q [R][d], k [R][d], v [R][dv]
+__global__ void bb_split_cols_kernel(const float* __restrict__ src, float* __restrict__ q, float* __restrict__ k,
+                                     float* __restrict__ v, int R, int d, int dv) {
+  const int nn = 2 * d + dv;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * nn) return;
+  const int r = i / nn, c = i - r * nn;
+  if (c < d) q[r * d + c] = src[i];
+  else if (c < 2 * d) k[r * d + c - d] = src[i];
+  else v[r * dv + c - 2 * d] = src[i];
 }
 
-// one CTA per row: P = softmax(S) in place
-__global__ void __launch_bounds__(256) bb_softmax_rows_kernel(float* __restrict__ S, int n) {
+// wcat [C][2 d + dv] = [Wq | Wk | Wv] row by row: the K-major "transposed" operand of dX = dY + [dQ dK dV] Wcat^T
+__global__ void bb_concat_w_kernel(const float* __restrict__ Wq, const float* __restrict__ Wk, const float* __restrict__ Wv,
+                                   float* __restrict__ wcat, int C, int d, int dv) {
+  const int nn = 2 * d + dv;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * nn) return;
+  const int r = i / nn, c = i - r * nn;
+  wcat[i] = c < d ? Wq[r * d + c] : (c < 2 * d ? Wk[r * d + c - d] : Wv[r * dv + c - 2 * d]);
+}
+
+// dgamma += sum Wo * dWo' + sum bo * dbo'; dWo = gamma dWo', dbo = gamma dbo'   (many CTAs; dgamma zeroed by the caller)
+__global__ void __launch_bounds__(256)
+bb_finalize_kernel(const float* __restrict__ Wo, const float* __restrict__ bo, const float* __restrict__ gamma,
+                   float* __restrict__ dWo, float* __restrict__ dbo, float* __restrict__ dgamma, int nW, int C) {
   __shared__ float red[32];
-  float* row = S + (size_t)blockIdx.x * n;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, row[i]);
-  mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  mx = red[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-  float sum = 0.f;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float e = __expf(row[i] - mx);
-    row[i] = e;
-    sum += e;
+  const float gm = *gamma;
+  float acc = 0.f;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < nW) {
+    const float g = dWo[i];
+    acc = Wo[i] * g;
+    dWo[i] = g * gm;
+  } else if (i - nW < C) {
+    const float g = dbo[i - nW];
+    acc = bo[i - nW] * g;
+    dbo[i - nW] = g * gm;
   }
-  sum = block_sum(sum, red);
-  const float inv = 1.0f / sum;
-  for (int i = threadIdx.x; i < n; i += 256) row[i] *= inv;
-}
-
-// one CTA per row: dP <- P * (dP - sum_j P_j dP_j)
-__global__ void __launch_bounds__(256) bb_ds_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, int n) {
-  __shared__ float red[32];
-  const float* p = P + (size_t)blockIdx.x * n;
-  float* g = dP + (size_t)blockIdx.x * n;
-  float dot = 0.f;
-  for (int i = threadIdx.x; i < n; i += 256) dot = fmaf(p[i], g[i], dot);
-  dot = block_sum(dot, red);
-  for (int i = threadIdx.x; i < n; i += 256) g[i] = p[i] * (g[i] - dot);
-}
-
-__global__ void bb_scale_kernel(float* __restrict__ x, const float* __restrict__ s, long long n) {
-  const float f = *s;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= f;
-}
-
-// out = a + b  or  out += b
-__global__ void bb_add_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = (a ? a[i] : out[i]) + b[i];
-}
-
-// out[c] = sum_r x[r, c]   (out zeroed by the caller; fp32 partial sums per CTA, one atomic per column and CTA)
-__global__ void __launch_bounds__(256) bb_colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows,
-                                                        int cols, long long rows_per_block) {
-  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  for (int c = blockIdx.x * 256 + threadIdx.x; c < cols; c += gridDim.x * 256) {
-    float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += x[r * cols + c];
-    atomicAdd(out + c, acc);
-  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(dgamma, acc);
 }
 
 sagan_conv_geom dense_geom(long long rows, int cin, int cout) {
@@ -115,7 +80,7 @@ sagan_conv_geom dense_geom(long long rows, int cin, int cout) {
 }
 
 struct BbLayout {
-  size_t q, k, v, dq, dk, dv, da, kt, vt, s, dp, tr, tmp, total;   // float offsets
+  size_t dqkv, dwcat, dbcat, wcat, one, wt, bcat, wot, zero, qb, kb, vb, dab, lse2, dd, total;   // float offsets (256-byte aligned)
 };
 
 BbLayout bb_layout(int B, int N, int C) {
@@ -123,12 +88,12 @@ BbLayout bb_layout(int B, int N, int C) {
   BbLayout t;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
-  t.q = take(T * d); t.k = take(T * d); t.v = take(T * dv);
-  t.dq = take(T * d); t.dk = take(T * d); t.dv = take(T * dv);
-  t.da = take(T * dv);
-  t.kt = take((size_t)N * d); t.vt = take((size_t)N * dv);
-  t.s = take((size_t)N * N); t.dp = take((size_t)N * N); t.tr = take((size_t)N * N);
-  t.tmp = take(T * C);
+  t.dqkv = take(T * (2 * d + dv));                       // [dQ | dK | dV] rows
+  t.dwcat = take((size_t)C * (2 * d + dv)); t.dbcat = take(2 * d + dv); t.wcat = take((size_t)C * (2 * d + dv)); t.one = take(1);
+  t.wt = take((size_t)C * (2 * d + dv)); t.bcat = take(2 * d + dv); t.wot = take((size_t)C * dv / 2); t.zero = take(C);
+  t.qb = take(T * 32); t.kb = take(T * 32);               // bf16 [T][64]
+  t.vb = take(T * dv / 2); t.dab = take(T * dv / 2);      // bf16 [T][dv]
+  t.lse2 = take(T); t.dd = take(T);
   t.total = o + 64;
   return t;
 }
@@ -143,9 +108,20 @@ size_t attn_big_bwd_workspace_bytes(int B, int N, int C) { return bb_layout(B, N
     if (rc_) return rc_;     \
   } while (0)
 
+// gemm_tc.cu / attn_tc_big.cu / attn_big_fbwd.cu
+int gemm_tf32_qkv(const float* x, const float* wt, const float* bcat, __nv_bfloat16* q, __nv_bfloat16* k,
+                  __nv_bfloat16* v, long long M, int K, int d, int dv, float q_scale, cudaStream_t st);
+int attn_big_weights_launch(const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
+                            const float* bv, const float* Wo, float* Wt, float* bcat, __nv_bfloat16* WoT, int C, cudaStream_t st);
+int attn_big_fused_bwd_core(const __nv_bfloat16* Qb, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb,
+                            const __nv_bfloat16* dAb, const float* A, const float* lse, const float* gamma, float* lse2,
+                            float* Dd, float* dQKV, int B, int N, int C, cudaStream_t st);
+int gemm_tf32_residual(const float* a, const float* wt, const float* bias, const float* res, const float* res_scale,
+                       float* y, long long M, int K, int N, cudaStream_t st);
+
 int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
                     const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma, const float* A,
-                    float* dX, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo,
+                    const float* lse, float* dX, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo,
                     float* dbo, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
   const BbLayout t = bb_layout(B, N, C);
   if (ws_bytes < t.total * sizeof(float)) {
@@ -155,89 +131,57 @@ int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const floa
   const int d = C / 8, dv = C / 2;
   const long long T = (long long)B * N;
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  float *Q = base + t.q, *K = base + t.k, *V = base + t.v, *dQ = base + t.dq, *dK = base + t.dk, *dV = base + t.dv;
-  float *dA = base + t.da, *KT = base + t.kt, *VT = base + t.vt, *S = base + t.s, *dP = base + t.dp, *TR = base + t.tr;
-  float* tmp = base + t.tmp;
+  const int NN = 2 * d + dv;
+  float *dQKV = base + t.dqkv, *dWcat = base + t.dwcat, *dbcat = base + t.dbcat, *Wcat = base + t.wcat, *one = base + t.one;
+  float *Wt = base + t.wt, *bcat = base + t.bcat, *zero = base + t.zero, *lse2 = base + t.lse2, *Dd = base + t.dd;
+  __nv_bfloat16 *WoT = (__nv_bfloat16*)(base + t.wot), *Qb = (__nv_bfloat16*)(base + t.qb), *Kb = (__nv_bfloat16*)(base + t.kb),
+                *Vb = (__nv_bfloat16*)(base + t.vb), *dAb = (__nv_bfloat16*)(base + t.dab);
   const int TC = SAGAN_MATH_BF16_TC;
   const bool want_w = dWq != nullptr;
-  const int ew_blocks = num_sms() * 8;
 
-  // ---- projections and the gradient of the attention output
-  const sagan_conv_geom gq = dense_geom(T, C, d), gv = dense_geom(T, C, dv), go = dense_geom(T, dv, C);
-  BB_CALL(sagan_conv2d_fwd(X, Wq, bq, Q, &gq, SAGAN_ACT_NONE, 0.f, TC, st));
-  BB_CALL(sagan_conv2d_fwd(X, Wk, bk, K, &gq, SAGAN_ACT_NONE, 0.f, TC, st));
-  BB_CALL(sagan_conv2d_fwd(X, Wv, bv, V, &gv, SAGAN_ACT_NONE, 0.f, TC, st));
-  BB_CALL(sagan_conv2d_dgrad(dY, Wo, dA, &go, TC, st));                      // dA' = dY Wo^T
-  const dim3 tb(32, 8);
-  auto colsum = [&](const float* x, float* out, int cols) -> int {
-    SAGAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
-    const long long rpb = 512;
-    bb_colsum_kernel<<<dim3(ceil_div(cols, 256), (unsigned)ceil_div<long long>(T, rpb)), 256, 0, st>>>(x, out, T, cols, rpb);
-    SAGAN_LAUNCH_CHECK();
-    return 0;
-  };
-  // G = L^T R for token-major L [T, l], R [T, r]: transpose L into tmp, then a forward GEMM whose reduction runs over T
-  auto gram = [&](const float* Lm, int l, const float* Rm, int r, float* out) -> int {
-    bb_transpose_kernel<<<dim3(ceil_div(l, 32), (unsigned)ceil_div<long long>(T, 32)), tb, 0, st>>>(Lm, tmp, (int)T, l);
-    SAGAN_LAUNCH_CHECK();
-    const sagan_conv_geom g = dense_geom(l, (int)T, r);
-    return sagan_conv2d_fwd(tmp, Rm, nullptr, out, &g, SAGAN_ACT_NONE, 0.f, TC, st);
+  // ---- bf16 operands of the flash kernels: the forward's own projection GEMM, and dA' = dY Wo^T through the same GEMM
+  //      (Wo [dv, C] row-major IS the K-major transposed operand; no bias; all columns go to the "v" output)
+  BB_CALL(attn_big_weights_launch(Wq, bq, Wk, bk, Wv, bv, Wo, Wt, bcat, WoT, C, st));
+  if (d < 64) {   // rows of Q / K are padded to one 128-byte swizzle span
+    SAGAN_CUDA(cudaMemsetAsync(Qb, 0, (size_t)T * 64 * 2, st));
+    SAGAN_CUDA(cudaMemsetAsync(Kb, 0, (size_t)T * 64 * 2, st));
+  }
+  SAGAN_CUDA(cudaMemsetAsync(zero, 0, sizeof(float) * C, st));
+  BB_CALL(gemm_tf32_qkv(X, Wt, bcat, Qb, Kb, Vb, T, C, d, dv, 1.4426950408889634f, st));
+  BB_CALL(gemm_tf32_qkv(dY, Wo, zero, nullptr, nullptr, dAb, T, C, 0, dv, 1.0f, st));
+  // G = L^T R and the column sums of R for token-major L [T, l], R [T, r]: the backward-filter form of the 1x1 conv
+  // (split-bf16 tensor-core kernel: both operands read MN-major, reduction over the tokens split across CTAs, the
+  // ones column yields colsum(R) for free) -- no transposed copies
+  auto gram = [&](const float* Lm, int l, const float* Rm, int r, float* out, float* colsum_out) -> int {
+    const sagan_conv_geom g = dense_geom(T, l, r);
+    return sagan_conv2d_wgrad(Lm, Rm, out, colsum_out, &g, TC, st);
   };
   if (want_w) {
-    BB_CALL(gram(A, dv, dY, C, dWo));                                         // dWo' = A^T dY
-    BB_CALL(colsum(dY, dbo, C));                                              // dbo' = colsum(dY)
-    BB_CALL(attn_bwd_finalize_launch(Wo, bo, gamma, dWo, dbo, dgamma, dv * C, C, st));
-  }
-  bb_scale_kernel<<<ew_blocks, 256, 0, st>>>(dA, gamma, T * dv);
-  SAGAN_LAUNCH_CHECK();
-
-  // ---- per sample: the score-shaped part
-  const sagan_conv_geom gs = dense_geom(N, d, N), gp = dense_geom(N, dv, N);          // S = theta phi^T, dP = dA g^T
-  const sagan_conv_geom gdv = dense_geom(N, N, dv), gdk = dense_geom(N, N, d);        // P^T dA; dS^T theta and dS phi
-  const dim3 tgrid(ceil_div(N, 32), ceil_div(N, 32));
-  for (int b = 0; b < B; ++b) {
-    const size_t r0 = (size_t)b * N;
-    bb_transpose_kernel<<<dim3(ceil_div(d, 32), ceil_div(N, 32)), tb, 0, st>>>(K + r0 * d, KT, N, d);
+    BB_CALL(gram(A, dv, dY, C, dWo, dbo));                                    // dWo' = A^T dY, dbo' = colsum(dY)
+    SAGAN_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float), st));
+    bb_finalize_kernel<<<ceil_div(dv * C + C, 256), 256, 0, st>>>(Wo, bo, gamma, dWo, dbo, dgamma, dv * C, C);
     SAGAN_LAUNCH_CHECK();
-    bb_transpose_kernel<<<dim3(ceil_div(dv, 32), ceil_div(N, 32)), tb, 0, st>>>(V + r0 * dv, VT, N, dv);
-    SAGAN_LAUNCH_CHECK();
-    BB_CALL(sagan_conv2d_fwd(Q + r0 * d, KT, nullptr, S, &gs, SAGAN_ACT_NONE, 0.f, TC, st));
-    bb_softmax_rows_kernel<<<N, 256, 0, st>>>(S, N);
-    SAGAN_LAUNCH_CHECK();
-    BB_CALL(sagan_conv2d_fwd(dA + r0 * dv, VT, nullptr, dP, &gp, SAGAN_ACT_NONE, 0.f, TC, st));
-    bb_transpose_kernel<<<tgrid, tb, 0, st>>>(S, TR, N, N);
-    SAGAN_LAUNCH_CHECK();
-    BB_CALL(sagan_conv2d_fwd(TR, dA + r0 * dv, nullptr, dV + r0 * dv, &gdv, SAGAN_ACT_NONE, 0.f, TC, st));   // dg = P^T dA
-    bb_ds_rows_kernel<<<N, 256, 0, st>>>(S, dP, N);                                      // dP <- dS
-    SAGAN_LAUNCH_CHECK();
-    bb_transpose_kernel<<<tgrid, tb, 0, st>>>(dP, TR, N, N);
-    SAGAN_LAUNCH_CHECK();
-    BB_CALL(sagan_conv2d_fwd(TR, Q + r0 * d, nullptr, dK + r0 * d, &gdk, SAGAN_ACT_NONE, 0.f, TC, st));      // dphi = dS^T theta
-    BB_CALL(sagan_conv2d_fwd(dP, K + r0 * d, nullptr, dQ + r0 * d, &gdk, SAGAN_ACT_NONE, 0.f, TC, st));        // dtheta = dS phi
   }
 
-  // ---- back through the projections (the weight gradients first: they use tmp for X^T)
+  // ---- the score-shaped part: two flash launches (dK, dV | dQ), gamma folded into their epilogues
+  BB_CALL(attn_big_fused_bwd_core(Qb, Kb, Vb, dAb, A, lse, gamma, lse2, Dd, dQKV, B, N, C, st));
+
+  // ---- back through the projections, on the concatenated [dQ | dK | dV] rows
   if (want_w) {
-    bb_transpose_kernel<<<dim3(ceil_div(C, 32), (unsigned)ceil_div<long long>(T, 32)), tb, 0, st>>>(X, tmp, (int)T, C);
+    // [dWq | dWk | dWv] = X^T dQKV (one GEMM whose reduction runs over the tokens), [dbq | dbk | dbv] = column sums
+    BB_CALL(gram(X, C, dQKV, NN, dWcat, dbcat));
+    bb_split_cols_kernel<<<ceil_div(C * NN, 256), 256, 0, st>>>(dWcat, dWq, dWk, dWv, C, d, dv);
     SAGAN_LAUNCH_CHECK();
-    const sagan_conv_geom gwq = dense_geom(C, (int)T, d), gwv = dense_geom(C, (int)T, dv);
-    BB_CALL(sagan_conv2d_fwd(tmp, dQ, nullptr, dWq, &gwq, SAGAN_ACT_NONE, 0.f, TC, st));
-    BB_CALL(sagan_conv2d_fwd(tmp, dK, nullptr, dWk, &gwq, SAGAN_ACT_NONE, 0.f, TC, st));
-    BB_CALL(sagan_conv2d_fwd(tmp, dV, nullptr, dWv, &gwv, SAGAN_ACT_NONE, 0.f, TC, st));
-    BB_CALL(colsum(dQ, dbq, d));
-    BB_CALL(colsum(dK, dbk, d));
-    BB_CALL(colsum(dV, dbv, dv));
+    bb_split_cols_kernel<<<ceil_div(NN, 256), 256, 0, st>>>(dbcat, dbq, dbk, dbv, 1, d, dv);
+    SAGAN_LAUNCH_CHECK();
   }
   if (dX) {
-    BB_CALL(sagan_conv2d_dgrad(dQ, Wq, tmp, &gq, TC, st));
-    bb_add_kernel<<<ew_blocks, 256, 0, st>>>(dX, dY, tmp, T * C);
+    // dX = dY + dQKV [Wq | Wk | Wv]^T: one CTA-pair tf32 GEMM with the residual epilogue
+    bb_concat_w_kernel<<<ceil_div(C * NN, 256), 256, 0, st>>>(Wq, Wk, Wv, Wcat, C, d, dv);
     SAGAN_LAUNCH_CHECK();
-    BB_CALL(sagan_conv2d_dgrad(dK, Wk, tmp, &gq, TC, st));
-    bb_add_kernel<<<ew_blocks, 256, 0, st>>>(dX, nullptr, tmp, T * C);
+    bb_set_kernel<<<1, 1, 0, st>>>(one, 1.0f);
     SAGAN_LAUNCH_CHECK();
-    BB_CALL(sagan_conv2d_dgrad(dV, Wv, tmp, &gv, TC, st));
-    bb_add_kernel<<<ew_blocks, 256, 0, st>>>(dX, nullptr, tmp, T * C);
-    SAGAN_LAUNCH_CHECK();
+    BB_CALL(gemm_tf32_residual(dQKV, Wcat, zero, dY, one, dX, T, NN, C, st));
   }
   return 0;
 }

@@ -695,8 +695,8 @@ int attn_bwd_finalize_launch(const float* Wo, const float* bo, const float* gamm
 size_t attn_big_bwd_workspace_bytes(int B, int N, int C);
 int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
                     const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma, const float* A,
-                    float* dX, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv, float* dWo,
-                    float* dbo, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+                    const float* lse, float* dX, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv,
+                    float* dWo, float* dbo, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 bool attn_tc_big_supported(int N, int C);
 }  // namespace sagan
 
@@ -782,8 +782,8 @@ static int attn_bwd_impl(const char* who, const float* dY, const float* X, const
                         dWv, dbv, dWo, dbo, dgamma, B, N, PH, PW, (float*)ws, ws_bytes, st);
   }
   if (math_mode == SAGAN_MATH_BF16_TC && PH == 0 && attn_tc_big_supported(N, C))
-    return attn_tc_big_bwd(dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, A_saved, dX, dWq, dbq, dWk, dbk, dWv, dbv, dWo,
-                           dbo, dgamma, B, N, C, ws, ws_bytes, st);
+    return attn_tc_big_bwd(dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, A_saved, lse, dX, dWq, dbq, dWk, dbk, dWv, dbv,
+                           dWo, dbo, dgamma, B, N, C, ws, ws_bytes, st);
   if (math_mode == SAGAN_MATH_FP32_STRICT || C == 8) {
     SAGAN_ATTN_DISPATCH(attn_bwd_strict_t, dY, X, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, lse, A_saved, dX, dWq, dbq, dWk,
                         dbk, dWv, dbv, dWo, dbo, dgamma, B, N, PH, PW, (float*)ws, st);

@@ -362,6 +362,14 @@ __global__ void attn_big_weights_kernel(const float* __restrict__ Wq, const floa
   if (i < NN) bcat[i] = i < d ? bq[i] : (i < 2 * d ? bk[i - d] : bv[i - 2 * d]);
 }
 
+int attn_big_weights_launch(const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
+                            const float* bv, const float* Wo, float* Wt, float* bcat, __nv_bfloat16* WoT, int C, cudaStream_t st) {
+  const int d = C / 8, dv = C / 2, nn = C * (2 * d + dv);
+  attn_big_weights_kernel<<<ceil_div(nn, 256), 256, 0, st>>>(Wq, bq, Wk, bk, Wv, bv, Wo, Wt, bcat, WoT, C, d, dv);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 struct BigLayout {
   size_t off_w, off_b, off_wo, off_q, off_k, off_v, off_ab, total;
 };

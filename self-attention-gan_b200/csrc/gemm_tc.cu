@@ -316,4 +316,16 @@ int gemm_bf16_residual(const __nv_bfloat16* a, const __nv_bfloat16* wt, const fl
   return launch_gemm<GT_BF16, GT_EPI_RESIDUAL>(a, wt, p, st);
 }
 
+// y = res + (*res_scale) * (a [M, K] fp32 * wt [N, K]^T fp32 + bias)   (kind::tf32 on the fp32 operands)
+int gemm_tf32_residual(const float* a, const float* wt, const float* bias, const float* res, const float* res_scale,
+                       float* y, long long M, int K, int N, cudaStream_t st) {
+  GemmP p{};
+  p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.res_scale = res_scale; p.out = y;
+  if (N % 4) {
+    set_err("gemm_tf32_residual: N must be a multiple of 4 (N=%d)", N);
+    return SAGAN_EUNSUPPORTED;
+  }
+  return launch_gemm<GT_TF32, GT_EPI_RESIDUAL>(a, wt, p, st);
+}
+
 }  // namespace sagan
