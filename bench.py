@@ -254,10 +254,13 @@ def kernel_rooflines(pk, math_mode):
     out["attn_bwd_pooled"] = attn_entry("attn_bwd_pooled", B, N, C, t_b, True, Nk=N // 4)
     if math_mode == MATH_BF16_TC:
         B, N, C = 16, 4096, 512
-        t_f, _ = attn_case(B, N, C, math_mode, False, 10)
+        t_f, t_b = attn_case(B, N, C, math_mode, True, 10)
         out["attn_fwd_C512"] = attn_entry("attn_fwd_C512", B, N, C, t_f, False)
         out["attn_fwd_C512"]["note"] = ("sweep regime (BASELINE.json configs[4]): projection GEMM + flash forward + "
                                         "output-conv GEMM, whole block; forward only")
+        out["attn_bwd_C512"] = attn_entry("attn_bwd_C512", B, N, C, t_b, True)
+        out["attn_bwd_C512"]["note"] = ("whole backward of the block: projection / dA GEMMs, two fused flash launches "
+                                        "(dK, dV | dQ; no [N, N] tensor in HBM), dX residual GEMM, weight-gradient GEMMs")
 
     def sn_entry(name, shapes, rule):
         Ws = [torch.randn(K, R, device="cuda") * 0.02 for R, K in shapes]
@@ -369,6 +372,21 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(worst, op=torch.distributed.ReduceOp.MAX)
         replica_diff = float(worst)
 
+    # ---- the same step with the down-sampled attention layers.py:96,100,113 reaches for (keys / values max-pooled 2x2 /
+    #      stride 2): NOT the headline workload (whose attention is the oracle's un-pooled reading) -- reported beside it
+    variant = None
+    if world == 1 and not args.attn_downsample and cfg.get("use_attention") and args.variant:
+        cfg_p = dict(cfg, attn_downsample=True)
+        tr_p = Trainer(cfg_p, global_batch_size=B, steps_per_epoch=n_records // B, seed=0, overlap_streams=args.overlap)
+        tr_p.capture(warmup=3, uint8_input=True)
+        for s in range(3):
+            tr_p.graph_step(dev_batches[s % 4], dev_labels[s % 4])
+        sec_p = timed(lambda s: tr_p.graph_step(dev_batches[s % 4], dev_labels[s % 4]), args.steps)
+        variant = {"config": "attn_downsample=True (SURVEY.md 8f-2)", "value": B * args.steps / sec_p, "unit": UNIT,
+                   "ms_per_step": sec_p / args.steps * 1e3, "final_losses": tr_p.losses()}
+        tr_p.graph = None
+        del tr_p
+
     # every collective is behind us: tear the communicator down on ALL ranks together (a rank that exits while
     # another still holds captured NCCL work can hang in the teardown), then rank 0 alone finishes the report
     if world > 1:
@@ -417,6 +435,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "kernels": {k: {kk: vv for kk, vv in v.items()} for k, v in roofs.items()},
         "cpu_baseline": cpu,
+        "attn_downsample_variant": variant,
         "final_losses": losses,
     }
     print(json.dumps(out), flush=True)
@@ -437,6 +456,8 @@ def main():
                          "headline workload, whose attention is the oracle's un-pooled reading")
     ap.add_argument("--math", default="bf16_tc", choices=["fp32_strict", "bf16_tc"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-variant", dest="variant", action="store_false",
+                    help="skip the extra timing of the step with down-sampled attention (N = 1 only)")
     ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="data-parallel gradient exchange (N > 1)")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="single-stream step (default: G(z) and D(real) of the D phase run as two graph branches)")

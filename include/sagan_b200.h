@@ -299,6 +299,13 @@ size_t sagan_dp_flag_bytes(void);
 int sagan_dp_set_timeout_ms(long long ms);
 int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
                       const float* hyper, unsigned int* epoch, unsigned int* status, sagan_stream_t stream);
+/* The same exchange, which in addition SUMS the replicas' loss sums (strategy.reduce(SUM, per-example loss),
+ * sagan/main.py:216-220): loss_peers[q] = peer-mapped address of replica q's [2] fp32 {sum L_D, sum L_G};
+ * loss_global [2] (local) receives the totals, identical on every replica.  Rides on the exchange's first barrier
+ * (every replica's backward, hence its loss kernels, has completed by then): no extra collective per step. */
+int sagan_dp_sum_adam_losses(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
+                             const float* hyper, unsigned int* epoch, unsigned int* status,
+                             const void* const* loss_peers, float* loss_global, sagan_stream_t stream);
 
 #ifdef __cplusplus
 }

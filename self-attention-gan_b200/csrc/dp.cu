@@ -30,6 +30,7 @@ struct DpPeers {
   const float* grads[DP_MAX_WORLD];
   float* params[DP_MAX_WORLD];
   unsigned int* flags[DP_MAX_WORLD];   // per replica: [2][DP_MAX_WORLD] uint32 (barrier A row, barrier B row)
+  const float* losses[DP_MAX_WORLD];   // optional: per replica [2] loss sums (peer-mapped), null = no loss reduction
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -81,13 +82,20 @@ __device__ __forceinline__ bool dp_barrier(const DpPeers& pr, int rank, int worl
 __global__ void __launch_bounds__(DP_THREADS)
 dp_sum_adam_kernel(const DpPeers pr, int rank, int world, long long n, float* __restrict__ v_shard,
                    const float* __restrict__ hyper, const unsigned int* __restrict__ epoch_ptr, unsigned int* status,
-                   long long timeout_ns) {
+                   long long timeout_ns, float* __restrict__ loss_global) {
   const unsigned int epoch = *epoch_ptr;
   // barrier A: only CTA 0 signals, every CTA waits on the local flags.  A CTA whose wait timed out (status raised)
   // skips the update but still takes part in the CTA count and barrier B below, so the counter never goes stale and
   // the peers are not made to wait for a signal that would never come.
   const bool arrived = dp_barrier(pr, rank, world, 0, epoch, status, blockIdx.x == 0, timeout_ns);
 
+  // strategy.reduce(SUM) of the per-replica loss sums (sagan/main.py:216-220) rides on the same barrier: every replica's
+  // backward -- hence its loss kernels -- is complete once barrier A has passed; fixed order => identical everywhere
+  if (loss_global && arrived && blockIdx.x == 0 && threadIdx.x < 2) {
+    float t = 0.f;
+    for (int q = 0; q < world; ++q) t += pr.losses[q][threadIdx.x];
+    loss_global[threadIdx.x] = t;
+  }
   const float lr_t = hyper[0], b2 = hyper[2], eps = hyper[3];     // beta_1 = 0 (sagan/main.py:119-120): m == g
   const long long per = n / world;                                 // n is a multiple of 4 * world (host pads)
   const long long base = (long long)rank * per;
@@ -141,9 +149,9 @@ extern "C" int sagan_dp_set_timeout_ms(long long ms) {
   return 0;
 }
 
-extern "C" int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
-                                 const float* hyper, unsigned int* epoch, unsigned int* status,
-                                 sagan_stream_t stream) {
+static int dp_sum_adam_impl(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
+                            const float* hyper, unsigned int* epoch, unsigned int* status, const void* const* loss_peers,
+                            float* loss_global, sagan_stream_t stream) {
   SAGAN_REQUIRE(peers && v_shard && hyper && epoch && status, "sagan_dp_sum_adam: null pointer");
   SAGAN_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world,
                 "sagan_dp_sum_adam: bad rank / world (%d / %d, at most %d replicas)", rank, world, DP_MAX_WORLD);
@@ -154,6 +162,10 @@ extern "C" int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int worl
     pr.grads[q] = (const float*)peers->grads[q];
     pr.params[q] = (float*)peers->params[q];
     pr.flags[q] = (unsigned int*)peers->flags[q];
+    if (loss_global) {
+      SAGAN_REQUIRE(loss_peers && loss_peers[q], "sagan_dp_sum_adam_losses: null loss pointer (replica %d)", q);
+      pr.losses[q] = (const float*)loss_peers[q];
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
   dp_bump_epoch_kernel<<<1, 1, 0, st>>>(epoch);
@@ -161,7 +173,20 @@ extern "C" int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int worl
   const long long n4 = n / world / 4;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(num_sms(), ceil_div<long long>(n4, DP_THREADS)));
   dp_sum_adam_kernel<<<blocks, DP_THREADS, 0, st>>>(pr, rank, world, n, v_shard, hyper, epoch, status,
-                                                       g_dp_timeout_ns.load());
+                                                       g_dp_timeout_ns.load(), loss_global);
   SAGAN_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int sagan_dp_sum_adam(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
+                                 const float* hyper, unsigned int* epoch, unsigned int* status,
+                                 sagan_stream_t stream) {
+  return dp_sum_adam_impl(peers, rank, world, n, v_shard, hyper, epoch, status, nullptr, nullptr, stream);
+}
+
+extern "C" int sagan_dp_sum_adam_losses(const sagan_dp_peers* peers, int rank, int world, long long n, float* v_shard,
+                                        const float* hyper, unsigned int* epoch, unsigned int* status,
+                                        const void* const* loss_peers, float* loss_global, sagan_stream_t stream) {
+  SAGAN_REQUIRE(loss_peers && loss_global, "sagan_dp_sum_adam_losses: null loss pointer");
+  return dp_sum_adam_impl(peers, rank, world, n, v_shard, hyper, epoch, status, loss_peers, loss_global, stream);
 }

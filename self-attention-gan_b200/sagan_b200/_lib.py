@@ -39,7 +39,7 @@ class SnBwdDesc(C.Structure):
 
 
 class DpPeers(C.Structure):
-    _fields_ = [("grads", C.c_void_p * 8), ("params", C.c_void_p * 8), ("flags", C.c_void_p * 8)]
+    _fields_ = [("grads", C.c_void_p * 8), ("params", C.c_void_p * 8), ("flags", C.c_void_p * 8)]      # sagan_dp_peers
 
 
 _P, _I, _F, _LL, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
@@ -85,6 +85,7 @@ SIGNATURES = {
     "sagan_dp_set_timeout_ms": (_I, [_LL]),
     "sagan_dp_flag_bytes": (_SZ, []),
     "sagan_dp_sum_adam": (_I, [C.POINTER(DpPeers), _I, _I, _LL, _P, _P, _P, _P, _P]),
+    "sagan_dp_sum_adam_losses": (_I, [C.POINTER(DpPeers), _I, _I, _LL, _P, _P, _P, _P, C.POINTER(_P), _P, _P]),
 }
 
 _lib = None

@@ -64,7 +64,9 @@ class PeerAdam:
     writes the new weights into every replica's parameter buffer.  One kernel per network per update, no NCCL on the
     data path.  The network's flat buffers must be symmetric-memory allocations (see `symmetric_allocator`)."""
 
-    def __init__(self, net, opt, dp):
+    def __init__(self, net, opt, dp, loss_sums=None):
+        """loss_sums: optional symmetric-memory [2] tensor {sum L_D, sum L_G}; when given, every `step()` also sums it
+        over the replicas into `self.loss_global` (sagan/main.py:216-220) inside the same kernel."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         from . import _lib
@@ -90,6 +92,12 @@ class PeerAdam:
             self.peers.params[q] = int(hp.buffer_ptrs[q])
             self.peers.flags[q] = int(hf.buffer_ptrs[q])
         self._handles = (hp, hg, hf)
+        self.loss_global = None
+        if loss_sums is not None:
+            hl = symm.rendezvous(loss_sums, group)
+            self._loss_peers = (C.c_void_p * dp.world)(*[int(hl.buffer_ptrs[q]) for q in range(dp.world)])
+            self.loss_global = torch.zeros(2, device=dev)
+            self._handles += (hl,)
         self.n = n
         self.v_shard = torch.zeros(n // dp.world, device=dev)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -100,6 +108,12 @@ class PeerAdam:
 
     def step(self):
         from . import _lib
+        if self.loss_global is not None:
+            _lib.check(_lib.load().sagan_dp_sum_adam_losses(
+                self._C.byref(self.peers), self.dp.rank, self.dp.world, self.n, self.v_shard.data_ptr(),
+                self.opt.hyper.data_ptr(), self.epoch.data_ptr(), self.status.data_ptr(), self._loss_peers,
+                self.loss_global.data_ptr(), torch.cuda.current_stream().cuda_stream), "sagan_dp_sum_adam_losses")
+            return
         _lib.check(_lib.load().sagan_dp_sum_adam(self._C.byref(self.peers), self.dp.rank, self.dp.world, self.n,
                                                  self.v_shard.data_ptr(), self.opt.hyper.data_ptr(),
                                                  self.epoch.data_ptr(), self.status.data_ptr(),

@@ -104,10 +104,13 @@ class Trainer:
         self.opt_D = FlatAdam(self.D, cfg["lr_d"], steps_per_epoch * ur, cfg["decay_rate"])     # main.py:115-118
         nets.set_flat_allocator(None)
         self.peer_G = self.peer_D = None
-        if self.dp_mode == "p2p":
-            self.peer_G = PeerAdam(self.G, self.opt_G, self.dp)
-            self.peer_D = PeerAdam(self.D, self.opt_D, self.dp)
         self.loss_sums = torch.zeros(2, device=self.device)     # [sum L_D (over update_ratio), sum L_G]
+        if self.dp_mode == "p2p":
+            # the loss sums live in symmetric memory: G's exchange kernel (the last kernel of a step, when both sums are
+            # complete on every replica) also reduces them over the replicas (main.py:216-220)
+            self.loss_sums = symmetric_allocator()(2, self.device)
+            self.peer_G = PeerAdam(self.G, self.opt_G, self.dp, loss_sums=self.loss_sums)
+            self.peer_D = PeerAdam(self.D, self.opt_D, self.dp)
         self.overlap_streams = overlap_streams
         self._side = torch.cuda.Stream(device=self.device) if overlap_streams else None
         if overlap_streams and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
@@ -222,10 +225,12 @@ class Trainer:
         sums = self.loss_sums
         denom = self.global_batch
         if self.world > 1:
-            if reduce:
-                sums = self.dp.sum_losses_(sums.clone())
-            else:
+            if not reduce:
                 denom = self.B
+            elif self.peer_G is not None:
+                sums = self.peer_G.loss_global          # summed over the replicas by the step's last exchange kernel
+            else:
+                sums = self.dp.sum_losses_(sums.clone())
         s = sums.tolist()
         self.check_exchange()
         ur = self.config.get("update_ratio", 1)
