@@ -10,11 +10,14 @@ example_configs/church64_attn.py model (z 128, gf 16, df 16, 64x64, attention at
 per-GPU batch 64, synthetic uniform[-1,1) images and N(0,1) noise.
 
 Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM (CUDA-graph replay of
-the whole step), `e2e` = images/s through the public Trainer API with the batch copied from pinned
-host memory and the two loss scalars read back every step.  `roofline` is the dominant kernel
-(self-attention at N = 4096) timed alone with CUDA events; `cpu_baseline` is the CPU oracle
-(torch-CPU restatement of the reference's TF graph; TensorFlow is not installable here) on a bounded
-sample.  `--impl reference` times that CPU oracle only.
+the whole step), `e2e` = images/s through the public Trainer API with the batch copied every step from
+pinned host memory as the reference's raw uint8 records (sagan/dataset.py:27-40; decoded on the device by
+the first node of the step graph) and the two loss scalars read back.  `roofline` is the dominant kernel
+(self-attention at N = 4096) timed alone with CUDA events; `kernels` holds the other kernel lines
+(down-sampled attention, the large-C block forward and backward, spectral norm); `cpu_baseline` is the CPU
+oracle (torch-CPU restatement of the reference's TF graph; TensorFlow is not installable here) on the same
+step and batch, a bounded number of steps.  `--impl reference` times that CPU oracle only.
+`--config cond128 | res128` run the 128x128 class-conditional configs (not the headline).
 """
 import argparse
 import json
