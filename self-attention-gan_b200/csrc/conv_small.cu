@@ -89,6 +89,63 @@ conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   }
 }
 
+// Stride-1 forward with a tiny output side (G's output layer 16 -> 3, generator.py:36): thread = PX consecutive output
+// pixels of one row.  The weights of a tap (CIN x COUT floats) are read from shared memory once per PX pixels and the
+// PX + KW - 1 input columns of a kernel row are loaded once and shared by the PX windows, which takes the kernel from
+// shared-memory-bound (4 FMA per 128-bit LDS at PX = 1: 54 us) to FMA / L1 bound.
+template <int CIN, int COUT, int PX, int KW>
+__global__ void __launch_bounds__(128)
+conv_small_fwd_s1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         float* __restrict__ y, CG g, int act, float slope) {
+  extern __shared__ __align__(16) float sw[];        // [KH*KW*CIN][COUT] + bias[COUT]
+  const int nw = g.K * COUT;
+  for (int i = threadIdx.x; i < nw; i += 128) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += 128) sw[nw + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int wgroups = g.Wo / PX;                     // host guarantees Wo % PX == 0
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (t >= (long long)g.B * g.Ho * wgroups) return;
+  const int b = (int)(t / (g.Ho * wgroups)), rem = (int)(t - (long long)b * g.Ho * wgroups);
+  const int ho = rem / wgroups, wo0 = (rem - ho * wgroups) * PX;
+  float acc[PX][COUT];
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[p][c] = sw[nw + c];
+  for (int kh = 0; kh < g.KH; ++kh) {
+    const int hi = ho - g.PT + kh;
+    if (hi < 0 || hi >= g.H) continue;
+    float xr[PX + KW - 1][CIN];                      // the input columns wo0 - PL .. wo0 - PL + PX + KW - 2 of this row
+#pragma unroll
+    for (int j = 0; j < PX + KW - 1; ++j) {
+      const int wi = wo0 - g.PL + j;
+      const bool ok = wi >= 0 && wi < g.W;
+      const float* xp = x + ((size_t)(b * g.H + hi) * g.W + (ok ? wi : 0)) * CIN;
+#pragma unroll
+      for (int c = 0; c < CIN; c += 4) {
+        const float4 v = ok ? ld4(xp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[j][c] = v.x; xr[j][c + 1] = v.y; xr[j][c + 2] = v.z; xr[j][c + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int kw = 0; kw < KW; ++kw) {
+      float wv[CIN * COUT];
+      cs_load_tap(sw + (kh * KW + kw) * CIN * COUT, wv);
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[p][co] = fmaf(xr[p + kw][ci], wv[ci * COUT + co], acc[p][co]);
+    }
+  }
+  float* yp = y + ((size_t)(b * g.Ho + ho) * g.Wo + wo0) * COUT;      // PX * COUT contiguous floats
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) yp[p * COUT + c] = cs_act(acc[p][c], act, slope);
+}
+
 // dx[b, hi, wi, ci] = sum over (kh, kw) with (hi + PT - kh) % S == 0, ho = (hi + PT - kh) / S in range (same for w):
 //                     sum_co dy[b, ho, wo, co] w[kh, kw, ci, co]
 template <int CIN, int COUT>
@@ -227,8 +284,11 @@ static int cs_pair(const CG& g) {
 bool conv_small_ok(const CG& g, const void* a, const void* b) {      // backward-data
   return cs_pair(g) != 0 && cs_al16(a) && cs_al16(b);
 }
-// forward: the 16 -> 3 output layer stays on the implicit-GEMM kernels (measured: 54 us direct against 30 us)
-bool conv_small_fwd_ok(const CG& g, const void* a, const void* b) { return cs_pair(g) == 1 && cs_al16(a) && cs_al16(b); }
+// forward: 3 -> 16 (one pixel per thread) and the stride-1 16 -> 3 output layer (four pixels per thread)
+static bool cs_fwd_s1(const CG& g) { return cs_pair(g) == 2 && g.S == 1 && g.KW == 4 && g.Wo % 4 == 0 && g.Wo == g.W && g.Ho == g.H; }
+bool conv_small_fwd_ok(const CG& g, const void* a, const void* b) {
+  return (cs_pair(g) == 1 || cs_fwd_s1(g)) && cs_al16(a) && cs_al16(b);
+}
 // backward-filter: only where all rows of dw fit the CTA (K <= 240 leaves >= COUT threads for the bias column sums)
 bool conv_small_wgrad_ok(const CG& g, const void* a, const void* b) {
   return cs_pair(g) == 1 && g.K + 16 <= CS_THREADS && cs_al16(a) && cs_al16(b);
@@ -240,7 +300,8 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
   if (cs_pair(g) == 1)
     conv_small_fwd_kernel<3, 16><<<nb, CS_THREADS, (g.K * 16 + 16) * sizeof(float), st>>>(x, w, bias, y, g, act, slope);
   else
-    conv_small_fwd_kernel<16, 3><<<nb, CS_THREADS, (g.K * 3 + 3) * sizeof(float), st>>>(x, w, bias, y, g, act, slope);
+    conv_small_fwd_s1_kernel<16, 3, 4, 4><<<(unsigned)ceil_div(g.M / 4, 128), 128, (g.K * 3 + 3) * sizeof(float), st>>>(
+        x, w, bias, y, g, act, slope);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
