@@ -12,6 +12,7 @@
 //         post (dX = dY + dQ Wq^T + dK Wk^T + dV Wv^T)
 //         weight grads as 1x1-conv wgrads (X^T dQ ...), dgamma / dWo / dbo from A^T dY.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -419,8 +420,10 @@ attn_bwd_post_kernel(const float* __restrict__ dY, const float* __restrict__ dQ,
 // All parameter gradients of the block in ONE launch (they are skinny GEMMs over the token axis):
 //   G1 = [X | 1]^T [dQ dK dV]   ((C+1) x (2d+dv))   -> dWq, dWk, dWv, dbq, dbk, dbv
 //   G2 = [A | 1]^T dY           ((dv+1) x C)        -> dWo' = A^T dY, dbo' = colsum(dY)   (scaled by gamma in finalize)
-// One thread per output element (strided when there are more outputs than threads), tokens staged through shared
-// memory in tiles of 32; per-CTA partial sums are combined with fp32 atomics (outputs zeroed by the caller).
+// Tokens are staged through shared memory in tiles.  A thread owns a 4 x 4 BLOCK of outputs (two 128-bit shared-memory
+// loads feed 16 FMAs; one output per thread was shared-memory-bound at 2 loads per FMA: 67 us at T = 262 144) and, when
+// there are fewer blocks than threads, one of TG interleaved token groups; the groups are folded through shared memory
+// and each CTA adds its partial sums with one fp32 atomic per output (outputs zeroed by the caller).
 template <int C>
 __global__ void __launch_bounds__(256)
 attn_wgrad_small_kernel(const float* __restrict__ X, const float* __restrict__ A, const float* __restrict__ dY,
@@ -428,72 +431,116 @@ attn_wgrad_small_kernel(const float* __restrict__ X, const float* __restrict__ A
                         float* __restrict__ dWq, float* __restrict__ dbq, float* __restrict__ dWk,
                         float* __restrict__ dbk, float* __restrict__ dWv, float* __restrict__ dbv,
                         float* __restrict__ dWo, float* __restrict__ dbo, long long T, int tokens_per_block) {
-  // token tile: as large as the 48 KB of static shared memory allow, so the global-load latency of a tile is paid
-  // 4x less often (the tiles are not double-buffered)
   constexpr int D = C / 8, DV = C / 2, TT = C <= 16 ? 128 : (C <= 32 ? 64 : 32);
   constexpr int LW = C + 1, RW = 2 * D + DV;          // G1: left width (X | 1), right width (dQ dK dV)
   constexpr int L2 = DV + 1, R2 = C;                  // G2: (A | 1), dY
-  constexpr int N1 = LW * RW, N2 = L2 * R2, NOUT = N1 + N2;
-  constexpr int PER = (NOUT + 255) / 256;
-  __shared__ float sL1[TT][LW + 1], sR1[TT][RW + 1], sL2[TT][L2 + 1], sR2[TT][R2 + 1];
-  float acc[PER];
-  int li[PER], ri[PER], which[PER];
+  constexpr int LWP = (LW + 3) / 4 * 4, RWP = (RW + 3) / 4 * 4, L2P = (L2 + 3) / 4 * 4, R2P = R2;   // padded to float4
+  constexpr int NB1 = (LWP / 4) * (RWP / 4), NB2 = (L2P / 4) * (R2P / 4), NBLK = NB1 + NB2;
+  constexpr int TG = NBLK >= 256 ? 1 : 256 / NBLK;    // token groups when there are fewer blocks than threads
+  constexpr int PER = (NBLK + 255) / 256;             // blocks per thread when there are more
+  __shared__ __align__(16) float sL1[TT][LWP], sR1[TT][RWP], sL2[TT][L2P], sR2[TT][R2P];
+  float acc[PER][16];
+  int lo[PER], ro[PER], which[PER];
+  const int tg = TG > 1 ? threadIdx.x / NBLK : 0;
 #pragma unroll
   for (int p = 0; p < PER; ++p) {
-    acc[p] = 0.f;
-    const int o = threadIdx.x + p * 256;
-    which[p] = o < N1 ? 1 : (o < NOUT ? 2 : 0);
-    const int oo = o < N1 ? o : o - N1;
-    li[p] = which[p] == 1 ? oo / RW : oo / R2;
-    ri[p] = which[p] == 1 ? oo % RW : oo % R2;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[p][e] = 0.f;
+    const int blk = TG > 1 ? threadIdx.x % NBLK : threadIdx.x + p * 256;
+    which[p] = (tg >= TG || blk >= NBLK) ? 0 : (blk < NB1 ? 1 : 2);
+    const int bb = blk < NB1 ? blk : blk - NB1;
+    const int rblocks = blk < NB1 ? RWP / 4 : R2P / 4;
+    lo[p] = (bb / rblocks) * 4;
+    ro[p] = (bb % rblocks) * 4;
   }
   const long long t0 = (long long)blockIdx.x * tokens_per_block;
   const long long t1 = min(T, t0 + tokens_per_block);
   for (long long tb = t0; tb < t1; tb += TT) {
     const int nt = (int)min((long long)TT, t1 - tb);
     __syncthreads();
-    for (int e = threadIdx.x; e < TT * LW; e += 256) {
-      const int r = e / LW, c = e % LW;
-      sL1[r][c] = r < nt ? (c < C ? X[(tb + r) * C + c] : 1.f) : 0.f;
+    // tile fill with 128-bit (dQ / dK: d floats) global loads; rows beyond nt and the padding columns are zero, the
+    // column after the data is the ones column that yields the bias gradients
+    for (int e = threadIdx.x; e < TT * (C / 4); e += 256) {
+      const int r = e / (C / 4), c = (e % (C / 4)) * 4;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&sL1[r][c]) = r < nt ? ld4(X + (tb + r) * C + c) : z;
+      *reinterpret_cast<float4*>(&sR2[r][c]) = r < nt ? ld4(dY + (tb + r) * C + c) : z;
     }
-    for (int e = threadIdx.x; e < TT * RW; e += 256) {
-      const int r = e / RW, c = e % RW;
-      float v = 0.f;
-      if (r < nt) v = c < D ? dQ[(tb + r) * D + c] : (c < 2 * D ? dK[(tb + r) * D + c - D] : dV[(tb + r) * DV + c - 2 * D]);
-      sR1[r][c] = v;
+    for (int e = threadIdx.x; e < TT * (DV / 4); e += 256) {
+      const int r = e / (DV / 4), c = (e % (DV / 4)) * 4;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&sL2[r][c]) = r < nt ? ld4(A + (tb + r) * DV + c) : z;
+      const float4 v = r < nt ? ld4(dV + (tb + r) * DV + c) : z;
+      sR1[r][2 * D + c] = v.x; sR1[r][2 * D + c + 1] = v.y; sR1[r][2 * D + c + 2] = v.z; sR1[r][2 * D + c + 3] = v.w;
     }
-    for (int e = threadIdx.x; e < TT * L2; e += 256) {
-      const int r = e / L2, c = e % L2;
-      sL2[r][c] = r < nt ? (c < DV ? A[(tb + r) * DV + c] : 1.f) : 0.f;
+    for (int e = threadIdx.x; e < TT * D; e += 256) {
+      const int r = e / D, c = e % D;
+      sR1[r][c] = r < nt ? dQ[(tb + r) * D + c] : 0.f;
+      sR1[r][D + c] = r < nt ? dK[(tb + r) * D + c] : 0.f;
     }
-    for (int e = threadIdx.x; e < TT * R2; e += 256) {
-      const int r = e / R2, c = e % R2;
-      sR2[r][c] = r < nt ? dY[(tb + r) * C + c] : 0.f;
+    for (int r = threadIdx.x; r < TT; r += 256) {
+#pragma unroll
+      for (int c = C; c < LWP; ++c) sL1[r][c] = (c == C && r < nt) ? 1.f : 0.f;
+#pragma unroll
+      for (int c = DV; c < L2P; ++c) sL2[r][c] = (c == DV && r < nt) ? 1.f : 0.f;
+#pragma unroll
+      for (int c = RW; c < RWP; ++c) sR1[r][c] = 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int p = 0; p < PER; ++p) {
-      if (which[p] == 1) {
-#pragma unroll 8
-        for (int r = 0; r < TT; ++r) acc[p] = fmaf(sL1[r][li[p]], sR1[r][ri[p]], acc[p]);
-      } else if (which[p] == 2) {
-#pragma unroll 8
-        for (int r = 0; r < TT; ++r) acc[p] = fmaf(sL2[r][li[p]], sR2[r][ri[p]], acc[p]);
+      if (which[p] == 0) continue;
+#pragma unroll 4
+      for (int r = tg; r < TT; r += TG) {
+        const float4 l4 = which[p] == 1 ? *reinterpret_cast<const float4*>(&sL1[r][lo[p]]) : *reinterpret_cast<const float4*>(&sL2[r][lo[p]]);
+        const float4 r4 = which[p] == 1 ? *reinterpret_cast<const float4*>(&sR1[r][ro[p]]) : *reinterpret_cast<const float4*>(&sR2[r][ro[p]]);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[p][i * 4 + j] = fmaf(lv[i], rv[j], acc[p][i * 4 + j]);
       }
     }
   }
+  // ---- fold the token groups (through the dead left tile), then one atomic per output and CTA
+  __syncthreads();
+  float* red = &sL1[0][0];
+  static_assert(TG == 1 || NBLK * 16 <= TT * LWP, "the fold buffer (16 floats per output block) must fit the left G1 tile");
+  auto emit = [&](int wh, int l0, int r0, const float* v) {
 #pragma unroll
-  for (int p = 0; p < PER; ++p) {
-    if (which[p] == 1) {
-      const int l = li[p], r = ri[p];
-      float* dst;
-      if (l < C) dst = r < D ? dWq + l * D + r : (r < 2 * D ? dWk + l * D + (r - D) : dWv + l * DV + (r - 2 * D));
-      else dst = r < D ? dbq + r : (r < 2 * D ? dbk + (r - D) : dbv + (r - 2 * D));
-      atomicAdd(dst, acc[p]);
-    } else if (which[p] == 2) {
-      const int l = li[p], r = ri[p];
-      atomicAdd(l < DV ? dWo + l * C + r : dbo + r, acc[p]);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = l0 + i, r = r0 + j;
+        if (wh == 1) {
+          if (l >= LW || r >= RW) continue;
+          float* dst;
+          if (l < C) dst = r < D ? dWq + l * D + r : (r < 2 * D ? dWk + l * D + (r - D) : dWv + l * DV + (r - 2 * D));
+          else dst = r < D ? dbq + r : (r < 2 * D ? dbk + (r - D) : dbv + (r - 2 * D));
+          atomicAdd(dst, v[i * 4 + j]);
+        } else {
+          if (l >= L2 || r >= R2) continue;
+          atomicAdd(l < DV ? dWo + l * C + r : dbo + r, v[i * 4 + j]);
+        }
+      }
+  };
+  if (TG > 1) {
+    // groups 1.. hand their partial sums to group 0 in rounds of 16 floats per thread
+    for (int g = 1; g < TG; ++g) {
+      if (tg == g && which[0])
+#pragma unroll
+        for (int e = 0; e < 16; ++e) red[(threadIdx.x % NBLK) * 16 + e] = acc[0][e];
+      __syncthreads();
+      if (tg == 0 && which[0])
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[0][e] += red[threadIdx.x * 16 + e];
+      __syncthreads();
     }
+    if (tg == 0 && which[0]) emit(which[0], lo[0], ro[0], acc[0]);
+  } else {
+#pragma unroll
+    for (int p = 0; p < PER; ++p)
+      if (which[p]) emit(which[p], lo[p], ro[p], acc[p]);
   }
 }
 
