@@ -263,6 +263,15 @@ int sagan_hinge_g(const float* d_fake, long long n, float scale, float* loss_sum
  * ------------------------------------------------------------------------------------------ */
 int sagan_adam_step(float* param, const float* grad, float* m, float* v, long long n,
                     const float* hyper, float grad_scale, sagan_stream_t stream);
+/* dst[i] += src[i] for n <= 64 tensors in one launch (gradient accumulation of the small parameters into a network's
+ * flat gradient bucket: what `tape.gradient` + `apply_gradients` leave to one accumulation op per variable). */
+typedef struct sagan_acc_desc {
+  float* dst;
+  const float* src;
+  long long n;
+} sagan_acc_desc;
+int sagan_accumulate_multi(const sagan_acc_desc* descs_host, int n, sagan_stream_t stream);
+
 /* Learning-rate schedule + Adam bias correction of sagan/main.py:111-120 evaluated on the device:
  *   lr   = lr0 * decay_rate ^ (iterations / decay_steps)          ExponentialDecay(..., staircase=True)
  *   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t),  t = iterations + 1   (Keras Adam)

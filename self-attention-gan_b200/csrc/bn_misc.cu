@@ -266,6 +266,23 @@ __global__ void adam_schedule_kernel(float* __restrict__ hyper, long long* __res
   *iterations = it + 1;                                                        // optimizer.iterations
 }
 
+// ------------------------------------------------------------------------------------ multi-tensor accumulate
+// dst[i] += src[i] for up to 64 small tensors in ONE launch: the gradients of the parameters that are not spectrally
+// normalised (biases, BatchNorm gamma / beta, attention gamma, head kernels) go into the network's flat gradient bucket
+// this way instead of one autograd accumulation kernel per parameter (42 launches per step at church64).
+constexpr int ACC_MAX = 64;
+struct AccTab {
+  float* dst[ACC_MAX];
+  const float* src[ACC_MAX];
+  int n[ACC_MAX];
+};
+__global__ void __launch_bounds__(256) accumulate_multi_kernel(const AccTab t) {
+  float* d = t.dst[blockIdx.y];
+  const float* s = t.src[blockIdx.y];
+  const int n = t.n[blockIdx.y];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) d[i] += s[i];
+}
+
 // ------------------------------------------------------------------------------------ weight normalisation
 // /root/reference/sagan/layers.py:75-135 (the TF-Addons WeightNormalization wrapper the `sagan/` tree wraps its layers
 // with): kernel = l2_normalize(v, all axes but the last) * g.  v is the [rows, cols] row-major view of the Keras kernel
@@ -480,6 +497,21 @@ extern "C" int sagan_u8_to_f32(const uint8_t* src, float* dst, long long n, floa
   SAGAN_REQUIRE((((uintptr_t)src) & 3) == 0 && al16(dst), "sagan_u8_to_f32: src must be 4-byte, dst 16-byte aligned");
   const int blocks = (int)std::min<long long>(num_sms() * 8, ceil_div<long long>(n, 1024));
   u8_to_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n, scale, shift);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_accumulate_multi(const sagan_acc_desc* descs, int n, sagan_stream_t stream) {
+  SAGAN_REQUIRE(descs && n >= 1 && n <= ACC_MAX, "sagan_accumulate_multi: n=%d outside [1,%d]", n, ACC_MAX);
+  AccTab t{};
+  long long biggest = 0;
+  for (int i = 0; i < n; ++i) {
+    SAGAN_REQUIRE(descs[i].dst && descs[i].src && descs[i].n > 0 && descs[i].n < (1ll << 31), "sagan_accumulate_multi: bad descriptor %d", i);
+    t.dst[i] = descs[i].dst; t.src[i] = descs[i].src; t.n[i] = (int)descs[i].n;
+    biggest = std::max(biggest, descs[i].n);
+  }
+  const int bx = (int)std::max<long long>(1, std::min<long long>(32, ceil_div<long long>(biggest, 1024)));
+  accumulate_multi_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(t);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }

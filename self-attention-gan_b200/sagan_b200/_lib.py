@@ -38,6 +38,10 @@ class SnBwdDesc(C.Structure):
                 ("cols", C.c_int32)]
 
 
+class AccDesc(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("n", C.c_longlong)]
+
+
 class DpPeers(C.Structure):
     _fields_ = [("grads", C.c_void_p * 8), ("params", C.c_void_p * 8), ("flags", C.c_void_p * 8)]      # sagan_dp_peers
 
@@ -80,6 +84,7 @@ SIGNATURES = {
     "sagan_hinge_d": (_I, [_P, _P, _LL, _F, _P, _P, _P, _P]),
     "sagan_hinge_g": (_I, [_P, _LL, _F, _P, _P, _P]),
     "sagan_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _F, _P]),
+    "sagan_accumulate_multi": (_I, [C.POINTER(AccDesc), _I, _P]),
     "sagan_adam_schedule": (_I, [_P, _P, C.c_double, C.c_double, _LL, C.c_double, C.c_double, C.c_double, _P]),
     "sagan_dp_max_world": (_I, []),
     "sagan_dp_set_timeout_ms": (_I, [_LL]),

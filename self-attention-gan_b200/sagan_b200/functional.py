@@ -402,6 +402,43 @@ class _SnGroupFn(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class _ParamSinkFn(torch.autograd.Function):
+    """Proxies for a network's parameters that are NOT spectrally normalised (biases, BatchNorm gamma / beta, attention
+    gamma, un-normalised head kernels).  Forward hands out aliases of the parameters; backward receives all their
+    gradients at once and adds them into the pre-allocated `.grad` views (the network's flat gradient bucket) with ONE
+    multi-tensor launch, returning None to autograd -- instead of one accumulation kernel per parameter."""
+
+    @staticmethod
+    def forward(ctx, holder, *params):
+        ctx.params = params
+        return tuple(p.detach() for p in params)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        out = [None] * len(grads)
+        todo = []
+        for i, (p, g) in enumerate(zip(ctx.params, grads)):
+            if g is None or not ctx.needs_input_grad[1 + i]:
+                continue
+            if p.grad is None:
+                out[i] = g                     # no bucket: let autograd keep the gradient
+            else:
+                todo.append((p.grad, g.contiguous()))
+        for a in range(0, len(todo), 64):
+            chunk = todo[a:a + 64]
+            descs = (_lib.AccDesc * len(chunk))()
+            for j, (dst, src) in enumerate(chunk):
+                descs[j] = _lib.AccDesc(_ptr(dst), _ptr(src), src.numel())
+            check(lib.sagan_accumulate_multi(descs, len(chunk), _stream()), "sagan_accumulate_multi")
+        return (None, *out)
+
+
+def param_proxies(params):
+    """Aliases of `params` whose gradients are accumulated into `p.grad` by one launch (see _ParamSinkFn)."""
+    return _ParamSinkFn.apply(None, *params)
+
+
 # ------------------------------------------------------------------------------------ losses / optimiser
 def hinge_d_grads(d_real, d_fake, global_batch, loss_sum):
     """sagan/main.py:24-27,183-184: accumulates sum(L) into loss_sum[0]; returns d(mean(L)/global_batch)/d logits."""

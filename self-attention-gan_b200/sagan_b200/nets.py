@@ -93,6 +93,16 @@ class Network(torch.nn.Module):
                                                 [m.factor for m in self._sn_layers])
             for i, m in enumerate(self._sn_layers):
                 m.adopt(self.sn_group, i)
+        # parameters that are not spectrally-normalised kernels (biases, BatchNorm gamma / beta, attention gamma,
+        # un-normalised head kernels): read through proxies during a forward, see _normalise_all
+        sn_kernels = {id(m._kernel()) for m in self._sn_layers}
+        self._plain = []
+        for mod in self.modules():
+            if isinstance(mod, nn.Layer):
+                for name in ("kernel", "bias", "gamma", "beta", "sigma"):
+                    p_ = mod.__dict__.get("_parameters", {}).get(name)
+                    if isinstance(p_, torch.nn.Parameter) and id(p_) not in sn_kernels:
+                        self._plain.append((mod, name, p_))
         self.finalized = True
 
     def named_flat_parameters(self):
@@ -103,6 +113,10 @@ class Network(torch.nn.Module):
 
     def _normalise_all(self, training):
         """One launch for all spectrally-normalised kernels; hands W_bar to each wrapper."""
+        if self._plain:
+            proxies = F.param_proxies([p_ for _, _, p_ in self._plain])
+            for (mod, name, _), px in zip(self._plain, proxies):
+                mod.__dict__.setdefault("_px", {})[name] = px
         if not self._sn_layers:
             return
         wbars = self.sn_group.normalized(update=training)

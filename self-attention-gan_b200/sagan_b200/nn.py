@@ -52,6 +52,14 @@ class Layer(torch.nn.Module):
             self.built = True
         return self.call(x, *args, **kwargs)
 
+    def _p(self, name):
+        """The parameter `name`, or its proxy for the current network forward (nets.Network hands out proxies whose
+        gradients are accumulated into the flat bucket by one launch, functional.param_proxies)."""
+        px = self.__dict__.get("_px")
+        if px is not None and name in px:
+            return px[name]
+        return getattr(self, name)
+
     @property
     def weights(self):
         """Keras order: kernel first (SpectralNormalization reads module.weights[0], layers.py:31,55)."""
@@ -91,11 +99,11 @@ class Conv2D(Layer):
         self.built = True
 
     def call_with_kernel(self, x, kernel):
-        return F.conv2d(x, kernel, self.bias, self.strides, self.padding, self.activation, self.leaky_slope,
+        return F.conv2d(x, kernel, self._p("bias"), self.strides, self.padding, self.activation, self.leaky_slope,
                         self.math_mode)
 
     def call(self, x):
-        return self.call_with_kernel(x, self.kernel)
+        return self.call_with_kernel(x, self._p("kernel"))
 
 
 class Conv2DTranspose(Layer):
@@ -125,10 +133,10 @@ class Conv2DTranspose(Layer):
 
     def call_with_kernel(self, x, kernel):
         y = F.conv2d_transpose(x, kernel, self.strides, self.padding, self.math_mode)
-        return F.bias_add(y, self.bias) if self.bias is not None else y
+        return F.bias_add(y, self._p("bias")) if self.bias is not None else y
 
     def call(self, x):
-        return self.call_with_kernel(x, self.kernel)
+        return self.call_with_kernel(x, self._p("kernel"))
 
 
 class Dense(Layer):
@@ -146,10 +154,10 @@ class Dense(Layer):
         self.built = True
 
     def call_with_kernel(self, x, kernel):
-        return F.dense(x, kernel, self.bias, self.math_mode)
+        return F.dense(x, kernel, self._p("bias"), self.math_mode)
 
     def call(self, x):
-        return self.call_with_kernel(x, self.kernel)
+        return self.call_with_kernel(x, self._p("kernel"))
 
 
 class BatchNormalization(Layer):
@@ -172,7 +180,7 @@ class BatchNormalization(Layer):
     def call(self, x, training=True):
         if not training:
             raise NotImplementedError("inference-mode BatchNormalization is outside the training hot path")
-        return F.batchnorm_lrelu(x, self.gamma, self.beta, self.moving_mean, self.moving_var, self.epsilon,
+        return F.batchnorm_lrelu(x, self._p("gamma"), self._p("beta"), self.moving_mean, self.moving_var, self.epsilon,
                                  self.momentum, self.leaky_slope)
 
 
@@ -369,7 +377,7 @@ class Embedding(Layer):
         return kernel.index_select(0, labels.long())
 
     def call(self, labels):
-        return self.call_with_kernel(labels, self.kernel)
+        return self.call_with_kernel(labels, self._p("kernel"))
 
 
 class Attention_Layer(Layer):
@@ -416,11 +424,11 @@ class Attention_Layer(Layer):
             kernels.append(wb.reshape(wb.shape[2], wb.shape[3]))
         phi, theta, g, o = self.SN_conv
         y = F.attention(x.reshape(B, H * W, Cc),
-                        kernels[1], theta.module.bias,       # queries: theta, layers.py:104-105
-                        kernels[0], phi.module.bias,         # keys:    phi,   layers.py:99
-                        kernels[2], g.module.bias,           # values:  g,     layers.py:112
-                        kernels[3], o.module.bias,           # output conv,    layers.py:119
-                        self.sigma, self.math_mode,
+                        kernels[1], theta.module._p("bias"), # queries: theta, layers.py:104-105
+                        kernels[0], phi.module._p("bias"),   # keys:    phi,   layers.py:99
+                        kernels[2], g.module._p("bias"),     # values:  g,     layers.py:112
+                        kernels[3], o.module._p("bias"),     # output conv,    layers.py:119
+                        self._p("sigma"), self.math_mode,
                         (H, W) if self.pool else None)       # layers.py:100,113 (MaxPool2D on phi and g)
         return y.reshape(B, H, W, Cc)
 
