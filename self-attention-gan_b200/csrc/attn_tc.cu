@@ -22,6 +22,7 @@
 // NS = number of S buffers: 2 lets QK_{j+1} run under softmax_j (ping-pong inside the CTA, one CTA per SM);
 // NS = 1 is used for small value dims where two CTAs share an SM and overlap each other instead.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -223,6 +224,23 @@ __device__ __forceinline__ float ex2_poly(float x) {
   const float f = x - (r - 12582912.0f);
   const float p = fmaf(fmaf(fmaf(5.517132208e-02f, f, 2.426105440e-01f), f, 6.932609677e-01f), f, 9.999281168e-01f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+// the same arithmetic on a pair of columns with packed fp32 instructions (bit-identical per lane to ex2_poly)
+__device__ __forceinline__ uint32_t ex2_poly2_bf16(f2 x) {
+  float a, b;
+  f2_unpack(x, a, b);
+  x = f2_pack(fmaxf(a, -125.0f), fmaxf(b, -125.0f));
+  const f2 magic = f2_pack(12582912.0f, 12582912.0f);
+  const f2 r = f2_add(x, magic);
+  const f2 f = f2_sub(x, f2_sub(r, magic));
+  f2 p = f2_fma(f2_pack(5.517132208e-02f, 5.517132208e-02f), f, f2_pack(2.426105440e-01f, 2.426105440e-01f));
+  p = f2_fma(p, f, f2_pack(6.932609677e-01f, 6.932609677e-01f));
+  p = f2_fma(p, f, f2_pack(9.999281168e-01f, 9.999281168e-01f));
+  float p0, p1, r0, r1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(r, r0, r1);
+  return pack_bf16x2(__int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23)),
+                     __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
 }
 
 template <int DVP, int NS, int NP, int CEPI>
@@ -431,15 +449,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j >= NP) mbar_wait(barPV + ((j - NP) & 1), ((j - NP) >> 1) & 1);
       uint8_t* sPj = sP + pb * L::P_BYTES;
       // ---- P' = bf16(exp2(S - m)), swizzled store (16 B = 8 keys per store); the row sum comes out of the PV MMA
+      const f2 neg_m = f2_pack(-m_used, -m_used);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float p0 = ex2_approx(__uint_as_float(r[g * 8 + 2 * i]) - m_used);
-          const float p1 = (TC_POLY_EXP && (i & 1)) ? ex2_poly(__uint_as_float(r[g * 8 + 2 * i + 1]) - m_used)
-                                                    : ex2_approx(__uint_as_float(r[g * 8 + 2 * i + 1]) - m_used);
-          pk[i] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 4; ++i) {     // S - m for two columns per FADD2; one column pair in four takes the FMA-pipe 2^x
+          const f2 x = f2_add(f2_pack(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1])), neg_m);
+          // TC_POLY_EXP = 1: 2 column pairs of 8 on the FMA pipe, 2: 3 of 8, 3: 4 of 8
+          if ((TC_POLY_EXP >= 1 && i == 3) || (TC_POLY_EXP == 2 && i == 1 && (g & 1)) || (TC_POLY_EXP >= 3 && i == 1)) {
+            pk[i] = ex2_poly2_bf16(x);
+          } else {
+            float x0, x1;
+            f2_unpack(x, x0, x1);
+            pk[i] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+          }
         }
         // key columns 64 h + [8g, 8g+8): 64-key sub-tile h, 16-byte chunk g
         *reinterpret_cast<uint4*>(sPj + h * (128 * 128) + sw128_offset(row, g)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -509,6 +533,419 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------ flash forward, four chains
+// C <= 32 (in-model shapes), PERSISTENT: one CTA per SM walks the (sample, 128-query tile) work items w = blockIdx.x,
+// blockIdx.x + gridDim.x, ...
+//
+// The kernel above runs every softmax thread of a CTA through the same phases at the same time (one S barrier, one
+// row-max exchange, one P barrier per tile) and pays ~5 us of prologue / epilogue per CTA.  Here the 128 key columns of
+// a tile are four CHAINS of 32 columns, each with its own S slice, running max and O accumulator:
+//   16 softmax warps: warp w <-> chain w >> 2, TMEM lane quarter w & 3; every scheduler hosts one warp of each chain
+//   S_q(g) = Q K_g[32 q .. 32 q + 32)^T        (M = 128, N = 32)  -> TMEM, NS buffers per chain
+//   P'_q(g) = bf16(exp2(S - m_q)) overwrites the first 16 columns of S_q(g) IN TMEM and is the A operand of
+//   O_q += P'_q(g) V_g[32 q .. )               (tcgen05.mma, A from TMEM): no shared-memory P tile, no proxy fence
+// No thread exchanges anything with another thread inside the key loop, and each waits on ONE barrier per tile.
+// A thread keeps ONE 32-column chunk in registers: as soon as a 16-column half has been turned into P', the same
+// registers take that half of S_q(g+1) (with NS = 3 -- C = 16: 3 x 128 + 4 x 32 TMEM columns -- that tile has been
+// complete since the previous one), so the TMEM round trip runs under the other half's exponentials.  (Two full
+// register sets, with the next row maximum computed under the current exponentials, measured the same per tile but
+// spilled at the 96 registers 608 threads leave.)
+// g counts key tiles across work items: the K / V rings, the S buffers and every barrier phase run on, so the TMA
+// producer and the MMA issuers are already loading and multiplying the next item's first tiles while the softmax
+// warps run the epilogue of the current one (fit of measured times over tiles-per-CTA: 5.3 us per non-persistent CTA
+// besides 0.63 us per tile).
+// The tensor pipe executes in issue order: QK_q(g+NS), issued after PV_q(g), cannot overwrite the P' columns early,
+// and "S_q(g+NS) ready" implies "PV_q(g) complete" (used by the lazy rescale and the epilogue).  m_q is integer-valued
+// per chain ("consistent rounding" holds per chain: bf16 rounding commutes with powers of two); the epilogue
+// combines the four accumulators with exact power-of-two factors.
+// What bounds it (tools/ubench/softmax_mix.cu, softmax_tmem.cu; 4 warps x 32 columns per scheduler = one tile):
+// MUFU alone 768 cycles at 3/4 of the exponentials, the whole register-only mix 866, with the TMEM load / store and
+// barrier operations of the tile body ~1000; the kernel runs at ~1200 cycles per tile plus 2.2 us per work item
+// (removing every MMA changes that by 7 %: it is the softmax warps' own instruction stream, not the tensor pipe).
+constexpr int TC4_THREADS = 608;     // 16 softmax warps + TMA producer + 2 MMA issuers (chains {0,1} and {2,3})
+constexpr int TC4_NK = 6, TC4_NV = 3;
+
+template <int DVP, int CEPI>
+struct Fwd4Smem {
+  static constexpr int QKB = qk_cols(CEPI) * 2;
+  static_assert(QKB == 32, "the chained kernel is built for C <= 32 (one MMA K step of split logits)");
+  static constexpr int NS = (3 * 128 + 4 * DVP <= 512) ? 3 : 2;      // S buffers per chain
+  static constexpr int Q_BYTES = 128 * QKB;
+  static constexpr int K_BYTES = 128 * QKB;
+  static constexpr int V_BYTES = 2 * DVP * 128;
+  static constexpr int OFF_Q = 0;                             // two buffers (work items k, k + 1)
+  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
+  static constexpr int OFF_V = (OFF_K + TC4_NK * K_BYTES + 1023) / 1024 * 1024;
+  static constexpr int OFF_W = OFF_V + TC4_NV * V_BYTES;
+  static constexpr int W_BYTES = (((CEPI / 2) * CEPI + CEPI) * 4 + 127) / 128 * 128;
+  static constexpr int OFF_X = OFF_W + W_BYTES;               // m_q of the four chains, [item parity][4][128]
+  static constexpr int OFF_BAR = OFF_X + 2 * 4 * 128 * 4;
+  static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+  static constexpr int OCOL = NS * 128;                       // S buffers, then one accumulator per chain
+  static_assert(OCOL + 4 * DVP <= 512, "TMEM columns");
+  static_assert(V_BYTES % 1024 == 0, "V tiles must stay 1024-byte aligned");
+  static_assert(TC4_NK >= NS + 1, "K ring");
+};
+
+template <int DVP, int CEPI>
+__global__ void __launch_bounds__(TC4_THREADS, 1)
+attn_fwd_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const float* __restrict__ X, const float* __restrict__ Wo,
+                    const float* __restrict__ bo, const float* __restrict__ gamma, float* __restrict__ Y,
+                    float* __restrict__ lse, float* __restrict__ A_saved, int N, int Npad, int Nk, int Nkpad, int dv,
+                    int nitems) {
+  using L = Fwd4Smem<DVP, CEPI>;
+  constexpr int NS = L::NS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + L::OFF_Q;
+  uint8_t* sK = smem + L::OFF_K;
+  uint8_t* sV = smem + L::OFF_V;
+  float* sW = reinterpret_cast<float*>(smem + L::OFF_W);
+  float* sX = reinterpret_cast<float*>(smem + L::OFF_X);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* barQfull = bars + 0;                 // [2]
+  uint64_t* barQfree = bars + 2;                 // [2] both issuers: the last QK MMA of the item has been issued and is done
+  uint64_t* barKfull = bars + 4;                 // [NK]
+  uint64_t* barKfree = barKfull + TC4_NK;        // [NK] both issuers: the QK MMAs that read the stage are done
+  uint64_t* barVfull = barKfree + TC4_NK;        // [NV]
+  uint64_t* barVfree = barVfull + TC4_NV;        // [NV] both issuers: the PV MMAs that read the stage are done
+  uint64_t* barS = barVfree + TC4_NV;            // [chain][NS] S_q(g) ready (=> PV_q(g - NS) complete), buffer g % NS
+  uint64_t* barP = barS + 4 * NS;                // [chain][NS] 128 arrivals: P'_q(g) is in TMEM
+  uint64_t* barOfree = barP + 4 * NS;            // 512 arrivals: the item's accumulators are in registers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(barOfree + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int nt = Nkpad / 128;                    // key tiles per item
+  const int nq = Npad / 128;                     // query tiles per sample
+  const int my_items = blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(barQfull + i, 1); mbar_init(barQfree + i, 2); }
+    for (int i = 0; i < TC4_NK; ++i) { mbar_init(barKfull + i, 1); mbar_init(barKfree + i, 2); }
+    for (int i = 0; i < TC4_NV; ++i) { mbar_init(barVfull + i, 1); mbar_init(barVfree + i, 2); }
+    for (int i = 0; i < 4 * NS; ++i) { mbar_init(barS + i, 1); mbar_init(barP + i, 128); }
+    mbar_init(barOfree, 512);
+    mbar_fence_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 16) {
+    // ================================================================ TMA producer: Q per item, K ring and V ring
+    if (elect_one_sync()) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      // positions of the next K tile and the next V tile to load: (item index k, tile j inside it), ring stage and use count
+      int kk = 0, kj = 0, ks = 0, ku = 0;
+      int vk = 0, vj = 0, vs = 0, vu = 0;
+      while (kk < my_items || vk < my_items) {
+        bool moved = false;
+        if (kk < my_items) {
+          bool ok = ku == 0 || mbar_try_wait(barKfree + ks, (ku - 1) & 1);
+          // the item's Q tile goes first, into buffer kk & 1 (free once the QK MMAs of item kk - 2 are done)
+          if (ok && kj == 0 && kk >= 2) ok = mbar_try_wait(barQfree + (kk & 1), ((kk >> 1) - 1) & 1);
+          if (ok) {
+            const int w = (int)blockIdx.x + kk * (int)gridDim.x;
+            const int b = w / nq, qt = w - b * nq;
+            if (kj == 0) {
+              mbar_expect_tx(barQfull + (kk & 1), L::Q_BYTES);
+              tma_load_2d(sQ + (kk & 1) * L::Q_BYTES, &tmQ, barQfull + (kk & 1), 0, b * Npad + qt * 128);
+            }
+            mbar_expect_tx(barKfull + ks, L::K_BYTES);
+            tma_load_2d(sK + ks * L::K_BYTES, &tmK, barKfull + ks, 0, b * Nkpad + kj * 128);
+            if (++kj == nt) { kj = 0; ++kk; }
+            if (++ks == TC4_NK) { ks = 0; ++ku; }
+            moved = true;
+          }
+        }
+        if (vk < my_items) {
+          if (vu == 0 || mbar_try_wait(barVfree + vs, (vu - 1) & 1)) {
+            const int w = (int)blockIdx.x + vk * (int)gridDim.x;
+            const int b = w / nq;
+            mbar_expect_tx(barVfull + vs, L::V_BYTES);
+            tma_load_2d(sV + vs * L::V_BYTES, &tmV, barVfull + vs, vj * 128, b * DVP);
+            tma_load_2d(sV + vs * L::V_BYTES + DVP * 128, &tmV, barVfull + vs, vj * 128 + 64, b * DVP);
+            if (++vj == nt) { vj = 0; ++vk; }
+            if (++vs == TC4_NV) { vs = 0; ++vu; }
+            moved = true;
+          }
+        }
+        if (!moved) __nanosleep(64);
+      }
+    }
+  } else if (warp >= 17) {
+    // ================================================================ MMA issuers: warp 17 chains {0, 1}, warp 18 chains {2, 3}
+    // The WHOLE warp runs the loop (uniform control flow, ring positions kept as wrapping counters, addresses in the
+    // uniform datapath); only the tcgen05 instructions are issued by the elected lane.  With the loop inside the
+    // elected thread the address arithmetic (divisions by the ring sizes, R2UR moves) cost ~70 cycles per MMA and the
+    // issuer, not the softmax, set the tile time (clock64 timeline: 565 cycles of issue per tile and issuer).
+    {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 32);
+      constexpr uint32_t IDESC_O = make_idesc_bf16(128, DVP);
+      const bool leader = elect_one_sync();
+      const int q0 = (warp - 17) * 2;
+      const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK) + q0 * (32 * L::QKB), sVa = smem_u32(sV);
+      const int total = my_items * nt;
+      // look-ahead position: the tile whose QK MMAs are issued next (item nk, tile nj, K stage sk, S buffer nb)
+      int nk = 0, nj = 0, sk = 0, nb = 0;
+      uint32_t pk = 0;
+      int gn = 0;
+      auto issue_qk_next = [&]() {       // S_q(gn) = Q_nk K_gn[32 q ..)^T for this issuer's two chains; commits NOT included
+        if (nj == 0) mbar_wait(barQfull + (nk & 1), (nk >> 1) & 1);
+        mbar_wait(barKfull + sk, pk);
+        tc_fence_after();
+      };
+      auto advance_next = [&]() {
+        if (leader) {
+          mma_commit(barKfree + sk);
+          if (nj == nt - 1) mma_commit(barQfree + (nk & 1));
+        }
+        if (++nj == nt) { nj = 0; ++nk; }
+        if (++sk == TC4_NK) { sk = 0; pk ^= 1; }
+        if (++nb == NS) nb = 0;
+        ++gn;
+      };
+      for (; gn < NS && gn < total;) {   // prologue: the first NS tiles
+        issue_qk_next();
+        if (leader) {
+          const uint64_t descQ = make_desc_sw32(sQa + (nk & 1) * L::Q_BYTES);
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            mma_bf16_ss(tmem_base + (uint32_t)(nb * 128 + (q0 + qq) * 32), descQ,
+                        make_desc_sw32(sKa + sk * L::K_BYTES + qq * (32 * L::QKB)), IDESC_S, false);
+            mma_commit(barS + (q0 + qq) * NS + nb);
+          }
+        }
+        advance_next();
+      }
+      // position of the tile whose PV MMAs are issued: item k, tile j, V stage sv, S buffer sb (phases pv, pb)
+      int k = 0, j = 0, sv = 0, sb = 0;
+      uint32_t pv = 0, pb = 0;
+      for (int g = 0; g < total; ++g) {
+        const bool has_next = gn < total;
+        mbar_wait(barVfull + sv, pv);
+        if (has_next) issue_qk_next();
+        if (j == 0 && k > 0) mbar_wait(barOfree, (k - 1) & 1);     // the previous item's accumulators have been read
+        tc_fence_after();
+        const uint32_t vbase = sVa + sv * L::V_BYTES;
+        const uint64_t descQ = make_desc_sw32(sQa + (nk & 1) * L::Q_BYTES);
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q = q0 + qq;
+          mbar_wait(barP + q * NS + sb, pb);                   // P'_q(g) is in TMEM
+          tc_fence_after();
+          if (leader) {
+            const uint32_t t_s = tmem_base + (uint32_t)(sb * 128 + q * 32);
+            // key steps 2q, 2q+1 of the tile: 64-key sub-tile q >> 1, 32-byte column blocks 2 (q & 1) and 2 (q & 1) + 1
+            const uint32_t vq = vbase + (q >> 1) * (DVP * 128) + (q & 1) * 64;
+            mma_bf16_ts_g<1>(tmem_base + L::OCOL + q * DVP, t_s, make_desc_sw128(vq), IDESC_O, j > 0);
+            mma_bf16_ts_g<1>(tmem_base + L::OCOL + q * DVP, t_s + 8, make_desc_sw128(vq + 32), IDESC_O, true);
+            if (has_next)      // S_q(g + NS) into the same buffer: ordered behind the two MMAs that read P' from it
+              mma_bf16_ss(t_s, descQ, make_desc_sw32(sKa + sk * L::K_BYTES + qq * (32 * L::QKB)), IDESC_S, false);
+            mma_commit(barS + q * NS + sb);                    // "S_q(g+NS) ready" == "PV_q(g) complete" when there is no such tile
+          }
+        }
+        if (leader) mma_commit(barVfree + sv);
+        if (has_next) advance_next();
+        if (++j == nt) { j = 0; ++k; }
+        if (++sv == TC4_NV) { sv = 0; pv ^= 1; }
+        if (++sb == NS) { sb = 0; pb ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ softmax warps
+    // (state that lives across the key loop is kept to a handful of 32-bit registers: two 32-column S chunks plus the
+    //  packed P' half already take 72 of the 104 a thread can have)
+    const int q = warp >> 2;
+    const uint32_t t_chain = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(q * 32);   // S_q, buffer 0, this lane quarter
+    const uint32_t bS = smem_u32(barS + q * NS);                    // barS[q][0]; barP[q][0] is 4 NS barriers further
+    constexpr uint32_t BP = 4 * NS * 8;
+    {
+      const int nW = dv * CEPI;
+      for (int e = threadIdx.x; e < nW; e += 512) sW[e] = Wo[e];
+      for (int e = threadIdx.x; e < CEPI; e += 512) sW[nW + e] = bo[e];
+    }
+    const int kv_last = Nk - (nt - 1) * 128 - q * 32;                // columns of this chunk that exist in the last key tile
+    uint32_t r[32];                // S_q of the current tile; each half is refilled with the next tile's as soon as it is used
+    uint32_t sb = 0, pb = 0;       // S buffer of the current tile (tiles are counted across items) and its phase
+    float m_used;                  // integer-valued (log2 units) once set
+
+    // chunk maximum; `last`: the tile is the item's last one, whose missing keys (ragged Nk) count as -inf
+    auto row_max = [&](bool last) -> float {
+      if (last && kv_last < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= kv_last) r[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+      }
+      return fmaxf(mx0, mx1);
+    };
+    auto landed = [&]() {
+      tmem_wait_ld();
+      // the loaded values exist from here on: keep the compiler from touching the registers before the wait
+#pragma unroll
+      for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+    };
+    auto exps = [&](int e, float nm, uint32_t (&pk)[8]) {   // columns 2e, 2e+1: S - m with one FADD2; one pair in four on the FMA pipe
+      const f2 x = f2_add(f2_pack(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), f2_pack(nm, nm));
+      if (TC_POLY_EXP && (e & 3) == 3) {
+        pk[e & 7] = ex2_poly2_bf16(x);
+      } else {
+        float x0, x1;
+        f2_unpack(x, x0, x1);
+        pk[e & 7] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+      }
+    };
+
+    for (int k = 0; k < my_items; ++k) {
+      m_used = -1.0e30f;           // finite, so that all-masked chunks give P' = 0
+      mbar_wait_a(bS + sb * 8, pb);
+      tc_fence_after();
+      tmem_ld32(t_chain + sb * 128, r);
+      landed();
+      float mx = row_max(nt == 1);
+      for (int rem = nt; rem > 0; --rem) {        // `rem` key tiles of the item are left including this one
+        const uint32_t sbn = sb + 1 == NS ? 0 : sb + 1;
+        const uint32_t pbn = sb + 1 == NS ? pb ^ 1 : pb;
+        // ---- lazy rescale of this chain's accumulator row (P' and the fp32 accumulators share the exponent range)
+        const bool need = mx > m_used + 32.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          if (rem < nt) {            // not the item's first tile: there is something to rescale
+            // "S of the tile NS after the previous one is ready" => PV_q of the previous tile and all before it are complete
+            mbar_wait_a(bS + (sb == 0 ? NS - 1 : sb - 1) * 8, (sb == 0 ? pb ^ 1 : pb) ^ 1);
+            tc_fence_after();
+            const float scale = need ? exp2f(m_used - ceilf(mx)) : 1.0f;     // exact power of two (0 from the initial value)
+            const uint32_t t_acc = t_chain - (uint32_t)(q * 32) + L::OCOL + q * DVP;
+#pragma unroll
+            for (int c = 0; c < DVP / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld16(t_acc + c * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
+              tmem_st16(t_acc + c * 16, o);
+            }
+            tmem_wait_st();
+          }
+          if (need) m_used = ceilf(mx);
+        }
+        const float nm = -m_used;
+        const bool more = rem > 1;
+        {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) exps(e, nm, pk);
+          tmem_st8(t_chain + sb * 128, pk);              // P' over the first 16 columns of S_q(g), stored in halves
+        }
+        // ---- the registers of the half just used take the same half of S_q(g+1) (with three buffers it has been complete
+        //      since the previous tile; with two it follows PV_q(g-1) and is ready about now)
+        if (more) {
+          mbar_wait_a(bS + sbn * 8, pbn);
+          tc_fence_after();
+          tmem_ld16(t_chain + sbn * 128, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        }
+        {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 8; e < 16; ++e) exps(e, nm, pk);
+          tmem_st8(t_chain + sb * 128 + 8, pk);
+        }
+        if (more) tmem_ld16(t_chain + sbn * 128 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive_a(bS + BP + sb * 8);
+        if (more) {
+          landed();
+          mx = row_max(rem == 2);
+        }
+        sb = sbn;
+        pb = pbn;
+      }
+
+      // ---- epilogue: the four chains' (m_q, O_q) of a row -> A = sum_q 2^(m_q - m) O_q / l', saved tensors,
+      //      fused output conv + gamma residual (each of the row's four threads writes a quarter of the channels)
+      constexpr int C = CEPI;
+      constexpr int DV = C / 2;
+      static_assert(DVP >= 2 * DV + 1, "V^T rows are [v_hi | v_lo | ones]");
+      const int row = (warp & 3) * 32 + (threadIdx.x & 31);         // query row inside the tile == TMEM lane
+      const uint32_t t_row = t_chain - (uint32_t)(q * 32);
+      const int w = (int)blockIdx.x + k * (int)gridDim.x;
+      const int b = w / nq, qt = w - b * nq;
+      const int i_tok = qt * 128 + row;
+      const bool valid = i_tok < N;
+      const long long grow = (long long)b * N + (valid ? i_tok : 0);
+      float4 xx[C / 16];
+#pragma unroll
+      for (int cc = 0; cc < C / 16; ++cc) xx[cc] = ld4(X + grow * C + q * (C / 4) + cc * 4);   // in flight under the TMEM reads
+      float* sXk = sX + (k & 1) * 512;
+      sXk[q * 128 + row] = m_used;
+      mbar_wait_a(bS + (sb == 0 ? NS - 1 : sb - 1) * 8, (sb == 0 ? pb ^ 1 : pb) ^ 1);   // PV_q of the item's last tile is complete
+      tc_fence_before();
+      asm volatile("bar.sync 1, 512;" ::: "memory");                     // also orders the sW fill above
+      tc_fence_after();
+      const float m0 = sXk[row], m1 = sXk[128 + row], m2 = sXk[256 + row], m3 = sXk[384 + row];
+      const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      const float sc[4] = {exp2f(m0 - m), exp2f(m1 - m), exp2f(m2 - m), exp2f(m3 - m)};
+      float a[DVP];
+#pragma unroll
+      for (int i = 0; i < DVP; ++i) a[i] = 0.f;
+#pragma unroll
+      for (int acc = 0; acc < 4; ++acc) {
+#pragma unroll
+        for (int c = 0; c < DVP / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(t_row + L::OCOL + acc * DVP + c * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[c * 16 + i] = fmaf(__uint_as_float(r[i]), sc[acc], a[c * 16 + i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(barOfree);               // the next item's first PV MMAs may overwrite the accumulators
+      const float l = a[2 * DV];           // l' = sum_j P'_ij, accumulated by the MMA through the ones row
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) a[v] = (a[v] + a[DV + v]) * inv;
+      if (valid) {
+        if (q == 0) {
+#pragma unroll
+          for (int v = 0; v < DV; v += 4) st4(A_saved + grow * DV + v, make_float4(a[v], a[v + 1], a[v + 2], a[v + 3]));
+          lse[grow] = (m + log2f(l)) * TC_LN2;
+        }
+        const float gm = *gamma;
+#pragma unroll
+        for (int cc = 0; cc < C / 4; cc += 4) {
+          const int c = q * (C / 4) + cc;
+          float o[4] = {sW[DV * C + c], sW[DV * C + c + 1], sW[DV * C + c + 2], sW[DV * C + c + 3]};
+#pragma unroll
+          for (int v = 0; v < DV; ++v) {
+            const float4 wv = *reinterpret_cast<const float4*>(&sW[v * C + c]);
+            o[0] = fmaf(a[v], wv.x, o[0]); o[1] = fmaf(a[v], wv.y, o[1]);
+            o[2] = fmaf(a[v], wv.z, o[2]); o[3] = fmaf(a[v], wv.w, o[3]);
+          }
+          const float4 x4 = xx[cc / 4];
+          st4(Y + grow * C + c,
+              make_float4(fmaf(gm, o[0], x4.x), fmaf(gm, o[1], x4.y), fmaf(gm, o[2], x4.z), fmaf(gm, o[3], x4.w)));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -565,6 +1002,24 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return 0;
 }
 
+template <int DVP, int CEPI>
+static int launch_fwd4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const float* X,
+                       const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A, int B, int N,
+                       int Npad, int Nk, int Nkpad, int dv, cudaStream_t st) {
+  using L = Fwd4Smem<DVP, CEPI>;
+  auto kern = attn_fwd_tc4_kernel<DVP, CEPI>;
+  static bool configured = false;
+  if (!configured) {
+    SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int nitems = B * (Npad / 128);
+  const int grid = nitems < num_sms() ? nitems : num_sms();      // persistent: one CTA per SM
+  kern<<<grid, TC4_THREADS, L::TOTAL, st>>>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, N, Npad, Nk, Nkpad, dv, nitems);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
 // PH, PW > 0: keys / values max-pooled 2x2 / stride 2 over the [PH, PW] token grid (N == PH * PW), else PH = PW = 0
 int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk, const float* Wv,
                 const float* bv, const float* Wo, const float* bo, const float* gamma, float* Y, float* lse, float* A,
@@ -612,6 +1067,9 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
   if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tkp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Nkpad, (uint64_t)t.Nkpad * 2, (uint32_t)t.DVP))) return rc;
   const int dv = C / 2;
+  static const bool chained = getenv("SAGAN_FWD_UNCHAINED") == nullptr;
+  if (chained && C == 16) return launch_fwd4<32, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, B, N, t.Npad, t.Nk, t.Nkpad, dv, st);
+  if (chained && C == 32) return launch_fwd4<48, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, B, N, t.Npad, t.Nk, t.Nkpad, dv, st);
   switch (C) {
     case 16: return launch_fwd<32, 1, 2, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, t.Nk, t.Nkpad, dv, t.kq_steps, st);
     case 32: return launch_fwd<48, 1, 2, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, nullptr, B, N, t.Npad, t.Nk, t.Nkpad, dv, t.kq_steps, st);

@@ -65,6 +65,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// the same on shared-window addresses (one 32-bit register per barrier array instead of a generic pointer)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MBAR_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra MBAR_DONE_%=;\n\t"
+      "bra MBAR_WAIT_%=;\n\t"
+      "MBAR_DONE_%=:\n\t}"
+      ::"r"(bar_addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -220,6 +236,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 // ------------------------------------------------------------------ CTA pairs (cta_group::2) and clusters
 // A pair of CTAs (cluster ranks 2p, 2p+1) runs ONE tcgen05.mma over both SMs: M = 256 (128 rows per CTA, each in its own
 // TMEM), and each CTA supplies half of the B operand's N extent from its own shared memory, so the pair reads every
@@ -328,6 +350,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): two IEEE round-to-nearest operations per issued instruction,
+// bit-identical per lane to the scalar forms.  The softmax / dS inner loops are issue-bound, not FMA-pipe-bound.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 f2_pack(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 x, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
 }
 
 // byte offset of the 16-byte chunk (row, chunk) inside a SWIZZLE_128B tile whose rows are 128 B
