@@ -418,31 +418,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == TB_CWARPS + 1) {
     // ================================================================ MMA issuer
-    // The whole warp runs the loop (uniform control flow and addresses); only the tcgen05 instructions belong to the
-    // elected lane.  Inside a one-thread region the address arithmetic and R2UR moves cost ~50-70 cycles per MMA
-    // (measured on the forward: attn_tc.cu), and this issuer sits on the critical path of both chains.
-    {
-      const bool leader = elect_one_sync();
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 64);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
       constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
       const uint64_t dK_ = make_desc_rows<QKB>(smem_u32(sK)), dV_ = make_desc_rows<VAB>(smem_u32(sV));
-      auto issue_s = [&](int sa, int x) {      // S^T[:, 64 x .. 64 x + 64) = K Q_i^T (64 query rows of A stage sa)
-        if (leader) {
-          const uint64_t dQ_ = make_desc_rows<QKB>(smem_u32(sA + sa * L::ASTAGE + L::A_Q + x * (64 * QKB)));
-          for (int ks = 0; ks < kq_steps; ++ks)
-            mma_bf16_ss(tmem_base + L::ST_COL + x * 64, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-          mma_commit(barS + x);
-        }
+      auto issue_s = [&](int i, int x) {       // S^T[:, 64 x .. 64 x + 64) = K Q_i^T (64 query rows of the stage)
+        const uint64_t dQ_ = make_desc_rows<QKB>(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q + x * (64 * QKB)));
+        for (int ks = 0; ks < kq_steps; ++ks)
+          mma_bf16_ss(tmem_base + L::ST_COL + x * 64, dK_ + (uint64_t)(ks * 2), dQ_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barS + x);
       };
-      auto issue_dp = [&](int sa, int x) {     // dP^T[:, 64 x .. 64 x + 64) = V dA_i^T
-        if (leader) {
-          const uint64_t dA_ = make_desc_rows<VAB>(smem_u32(sA + sa * L::ASTAGE + L::A_DA + x * (64 * VAB)));
-          for (int ks = 0; ks < kv_steps; ++ks)
-            mma_bf16_ss(tmem_base + L::DP_COL + x * 64, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
-          mma_commit(barDP + x);
-          if (x == 1) mma_commit(barAfree + sa);                // last reader of the A stage
-        }
+      auto issue_dp = [&](int i, int x) {      // dP^T[:, 64 x .. 64 x + 64) = V dA_i^T
+        const uint64_t dA_ = make_desc_rows<VAB>(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_DA + x * (64 * VAB)));
+        for (int ks = 0; ks < kv_steps; ++ks)
+          mma_bf16_ss(tmem_base + L::DP_COL + x * 64, dV_ + (uint64_t)(ks * 2), dA_ + (uint64_t)(ks * 2), IDESC_S, ks > 0);
+        mma_commit(barDP + x);
+        if (x == 1) mma_commit(barAfree + (i % L::NA));     // last reader of the A stage
       };
       mbar_wait(barKV, 0);
       mbar_wait(barAfull, 0);
@@ -453,8 +445,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();                        // their MUFU / ALU / LSU phases at the same time
       issue_s(0, 1);
       issue_dp(0, 1);
-      int sa1 = 1 % L::NA;                     // A stage of tile i + 1 and its phase
-      uint32_t pa1 = 0;
       for (int i = 0; i < nq; ++i) {
         const uint8_t* st = sB + (i & 1) * L::BSTAGE;
         const uint64_t dAt_ = make_desc_sw128(smem_u32(st + L::B_DAT)), dQt_ = make_desc_sw128(smem_u32(st + L::B_QT));
@@ -462,10 +452,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
           if (i + 1 < nq) {
-            if (x == 0) mbar_wait(barAfull + sa1, pa1);
+            if (x == 0) mbar_wait(barAfull + ((i + 1) % L::NA), ((i + 1) / L::NA) & 1);
             mbar_wait(barSfree + x, i & 1);          // every compute thread of the half holds S^T_i in registers
             tc_fence_after();
-            issue_s(sa1, x);                         // runs under the exp / dS math of tile i
+            issue_s(i + 1, x);                       // runs under the exp / dS math of tile i
           }
           if (x == 0) mbar_wait(barBfull + (i & 1), (i >> 1) & 1);
           mbar_wait(barTiles + x, i & 1);            // P'^T_i / dS^T_i are in TMEM (and every thread holds dP^T_i)
@@ -473,61 +463,52 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           // dV += P'^T dA_i ; dK += dS^T Q_i : A operands from TMEM, 16 queries per step.  The tensor pipe executes in
           // issue order, so dP^T_{i+1} (issued right after the MMAs that read the aliased P'^T / dS^T_lo columns)
           // cannot overwrite them early; the dS^T_hi MMAs follow it.
-          if (leader) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const int ks = x * 4 + k4;
-              const uint32_t a_pt = tmem_base + L::DP_COL + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
-              const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-              mma_bf16_ts(tmem_base + L::DV_COL, a_pt, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
-                          IDESC_DV, acc0 || (ks > 0));
-              mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
-            }
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = x * 4 + k4;
+            const uint32_t a_pt = tmem_base + L::DP_COL + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8);
+            const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+            mma_bf16_ts(tmem_base + L::DV_COL, a_pt, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
+                        IDESC_DV, acc0 || (ks > 0));
+            mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
           }
-          if (i + 1 < nq) issue_dp(sa1, x);
-          if (leader) {
+          if (i + 1 < nq) issue_dp(i + 1, x);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const int ks = x * 4 + k4;
-              const uint32_t a_hi = tmem_base + L::DSH_COL + (uint32_t)(ks * 8);
-              const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-              mma_bf16_ts(tmem_base + L::DKH_COL, a_hi, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
-            }
-            mma_commit(barGh + x);
-            if (x == 1) mma_commit(barBfree + (i & 1));
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = x * 4 + k4;
+            const uint32_t a_hi = tmem_base + L::DSH_COL + (uint32_t)(ks * 8);
+            const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+            mma_bf16_ts(tmem_base + L::DKH_COL, a_hi, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
           }
+          mma_commit(barGh + x);
+          if (x == 1) mma_commit(barBfree + (i & 1));
         }
-        if (++sa1 == L::NA) { sa1 = 0; pa1 ^= 1; }
       }
-      if (leader) mma_commit(barDone);
+      mma_commit(barDone);
     }
   } else if (warp == TB_CWARPS + 2) {
     // ================================================================ second MMA issuer: dQ_i = dS_i K_j
-    {
-      const bool leader = elect_one_sync();
+    // (issuing one tcgen05.mma costs the elected thread ~35 cycles; 43 per tile from one thread were the critical path)
+    if (elect_one_sync()) {
       constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
       const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
       mbar_wait(barKV, 0);
-      int sd = 0;                                  // dS^T buffer of tile i
       for (int i = 0; i < nq; ++i) {
         mbar_wait(barTiles, i & 1);
         mbar_wait(barTiles + 1, i & 1);
         tc_fence_after();
-        if (leader) {
-          const uint32_t ds = smem_u32(sDS + sd * L::DS_BUF);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {   // K = 16 keys per step: the dS^T tiles read MN-major (M = queries contiguous)
-            const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
-            mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(ds + ks * 16 * 128, L::TILE, 1024),
-                        dKt_ + b16, IDESC_DQ, ks > 0);
-            mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(ds + 2 * L::TILE + ks * 16 * 128, L::TILE, 1024),
-                        dKt_ + b16, IDESC_DQ, ks > 0);
-          }
-          mma_commit(barQd + (i & 1));
+        for (int ks = 0; ks < 8; ++ks) {   // K = 16 keys per step: the dS^T tiles read MN-major (M = queries contiguous)
+          const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
+          const uint32_t ds = smem_u32(sDS + (i % NDS) * L::DS_BUF);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(ds + ks * 16 * 128, L::TILE, 1024),
+                      dKt_ + b16, IDESC_DQ, ks > 0);
+          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(ds + 2 * L::TILE + ks * 16 * 128, L::TILE, 1024),
+                      dKt_ + b16, IDESC_DQ, ks > 0);
         }
-        if (++sd == NDS) sd = 0;
+        mma_commit(barQd + (i & 1));
       }
-      if (leader) mma_commit(barDone);
+      mma_commit(barDone);
     }
   } else {
     // ================================================================ compute warps
@@ -602,19 +583,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_wait_ld();
         const float* dvec = reinterpret_cast<const float*>(sB + s * L::BSTAGE + L::B_VEC) + 128 + h * 32;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {       // two query columns per packed fp32 instruction (FMUL2 / FADD2)
-          f2 dp = f2_pack(__uint_as_float(rp[2 * e]), __uint_as_float(rp[2 * e + 1]));
-          if (!SPLIT_DA) {         // (folded operands: the MMA delivered dP - D_i already)
+        for (int e = 0; e < 16; ++e) {
+          float g0, g1;
+          if (SPLIT_DA) {          // folded: the MMA delivered dP - D_i
+            g0 = pf[2 * e] * __uint_as_float(rp[2 * e]);
+            g1 = pf[2 * e + 1] * __uint_as_float(rp[2 * e + 1]);
+          } else {
             const float2 dd = *reinterpret_cast<const float2*>(dvec + 2 * e);
-            dp = f2_sub(dp, f2_pack(dd.x, dd.y));
+            g0 = pf[2 * e] * (__uint_as_float(rp[2 * e]) - dd.x);
+            g1 = pf[2 * e + 1] * (__uint_as_float(rp[2 * e + 1]) - dd.y);
           }
-          const f2 g = f2_mul(f2_pack(pf[2 * e], pf[2 * e + 1]), dp);
-          float g0, g1, l0, l1;
-          f2_unpack(g, g0, g1);
           const uint32_t hk = pack_bf16x2(g0, g1);
           hi[e] = hk;
-          f2_unpack(f2_sub(g, f2_pack(__uint_as_float(hk << 16), __uint_as_float(hk & 0xffff0000u))), l0, l1);
-          lo[e] = pack_bf16x2(l0, l1);
+          lo[e] = pack_bf16x2(g0 - __uint_as_float(hk << 16), g1 - __uint_as_float(hk & 0xffff0000u));
         }
       }
       // ---- A operands of the dV / dK MMAs -> TMEM.  P'^T and dS^T_lo go over this thread's own dP^T columns, which

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsagan_b200.so")
+# SAGAN_B200_LIB: another build of the same library (A/B kernel measurements on one box); still no fallback
+LIB_PATH = os.environ.get("SAGAN_B200_LIB") or os.path.join(_HERE, "libsagan_b200.so")
 
 MATH_FP32_STRICT = 0
 MATH_BF16_TC = 1

@@ -409,6 +409,21 @@ def test_attention_fwd_bwd_vs_oracle_n4096(F, mode_name):
         _check_attn_grads("B1_N4096_C16", mode_name, y, dx, gw, X, dY, Y_ref, g_ref, TC_TOL, TC_TOL, 1e-2)
 
 
+@pytest.mark.parametrize("shape", [(45, 512, 16), (23, 900, 32), (160, 100, 16)])
+def test_attention_tc_persistent_work_items(F, shape):
+    """The C <= 32 tensor-core forward is a persistent kernel (one CTA per SM walks the (sample, 128-query tile) work
+    items, barrier phases and K / V rings running on across items): more items than the 148 SMs, so CTAs take 2 (and 3)
+    items, with 1 / 4 / 8 key tiles per item, full and ragged last tiles, both S-buffer depths (C = 16: 3, C = 32: 2).
+    Forward and every gradient against the fp64 oracle."""
+    B, N, C = shape
+    X, dY, w = oattn.make_inputs(B, N, C, seed=77 + N, gamma=0.37, dtype=np.float32)
+    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    Y_ref = oattn.forward(X.astype(np.float64), **w64)
+    g_ref = oattn.backward(dY.astype(np.float64), X.astype(np.float64), **w64)
+    y, dx, gw = _run_attn(F, X, dY, w, F.MATH_BF16_TC)
+    _check_attn_grads(f"B{B}_N{N}_C{C}", "tc", y, dx, gw, X, dY, Y_ref, g_ref, TC_TOL, TC_TOL, 1e-2)
+
+
 @pytest.mark.parametrize("shape", [(4, 4096, 16), (4, 1024, 32), (2, 1024, 64), (3, 1000, 16)])
 def test_attention_tc_vs_strict_full_size(F, shape):
     """In-model sizes (N = 4096 / 1024): the tensor-core forward against the fp32 CUDA-core forward."""
