@@ -19,7 +19,7 @@ timeout 400 ncu --metrics $M --clock-control none -k regex:"attn_|gemm_|conv_tc"
 timeout 300 python tools/kernel_bench.py sn --rows 4096 --cols 4096 --iters 1 > /dev/null 2>&1 && \
 timeout 300 ncu --metrics $M --clock-control none -k regex:sn_power --csv --log-file $O/r2_metrics_sn_4096x4096.csv python tools/kernel_bench.py sn --rows 4096 --cols 4096 --iters 1 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_tc_kernel --launch-skip 2 -c 1 -o $O/r2_attn_bwd_full python tools/kernel_bench.py attn --B 64 --N 4096 --C 16 --bwd --iters 1 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_tc_kernel --launch-skip 2 -c 1 -o $O/r2_attn_fwd_full python tools/kernel_bench.py attn --B 64 --N 4096 --C 16 --iters 1 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_tc4_kernel --launch-skip 2 -c 1 -o $O/r2_attn_fwd_full python tools/kernel_bench.py attn --B 64 --N 4096 --C 16 --iters 1 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_big_kernel --launch-skip 2 -c 1 -o $O/r2_attn_bwd_big_full python tools/kernel_bench.py attn --B 16 --N 4096 --C 512 --bwd --iters 1 > /dev/null 2>&1
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-variant > /dev/null 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r2_launches_bf16_tc_step.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-variant > /dev/null 2>&1
