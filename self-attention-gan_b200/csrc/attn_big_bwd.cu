@@ -17,9 +17,16 @@
 // 9.6 ms at B=16, N=4096, C=512 and 21 ms at B=256, N=256, C=128).
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sagan {
+
+// gram_tc.cu
+bool gram_split_supported(int l, int r, long long T);
+int gram_split(const float* L, int l, const float* R, int r, float* G, float* colsum, long long T, cudaStream_t st);
+
 
 int attn_bwd_finalize_launch(const float* Wo, const float* bo, const float* gamma, float* dWo, float* dbo, float* dgamma,
                              int nW, int C, cudaStream_t st);   // attn_strict.cu
@@ -153,6 +160,8 @@ int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const floa
   // (split-bf16 tensor-core kernel: both operands read MN-major, reduction over the tokens split across CTAs, the
   // ones column yields colsum(R) for free) -- no transposed copies
   auto gram = [&](const float* Lm, int l, const float* Rm, int r, float* out, float* colsum_out) -> int {
+    // gram_tc.cu: TMA-fed, fp32 -> split-bf16 conversion inside the CTA, reduction split over the tokens
+    if (gram_split_supported(l, r, T) && !getenv("SAGAN_GRAM_CONV")) return gram_split(Lm, l, Rm, r, out, colsum_out, T, st);
     const sagan_conv_geom g = dense_geom(T, l, r);
     return sagan_conv2d_wgrad(Lm, Rm, out, colsum_out, &g, TC, st);
   };

@@ -42,12 +42,14 @@ __global__ void __launch_bounds__(608, 1) tile_kernel(uint32_t* out, int iters, 
   __shared__ uint64_t bars[4];
   __shared__ uint32_t tmem_ptr;
   __shared__ volatile int stop;
+  __shared__ uint64_t tok[4][4];     // [scheduler][chain]: "the MUFU burst before yours on this scheduler is issued"
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) stop = 0;
   if (threadIdx.x == 0) {
     mbar_init(bars + 0, 1);            // never arrived on: waiting for parity 1 succeeds at once
     mbar_init(bars + 1, (1 << 20) - 1);
-    mbar_init(bars + 2, 1);      // sink for the arrivals
+    mbar_init(bars + 2, 1);
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) mbar_init(&tok[a][b], 32);      // sink for the arrivals
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_ptr, 512);
@@ -122,6 +124,38 @@ __global__ void __launch_bounds__(608, 1) tile_kernel(uint32_t* out, int iters, 
       }
     };
     load_next(j + 1, nxt);
+    if (MODE & 2048) {
+      // token ring: the four warps of a scheduler take turns issuing their 12-MUFU bursts
+      const int sm = warp & 3;
+      // burst index of this warp: b = 2 j (+1); ring position: chain q waits for chain q-1's same burst (chain 0 for chain 3's previous)
+      auto burst = [&](int b, int e0) {
+        f2 x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = f2_add(f2_pack(__uint_as_float(cur[2 * (e0 + e)]), __uint_as_float(cur[2 * (e0 + e) + 1])), neg_m);
+        // wait for the token: chain 0 waits for chain 3's burst b-1, chain q for chain q-1's burst b
+        if (q == 0) { if (b > 0) mbar_wait(&tok[sm][3], (b - 1) & 1); }
+        else mbar_wait(&tok[sm][q - 1], b & 1);
+        float y[16];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (((e0 + e) & 3) == 3) continue;
+          float x0, x1;
+          f2_unpack(x[e], x0, x1);
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y[2 * e]) : "f"(x0));
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y[2 * e + 1]) : "f"(x1));
+        }
+        mbar_arrive(&tok[sm][q]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (((e0 + e) & 3) == 3) pk[e0 + e] = ex2_poly2_bf16(x[e]);
+          else pk[e0 + e] = pack_bf16x2(y[2 * e], y[2 * e + 1]);
+        }
+      };
+      burst(2 * j, 0);
+      landed(nxt);
+      if (MODE & 32) mx = row_max(nxt);
+      burst(2 * j + 1, 8);
+    } else {
 #pragma unroll
     for (int e = 0; e < 8; ++e) exps(e);
     landed(nxt);
@@ -129,6 +163,7 @@ __global__ void __launch_bounds__(608, 1) tile_kernel(uint32_t* out, int iters, 
     else cur[0] ^= nxt[0] & 1u;
 #pragma unroll
     for (int e = 8; e < 16; ++e) exps(e);
+    }
     if (MODE & 2) {
       tmem_st16(t_row + (uint32_t)((j % 3) * 128 + q * 32), pk);
       if (MODE & 4) {
@@ -150,6 +185,10 @@ __global__ void __launch_bounds__(608, 1) tile_kernel(uint32_t* out, int iters, 
   float mx = 0.f;
   asm volatile("bar.sync 1, 512;" ::: "memory");
   const long long t0 = clock64();
+  if (MODE & 512) {       // chains start a quarter of a tile apart
+    const long long until = t0 + q * 240;
+    while (clock64() < until) { }
+  }
   for (int j = 0; j < iters; j += 2) {
     tile(j, ra, rb, mx);
     tile(j + 1, rb, ra, mx);
@@ -192,6 +231,8 @@ int main() {
   run<64 + 32 + 16 + 1 + 8 + 2 + 4>("+ wait::st, fence, arrive  (= the kernel's tile body)", out, cyc);
   run<64 + 32 + 16 + 1 + 8 + 2 + 4 + 128>("tile body + 3 warps spinning on try_wait (no hint)", out, cyc);
   run<64 + 32 + 16 + 1 + 8 + 2 + 4 + 128 + 256>("tile body + 3 warps spinning on try_wait with the suspend hint", out, cyc);
+  run<64 + 32 + 16 + 1 + 8 + 2 + 4 + 512>("tile body, chains started a quarter tile apart", out, cyc);
+  run<64 + 32 + 16 + 1 + 8 + 2 + 4 + 2048>("tile body, MUFU bursts passed round the scheduler's four warps", out, cyc);
   run<64 + 32 + 16 + 2 + 4>("math + check + STTM + wait::st + arrive (no LDTM)", out, cyc);
   run<1 + 8 + 2 + 4>("skeleton: LDTM + wait + STTM + arrive, XOR packing, no max", out, cyc);
   run<1>("LDTM only + XOR", out, cyc);
