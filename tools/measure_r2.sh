@@ -15,7 +15,7 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes
 timeout 300 python tools/kernel_bench.py attn --B 64 --N 4096 --C 16 --bwd --iters 1 > /dev/null 2>&1 && \
 timeout 400 ncu --metrics $M --clock-control none -k regex:attn_ --csv --log-file $O/r2_metrics_attn.csv python tools/kernel_bench.py attn --B 64 --N 4096 --C 16 --bwd --iters 1 > /dev/null 2>&1
 timeout 300 python tools/kernel_bench.py attn --B 16 --N 4096 --C 512 --bwd --iters 1 > /dev/null 2>&1 && \
-timeout 400 ncu --metrics $M --clock-control none -k regex:"attn_|gemm_|conv_tc" --csv --log-file $O/r2_metrics_big.csv python tools/kernel_bench.py attn --B 16 --N 4096 --C 512 --bwd --iters 1 > /dev/null 2>&1
+timeout 400 ncu --metrics $M --clock-control none -k regex:"attn_|gemm_|gram_|conv_tc" --csv --log-file $O/r2_metrics_big.csv python tools/kernel_bench.py attn --B 16 --N 4096 --C 512 --bwd --iters 1 > /dev/null 2>&1
 timeout 300 python tools/kernel_bench.py sn --rows 4096 --cols 4096 --iters 1 > /dev/null 2>&1 && \
 timeout 300 ncu --metrics $M --clock-control none -k regex:sn_power --csv --log-file $O/r2_metrics_sn_4096x4096.csv python tools/kernel_bench.py sn --rows 4096 --cols 4096 --iters 1 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_tc_kernel --launch-skip 2 -c 1 -o $O/r2_attn_bwd_full python tools/kernel_bench.py attn --B 64 --N 4096 --C 16 --bwd --iters 1 > /dev/null 2>&1
