@@ -161,7 +161,8 @@ int attn_tc_big_bwd(const float* dY, const float* X, const float* Wq, const floa
   // ones column yields colsum(R) for free) -- no transposed copies
   auto gram = [&](const float* Lm, int l, const float* Rm, int r, float* out, float* colsum_out) -> int {
     // gram_tc.cu: TMA-fed, fp32 -> split-bf16 conversion inside the CTA, reduction split over the tokens
-    if (gram_split_supported(l, r, T) && !getenv("SAGAN_GRAM_CONV")) return gram_split(Lm, l, Rm, r, out, colsum_out, T, st);
+    static const bool conv_form = getenv("SAGAN_GRAM_CONV") != nullptr;      // diagnostics only: the round-2a path
+    if (gram_split_supported(l, r, T) && !conv_form) return gram_split(Lm, l, Rm, r, out, colsum_out, T, st);
     const sagan_conv_geom g = dense_geom(T, l, r);
     return sagan_conv2d_wgrad(Lm, Rm, out, colsum_out, &g, TC, st);
   };

@@ -1067,7 +1067,7 @@ int attn_tc_fwd(const float* X, const float* Wq, const float* bq, const float* W
   if ((rc = make_tmap_bf16_2d(&tk, Kb, (uint64_t)Tkp, qkc, qkc * 2, 128, qkc, qkc == 16 ? 32 : 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, Vt, (uint64_t)B * t.DVP, (uint64_t)t.Nkpad, (uint64_t)t.Nkpad * 2, (uint32_t)t.DVP))) return rc;
   const int dv = C / 2;
-  static const bool chained = getenv("SAGAN_FWD_UNCHAINED") == nullptr;
+  static const bool chained = getenv("SAGAN_FWD_UNCHAINED") == nullptr;      // diagnostics only: the round-1 kernel for C <= 32
   if (chained && C == 16) return launch_fwd4<32, 16>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, B, N, t.Npad, t.Nk, t.Nkpad, dv, st);
   if (chained && C == 32) return launch_fwd4<48, 32>(tq, tk, tv, X, Wo, bo, gamma, Y, lse, A, B, N, t.Npad, t.Nk, t.Nkpad, dv, st);
   switch (C) {

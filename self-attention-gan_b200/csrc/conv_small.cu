@@ -379,7 +379,8 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
   else {
     // tiled form: TR output rows x the whole width = 512 pixels per CTA
     const int TR = g.Wo > 0 && 512 % g.Wo == 0 ? 512 / g.Wo : 0;
-    if (TR >= 1 && g.Ho % TR == 0 && g.KH == 4 && !getenv("SAGAN_CONV_SMALL_UNTILED")) {
+    static const bool untiled = getenv("SAGAN_CONV_SMALL_UNTILED") != nullptr;   // diagnostics only
+    if (TR >= 1 && g.Ho % TR == 0 && g.KH == 4 && !untiled) {
       const int ngrp = (g.W + 4 - 1 + 3) / 4;
       const size_t smem = (size_t)((g.K * 3 + 3 + 3) / 4 * 4) * sizeof(float) + (size_t)(TR + g.KH - 1) * ngrp * CS_GRP;
       static size_t configured = 0;
