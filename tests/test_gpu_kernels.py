@@ -123,6 +123,9 @@ CONV_CASES = [  # B, H, W, Cin, Cout, k, stride   (the D / G layer shapes at sma
     (2, 64, 64, 3, 16, 4, 2), (2, 32, 32, 16, 32, 4, 2), (2, 8, 8, 64, 128, 4, 2),
     (2, 64, 64, 16, 3, 4, 1), (2, 4, 4, 128, 1, 4, 1), (3, 9, 7, 5, 6, 3, 2), (2, 16, 16, 16, 2, 1, 1),
     (1, 5, 5, 8, 20, 3, 1),
+    # the generator's output conv at other widths (shared-memory-tiled direct kernel: 16 / 8 / 4 output rows per CTA) and
+    # at a width the tiled form does not take (48: 512 % 48 != 0 -> thread-per-four-pixels form)
+    (2, 32, 32, 16, 3, 4, 1), (1, 128, 128, 16, 3, 4, 1), (1, 64, 48, 16, 3, 4, 1),
 ]
 
 
