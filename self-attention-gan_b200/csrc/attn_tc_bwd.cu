@@ -21,6 +21,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "attn_pool.cuh"
@@ -39,6 +42,51 @@ constexpr int TB_COLS = 64;   // widest bf16 row of the K-major operand buffers 
 __host__ __device__ constexpr int tb_kq(int C) { return ((3 * (C / 8) + 15) / 16) * 16; }
 __host__ __device__ constexpr int tb_kv(int C) { return C <= 32 ? ((3 * (C / 2) + 2 + 15) / 16) * 16 : C; }
 
+// ------------------------------------------------------------------------------------ dS as ONE fp16 term (C <= 32)
+// dS = P' (dP - D) feeds two GEMMs that cancel (sum_j dS_ij = 0): bf16 (8 significant bits) needed a hi + lo pair of
+// tiles -- an unpack, a subtraction, a second pack, a TMEM store, two shared-memory stores per pair of scores and 16
+// more MMAs per tile (2.5 of the 15 warp instructions per score).  fp16 carries 11 significant bits in ONE term and
+// measures the same gradient errors (bound by the bf16 rounding of P' either way); kind::f16 does not mix an fp16 A with
+// a bf16 B (illegal instruction), so the transposed operands Q^T / K^T of those GEMMs are fp16 hi / lo pairs as well.
+// fp16 has 5 exponent bits: the gradient is normalised per sample by a power of two s_b taken from max |dY| (one small
+// reduction kernel), applied exactly to dA' and D' by the prep kernel and taken out of dQ / dK in the epilogues.
+__device__ __forceinline__ __nv_bfloat16 tb_f16_bits(float x) {          // fp16 bits through a bf16-typed pointer
+  const __half h = __float2half_rn(x);
+  return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
+__device__ __forceinline__ float tb_f16_round(float x) { return __half2float(__float2half_rn(x)); }
+template <bool F16>
+__device__ __forceinline__ __nv_bfloat16 tb_t_hi(float x) { return F16 ? tb_f16_bits(x) : __float2bfloat16_rn(x); }
+template <bool F16>
+__device__ __forceinline__ __nv_bfloat16 tb_t_lo(float x) {
+  return F16 ? tb_f16_bits(x - tb_f16_round(x)) : __float2bfloat16_rn(x - __bfloat162float(__float2bfloat16_rn(x)));
+}
+
+// gmax[b] = max |dY[b, :, :]| (as the bits of a non-negative float: atomicMax on unsigned keeps the order); zeroed by the caller
+__global__ void __launch_bounds__(256)
+attn_dy_absmax_kernel(const float* __restrict__ dY, unsigned* __restrict__ gmax, long long per_sample) {
+  const int b = blockIdx.y;
+  const float* p = dY + (size_t)b * per_sample;
+  float m = 0.f;
+  const long long n4 = per_sample >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = ld4(p + 4 * i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < per_sample; i += (long long)gridDim.x * 256)
+    m = fmaxf(m, fabsf(p[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m <= 3.0e38f) atomicMax(gmax + b, __float_as_uint(m));
+}
+// s_b = 2^(5 - floor(log2(max |gamma dY|))): the scaled gradient peaks in [32, 64) (1 for an all-zero / non-finite sample)
+__device__ __forceinline__ float tb_grad_scale(unsigned gmax_bits, float gamma) {
+  const float m = __uint_as_float(gmax_bits) * fabsf(gamma);
+  if (!(m > 0.f) || !(m <= 3.0e38f)) return 1.0f;
+  int e = (int)((__float_as_uint(m) >> 23) & 255u) - 127;      // floor(log2 m) for normal m (denormal: -127)
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return __uint_as_float((unsigned)(127 + 5 - e) << 23);
+}
+
 // ------------------------------------------------------------------------------------ prep (small C)
 // one thread per PADDED token; recomputes theta/phi/g from X and forms dA = gamma dY Wo^T, D = dA . A
 // KSIDE = false (down-sampled keys / values): the key-side rows (Kb, Kt, Vb) come from attn_bwd_prep_pool_tc_kernel.
@@ -51,8 +99,9 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
                         __nv_bfloat16* __restrict__ Qb, __nv_bfloat16* __restrict__ Kb, __nv_bfloat16* __restrict__ Vb,
                         __nv_bfloat16* __restrict__ dAb, __nv_bfloat16* __restrict__ dAt, __nv_bfloat16* __restrict__ Qt,
                         __nv_bfloat16* __restrict__ Kt, float* __restrict__ lse2, float* __restrict__ Dd,
-                        float* __restrict__ dA_f32, int B, int N, int Npad) {
+                        const unsigned* __restrict__ gmax, float* __restrict__ sinv, int B, int N, int Npad) {
   constexpr int D = C / 8, DV = C / 2;
+  constexpr bool F16 = C <= 32;                      // dS and the transposed operands of its GEMMs in fp16 (see above)
   constexpr bool SPLIT3 = DV <= 16;                  // 3-term split of the dP contraction fits a 64-column row
   constexpr bool SPLIT_DA = DV <= 16;                // dA^T rows [hi | lo] for the dV GEMM
   constexpr int DVP = SPLIT_DA ? (2 * DV < 16 ? 16 : 2 * DV) : DV;
@@ -104,12 +153,12 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
     a = valid ? a : 0.f;
     kk = valid ? kk : 0.f;
     // transposed (un-scaled) copies: rows [hi at 0..7 | lo at 8..15]
-    const __nv_bfloat16 qh = __float2bfloat16_rn(a), kh = __float2bfloat16_rn(kk);
-    Qt[((long long)b * 16 + j) * Npad + n] = qh;
-    Qt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(a - __bfloat162float(qh));
+    const __nv_bfloat16 kh = __float2bfloat16_rn(kk);
+    Qt[((long long)b * 16 + j) * Npad + n] = tb_t_hi<F16>(a);
+    Qt[((long long)b * 16 + 8 + j) * Npad + n] = tb_t_lo<F16>(a);
     if (KSIDE) {
-      Kt[((long long)b * 16 + j) * Npad + n] = kh;
-      Kt[((long long)b * 16 + 8 + j) * Npad + n] = __float2bfloat16_rn(kk - __bfloat162float(kh));
+      Kt[((long long)b * 16 + j) * Npad + n] = tb_t_hi<F16>(kk);
+      Kt[((long long)b * 16 + 8 + j) * Npad + n] = tb_t_lo<F16>(kk);
     }
     const float as = a * TB_LOG2E;
     const float a_hi = __bfloat162float(__float2bfloat16_rn(as)), k_hi = __bfloat162float(kh);
@@ -143,7 +192,11 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
                          pack_bf16x2(k[g * 8 + 4], k[g * 8 + 5]), pack_bf16x2(k[g * 8 + 6], k[g * 8 + 7]));
   }
   // ---- g (values) and dA' = f gamma dY Wo^T, D' = dA' . A, with f = 2^(M - lse') the normaliser of P' (see top)
-  const float gm = *gamma * exp2f(Mi - l2);
+  // (F16: times the sample's power-of-two gradient scale; dA^T for the dV GEMM stays un-scaled)
+  const float sb = F16 ? tb_grad_scale(gmax[b], *gamma) : 1.0f;
+  const float sb_inv = 1.0f / sb;
+  if (F16 && n == 0) sinv[b] = sb_inv;
+  const float gm = *gamma * exp2f(Mi - l2) * sb;
   float v[KV], da[KV];
 #pragma unroll
   for (int j = 0; j < KV; ++j) { v[j] = 0.f; da[j] = 0.f; }
@@ -174,8 +227,9 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
       if (valid) dd = fmaf(gh, A[t * DV + j], dd);
     }
     // transposed dA rows for dV = P^T dA: [hi | lo] when they fit
-    dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(g);
-    if (SPLIT_DA) dAt[((long long)b * DVP + DV + j) * Npad + n] = __float2bfloat16_rn(g - gh);
+    const float gu = g * sb_inv, guh = __bfloat162float(__float2bfloat16_rn(gu));
+    dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(gu);
+    if (SPLIT_DA) dAt[((long long)b * DVP + DV + j) * Npad + n] = __float2bfloat16_rn(gu - guh);
   }
   if (FOLD) {
     const float d_hi = __bfloat162float(__float2bfloat16_rn(dd));
@@ -196,7 +250,6 @@ attn_bwd_prep_tc_kernel(const float* __restrict__ X, const float* __restrict__ d
   for (int j = (SPLIT_DA ? 2 * DV : DV); j < DVP; ++j) dAt[((long long)b * DVP + j) * Npad + n] = __float2bfloat16_rn(0.f);
   lse2[tp] = valid ? Mi : INFINITY;                  // integer shift M_i; +inf => P' = 0 for padded queries
   Dd[tp] = valid ? dd : 0.f;
-  (void)dA_f32;
 }
 
 // ------------------------------------------------------------------------------------ prep, down-sampled keys / values
@@ -247,8 +300,8 @@ attn_bwd_prep_pool_tc_kernel(const float* __restrict__ X, const float* __restric
   for (int j = 0; j < D; ++j) {
     const __nv_bfloat16 kh = __float2bfloat16_rn(kk[j]);
     const float k_hi = __bfloat162float(kh);
-    Kt[((long long)b * 16 + j) * Nkpad + n] = kh;
-    Kt[((long long)b * 16 + 8 + j) * Nkpad + n] = __float2bfloat16_rn(kk[j] - k_hi);
+    Kt[((long long)b * 16 + j) * Nkpad + n] = tb_t_hi<(C <= 32)>(kk[j]);
+    Kt[((long long)b * 16 + 8 + j) * Nkpad + n] = tb_t_lo<(C <= 32)>(kk[j]);
     k[j] = k_hi; k[D + j] = k_hi; k[2 * D + j] = kk[j] - k_hi;
   }
 #pragma unroll
@@ -324,8 +377,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdA,
                    const __grid_constant__ CUtensorMap tmdAt, const __grid_constant__ CUtensorMap tmQt,
                    const __grid_constant__ CUtensorMap tmKt, const float* __restrict__ lse2,
-                   const float* __restrict__ Dd, float* __restrict__ dQ, float* __restrict__ dK,
-                   float* __restrict__ dV, int N, int Npad, int Nk, int Nkpad, int d, int dv, int kq_steps, int kv_steps) {
+                   const float* __restrict__ Dd, const float* __restrict__ sinv, float* __restrict__ dQ,
+                   float* __restrict__ dK, float* __restrict__ dV, int N, int Npad, int Nk, int Nkpad, int d, int dv,
+                   int kq_steps, int kv_steps) {
+  constexpr bool F16 = SPLIT_DA;       // dS as one fp16 term, scaled by the sample's s_b (prep kernel): no lo tiles, no lo MMAs
   // N queries (Npad padded), Nk keys / values (Nkpad padded; grid.x = Nkpad / 128); Nk == N unless down-sampled
   using L = BwdSmem<DVP, QKB, VAB, NDS>;
   extern __shared__ uint8_t smem_raw[];
@@ -421,7 +476,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (elect_one_sync()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 64);
       constexpr uint32_t IDESC_DV = make_idesc_bf16(128, DVP);
-      constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16);
+      constexpr uint32_t F16_FMT = F16 ? ~((7u << 7) | (7u << 10)) : ~0u;       // A, B format 0 = fp16
+      constexpr uint32_t IDESC_DK = make_idesc_bf16(128, 16) & F16_FMT;
       const uint64_t dK_ = make_desc_rows<QKB>(smem_u32(sK)), dV_ = make_desc_rows<VAB>(smem_u32(sV));
       auto issue_s = [&](int i, int x) {       // S^T[:, 64 x .. 64 x + 64) = K Q_i^T (64 query rows of the stage)
         const uint64_t dQ_ = make_desc_rows<QKB>(smem_u32(sA + (i % L::NA) * L::ASTAGE + L::A_Q + x * (64 * QKB)));
@@ -470,7 +526,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint64_t b16 = (uint64_t)((ks >> 2) * ((16 * 128) >> 4) + (ks & 3) * 2);
             mma_bf16_ts(tmem_base + L::DV_COL, a_pt, dAt_ + (uint64_t)((ks >> 2) * ((DVP * 128) >> 4) + (ks & 3) * 2),
                         IDESC_DV, acc0 || (ks > 0));
-            mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
+            if (!F16) mma_bf16_ts(tmem_base + L::DKL_COL, a_pt + 16, dQt_ + b16, IDESC_DK, acc0 || (ks > 0));
           }
           if (i + 1 < nq) issue_dp(i + 1, x);
 #pragma unroll
@@ -490,7 +546,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ================================================================ second MMA issuer: dQ_i = dS_i K_j
     // (issuing one tcgen05.mma costs the elected thread ~35 cycles; 43 per tile from one thread were the critical path)
     if (elect_one_sync()) {
-      constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0);
+      constexpr uint32_t IDESC_DQ = make_idesc_bf16(128, 16, /*a_mn_major=*/1, 0) & (F16 ? ~((7u << 7) | (7u << 10)) : ~0u);
       const uint64_t dKt_ = make_desc_sw128(smem_u32(sKt));
       mbar_wait(barKV, 0);
       for (int i = 0; i < nq; ++i) {
@@ -503,8 +559,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint32_t ds = smem_u32(sDS + (i % NDS) * L::DS_BUF);
           mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32, make_desc_sw128_mn(ds + ks * 16 * 128, L::TILE, 1024),
                       dKt_ + b16, IDESC_DQ, ks > 0);
-          mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(ds + 2 * L::TILE + ks * 16 * 128, L::TILE, 1024),
-                      dKt_ + b16, IDESC_DQ, ks > 0);
+          if (!F16)
+            mma_bf16_ss(tmem_base + L::DQ_COL + (i & 1) * 32 + 16, make_desc_sw128_mn(ds + 2 * L::TILE + ks * 16 * 128, L::TILE, 1024),
+                        dKt_ + b16, IDESC_DQ, ks > 0);
         }
         mma_commit(barQd + (i & 1));
       }
@@ -519,11 +576,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int krow = qd * 32 + lane;                                // key row inside the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16);
     const bool key_ok = kt * 128 + krow < Nk;
+    const float unscale = F16 ? sinv[b] : 1.0f;              // 1 / s_b: dQ and dK come out of the MMAs scaled
     // dQ_i tile (TMEM lanes = queries) -> atomicAdd; the four column groups take turns so the atomics are spread evenly
     auto flush_dq = [&](int i) {
       if (h == (i & 3)) {
         uint32_t r[32];
-        tmem_ld32(t_row + L::DQ_COL + (i & 1) * 32, r);      // [from dS_hi: K_hi (8) K_lo (8) | from dS_lo: K_hi K_lo]
+        if (F16) {                                            // [K_hi (8) | K_lo (8)] from the one fp16 dS term
+          tmem_ld16(t_row + L::DQ_COL + (i & 1) * 32, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+#pragma unroll
+          for (int c = 16; c < 32; ++c) r[c] = 0u;
+        } else {
+          tmem_ld32(t_row + L::DQ_COL + (i & 1) * 32, r);    // [from dS_hi: K_hi (8) K_lo (8) | from dS_lo: K_hi K_lo]
+        }
         tmem_wait_ld();
         const int qrow = i * 128 + krow;
         if (qrow < N) {
@@ -531,8 +595,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             if (c < d)
-              atomicAdd(dst + c, (__uint_as_float(r[c]) + __uint_as_float(r[8 + c])) +
-                                     (__uint_as_float(r[16 + c]) + __uint_as_float(r[24 + c])));
+              atomicAdd(dst + c, ((__uint_as_float(r[c]) + __uint_as_float(r[8 + c])) +
+                                  (__uint_as_float(r[16 + c]) + __uint_as_float(r[24 + c]))) * unscale);
         }
       }
     };
@@ -593,9 +657,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             g0 = pf[2 * e] * (__uint_as_float(rp[2 * e]) - dd.x);
             g1 = pf[2 * e + 1] * (__uint_as_float(rp[2 * e + 1]) - dd.y);
           }
-          const uint32_t hk = pack_bf16x2(g0, g1);
-          hi[e] = hk;
-          lo[e] = pack_bf16x2(g0 - __uint_as_float(hk << 16), g1 - __uint_as_float(hk & 0xffff0000u));
+          if (F16) {
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(g1), "f"(g0));      // first source -> upper half
+            lo[e] = 0u;
+          } else {
+            const uint32_t hk = pack_bf16x2(g0, g1);
+            hi[e] = hk;
+            lo[e] = pack_bf16x2(g0 - __uint_as_float(hk << 16), g1 - __uint_as_float(hk & 0xffff0000u));
+          }
         }
       }
       // ---- A operands of the dV / dK MMAs -> TMEM.  P'^T and dS^T_lo go over this thread's own dP^T columns, which
@@ -603,7 +672,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       //      before it) are complete.  dS^T_hi waits for the MMAs issued after dP^T_i, the shared-memory dS^T tiles
       //      for the dQ MMAs of tile i-1.
       tmem_st16(t_row + L::DP_COL + h * 32, pp);
-      tmem_st16(t_row + L::DP_COL + h * 32 + 16, lo);
+      if (!F16) tmem_st16(t_row + L::DP_COL + h * 32 + 16, lo);
       if (i >= 1) {
         mbar_wait(barGh + x, (i - 1) & 1);
         tc_fence_after();
@@ -620,7 +689,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int g = 0; g < 4; ++g) {
         const uint32_t off = sw128_offset(krow, (h & 1) * 4 + g);
         *reinterpret_cast<uint4*>(dst + off) = make_uint4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
-        *reinterpret_cast<uint4*>(dsl + off) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
+        if (!F16) *reinterpret_cast<uint4*>(dsl + off) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
       }
       tmem_wait_st();
       fence_proxy_async_smem();
@@ -673,14 +742,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       uint32_t r[32];
-      tmem_ld32(t_row + L::DKH_COL, r);                       // [from dS_hi: Q_hi (8) Q_lo (8) | from dS_lo: Q_hi Q_lo]
+      if (F16) {                                              // [Q_hi (8) | Q_lo (8)] from the one fp16 dS term
+        tmem_ld16(t_row + L::DKH_COL, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+#pragma unroll
+        for (int c = 16; c < 32; ++c) r[c] = 0u;
+      } else {
+        tmem_ld32(t_row + L::DKH_COL, r);                     // [from dS_hi: Q_hi (8) Q_lo (8) | from dS_lo: Q_hi Q_lo]
+      }
       tmem_wait_ld();
       if (key < Nk) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           if (c < d)
-            dK[grow * d + c] = (__uint_as_float(r[c]) + __uint_as_float(r[8 + c])) +
-                               (__uint_as_float(r[16 + c]) + __uint_as_float(r[24 + c]));
+            dK[grow * d + c] = ((__uint_as_float(r[c]) + __uint_as_float(r[8 + c])) +
+                                (__uint_as_float(r[16 + c]) + __uint_as_float(r[24 + c]))) * unscale;
       }
     }
     tc_fence_before();
@@ -695,7 +770,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------ host
 struct TbLayout {
   int Npad, Nk, Nkpad, DVP, kq_steps, kv_steps;
-  size_t off_q, off_k, off_v, off_da, off_dat, off_qt, off_kt, off_lse, off_dd, off_dkp, off_dvp, off_ik, off_iv, total;
+  size_t off_q, off_k, off_v, off_da, off_dat, off_qt, off_kt, off_lse, off_dd, off_gmax, off_sinv, off_dkp, off_dvp, off_ik, off_iv, total;
 };
 
 // Nk = number of keys / values (N, or N / 4 when they are down-sampled: then the pooled gradients and the argmax codes
@@ -721,6 +796,8 @@ static TbLayout tb_layout(int B, int N, int Nk, int C) {
   t.off_kt = take((size_t)B * 16 * t.Nkpad * 2);
   t.off_lse = take(T * 4);
   t.off_dd = take(T * 4);
+  t.off_gmax = take((size_t)B * 4);                       // per-sample max |dY| and 1 / s_b (fp16 dS path)
+  t.off_sinv = take((size_t)B * 4);
   t.off_dkp = t.off_dvp = t.off_ik = t.off_iv = 0;
   if (Nk != N) {
     t.off_dkp = take((size_t)B * Nk * d * 4);
@@ -748,23 +825,32 @@ static int run_prep(const float* X, const float* dY, const float* A, const float
                 *dAt = (__nv_bfloat16*)(base + t.off_dat), *Qt = (__nv_bfloat16*)(base + t.off_qt),
                 *Kt = (__nv_bfloat16*)(base + t.off_kt);
   float *lse2 = (float*)(base + t.off_lse), *Dd = (float*)(base + t.off_dd);
+  unsigned* gmax = (unsigned*)(base + t.off_gmax);
+  float* sinv = (float*)(base + t.off_sinv);
+  if (C <= 32) {       // fp16 dS: the sample's gradient scale comes from max |dY|
+    SAGAN_CUDA(cudaMemsetAsync(gmax, 0, (size_t)B * 4, st));
+    const long long per_sample = (long long)N * C;
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_sample, 256 * 16), (4 * num_sms() + B - 1) / B));
+    attn_dy_absmax_kernel<<<dim3(gx, B), 256, 0, st>>>(dY, gmax, per_sample);
+    SAGAN_LAUNCH_CHECK();
+  }
   if (PH > 0) {
     attn_bwd_prep_tc_kernel<C, false><<<nb, 128, 0, st>>>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, Qb, Kb, Vb, dAb,
-                                                          dAt, Qt, Kt, lse2, Dd, nullptr, B, N, t.Npad);
+                                                          dAt, Qt, Kt, lse2, Dd, gmax, sinv, B, N, t.Npad);
     SAGAN_LAUNCH_CHECK();
     attn_bwd_prep_pool_tc_kernel<C><<<(unsigned)ceil_div<long long>((long long)B * t.Nkpad, 128), 128, 0, st>>>(
         X, Wk, bk, Wv, bv, Kb, Vb, Kt, base + t.off_ik, base + t.off_iv, B, PH, PW, t.Nk, t.Nkpad);
   } else {
     attn_bwd_prep_tc_kernel<C, true><<<nb, 128, 0, st>>>(X, dY, A, lse, Wq, bq, Wk, bk, Wv, bv, Wo, gamma, Qb, Kb, Vb, dAb,
-                                                         dAt, Qt, Kt, lse2, Dd, nullptr, B, N, t.Npad);
+                                                         dAt, Qt, Kt, lse2, Dd, gmax, sinv, B, N, t.Npad);
   }
   SAGAN_LAUNCH_CHECK();
   return 0;
 }
 
 template <int DVP, bool SPLIT_DA, int QKB, int VAB, int NDS>
-static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, float* dQ, float* dK, float* dV, int B,
-                      int N, const TbLayout& t, int d, int dv, cudaStream_t st) {
+static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, const float* sinv, float* dQ, float* dK,
+                      float* dV, int B, int N, const TbLayout& t, int d, int dv, cudaStream_t st) {
   using L = BwdSmem<DVP, QKB, VAB, NDS>;
   auto kern = attn_bwd_tc_kernel<DVP, SPLIT_DA, QKB, VAB, NDS>;
   static bool configured = false;
@@ -772,7 +858,7 @@ static int launch_bwd(const CUtensorMap* m, const float* lse2, const float* Dd, 
     SAGAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<dim3(t.Nkpad / 128, B), TB_THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], lse2, Dd, dQ, dK, dV,
+  kern<<<dim3(t.Nkpad / 128, B), TB_THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], lse2, Dd, sinv, dQ, dK, dV,
                                                              N, t.Npad, t.Nk, t.Nkpad, d, dv, t.kq_steps, t.kv_steps);
   SAGAN_LAUNCH_CHECK();
   return 0;
@@ -815,12 +901,13 @@ int attn_tc_bwd_core(const float* X, const float* dY, const float* A, const floa
   if ((rc = make_tmap_bf16_2d(&m[6], base + t.off_kt, (uint64_t)B * 16, t.Nkpad, (uint64_t)t.Nkpad * 2, 16))) return rc;
   const float* lse2 = (const float*)(base + t.off_lse);
   const float* Dd = (const float*)(base + t.off_dd);
+  const float* sinv = (const float*)(base + t.off_sinv);
   const int d = C / 8, dv = C / 2;
   float* dKo = pool ? (float*)(base + t.off_dkp) : dK;
   float* dVo = pool ? (float*)(base + t.off_dvp) : dV;
-  if (C == 16) rc = launch_bwd<16, true, 32, 64, 2>(m, lse2, Dd, dQ, dKo, dVo, B, N, t, d, dv, st);
-  else if (C == 32) rc = launch_bwd<32, true, 32, 128, 1>(m, lse2, Dd, dQ, dKo, dVo, B, N, t, d, dv, st);
-  else rc = launch_bwd<32, false, 64, 128, 1>(m, lse2, Dd, dQ, dKo, dVo, B, N, t, d, dv, st);
+  if (C == 16) rc = launch_bwd<16, true, 32, 64, 2>(m, lse2, Dd, sinv, dQ, dKo, dVo, B, N, t, d, dv, st);
+  else if (C == 32) rc = launch_bwd<32, true, 32, 128, 1>(m, lse2, Dd, sinv, dQ, dKo, dVo, B, N, t, d, dv, st);
+  else rc = launch_bwd<32, false, 64, 128, 1>(m, lse2, Dd, sinv, dQ, dKo, dVo, B, N, t, d, dv, st);
   if (rc || !pool) return rc;
   return attn_unpool_launch(dKo, dVo, base + t.off_ik, base + t.off_iv, dK, dV, B, PH, PW, C, st);
 }

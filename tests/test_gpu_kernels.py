@@ -412,6 +412,29 @@ def test_attention_fwd_bwd_vs_oracle_n4096(F, mode_name):
         _check_attn_grads("B1_N4096_C16", mode_name, y, dx, gw, X, dY, Y_ref, g_ref, TC_TOL, TC_TOL, 1e-2)
 
 
+@pytest.mark.parametrize("shape", [(3, 512, 16), (2, 1024, 32)])
+@pytest.mark.parametrize("log2_scale", [-40, -24, 14])
+def test_attention_tc_backward_gradient_range(F, shape, log2_scale):
+    """The C <= 32 tensor-core backward carries dS = P' (dP - D) as ONE fp16 term (5 exponent bits), normalised per
+    sample by a power of two taken from max |dY|.  Gradients of the size a GAN step really sees (|dY| ~ 1e-7 ... 1e-12)
+    and large ones must come out as accurately as O(1) ones: with dY scaled by an exact power of two every gradient
+    must scale by exactly that factor (one sample is scaled a further 2^-9 so the samples' scales differ)."""
+    B, N, C = shape
+    X, dY, w = oattn.make_inputs(B, N, C, seed=91 + C, gamma=0.37, dtype=np.float32)
+    per_sample = np.ones((B, 1, 1), np.float32)
+    per_sample[-1] = 2.0 ** -9
+    _, dx0, gw0 = _run_attn(F, X, dY * per_sample, w, F.MATH_BF16_TC)
+    c = np.float32(2.0 ** log2_scale)
+    _, dx1, gw1 = _run_attn(F, X, dY * per_sample * c, w, F.MATH_BF16_TC)
+    # the residual path adds dY itself: compare the attention part of dX
+    att0, att1 = dx0 - dY * per_sample, (dx1 - dY * per_sample * c) / c
+    assert rel_l2(att1, att0) < 1e-5, rel_l2(att1, att0)
+    for k in oattn.WEIGHT_NAMES:
+        if k == "bphi":
+            continue
+        assert rel_l2(gw1[k] / c, gw0[k]) < 1e-4, (k, rel_l2(gw1[k] / c, gw0[k]))      # atomics: summation order differs
+
+
 @pytest.mark.parametrize("shape", [(45, 512, 16), (23, 900, 32), (160, 100, 16)])
 def test_attention_tc_persistent_work_items(F, shape):
     """The C <= 32 tensor-core forward is a persistent kernel (one CTA per SM walks the (sample, 128-query tile) work
