@@ -14,13 +14,31 @@ op like the reference's TF graph) of the reference algorithm:
                            /root/reference/sagan/models/discriminator.py:7-36
   * `oracle.train`      <- /root/reference/sagan/main.py:21-27,111-120,171-229
 
-PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or
-published numbers for this path (its tests assert output shapes only,
-test/test_generator.py:26, test/test_discriminator.py:28) and its arithmetic
-lives in an absent, un-pinned third-party dependency (`tensorflow`, TF 2.0-era
-API; not installed in this image, no network).  The restatement is therefore
-anchored on the reference's own call sites and on self-consistency checks
-(finite differences, torch-autograd vs analytic gradients, fp32 vs fp64); the
-readings chosen where the literal reference code is ill-formed are listed in
-DESIGN.md ("Oracle readings").
+PARITY: PINNED TO THE REFERENCE'S OWN CODE FOR THE FORWARD PATH, UNPINNED BELOW IT.
+The reference ships no golden vectors, known-answer tests or published numbers
+for this path (its tests assert output shapes only, test/test_generator.py:26,
+test/test_discriminator.py:28) and its arithmetic primitives live in an absent,
+un-pinned third-party dependency (`tensorflow`, TF 2.0-era API; not installable
+in this image, no network).  What CAN run here is the reference's Python itself:
+`tests/golden/make_reference_vectors.py` imports /root/reference/layers.py,
+sagan/models/generator.py, sagan/models/discriminator.py and the hinge losses of
+sagan/main.py:21-27 UNMODIFIED, with `tests/golden/tfshim/tensorflow` (a float64
+numpy stand-in for the few tf / Keras symbols they use) on the import path, and
+freezes what they compute in `tests/golden/reference_layers.npz`:
+l2normalize; SpectralNormalization._make_param / update_uv (u, v, sigma,
+W / sigma over two calls, Keras Dense / Conv2D / Conv2DTranspose kernel layouts,
+Ip 1-3, factor); Attention_Layer.build / call; hinge_loss_d / hinge_loss_g;
+get_generator / get_discriminator (patch head and projection head) layer by
+layer.  `tests/test_reference_vectors.py` holds this oracle to those numbers
+at 1e-12 and the CUDA kernels at the north_star tolerances.
+
+Still unpinned (no reference code to execute, or TF itself needed): TensorFlow's
+own kernels under those calls (matmul / conv / softmax semantics come from the
+stand-in, per their documentation); the gradients (tf.GradientTape; the oracle's
+analytic gradients are checked against torch autograd and finite differences
+instead); Keras Adam / ExponentialDecay and the step schedule of
+sagan/main.py:111-120,171-229 (main.py does not import as shipped); attention at
+C > 8 in the literal code (its MaxPool2D(2, 1) + raw reshape is ill-formed, see
+make_reference_vectors.py).  The readings chosen where the literal reference
+code is ill-formed are listed in DESIGN.md ("Oracle readings").
 """

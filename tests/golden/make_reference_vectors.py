@@ -1,0 +1,339 @@
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN PYTHON (run in the build container only).
+
+The reference holds no golden vectors and TensorFlow is not installable here, so `make_golden.py` can only freeze the
+oracle's own outputs.  This script closes the loop from the other side: it imports the UNMODIFIED reference files from
+/root/reference with `tests/golden/tfshim/tensorflow` (a float64 numpy stand-in for the few `tf.*` / Keras symbols
+those files use) on the import path, drives them with seeded inputs and writes what THEIR code computes to
+`reference_layers.npz`.  `tests/test_reference_vectors.py` then holds the oracle (CPU) and the CUDA kernels (GPU)
+to these numbers.  What is pinned is the reference's algorithm as written -- which matrix is reshaped how, what is
+normalised by what, the order of the u / v updates, the channel split, where biases and the residual enter, which
+layers the builders wire in which order with which kernel sizes / strides / padding / bias flags; NOT TensorFlow's
+kernels (matmul, conv, softmax come from the stand-in, with their documented semantics).
+
+    python tests/golden/make_reference_vectors.py        # needs /root/reference; writes tests/golden/reference_layers.npz
+
+Sections of the fixture
+  l2n_*    `l2normalize`                                      layers.py:4-5
+  sn*_     `SpectralNormalization.build / _make_param / update_uv` on real Keras-layout kernels (Dense, Conv2D,
+           Conv2DTranspose, 1x1 Conv2D), Ip in {1, 2, 3}, factor in {None, 2}; sigma and W / sigma are locals of
+           `update_uv` (layers.py:62-68, never returned: SURVEY.md appendix A.1), read from its frame at return.
+           Two consecutive calls, so the persistence of u is pinned too.
+  attn_*   `Attention_Layer.build / call` (layers.py:71-120).  The literal call max-pools keys and values with
+           MaxPool2D(2, 1) and then reshapes to the un-pooled token count (layers.py:100-101,113-114), which is
+           ill-formed at every real shape; it is executed here with that one layer class
+           replaced by the identity, at C = 8 where d = C // 8 = 1 makes the raw reshape of layers.py:101 a true
+           transpose -- there the reference's literal dataflow IS the paper form the oracle implements.  The channel
+           split (c//8, c//8, c//2, c) is read off the built layer for several C.  A second block records the literal
+           (pooled, broadcasting) result at the one degenerate shape where it runs (B=4, 2x2 map), for the record.
+  hinge_*  `hinge_loss_g / hinge_loss_d`, the two function definitions compiled from sagan/main.py:21-27 (the module
+           itself cannot be imported: SURVEY.md appendix A.7).
+  gen_* / dis_*   `get_generator / get_discriminator` of sagan/models/*.py run on concrete arrays (eager `Input`):
+           every layer the builder creates, in order, with its kernel; the image / logits that come out.  The literal
+           wrapper's forward uses the RAW kernel (appendix A.1), so the kernels are pre-scaled to sigma = 1 under the
+           stored u, which makes the literal forward equal to the normalised forward the oracle computes.
+           Attention is off in these two runs (see attn_* for why) and BatchNormalization runs on batch statistics.
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+OUT = os.path.join(HERE, "reference_layers.npz")
+
+
+def _import_reference():
+    assert os.path.isdir(REF), "the reference tree is only present in the build container"
+    sys.path.insert(0, os.path.join(HERE, "tfshim"))
+    sys.path.insert(0, REF)
+    import tensorflow as tf            # the stand-in
+    assert tf.__version__.endswith("numpy-shim")
+    import layers as ref_layers        # /root/reference/layers.py, unmodified
+    assert os.path.samefile(ref_layers.__file__, os.path.join(REF, "layers.py"))
+    return tf, ref_layers
+
+
+def _locals_at_return(fn, code_name):
+    """Runs fn() and returns (result, f_locals of the frame named `code_name` at its return)."""
+    box = {}
+
+    def tracer(frame, event, arg):
+        if event == "call" and frame.f_code.co_name == code_name:
+            def local(frame, event, arg):
+                if event == "return":
+                    box.update(frame.f_locals)
+                return local
+            return local
+        return None
+
+    sys.settrace(tracer)
+    try:
+        res = fn()
+    finally:
+        sys.settrace(None)
+    return res, box
+
+
+def rng_of(seed):
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def section_l2n(tf, ref, out):
+    r = rng_of(11)
+    for i, shape in enumerate([(1, 7), (1, 4096), (3, 5)]):
+        x = r.standard_normal(shape)
+        out["l2n_%d_x" % i] = x
+        out["l2n_%d_y" % i] = ref.l2normalize(tf.Tensor(x)).numpy()
+    out["l2n_zero_y"] = ref.l2normalize(tf.Tensor(np.zeros((1, 4)))).numpy()      # eps keeps 0 / 0 finite
+
+
+SN_CASES = [
+    # (tag, layer ctor, input shape, Ip, factor)
+    ("dense", lambda L: L.Dense(512), [4, 96], 1, None),                                      # kernel [96, 512]
+    ("conv_d0", lambda L: L.Conv2D(16, 4, 2, padding="same"), [4, 64, 64, 3], 1, None),        # [4,4,3,16]
+    ("conv_d1", lambda L: L.Conv2D(32, 4, 2, padding="same"), [4, 32, 32, 16], 2, None),       # [4,4,16,32]
+    ("deconv_g0", lambda L: L.Conv2DTranspose(32, 4, 2, padding="same", use_bias=False), [4, 4, 4, 64], 1, None),
+    ("deconv_g3", lambda L: L.Conv2DTranspose(16, 4, 2, padding="same", use_bias=False), [4, 32, 32, 32], 3, None),
+    ("conv1x1_q", lambda L: L.Conv2D(4, 1, 1), [4, 8, 8, 32], 1, None),                        # [1,1,32,4]
+    ("conv1x1_o", lambda L: L.Conv2D(32, 1, 1), [4, 8, 8, 16], 1, 2.0),                        # factor
+    ("conv3x3", lambda L: L.Conv2D(24, 3, 1, padding="same"), [2, 8, 8, 10], 2, 0.5),
+]
+
+
+def section_sn(tf, ref, out):
+    L = tf.keras.layers
+    tags = []
+    for ci, (tag, ctor, in_shape, Ip, factor) in enumerate(SN_CASES):
+        tf.random.set_seed(100 + ci)
+        L.seed_initializers(200 + ci)
+        module = ctor(L)
+        sn = ref.SpectralNormalization(module, Ip=Ip, factor=factor)
+        sn.build(tf.TensorShape(in_shape))                       # layers.py:40-43: builds the module, makes u / v
+        W = module.weights[0]
+        # a kernel with a non-trivial spectrum (glorot init would do; this has larger dynamic range)
+        W.assign(rng_of(300 + ci).standard_normal(W.shape) * 0.05)
+        p = "sn_%s_" % tag
+        out[p + "W"], out[p + "u0"], out[p + "v0"] = W.numpy().copy(), sn.u.numpy().copy(), sn.v.numpy().copy()
+        out[p + "Ip"], out[p + "factor"] = np.int64(Ip), np.float64(factor if factor else 0.0)
+        for call in (1, 2):
+            _, loc = _locals_at_return(sn.update_uv, "update_uv")
+            out[p + "u%d" % call], out[p + "v%d" % call] = sn.u.numpy().copy(), sn.v.numpy().copy()
+            out[p + "sigma%d" % call] = np.float64(loc["sigma"].numpy())
+            if call == 1:
+                out[p + "Wbar1"] = loc["W"].numpy().copy()
+            out[p + "Wmat_shape"] = np.asarray(loc["W_mat"].shape, dtype=np.int64)
+        tags.append(tag)
+    out["sn_tags"] = np.asarray(tags)
+    # the constructor's argument check (layers.py:17-18)
+    try:
+        ref.SpectralNormalization(L.Dense(4), Ip=0)
+        raised = ""
+    except ValueError as e:
+        raised = str(e)
+    out["sn_ip0_error"] = np.asarray(raised)
+
+
+class _IdentityPool:
+    """Stands in for keras.layers.MaxPool2D inside Attention_Layer.call for the well-formed run (see module docstring)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, x):
+        return x
+
+
+def _set_attention_weights(att, seed, gamma):
+    """Seeded kernels / biases for the four 1x1 convs.  layers.py:87-90 builds each wrapped conv once by hand and
+    Keras builds it again on first call, so a conv owns two kernels (weights[0] and .kernel): both get the same values."""
+    r = rng_of(seed)
+    got = {}
+    for name, wrap in zip(("phi", "theta", "g", "o"), att.SN_conv):
+        m = wrap.module
+        shape = m.kernel.shape
+        k = r.standard_normal(shape) * (0.6 if name in ("phi", "theta") else 0.3)
+        b = r.standard_normal(shape[-1:]) * 0.1
+        for w in m.weights:
+            w.assign(k if len(w.shape) == 4 else b)
+        got["W" + name], got["b" + name] = k.reshape(shape[2], shape[3]).copy(), b.copy()
+    att.sigma.assign(np.float64(gamma))
+    got["gamma"] = np.float64(gamma)
+    return got
+
+
+def section_attention(tf, ref, out):
+    L = tf.keras.layers
+    # channel split of build() for several C
+    splits = []
+    for C in (8, 16, 32, 64, 128):
+        att = ref.Attention_Layer()
+        att.build(tf.TensorShape([2, 4, 4, C]))
+        splits.append([C] + [int(w.module.filters) for w in att.SN_conv])
+        assert att.sigma.shape == () and float(att.sigma.numpy()) == 0.0          # zero-initialised scalar
+    out["attn_split"] = np.asarray(splits, dtype=np.int64)
+
+    # well-formed run: identity instead of MaxPool2D(2, 1), C = 8 (d = 1)
+    real_pool = L.MaxPool2D
+    cases = [(2, 4, 4, 8, 0.37), (3, 8, 8, 8, -1.25), (1, 16, 16, 8, 0.0)]
+    for i, (B, H, Wd, C, gamma) in enumerate(cases):
+        tf.random.set_seed(400 + i)
+        L.seed_initializers(500 + i)
+        X = rng_of(600 + i).standard_normal((B, H, Wd, C))
+        att = ref.Attention_Layer()
+        L.MaxPool2D = _IdentityPool
+        try:
+            att(tf.Tensor(X))                                     # builds (twice, as Keras would)
+            w = _set_attention_weights(att, 700 + i, gamma)
+            Y = att(tf.Tensor(X)).numpy()
+        finally:
+            L.MaxPool2D = real_pool
+        p = "attn_%d_" % i
+        out[p + "X"], out[p + "Y"] = X, Y
+        for k, v in w.items():
+            out[p + k] = v
+    out["attn_cases"] = np.int64(len(cases))
+
+    # literal run (real MaxPool2D(2, 1)) at the one shape family where the reshapes go through: a 2x2 map, B = 4
+    tf.random.set_seed(450)
+    L.seed_initializers(550)
+    X = rng_of(650).standard_normal((4, 2, 2, 16))
+    att = ref.Attention_Layer()
+    att(tf.Tensor(X))
+    w = _set_attention_weights(att, 750, 0.5)
+    out["attnlit_X"], out["attnlit_Y"] = X, att(tf.Tensor(X)).numpy()
+    for k, v in w.items():
+        out["attnlit_" + k] = v
+
+
+def section_hinge(tf, out):
+    src = open(os.path.join(REF, "sagan", "main.py")).read()
+    tree = ast.parse(src)
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("hinge_loss_g", "hinge_loss_d")]
+    assert len(fns) == 2
+    ns = {"tf": tf}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), os.path.join(REF, "sagan", "main.py"), "exec"), ns)
+    r = rng_of(21)
+    real, fake = r.standard_normal((6, 4, 4, 1)) * 2, r.standard_normal((6, 4, 4, 1)) * 2
+    out["hinge_real"], out["hinge_fake"] = real, fake
+    out["hinge_d"] = ns["hinge_loss_d"](tf.Tensor(real), tf.Tensor(fake)).numpy()
+    out["hinge_g"] = ns["hinge_loss_g"](tf.Tensor(fake)).numpy()
+
+
+def _import_builder(tf, ref_layers, which):
+    """sagan/models/<which>.py does `from layers import SpectralNormalization, AttentionLayer[, SNConv2D, SNDense]`
+    (names the top-level layers.py spells differently or lacks: SURVEY.md appendix A.7).  The module object named
+    `layers` it sees is the reference's layers.py plus those names; the builder file itself is read unmodified."""
+    import importlib.util
+    import types
+    facade = types.ModuleType("layers")
+    facade.__dict__.update(ref_layers.__dict__)
+    facade.AttentionLayer = ref_layers.Attention_Layer
+    facade.SNConv2D = facade.SNDense = None                      # imported by discriminator.py, unused by the vanilla builder
+    saved = sys.modules.get("layers")
+    sys.modules["layers"] = facade
+    try:
+        path = os.path.join(REF, "sagan", "models", which + ".py")
+        spec = importlib.util.spec_from_file_location("ref_sagan_" + which, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules["layers"] = saved
+    return mod
+
+
+def _prescale_to_unit_sigma(ref_layers, model_layers, seed):
+    """Seeded kernels for every layer; a wrapped module's kernel is divided by the sigma the reference's own update_uv
+    computes for it from the wrapper's current u, so that sigma(kernel; u) = 1 and W / sigma = W."""
+    r = rng_of(seed)
+    wrapped = {id(l.module): l for l in model_layers if isinstance(l, ref_layers.SpectralNormalization)}
+    for l in model_layers:
+        if isinstance(l, ref_layers.SpectralNormalization) or not l.weights:
+            continue
+        for w in l.weights:
+            if w.name in ("kernel", "embeddings"):
+                w.assign(r.standard_normal(w.shape) * 0.08)
+            elif w.name == "bias":
+                w.assign(r.standard_normal(w.shape) * 0.05)
+        if id(l) in wrapped:
+            sn = wrapped[id(l)]
+            u_keep, v_keep = sn.u, sn.v
+            _, loc = _locals_at_return(sn.update_uv, "update_uv")
+            l.weights[0].assign(l.weights[0].numpy() / float(loc["sigma"].numpy()))
+            sn.u, sn.v = u_keep, v_keep                          # the probe must not advance the stored u
+
+
+def _dump_layers(ref_layers, model_layers, prefix, out):
+    """Creation-ordered description of what the builder wired: kind, hyper-parameters, kernels, and for wrapped
+    modules the u the wrapper holds."""
+    kinds = []
+    wrapped = {id(l.module): l for l in model_layers if isinstance(l, ref_layers.SpectralNormalization)}
+    n = 0
+    for l in model_layers:
+        if isinstance(l, ref_layers.SpectralNormalization):
+            continue
+        kind = type(l).__name__
+        desc = [kind, "sn" if id(l) in wrapped else "plain"]
+        for attr in ("filters", "units", "kernel_size", "strides", "padding", "use_bias", "activation", "alpha",
+                     "epsilon", "momentum"):
+            if hasattr(l, attr):
+                desc.append("%s=%s" % (attr, getattr(l, attr)))
+        kinds.append(" ".join(desc))
+        for w in l.weights:
+            out["%sL%d_%s" % (prefix, n, w.name)] = w.numpy().copy()
+        if id(l) in wrapped:
+            out["%sL%d_u" % (prefix, n)] = wrapped[id(l)].u.numpy().copy()
+        n += 1
+    out[prefix + "layers"] = np.asarray(kinds)
+
+
+def section_builders(tf, ref_layers, out):
+    K, L = tf.keras, tf.keras.layers
+    cfg = dict(z_dim=32, gf_dim=4, df_dim=4, img_size=64, use_attention=False, attn_dim_G=[32, 64],
+               attn_dim_D=[8, 4], use_label=False, batch_size=2, num_classes=1)
+    B = cfg["batch_size"]
+    # generator: the first pass builds the layers, then kernels are seeded and the builder's own layers re-applied
+    gen = _import_builder(tf, ref_layers, "generator")
+    dis = _import_builder(tf, ref_layers, "discriminator")
+    cfg_label = dict(cfg, use_label=True, num_classes=10)        # projection head (discriminator.py:26-33)
+    for which, mod, fn, data, cfg in (
+            ("gen_", gen, "get_generator", rng_of(31).standard_normal((B, cfg["z_dim"])), cfg),
+            ("dis_", dis, "get_discriminator", rng_of(32).uniform(-1, 1, (B, 64, 64, 3)), cfg),
+            ("disc_", dis, "get_discriminator", rng_of(33).uniform(-1, 1, (B, 64, 64, 3)), cfg_label)):
+        tf.random.set_seed(40)
+        L.seed_initializers(41)
+        labels = np.asarray([7, 2], dtype=np.int32) if cfg["use_label"] else np.zeros((B,), dtype=np.int32)
+        out[which + "labels"] = labels
+        K.feed(data, labels)
+        model = getattr(mod, fn)(cfg)                            # pass 1: creates + builds every layer
+        layers1 = list(model.layers)
+        _prescale_to_unit_sigma(ref_layers, layers1, 50)
+        _dump_layers(ref_layers, layers1, which, out)            # kernels and the u each wrapper holds BEFORE pass 2
+        # pass 2: same layer OBJECTS, replayed in creation order by handing them back to the builder's constructors
+        replay = L.replay(layers1)
+        with replay:
+            K.feed(data, labels)
+            model2 = getattr(mod, fn)(cfg)
+        assert replay.done(), "builder created a different layer sequence on the second pass"
+        out[which + "in"] = data
+        out[which + "out"] = model2.outputs.numpy()
+
+
+def main():
+    tf, ref = _import_reference()
+    out = {}
+    section_l2n(tf, ref, out)
+    section_sn(tf, ref, out)
+    section_attention(tf, ref, out)
+    section_hinge(tf, out)
+    section_builders(tf, ref, out)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, "(%d arrays, %.0f kB)" % (len(out), os.path.getsize(OUT) / 1e3))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""A numpy-backed stand-in for the handful of `tensorflow` symbols the reference's hot-path files touch.
+
+TEST INFRASTRUCTURE ONLY.  TensorFlow cannot be installed in this environment (no network, not in the wheelhouse),
+so the reference's own Python (`/root/reference/layers.py`, the model builders under `/root/reference/sagan/models/`,
+the loss functions of `/root/reference/sagan/main.py`) cannot run as shipped.  This package lets those files be
+IMPORTED AND EXECUTED UNMODIFIED by `tests/golden/make_reference_vectors.py`: every line of control flow, every
+reshape, transposition, normalisation and reduction executed is the reference's; only the primitive array operations
+underneath (`tf.matmul`, `tf.norm`, `tf.reshape`, `tf.nn.softmax`, Keras `Conv2D` ...) are supplied here, in float64,
+with the semantics TensorFlow documents for them.  It is eager: there is no graph, `tf.function` is the identity.
+
+Nothing outside `tests/golden/make_reference_vectors.py` imports this package; it is never on the product path and
+does not travel into the GPU tests (they read the `.npz` fixtures the script wrote).
+"""
+import numpy as _np
+
+from . import _core
+from ._core import Tensor, TensorShape, Variable, convert as convert_to_tensor  # noqa: F401
+from . import keras  # noqa: F401
+from . import nn  # noqa: F401
+from . import random  # noqa: F401
+from . import math  # noqa: F401
+
+float32 = "float32"
+float64 = "float64"
+int32 = "int32"
+int64 = "int64"
+
+__version__ = "0.0-numpy-shim"
+
+
+def function(fn=None, **_kw):
+    """tf.function: eager here, so the decorated Python runs as written (layers.py:50)."""
+    if fn is None:
+        return lambda f: f
+    return fn
+
+
+def _a(x):
+    return _core.raw(x)
+
+
+def reshape(t, shape):
+    return Tensor(_np.reshape(_a(t), [int(s) for s in shape]))
+
+
+def transpose(t, perm=None):
+    return Tensor(_np.transpose(_a(t), perm))
+
+
+def matmul(a, b):
+    """Batched matrix product over the last two axes with broadcasting of the leading ones (tf.matmul)."""
+    return Tensor(_np.matmul(_a(a), _a(b)))
+
+
+def norm(t):
+    """tf.norm with default arguments: the Euclidean norm of ALL elements (Frobenius for matrices)."""
+    return Tensor(_np.sqrt(_np.sum(_np.square(_a(t)))))
+
+
+def reduce_sum(t, axis=None, keepdims=False):
+    if isinstance(axis, list):
+        axis = tuple(axis)
+    return Tensor(_np.sum(_a(t), axis=axis, keepdims=keepdims))
+
+
+def reduce_mean(t, axis=None, keepdims=False):
+    if isinstance(axis, list):
+        axis = tuple(axis)
+    return Tensor(_np.mean(_a(t), axis=axis, keepdims=keepdims))
+
+
+def one_hot(indices, depth):
+    idx = _a(indices).astype(_np.int64)
+    return Tensor(_np.eye(int(depth), dtype=_np.float64)[idx])
+
+
+def ones_like(t):
+    return Tensor(_np.ones_like(_a(t)))
+
+
+def zeros_like(t):
+    return Tensor(_np.zeros_like(_a(t)))
+
+
+def tanh(t):
+    return Tensor(_np.tanh(_a(t)))

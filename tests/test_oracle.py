@@ -1,6 +1,7 @@
 """CPU tests of the oracle itself (no GPU): golden fixtures, analytic-vs-autograd gradients, finite
-differences, fp32-vs-fp64 agreement.  The reference holds no golden vectors for this path
-(parity unpinned, see oracle/__init__.py), so the oracle is pinned by self-consistency."""
+differences, fp32-vs-fp64 agreement.  The reference holds no golden vectors for this path: the forward path is
+pinned to the reference's own code in tests/test_reference_vectors.py, the gradients and the optimiser here, by
+self-consistency (see oracle/__init__.py)."""
 import os
 import sys
 

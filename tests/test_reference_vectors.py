@@ -1,0 +1,312 @@
+"""Parity against vectors produced by the REFERENCE'S OWN CODE (tests/golden/reference_layers.npz).
+
+`tests/golden/make_reference_vectors.py` imports /root/reference/layers.py, sagan/models/generator.py,
+sagan/models/discriminator.py and the hinge-loss definitions of sagan/main.py UNMODIFIED (with a float64 numpy stand-in
+for the `tensorflow` module, since TensorFlow cannot be installed) and records what they compute.  Here:
+
+* not-gpu tests hold the ORACLE (oracle/sn.py, attention.py, train.py, nets.py) to those numbers at fp64 round-off
+  (1e-12): this is what pins the oracle to the reference rather than to our reading of it;
+* gpu tests hold the CUDA kernels, called through the C ABI, to the same numbers at the north_star tolerances
+  (sigma / u / v 1e-5 relative; attention and model outputs 1e-5 relative L2 in the strict mode).
+
+Nothing here reads /root/reference or the stand-in at run time: only the committed fixture.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as oattn
+from oracle import nets as onets
+from oracle import sn as osn
+from oracle import train as otrain
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_layers.npz")
+FP64_TOL = 1e-12
+STRICT_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(GOLD)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def _factor(ref, tag):
+    f = float(ref[f"sn_{tag}_factor"])
+    return f if f else None
+
+
+# ------------------------------------------------------------------------------------------------ oracle == reference
+def test_oracle_l2normalize_matches_reference(ref):
+    for i in range(3):
+        assert rel_l2(osn.l2normalize(ref[f"l2n_{i}_x"]), ref[f"l2n_{i}_y"]) < FP64_TOL
+    assert np.array_equal(osn.l2normalize(np.zeros((1, 4))), ref["l2n_zero_y"])
+
+
+def test_oracle_power_iteration_matches_reference_update_uv(ref):
+    """layers.py:30-38,50-68 executed by the reference on Dense / Conv2D / Conv2DTranspose / 1x1 kernels in their Keras
+    layouts: u, v after one and two calls, sigma, W / sigma, the [R, K] the kernel is reshaped to."""
+    for tag in ref["sn_tags"]:
+        p = f"sn_{tag}_"
+        W, u0, Ip, factor = ref[p + "W"], ref[p + "u0"], int(ref[p + "Ip"]), _factor(ref, tag)
+        assert tuple(osn.matricize(W).shape) == tuple(ref[p + "Wmat_shape"]), tag
+        R, K = ref[p + "Wmat_shape"]
+        assert R == W.shape[-1] and u0.shape == (1, R) and ref[p + "v0"].shape == (1, K), tag   # _make_param shapes
+        assert abs(np.linalg.norm(u0) - 1) < 1e-12 and abs(np.linalg.norm(ref[p + "v0"]) - 1) < 1e-12
+        u1, v1, s1, Wb1 = osn.power_iteration(W, u0, Ip, factor)
+        assert rel_l2(u1, ref[p + "u1"]) < FP64_TOL and rel_l2(v1, ref[p + "v1"]) < FP64_TOL, tag
+        assert abs(s1 - ref[p + "sigma1"]) < FP64_TOL * abs(s1), tag
+        assert rel_l2(Wb1, ref[p + "Wbar1"]) < FP64_TOL and Wb1.shape == W.shape, tag
+        u2, v2, s2, _ = osn.power_iteration(W, u1, Ip, factor)       # u persists into the next call
+        assert rel_l2(u2, ref[p + "u2"]) < FP64_TOL and rel_l2(v2, ref[p + "v2"]) < FP64_TOL, tag
+        assert abs(s2 - ref[p + "sigma2"]) < FP64_TOL * abs(s2), tag
+    with pytest.raises(ValueError) as e:
+        osn.power_iteration(np.ones((2, 2)), np.ones((1, 2)), Ip=0)
+    assert str(e.value) == str(ref["sn_ip0_error"])
+
+
+def test_oracle_nets_spectral_norm_matches_reference(ref):
+    """The torch restatement inside oracle/nets.py (what the model-level oracle uses) against the same vectors."""
+    for tag in ref["sn_tags"]:
+        p = f"sn_{tag}_"
+        st = {"k": torch.tensor(ref[p + "u0"])}
+        Wb = onets.spectral_norm(torch.tensor(ref[p + "W"]), st, "k", True, int(ref[p + "Ip"]), _factor(ref, tag))
+        assert rel_l2(Wb.numpy(), ref[p + "Wbar1"]) < FP64_TOL and rel_l2(st["k"].numpy(), ref[p + "u1"]) < FP64_TOL
+
+
+def _attn_args(ref, p):
+    return dict(Wphi=ref[p + "Wphi"], bphi=ref[p + "bphi"], Wtheta=ref[p + "Wtheta"], btheta=ref[p + "btheta"],
+                Wg=ref[p + "Wg"], bg=ref[p + "bg"], Wo=ref[p + "Wo"], bo=ref[p + "bo"], gamma=float(ref[p + "gamma"]))
+
+
+def test_oracle_attention_matches_reference_call(ref):
+    """Attention_Layer.call (layers.py:93-120) run by the reference with the ill-formed MaxPool2D(2, 1) replaced by
+    the identity, at C = 8 where its raw reshape of phi is a true transpose."""
+    for C, d1, d2, dv, co in ref["attn_split"]:
+        assert (d1, dv) == oattn.channel_split(int(C)) and d2 == d1 and co == C
+    for i in range(int(ref["attn_cases"])):
+        p = f"attn_{i}_"
+        X = ref[p + "X"]
+        B, H, W, C = X.shape
+        Y = oattn.forward(X.reshape(B, H * W, C), **_attn_args(ref, p)).reshape(X.shape)
+        assert rel_l2(Y, ref[p + "Y"]) < FP64_TOL
+        if float(ref[p + "gamma"]) == 0.0:
+            assert np.array_equal(ref[p + "Y"], X)                    # zero-initialised gamma: identity block
+
+
+def test_reference_literal_pooled_call_is_not_attention(ref):
+    """Documents SURVEY.md appendix A.5 with the reference's own numbers: at the one shape family where the literal
+    MaxPool2D(2, 1) + reshape goes through (2x2 map, B = 4), the four samples' pooled keys / values are folded into ONE
+    [d, 4] / [4, dv] matrix shared (broadcast) by every sample.  Reproduced here in numpy from the recorded weights."""
+    p = "attnlit_"
+    X, a = ref[p + "X"], _attn_args(ref, p)
+    B, H, W, C = X.shape
+    Xf = X.reshape(B, H * W, C)
+    phi = (Xf @ a["Wphi"] + a["bphi"]).max(axis=1)                    # 2x2 window, stride 1 on a 2x2 map: one value
+    g = (Xf @ a["Wg"] + a["bg"]).max(axis=1)
+    theta = Xf @ a["Wtheta"] + a["btheta"]
+    phi_m = phi.reshape(1, C // 8, H * W)                              # the batch axis is folded into the tokens
+    g_m = g.reshape(1, H * W, C // 2)
+    S = theta @ phi_m
+    P = np.exp(S - S.max(-1, keepdims=True))
+    P /= P.sum(-1, keepdims=True)
+    Y = Xf + a["gamma"] * ((P @ g_m) @ a["Wo"] + a["bo"])
+    assert rel_l2(Y.reshape(X.shape), ref[p + "Y"]) < FP64_TOL
+    assert rel_l2(oattn.forward(Xf, **a).reshape(X.shape), ref[p + "Y"]) > 1e-3     # and it is not the paper form
+
+
+def test_oracle_hinge_losses_match_reference(ref):
+    real, fake = torch.tensor(ref["hinge_real"]), torch.tensor(ref["hinge_fake"])
+    assert np.array_equal(otrain.hinge_loss_d(real, fake).numpy(), ref["hinge_d"])
+    assert np.array_equal(otrain.hinge_loss_g(fake).numpy(), ref["hinge_g"])
+
+
+# the configuration the builders were run with (make_reference_vectors.section_builders)
+BUILDER_CFG = dict(z_dim=32, gf_dim=4, df_dim=4, img_size=64, use_attention=False, attn_dim_G=[32, 64],
+                   attn_dim_D=[8, 4], use_label=False, batch_size=2, num_classes=1)
+
+
+def _gen_params(ref):
+    """Maps the creation-ordered layers the reference's get_generator built onto the oracle's parameter names, checking
+    on the way that each layer is what generator.py:7-37 says (kind, width, 4x4 / stride 2 / same, bias flag, slope)."""
+    desc = list(ref["gen_layers"])
+    gf, n = BUILDER_CFG["gf_dim"], 4
+    assert desc[0] == f"Dense sn units={4 * 4 * gf * 16} use_bias=True activation=None"
+    p = {"dense.kernel": ref["gen_L0_kernel"], "dense.bias": ref["gen_L0_bias"]}
+    u = {"dense.u": ref["gen_L0_u"]}
+    for i in range(n):
+        cout = gf * 2 ** (n - 1 - i)
+        j = 1 + 3 * i
+        assert desc[j] == (f"Conv2DTranspose sn filters={cout} kernel_size=(4, 4) strides=(2, 2) padding=same "
+                           "use_bias=False activation=None")
+        assert desc[j + 1] == "BatchNormalization plain epsilon=0.001 momentum=0.99"
+        assert desc[j + 2] == "LeakyReLU plain alpha=0.1"
+        p[f"block{i}.deconv.kernel"] = ref[f"gen_L{j}_kernel"]
+        p[f"block{i}.bn.gamma"], p[f"block{i}.bn.beta"] = ref[f"gen_L{j + 1}_gamma"], ref[f"gen_L{j + 1}_beta"]
+        u[f"block{i}.deconv.u"] = ref[f"gen_L{j}_u"]
+    assert desc[13] == "Conv2D plain filters=3 kernel_size=(4, 4) strides=(1, 1) padding=same use_bias=False activation=tanh"
+    assert len(desc) == 14
+    p["head.kernel"] = ref["gen_L13_kernel"]
+    return p, u
+
+
+def _dis_params(ref, prefix, cfg):
+    desc = list(ref[prefix + "layers"])
+    df, n = cfg["df_dim"], 4
+    p, u = {}, {}
+    for i in range(n):
+        j = 2 * i
+        assert desc[j] == (f"Conv2D sn filters={df * 2 ** i} kernel_size=(4, 4) strides=(2, 2) padding=same "
+                           "use_bias=True activation=None")
+        assert desc[j + 1] == "LeakyReLU plain alpha=0.1"
+        p[f"block{i}.conv.kernel"], p[f"block{i}.conv.bias"] = ref[f"{prefix}L{j}_kernel"], ref[f"{prefix}L{j}_bias"]
+        u[f"block{i}.conv.u"] = ref[f"{prefix}L{j}_u"]
+    if cfg["use_label"]:
+        assert desc[8:] == ["Dense plain units=1 use_bias=True activation=None", "Embedding plain"]
+        p["head.dense.kernel"], p["head.dense.bias"] = ref[prefix + "L8_kernel"], ref[prefix + "L8_bias"]
+        p["head.embedding"] = ref[prefix + "L9_embeddings"]
+    else:
+        assert desc[8:] == ["Conv2D plain filters=1 kernel_size=(4, 4) strides=(1, 1) padding=same use_bias=True activation=None"]
+        p["head.kernel"], p["head.bias"] = ref[prefix + "L8_kernel"], ref[prefix + "L8_bias"]
+    return p, u
+
+
+def _t64(d):
+    return {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in d.items()}
+
+
+def test_oracle_generator_matches_reference_builder(ref):
+    """get_generator (sagan/models/generator.py:14-37) run by the reference on a concrete z: same layers in the same
+    order as oracle.nets.generator_spec, same image out of oracle.nets.generator_forward."""
+    p, u = _gen_params(ref)
+    assert {k: tuple(v.shape) for k, v in p.items()} == dict(onets.generator_spec(BUILDER_CFG))
+    assert list(u) == list(onets.sn_keys(onets.generator_spec(BUILDER_CFG)))
+    st = _t64(u)
+    img = onets.generator_forward(_t64(p), st, torch.tensor(ref["gen_in"]), BUILDER_CFG)
+    assert rel_l2(img.numpy(), ref["gen_out"]) < 1e-11
+    for k in u:                                                       # kernels were pre-scaled to sigma = 1
+        assert abs(float(st[k + ":sigma"]) - 1) < 1e-10          # (the 1e-12 eps of l2normalize is not scale-free)
+
+
+@pytest.mark.parametrize("prefix", ["dis_", "disc_"])
+def test_oracle_discriminator_matches_reference_builder(ref, prefix):
+    """get_discriminator (sagan/models/discriminator.py:13-36): the patch-logit head and the projection head."""
+    cfg = dict(BUILDER_CFG, use_label=True, num_classes=10) if prefix == "disc_" else BUILDER_CFG
+    p, u = _dis_params(ref, prefix, cfg)
+    assert {k: tuple(v.shape) for k, v in p.items()} == dict(onets.discriminator_spec(cfg))
+    assert list(u) == list(onets.sn_keys(onets.discriminator_spec(cfg)))
+    labels = torch.tensor(ref[prefix + "labels"].astype(np.int64))
+    out = onets.discriminator_forward(_t64(p), _t64(u), torch.tensor(ref[prefix + "in"]), cfg, labels=labels)
+    assert out.shape == ref[prefix + "out"].shape
+    assert rel_l2(out.numpy(), ref[prefix + "out"]) < 1e-11
+
+
+# ------------------------------------------------------------------------------------------------- CUDA == reference
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+@pytest.fixture(scope="module")
+def F():
+    import sagan_b200.functional as F
+    from sagan_b200 import _lib
+    _lib.load()
+    return F
+
+
+@pytest.mark.gpu
+def test_cuda_power_iteration_matches_reference_update_uv(F, ref):
+    """sagan_sn_plan_run on the reference's kernels (Keras layouts, raw [last dim, -1] matricisation): u, v, sigma,
+    W / sigma of the first and second call within 1e-5 of what the reference's update_uv computed."""
+    tags = list(ref["sn_tags"])
+    by_ip = {}
+    for t in tags:
+        by_ip.setdefault(int(ref[f"sn_{t}_Ip"]), []).append(t)
+    for Ip, group_tags in by_ip.items():
+        Ws = [cu(ref[f"sn_{t}_W"]) for t in group_tags]
+        us = [cu(ref[f"sn_{t}_u0"]) for t in group_tags]
+        g = F.SpectralNormGroup(Ws, us, Ip, [_factor(ref, t) for t in group_tags])
+        for call in (1, 2):
+            g.run()
+            torch.cuda.synchronize()
+            for i, t in enumerate(group_tags):
+                p = f"sn_{t}_"
+                assert rel_l2(g.u(i).cpu().numpy(), ref[p + f"u{call}"]) < STRICT_TOL, (t, call)
+                assert rel_l2(g.v(i).cpu().numpy(), ref[p + f"v{call}"]) < STRICT_TOL, (t, call)
+                s = float(ref[p + f"sigma{call}"])
+                assert abs(float(g.sigma(i).cpu()) - s) < STRICT_TOL * abs(s), (t, call)
+                if call == 1:
+                    wb = g.w_bar(i).cpu().numpy()
+                    assert rel_l2(wb, ref[p + "Wbar1"]) < STRICT_TOL and wb.shape == ref[p + "W"].shape, t
+
+
+@pytest.mark.gpu
+def test_cuda_attention_matches_reference_call(F, ref):
+    """sagan_attn_fwd (strict mode; C = 8 has no tensor-core form) against Attention_Layer.call's own output."""
+    for i in range(int(ref["attn_cases"])):
+        p = f"attn_{i}_"
+        X, a = ref[p + "X"], _attn_args(ref, p)
+        B, H, W, C = X.shape
+        y = F.attention(cu(X.reshape(B, H * W, C)), cu(a["Wtheta"]), cu(a["btheta"]), cu(a["Wphi"]), cu(a["bphi"]),
+                        cu(a["Wg"]), cu(a["bg"]), cu(a["Wo"]), cu(a["bo"]), cu(np.float32(a["gamma"])),
+                        F.MATH_FP32_STRICT)
+        torch.cuda.synchronize()
+        assert rel_l2(y.cpu().numpy().reshape(X.shape), ref[p + "Y"]) < STRICT_TOL, i
+
+
+@pytest.mark.gpu
+def test_cuda_hinge_matches_reference(F, ref):
+    real, fake = cu(ref["hinge_real"]), cu(ref["hinge_fake"])
+    loss = torch.zeros(1, device="cuda")
+    n = real.shape[0]
+    g_real, g_fake = F.hinge_d_grads(real, fake, n, loss)
+    torch.cuda.synchronize()
+    # the differentiated scalar is mean(L) / global_batch (sagan/main.py:184): loss accumulates sum(L)
+    assert abs(float(loss) - ref["hinge_d"].sum()) < 1e-5 * abs(ref["hinge_d"].sum())
+    scale = 1.0 / (ref["hinge_d"].size * n)
+    assert np.allclose(g_real.cpu().numpy(), np.where(1 - ref["hinge_real"] > 0, -scale, 0.0), rtol=1e-6, atol=0)
+    assert np.allclose(g_fake.cpu().numpy(), np.where(1 + ref["hinge_fake"] > 0, scale, 0.0), rtol=1e-6, atol=0)
+
+
+def _gpu_net(kind, cfg):
+    from sagan_b200 import nets
+    torch.manual_seed(0)
+    return nets.get_generator(cfg) if kind == "G" else nets.get_discriminator(cfg)
+
+
+@pytest.mark.gpu
+def test_cuda_generator_matches_reference_builder(F, ref):
+    """The host-side Generator (nets.py) over the CUDA kernels, loaded with the kernels the reference's get_generator
+    built, reproduces the image the reference computed (strict mode, 1e-5)."""
+    p, u = _gen_params(ref)
+    net = _gpu_net("G", dict(BUILDER_CFG))
+    z = cu(ref["gen_in"])
+    with torch.no_grad():
+        net([torch.zeros_like(z), None])                              # build pass (creates the parameters)
+        net.load_keras_weights(p, u)
+        img = net([z, None], training=True)
+    torch.cuda.synchronize()
+    assert rel_l2(img.cpu().numpy(), ref["gen_out"]) < STRICT_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prefix", ["dis_", "disc_"])
+def test_cuda_discriminator_matches_reference_builder(F, ref, prefix):
+    cfg = dict(BUILDER_CFG, use_label=True, num_classes=10) if prefix == "disc_" else dict(BUILDER_CFG)
+    p, u = _dis_params(ref, prefix, cfg)
+    net = _gpu_net("D", cfg)
+    img = cu(ref[prefix + "in"])
+    labels = torch.as_tensor(ref[prefix + "labels"].astype(np.int64)).cuda() if cfg["use_label"] else None
+    with torch.no_grad():
+        net([torch.zeros_like(img), labels])                          # build pass
+        net.load_keras_weights(p, u)
+        out = net([img, labels], training=True)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu().numpy(), ref[prefix + "out"]) < STRICT_TOL
