@@ -32,6 +32,8 @@ Sections of the fixture
            wrapper's forward uses the RAW kernel (appendix A.1), so the kernels are pre-scaled to sigma = 1 under the
            stored u, which makes the literal forward equal to the normalised forward the oracle computes.
            Attention is off in these two runs (see attn_* for why) and BatchNormalization runs on batch statistics.
+  rgen_* / rdis_*  the legacy residual builders models/generator.py:23-43, models/discriminator.py:40-57 the same way,
+           at widths where their Attention_Layer sees C = 8, so attention stays IN (identity pool).
 """
 import ast
 import os
@@ -223,7 +225,7 @@ def section_hinge(tf, out):
     out["hinge_g"] = ns["hinge_loss_g"](tf.Tensor(fake)).numpy()
 
 
-def _import_builder(tf, ref_layers, which):
+def _import_builder(tf, ref_layers, which, tree="sagan/models"):
     """sagan/models/<which>.py does `from layers import SpectralNormalization, AttentionLayer[, SNConv2D, SNDense]`
     (names the top-level layers.py spells differently or lacks: SURVEY.md appendix A.7).  The module object named
     `layers` it sees is the reference's layers.py plus those names; the builder file itself is read unmodified."""
@@ -236,8 +238,8 @@ def _import_builder(tf, ref_layers, which):
     saved = sys.modules.get("layers")
     sys.modules["layers"] = facade
     try:
-        path = os.path.join(REF, "sagan", "models", which + ".py")
-        spec = importlib.util.spec_from_file_location("ref_sagan_" + which, path)
+        path = os.path.join(REF, *tree.split("/"), which + ".py")
+        spec = importlib.util.spec_from_file_location("ref_" + tree.replace("/", "_") + "_" + which, path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:
@@ -246,24 +248,32 @@ def _import_builder(tf, ref_layers, which):
     return mod
 
 
-def _prescale_to_unit_sigma(ref_layers, model_layers, seed):
+def _prescale_to_unit_sigma(ref_layers, model_layers, seed, attn_gamma=0.37):
     """Seeded kernels for every layer; a wrapped module's kernel is divided by the sigma the reference's own update_uv
-    computes for it from the wrapper's current u, so that sigma(kernel; u) = 1 and W / sigma = W."""
+    computes for it from the wrapper's current u, so that sigma(kernel; u) = 1 and W / sigma = W.  A conv built twice
+    (Attention_Layer's, layers.py:87-90 + Keras' own build) owns two kernels -- weights[0], which update_uv reads, and
+    .kernel, which call uses: both get the same values."""
     r = rng_of(seed)
     wrapped = {id(l.module): l for l in model_layers if isinstance(l, ref_layers.SpectralNormalization)}
     for l in model_layers:
         if isinstance(l, ref_layers.SpectralNormalization) or not l.weights:
             continue
+        vals = {}
         for w in l.weights:
-            if w.name in ("kernel", "embeddings"):
-                w.assign(r.standard_normal(w.shape) * 0.08)
-            elif w.name == "bias":
-                w.assign(r.standard_normal(w.shape) * 0.05)
+            if w.name in ("kernel", "embeddings", "bias"):
+                if w.name not in vals:
+                    vals[w.name] = r.standard_normal(w.shape) * (0.05 if w.name == "bias" else 0.08)
+                w.assign(vals[w.name])
+            elif w.name == "sigma":
+                w.assign(np.float64(attn_gamma))
         if id(l) in wrapped:
             sn = wrapped[id(l)]
             u_keep, v_keep = sn.u, sn.v
             _, loc = _locals_at_return(sn.update_uv, "update_uv")
-            l.weights[0].assign(l.weights[0].numpy() / float(loc["sigma"].numpy()))
+            sig = float(loc["sigma"].numpy())
+            for w in l.weights:
+                if w.name in ("kernel", "embeddings"):
+                    w.assign(w.numpy() / sig)
             sn.u, sn.v = u_keep, v_keep                          # the probe must not advance the stored u
 
 
@@ -277,7 +287,7 @@ def _dump_layers(ref_layers, model_layers, prefix, out):
         if isinstance(l, ref_layers.SpectralNormalization):
             continue
         kind = type(l).__name__
-        desc = [kind, "sn" if id(l) in wrapped else "plain"]
+        desc = [kind, "sn" if id(l) in wrapped else "plain"] + (["inner"] if l._inner else [])
         for attr in ("filters", "units", "kernel_size", "strides", "padding", "use_bias", "activation", "alpha",
                      "epsilon", "momentum"):
             if hasattr(l, attr):
@@ -323,6 +333,39 @@ def section_builders(tf, ref_layers, out):
         out[which + "out"] = model2.outputs.numpy()
 
 
+def section_res_builders(tf, ref_layers, out):
+    """The legacy residual builders, models/generator.py:23-43 and models/discriminator.py:40-57, at
+    widths where their Attention_Layer sees C = 8 (gf_dim 2, df_dim 4), with the identity pool (see attn_*), called with
+    training=True (batch-statistics BatchNormalization; the wrapper then skips update_uv, layers.py:46)."""
+    K, L = tf.keras, tf.keras.layers
+    B, ncls = 2, 5
+    gen = _import_builder(tf, ref_layers, "generator", "models")
+    dis = _import_builder(tf, ref_layers, "discriminator", "models")
+    labels = np.asarray([3, 1], dtype=np.int32)
+    real_pool = L.MaxPool2D
+    L.MaxPool2D = _IdentityPool
+    try:
+        for which, build, data in (
+                ("rgen_", lambda: gen.get_generator(ncls, gf_dim=2, training=True), rng_of(61).standard_normal((B, 128))),
+                ("rdis_", lambda: dis.get_discriminator(ncls, df_dim=4, training=True),
+                 rng_of(62).uniform(-1, 1, (B, 128, 128, 3)))):
+            tf.random.set_seed(70)
+            L.seed_initializers(71)
+            K.feed(data, labels)
+            model = build()
+            layers1 = list(model.layers)
+            _prescale_to_unit_sigma(ref_layers, layers1, 80)
+            _dump_layers(ref_layers, layers1, which, out)
+            replay = L.replay(layers1)
+            with replay:
+                K.feed(data, labels)
+                model2 = build()
+            assert replay.done()
+            out[which + "in"], out[which + "labels"], out[which + "out"] = data, labels, model2.outputs.numpy()
+    finally:
+        L.MaxPool2D = real_pool
+
+
 def main():
     tf, ref = _import_reference()
     out = {}
@@ -331,6 +374,7 @@ def main():
     section_attention(tf, ref, out)
     section_hinge(tf, out)
     section_builders(tf, ref, out)
+    section_res_builders(tf, ref, out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "(%d arrays, %.0f kB)" % (len(out), os.path.getsize(OUT) / 1e3))
 

@@ -28,3 +28,11 @@ class Model:
     def __init__(self, inputs=None, outputs=None, name=None):
         self.inputs, self.outputs = inputs, outputs
         self.layers = list(layers.created)
+
+
+class Sequential:                     # imported by the legacy builders (models/generator.py:2), never used by them
+    pass
+
+
+class optimizers:                     # likewise
+    pass

@@ -26,6 +26,7 @@ def _same_pads(n, k, s):
     return total // 2, total - total // 2
 
 
+_depth = [0]            # > 0 while some layer's build() is running
 _replay = [None]        # a list of already-built layers to hand out again (see replay()), or None
 
 
@@ -35,7 +36,7 @@ class replay:
     second time over layers whose kernels a script has set, without editing the builder."""
 
     def __init__(self, recorded):
-        self.rec = list(recorded)
+        self.rec = [l for l in recorded if not l._inner]      # inner layers are not constructed again (owner is built)
 
     def __enter__(self):
         _replay[0] = self.rec
@@ -64,6 +65,7 @@ class Layer:
         self.built = False
         self._weights = []
         self.name = name
+        self._inner = _depth[0] > 0         # constructed inside another layer's build (Attention_Layer's four convs)
         created.append(self)
 
     @property
@@ -98,7 +100,11 @@ class Layer:
     def __call__(self, inputs, *args, **kwargs):
         if not self.built:
             shp = [t.shape for t in inputs] if isinstance(inputs, (list, tuple)) else inputs.shape
-            self.build(shp)
+            _depth[0] += 1
+            try:
+                self.build(shp)
+            finally:
+                _depth[0] -= 1
             self.built = True
         return self.call(inputs, *args, **kwargs)
 
@@ -218,6 +224,9 @@ class BatchNormalization(Layer):
 
     def call(self, inputs, training=True):
         x = raw(inputs)
+        if not training:
+            return Tensor((x - raw(self.moving_mean)) / np.sqrt(raw(self.moving_variance) + self.epsilon)
+                          * raw(self.gamma) + raw(self.beta))
         ax = tuple(range(x.ndim - 1))
         mean, var = x.mean(axis=ax), x.var(axis=ax)
         self.moving_mean.assign(raw(self.moving_mean) * self.momentum + mean * (1 - self.momentum))
@@ -233,6 +242,11 @@ class LeakyReLU(Layer):
     def call(self, inputs):
         a = raw(inputs)
         return Tensor(np.where(a >= 0, a, self.alpha * a))
+
+
+class ReLU(Layer):
+    def call(self, inputs):
+        return Tensor(np.maximum(raw(inputs), 0.0))
 
 
 class MaxPool2D(Layer):
@@ -277,5 +291,5 @@ def add(inputs):
     return Tensor(out)
 
 
-__all__ = ["Layer", "Conv2D", "Conv2DTranspose", "Dense", "Embedding", "BatchNormalization", "LeakyReLU", "MaxPool2D",
+__all__ = ["Layer", "ReLU", "Conv2D", "Conv2DTranspose", "Dense", "Embedding", "BatchNormalization", "LeakyReLU", "MaxPool2D",
            "MaxPooling2D", "Concatenate", "Reshape", "add", "TensorShape"]

@@ -208,6 +208,112 @@ def test_oracle_discriminator_matches_reference_builder(ref, prefix):
     assert rel_l2(out.numpy(), ref[prefix + "out"]) < 1e-11
 
 
+RES_CFG = dict(model="resnet", z_dim=128, gf_dim=2, df_dim=4, img_size=128, num_classes=5, use_label=True,
+               use_attention=True, attn_dim_G=[32], batch_size=2)
+
+
+class _Cursor:
+    """Walks the creation-ordered layer list the reference's builder produced, asserting each entry on the way."""
+
+    def __init__(self, ref, prefix):
+        self.ref, self.prefix, self.desc, self.i = ref, prefix, list(ref[prefix + "layers"]), 0
+
+    def take(self, expect):
+        assert self.desc[self.i] == expect, (self.i, self.desc[self.i], expect)
+        self.i += 1
+        return self.i - 1
+
+    def arr(self, idx, name):
+        return self.ref[f"{self.prefix}L{idx}_{name}"]
+
+    def conv(self, kind, filters, k, s, name, p, u, inner=False, act=None, padding="same"):
+        idx = self.take(f"{kind} sn {'inner ' if inner else ''}filters={filters} kernel_size=({k}, {k}) strides=({s}, {s}) "
+                        f"padding={padding} use_bias=True activation={act}")
+        p[name + ".kernel"], p[name + ".bias"], u[name + ".u"] = self.arr(idx, "kernel"), self.arr(idx, "bias"), self.arr(idx, "u")
+
+    def bn(self, name, p):
+        idx = self.take("BatchNormalization plain epsilon=0.001 momentum=0.99")
+        p[name + ".gamma"], p[name + ".beta"] = self.arr(idx, "gamma"), self.arr(idx, "beta")
+
+    def attention(self, prefix, C, p, u):
+        idx = self.take("Attention_Layer plain")
+        p[prefix + ".sigma"] = self.arr(idx, "sigma")
+        for nm, f in (("phi", C // 8), ("theta", C // 8), ("g", C // 2), ("o", C)):       # layers.py:82-85 order
+            self.conv("Conv2D", f, 1, 1, f"{prefix}.{nm}", p, u, inner=True, padding="valid")
+
+    def done(self):
+        return self.i == len(self.desc)
+
+
+def _res_gen_params(ref):
+    """models/generator.py:6-43 as the reference built it -> oracle.resnets parameter names."""
+    c, p, u = _Cursor(ref, "rgen_"), {}, {}
+    gf = RES_CFG["gf_dim"]
+    c.take("Concatenate plain")                                                              # :27
+    idx = c.take(f"Dense sn units={4 * 4 * gf * 16} use_bias=True activation=None")         # :28
+    p["dense.kernel"], p["dense.bias"], u["dense.u"] = c.arr(idx, "kernel"), c.arr(idx, "bias"), c.arr(idx, "u")
+    for i, mult in enumerate((16, 8, 4, 2, 1)):                                              # :31-37
+        ch = gf * mult
+        c.bn(f"block{i}.pre.bn", p), c.take("ReLU plain")                                    # :7-8
+        c.conv("Conv2DTranspose", ch, 3, 2, f"block{i}.deconv1", p, u)                       # :11-12
+        c.bn(f"block{i}.mid.bn", p), c.take("ReLU plain")                                    # :13-14
+        c.conv("Conv2D", ch, 3, 1, f"block{i}.conv2", p, u)                                  # :15-16
+        c.conv("Conv2DTranspose", ch, 3, 2, f"block{i}.deconv_sc", p, u)                     # :18-19
+        if i == 2:
+            c.attention(f"block{i}.attn", ch, p, u)                                          # :34 (after the 32x32 block)
+    c.bn("final.bn", p), c.take("ReLU plain")                                                # :39-40
+    c.conv("Conv2D", 3, 3, 1, "final.conv", p, u, act="tanh")                                # :41-42
+    assert c.done()
+    return p, u
+
+
+def _res_dis_params(ref):
+    """models/discriminator.py:6-57 -> oracle.resnets parameter names."""
+    c, p, u = _Cursor(ref, "rdis_"), {}, {}
+    df = RES_CFG["df_dim"]
+    c.conv("Conv2D", df, 3, 1, "opt.conv1", p, u), c.take("ReLU plain")                      # :7-9
+    c.conv("Conv2D", df, 3, 2, "opt.conv2", p, u)                                            # :11-12
+    c.conv("Conv2D", df, 3, 2, "opt.conv_sc", p, u)                                          # :14-15
+    for i, (mult, stride) in enumerate(((2, 2), (4, 2), (8, 2), (16, 2), (16, 1))):          # :41-47
+        ch = df * mult
+        c.take("ReLU plain"), c.conv("Conv2D", ch, 3, 1, f"block{i}.conv1", p, u)            # :22-24
+        c.take("ReLU plain"), c.conv("Conv2D", ch, 3, stride, f"block{i}.conv2", p, u)       # :26-28
+        c.take("ReLU plain"), c.conv("Conv2D", ch, 3, stride, f"block{i}.conv_sc", p, u)     # :30-32
+        if i == 0:
+            c.attention(f"block{i}.attn", ch, p, u)                                          # :42
+    c.take("ReLU plain")                                                                     # :49
+    idx = c.take("Dense sn units=1 use_bias=True activation=None")                           # :52
+    p["head.dense.kernel"], p["head.dense.bias"], u["head.dense.u"] = c.arr(idx, "kernel"), c.arr(idx, "bias"), c.arr(idx, "u")
+    idx = c.take("Embedding sn")                                                             # :53-54
+    p["head.embedding"], u["head.embedding.u"] = c.arr(idx, "embeddings"), c.arr(idx, "u")
+    assert c.done()
+    return p, u
+
+
+def test_oracle_residual_generator_matches_reference_builder(ref):
+    """models/generator.py:23-43 run by the reference (attention at 32x32 with C = 8 included): same layers in the
+    same order as oracle.resnets.res_generator_spec, same image."""
+    from oracle import resnets as ores
+    p, u = _res_gen_params(ref)
+    assert {k: tuple(v.shape) for k, v in p.items()} == dict(ores.res_generator_spec(RES_CFG))
+    assert sorted(u) == sorted(ores.res_sn_keys(ores.res_generator_spec(RES_CFG)))
+    labels = torch.tensor(ref["rgen_labels"].astype(np.int64))
+    img = ores.res_generator_forward(_t64(p), _t64(u), torch.tensor(ref["rgen_in"]), labels, RES_CFG)
+    assert img.shape == ref["rgen_out"].shape == (2, 128, 128, 3)                            # test/test_generator.py:26
+    assert rel_l2(img.numpy(), ref["rgen_out"]) < 1e-10
+
+
+def test_oracle_residual_discriminator_matches_reference_builder(ref):
+    from oracle import resnets as ores
+    p, u = _res_dis_params(ref)
+    assert {k: tuple(v.shape) for k, v in p.items()} == dict(ores.res_discriminator_spec(RES_CFG))
+    assert sorted(u) == sorted(ores.res_sn_keys(ores.res_discriminator_spec(RES_CFG)))
+    labels = torch.tensor(ref["rdis_labels"].astype(np.int64))
+    out = ores.res_discriminator_forward(_t64(p), _t64(u), torch.tensor(ref["rdis_in"]), labels, RES_CFG)
+    assert out.shape == ref["rdis_out"].shape == (2, 1)                                      # test/test_discriminator.py:28
+    assert rel_l2(out.numpy(), ref["rdis_out"]) < 1e-10
+
+
 # ------------------------------------------------------------------------------------------------- CUDA == reference
 def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
@@ -310,3 +416,25 @@ def test_cuda_discriminator_matches_reference_builder(F, ref, prefix):
         out = net([img, labels], training=True)
     torch.cuda.synchronize()
     assert rel_l2(out.cpu().numpy(), ref[prefix + "out"]) < STRICT_TOL
+
+
+@pytest.mark.gpu
+def test_cuda_residual_nets_match_reference_builders(F, ref):
+    """The residual generator / discriminator (nets.ResGenerator / ResDiscriminator over the CUDA layers, strict mode)
+    loaded with the kernels the reference's legacy builders created: image and logits within 1e-5 / 2e-5."""
+    from sagan_b200 import nets
+    cfg = dict(RES_CFG)
+    pg, ug = _res_gen_params(ref)
+    pd, ud = _res_dis_params(ref)
+    torch.manual_seed(0)
+    G, D = nets.get_res_generator(cfg), nets.get_res_discriminator(cfg)
+    z, img = cu(ref["rgen_in"]), cu(ref["rdis_in"])
+    lg = torch.as_tensor(ref["rgen_labels"].astype(np.int64)).cuda()
+    ld = torch.as_tensor(ref["rdis_labels"].astype(np.int64)).cuda()
+    with torch.no_grad():
+        G([torch.zeros_like(z), lg]), D([torch.zeros_like(img), ld])  # build pass
+        G.load_keras_weights(pg, ug), D.load_keras_weights(pd, ud)
+        fake, logit = G([z, lg], training=True), D([img, ld], training=True)
+    torch.cuda.synchronize()
+    assert rel_l2(fake.cpu().numpy(), ref["rgen_out"]) < STRICT_TOL
+    assert rel_l2(logit.cpu().numpy(), ref["rdis_out"]) < 2e-5        # 19 fp32 conv layers deep, summed over 16 pixels
