@@ -102,9 +102,17 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
   }
   __syncthreads();
   const long long n = rows * C;
+  if (C & 3) {   // channel counts that are not a multiple of 4 (narrow test models): one element per thread
+    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * BN_THREADS) {
+      const int c = (int)(i % C);
+      const float o = fmaf(x[i], scale[c], shift[c]);
+      y[i] = o > 0.f ? o : o * slope;
+    }
+    return;
+  }
   const long long stride = (long long)gridDim.x * BN_THREADS * 4;
   for (long long i = ((long long)blockIdx.x * BN_THREADS + threadIdx.x) * 4; i < n; i += stride) {
-    const int c = (int)(i % C);   // C % 4 == 0 (checked by the wrapper)
+    const int c = (int)(i % C);   // C % 4 == 0 here
     const float4 v = ld4(x + i);
     float4 o;
     o.x = fmaf(v.x, scale[c + 0], shift[c + 0]); o.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
@@ -184,6 +192,15 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
   }
   __syncthreads();
   const long long n = rows * C;
+  if (C & 3) {   // scalar form, see bn_apply_kernel
+    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * BN_THREADS) {
+      const int c = (int)(i % C);
+      const float dz = y[i] > 0.f ? dy[i] : dy[i] * slope;
+      const float xh = (x[i] - kmu[c]) * kis[c];
+      dx[i] = ka[c] * (dz - kb[c] - xh * kc[c]);
+    }
+    return;
+  }
   const long long stride = (long long)gridDim.x * BN_THREADS * 4;
   for (long long i = ((long long)blockIdx.x * BN_THREADS + threadIdx.x) * 4; i < n; i += stride) {
     const int c = (int)(i % C);
@@ -380,7 +397,7 @@ extern "C" int sagan_bn_lrelu_fwd(const float* x, const float* gamma, const floa
                                   float eps, float momentum, float slope, void* ws, size_t ws_bytes,
                                   sagan_stream_t stream) {
   SAGAN_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, "sagan_bn_lrelu_fwd: null pointer");
-  SAGAN_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= BN_MAX_C, "sagan_bn_lrelu_fwd: need rows>0, C%%4==0, C<=%d (C=%d)", BN_MAX_C, C);
+  SAGAN_REQUIRE(rows > 0 && C > 0 && C <= BN_MAX_C, "sagan_bn_lrelu_fwd: need rows>0, 0<C<=%d (C=%d)", BN_MAX_C, C);
   SAGAN_REQUIRE(al16(x) && al16(y), "sagan_bn_lrelu_fwd: x/y must be 16-byte aligned");
   if (ws_bytes < sagan_bn_workspace_bytes(C)) {
     set_err("sagan_bn_lrelu_fwd: workspace %zu < %zu", ws_bytes, sagan_bn_workspace_bytes(C));
@@ -405,7 +422,7 @@ extern "C" int sagan_bn_lrelu_bwd(const float* dy, const float* x, const float* 
                                   sagan_stream_t stream) {
   SAGAN_REQUIRE(dy && x && y && gamma && save_mean && save_invstd && dx && dgamma && dbeta && ws,
                 "sagan_bn_lrelu_bwd: null pointer");
-  SAGAN_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= BN_MAX_C, "sagan_bn_lrelu_bwd: need rows>0, C%%4==0, C<=%d (C=%d)", BN_MAX_C, C);
+  SAGAN_REQUIRE(rows > 0 && C > 0 && C <= BN_MAX_C, "sagan_bn_lrelu_bwd: need rows>0, 0<C<=%d (C=%d)", BN_MAX_C, C);
   SAGAN_REQUIRE(al16(dy) && al16(x) && al16(y) && al16(dx), "sagan_bn_lrelu_bwd: tensors must be 16-byte aligned");
   if (ws_bytes < sagan_bn_workspace_bytes(C)) {
     set_err("sagan_bn_lrelu_bwd: workspace %zu < %zu", ws_bytes, sagan_bn_workspace_bytes(C));

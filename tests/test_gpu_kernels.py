@@ -205,7 +205,8 @@ def test_dense(F):
     assert rel_l2(gb.grad.cpu().numpy(), tb.grad.numpy()) < STRICT_TOL
 
 
-@pytest.mark.parametrize("shape", [(4, 8, 8, 128), (2, 64, 64, 16), (3, 5, 7, 12)])
+# (the last two: channel counts that are not a multiple of 4 take the scalar apply loops)
+@pytest.mark.parametrize("shape", [(4, 8, 8, 128), (2, 64, 64, 16), (3, 5, 7, 12), (2, 9, 5, 2), (3, 4, 5, 7)])
 def test_batchnorm_lrelu(F, shape):
     rng = np.random.Generator(np.random.PCG64(15))
     x = rng.standard_normal(shape) * 1.7 + 0.3
