@@ -223,6 +223,12 @@ int sagan_bn_lrelu_bwd(const float* dy, const float* x, const float* y, const fl
                        const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
                        float* dbeta, long long rows, int C, float slope, void* ws, size_t ws_bytes,
                        sagan_stream_t stream);
+/* Inference-mode BatchNormalization + LeakyReLU -- generator(..., training=False), the sample dumps of
+ * sagan/main.py:333 (Keras: (x - moving_mean) / sqrt(moving_var + eps) * gamma + beta).  No statistics, no
+ * workspace, nothing saved. */
+int sagan_bn_lrelu_infer(const float* x, const float* gamma, const float* beta, const float* moving_mean,
+                         const float* moving_var, float* y, long long rows, int C, float eps, float slope,
+                         sagan_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Weight normalisation: the wrapper the `sagan/` tree actually wraps its layers with

@@ -108,6 +108,12 @@ def batchnorm_train(x, gamma, beta, stats=None, key=None):
     return (x - mean) * torch.rsqrt(var + BN_EPS) * gamma + beta
 
 
+def batchnorm_infer(x, gamma, beta, stats, key):
+    """Keras BatchNormalization(training=False): the moving statistics (generator(..., training=False), the sample
+    dumps of sagan/main.py:333)."""
+    return (x - stats[key + ".moving_mean"]) * torch.rsqrt(stats[key + ".moving_var"] + BN_EPS) * gamma + beta
+
+
 def attention(x, p, sn_state, prefix, training=True, downsample=False):
     """layers.py:93-120 (paper form).  x NHWC.  downsample=True: phi and g max-pooled 2x2 / stride 2 before the
     attention map (layers.py:100,113 in the well-formed reading of oracle.attention.forward_pooled)."""
@@ -261,7 +267,10 @@ def generator_forward(p, sn_state, z, cfg, labels=None, training=True, bn_stats=
     for i, _ in enumerate(reversed(range(_power(cfg)))):
         W = spectral_norm(p[f"block{i}.deconv.kernel"], sn_state, f"block{i}.deconv.u", training)
         x = conv2d_transpose_same(x, W, 2)                                     # generator.py:8-9
-        x = batchnorm_train(x, p[f"block{i}.bn.gamma"], p[f"block{i}.bn.beta"], bn_stats, f"block{i}.bn")
+        if training or bn_stats is None:
+            x = batchnorm_train(x, p[f"block{i}.bn.gamma"], p[f"block{i}.bn.beta"], bn_stats, f"block{i}.bn")
+        else:
+            x = batchnorm_infer(x, p[f"block{i}.bn.gamma"], p[f"block{i}.bn.beta"], bn_stats, f"block{i}.bn")
         x = F.leaky_relu(x, LRELU)                                             # generator.py:11
         if cfg.get("use_attention") and x.shape[1] in cfg["attn_dim_G"]:       # generator.py:33-34
             x = attention(x, p, sn_state, f"block{i}.attn", training, bool(cfg.get("attn_downsample")))

@@ -123,6 +123,43 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
   }
 }
 
+// Inference-mode BatchNormalization + LeakyReLU (generator(..., training=False): the sample dumps of
+// sagan/main.py:333): y = lrelu((x - moving_mean) * rsqrt(moving_var + eps) * gamma + beta).  One pass, no statistics.
+__global__ void __launch_bounds__(BN_THREADS)
+bn_infer_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ moving_mean, const float* __restrict__ moving_var, float* __restrict__ y,
+                long long rows, int C, float eps, float slope) {
+  extern __shared__ float sm[];   // scale[C], shift[C]
+  float* scale = sm;
+  float* shift = sm + C;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    const float sc = gamma[c] * (1.0f / sqrtf(moving_var[c] + eps));
+    scale[c] = sc;
+    shift[c] = beta[c] - moving_mean[c] * sc;
+  }
+  __syncthreads();
+  const long long n = rows * C;
+  if (C & 3) {
+    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * BN_THREADS) {
+      const int c = (int)(i % C);
+      const float o = fmaf(x[i], scale[c], shift[c]);
+      y[i] = o > 0.f ? o : o * slope;
+    }
+    return;
+  }
+  const long long stride = (long long)gridDim.x * BN_THREADS * 4;
+  for (long long i = ((long long)blockIdx.x * BN_THREADS + threadIdx.x) * 4; i < n; i += stride) {
+    const int c = (int)(i % C);
+    const float4 v = ld4(x + i);
+    float4 o;
+    o.x = fmaf(v.x, scale[c + 0], shift[c + 0]); o.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
+    o.z = fmaf(v.z, scale[c + 2], shift[c + 2]); o.w = fmaf(v.w, scale[c + 3], shift[c + 3]);
+    o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+    o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+    st4(y + i, o);
+  }
+}
+
 // backward stage 1: partial dbeta = sum dz, dgamma = sum dz * xhat, with dz = dy * lrelu'(y)
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
@@ -412,6 +449,19 @@ extern "C" int sagan_bn_lrelu_fwd(const float* x, const float* gamma, const floa
   bn_apply_kernel<<<ablk, BN_THREADS, 2 * C * sizeof(float), st>>>(x, gamma, beta, y, (const float*)ws, nblk, save_mean,
                                                                    save_invstd, moving_mean, moving_var, rows, C, eps,
                                                                    momentum, slope);
+  SAGAN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sagan_bn_lrelu_infer(const float* x, const float* gamma, const float* beta, const float* moving_mean,
+                                    const float* moving_var, float* y, long long rows, int C, float eps, float slope,
+                                    sagan_stream_t stream) {
+  SAGAN_REQUIRE(x && gamma && beta && moving_mean && moving_var && y, "sagan_bn_lrelu_infer: null pointer");
+  SAGAN_REQUIRE(rows > 0 && C > 0 && C <= BN_MAX_C, "sagan_bn_lrelu_infer: need rows>0, 0<C<=%d (C=%d)", BN_MAX_C, C);
+  SAGAN_REQUIRE(al16(x) && al16(y), "sagan_bn_lrelu_infer: x/y must be 16-byte aligned");
+  const int blk = (int)std::min<long long>(num_sms() * 4, ceil_div<long long>(rows * C, BN_THREADS * 4));
+  bn_infer_kernel<<<blk, BN_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, gamma, beta, moving_mean, moving_var,
+                                                                                     y, rows, C, eps, slope);
   SAGAN_LAUNCH_CHECK();
   return 0;
 }

@@ -79,6 +79,7 @@ SIGNATURES = {
     "sagan_bn_workspace_bytes": (_SZ, [_I]),
     "sagan_bn_lrelu_fwd": (_I, [_P] * 8 + [_LL, _I, _F, _F, _F, _P, _SZ, _P]),
     "sagan_bn_lrelu_bwd": (_I, [_P] * 9 + [_LL, _I, _F, _P, _SZ, _P]),
+    "sagan_bn_lrelu_infer": (_I, [_P] * 6 + [_LL, _I, _F, _F, _P]),
     "sagan_wn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "sagan_wn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "sagan_u8_to_f32": (_I, [_P, _P, _LL, _F, _F, _P]),

@@ -195,6 +195,18 @@ def batchnorm_lrelu(x, gamma, beta, moving_mean=None, moving_var=None, eps=1e-3,
                             float(slope))
 
 
+def batchnorm_lrelu_infer(x, gamma, beta, moving_mean, moving_var, eps=1e-3, slope=0.1):
+    """Inference-mode BatchNormalization (moving statistics) followed by LeakyReLU(slope).  No gradient: this is the
+    `training=False` forward of the sample dumps (sagan/main.py:333)."""
+    x = x.detach().contiguous()
+    y = torch.empty_like(x)
+    Cc = x.shape[-1]
+    check(_lib.load().sagan_bn_lrelu_infer(_ptr(x), _ptr(gamma.detach()), _ptr(beta.detach()), _ptr(moving_mean),
+                                           _ptr(moving_var), _ptr(y), x.numel() // Cc, Cc, float(eps), float(slope),
+                                           _stream()), "sagan_bn_lrelu_infer")
+    return y
+
+
 # ------------------------------------------------------------------------------------ attention
 class _AttnFn(torch.autograd.Function):
     @staticmethod

@@ -67,6 +67,17 @@ class Network(torch.nn.Module):
         self.sn_group = None
         self._sn_layers = []
 
+    def __call__(self, inputs, training=True):
+        """model(inputs, training=...) as Keras models are called (sagan/main.py:178,181-182,198-199).  `training` is
+        also the learning phase of the BatchNormalization layers for the duration of the call: training=False is the
+        sample-dump forward (moving statistics, no power iteration)."""
+        prev = nn.learning_phase()
+        nn.set_learning_phase(training)
+        try:
+            return super().__call__(inputs, training=training)
+        finally:
+            nn.set_learning_phase(prev)
+
     def finalize(self):
         """Re-home every parameter into one flat buffer and every SN wrapper into one group."""
         params = [p for p in self.parameters()]

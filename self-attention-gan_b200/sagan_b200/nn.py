@@ -36,6 +36,19 @@ def _glorot_uniform(shape, fan_in, fan_out, gen=None):
     return (torch.rand(shape, generator=gen) * 2 - 1) * lim
 
 
+_LEARNING_PHASE = [True]
+
+
+def set_learning_phase(value):
+    """tf.keras.backend.set_learning_phase (sagan/main.py:239): the default `training` of BatchNormalization calls that
+    do not pass one.  nets.Network sets it from its own `training` argument for the duration of a forward."""
+    _LEARNING_PHASE[0] = bool(value)
+
+
+def learning_phase():
+    return _LEARNING_PHASE[0]
+
+
 class Layer(torch.nn.Module):
     """Keras Layer protocol: build(input_shape) once, then call()."""
 
@@ -177,9 +190,12 @@ class BatchNormalization(Layer):
         self.register_buffer("moving_var", torch.ones(c, device=dev))
         self.built = True
 
-    def call(self, x, training=True):
+    def call(self, x, training=None):
+        if training is None:
+            training = learning_phase()
         if not training:
-            raise NotImplementedError("inference-mode BatchNormalization is outside the training hot path")
+            return F.batchnorm_lrelu_infer(x, self.gamma, self.beta, self.moving_mean, self.moving_var, self.epsilon,
+                                           self.leaky_slope)
         return F.batchnorm_lrelu(x, self._p("gamma"), self._p("beta"), self.moving_mean, self.moving_var, self.epsilon,
                                  self.momentum, self.leaky_slope)
 

@@ -217,6 +217,13 @@ class Trainer:
         self._step_body(images, labels, noises_d, noise_g, fake_labels_d, fake_labels_g)
         return self.loss_sums
 
+    def sample(self, noise, labels=None):
+        """sagan/main.py:333: generator([fixed_vector, fixed_label], training=False) -- BatchNormalization on its moving
+        statistics, spectral normalisation with the W / sigma of the latest training forward (no power iteration).
+        Returns images NHWC in (-1, 1); main.py:334 maps them to uint8 with x * 127.5 + 128."""
+        with torch.no_grad():
+            return self.G([noise, labels], training=False)
+
     def losses(self, reduce=True):
         """Reported losses (main.py:216-229): sum over the GLOBAL batch (all replicas, `strategy.reduce(SUM)`) / global
         batch, mean over the rest.  Synchronises (device -> host read of two floats) and raises if the peer-memory

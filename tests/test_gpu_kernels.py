@@ -230,6 +230,25 @@ def test_batchnorm_lrelu(F, shape):
     assert rel_l2(mv.cpu().numpy(), stats["bn.moving_var"].numpy()) < STRICT_TOL
 
 
+@pytest.mark.parametrize("shape", [(4, 8, 8, 128), (3, 5, 7, 12), (2, 9, 5, 2), (3, 4, 5, 7)])
+@pytest.mark.parametrize("slope", [0.1, 0.0, 1.0])
+def test_batchnorm_lrelu_inference_mode(F, shape, slope):
+    """sagan_bn_lrelu_infer: Keras BatchNormalization(training=False) on the moving statistics + LeakyReLU / ReLU / none."""
+    rng = np.random.Generator(np.random.PCG64(16))
+    C = shape[-1]
+    x = rng.standard_normal(shape) * 1.7 + 0.3
+    gam, bet = rng.standard_normal(C) * 0.3 + 1, rng.standard_normal(C) * 0.2
+    mm, mv = rng.standard_normal(C) * 0.5, rng.uniform(0.3, 2.0, C)
+    t = lambda a: torch.tensor(a, dtype=torch.float64)
+    stats = {"bn.moving_mean": t(mm), "bn.moving_var": t(mv)}
+    ref = torch.nn.functional.leaky_relu(onets.batchnorm_infer(t(x), t(gam), t(bet), stats, "bn"), slope)
+    gmm, gmv = cu(mm), cu(mv)
+    y = F.batchnorm_lrelu_infer(cu(x), cu(gam), cu(bet), gmm, gmv, 1e-3, slope)
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu().numpy(), ref.numpy()) < STRICT_TOL
+    assert np.array_equal(gmm.cpu().numpy(), mm.astype(np.float32))          # the moving statistics are read-only here
+
+
 # ---------------------------------------------------------------------------------------- attention
 def _run_attn(F, X, dY, w, mode):
     t = {k: cu(np.asarray(v)).requires_grad_(True) for k, v in w.items()}

@@ -375,6 +375,32 @@ def test_loss_trajectory_free_running_vs_golden(mode_name):
     assert max(devs[:3]) < 1e-3
 
 
+def test_generator_inference_forward_matches_oracle():
+    """generator(..., training=False) -- the sample dumps of sagan/main.py:333: BatchNormalization on its moving
+    statistics, spectral normalisation with the stored u / v (no power iteration), nothing advanced."""
+    cfg = dict(mg.TEST_CFG)
+    orc, tr = make_pair(cfg, attn_sigma=0.37, bias_scale=0.05)
+    t64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    with torch.no_grad():
+        for s in range(3):                                    # a few training forwards move the statistics and u
+            _, _, ng = mg.step_inputs(cfg, s)
+            onets.generator_forward(orc.G, orc.G_sn, t64(ng), cfg, None, True, orc.bn_stats)
+            tr.G([cu(ng), None], training=True)
+        _, _, ng = mg.step_inputs(cfg, 7)
+        before = [b.clone() for b in _bn_buffers(tr)] + [tr.G.sn_group.out.clone()]
+        ref = onets.generator_forward(orc.G, orc.G_sn, t64(ng), cfg, None, False, orc.bn_stats)
+        img = tr.G([cu(ng), None], training=False)
+        again = tr.G([cu(ng), None], training=False)
+    torch.cuda.synchronize()
+    assert rel_l2(img.cpu().numpy(), ref.numpy()) < 2e-5
+    assert torch.equal(img, again)
+    for a, b in zip(before, [b for b in _bn_buffers(tr)] + [tr.G.sn_group.out]):
+        assert torch.equal(a, b)                              # neither the moving statistics nor u / v / sigma moved
+    # and it is not the training-mode forward
+    with torch.no_grad():
+        assert rel_l2(tr.G([cu(ng), None], training=True).cpu().numpy(), ref.numpy()) > 1e-3
+
+
 def _bn_buffers(tr):
     return [t for m in tr.G.modules() if hasattr(m, "moving_mean") for t in (m.moving_mean, m.moving_var)]
 
