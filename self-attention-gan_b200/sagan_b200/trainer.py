@@ -94,6 +94,12 @@ class Trainer:
             lab = torch.zeros(self.B, dtype=torch.int64, device=self.device) if cfg.get("use_label") else None
             img = self.G([z, lab])
             self.D([img, lab])
+            # Keras `model.build` creates variables without running data: the build pass above must not leave its
+            # all-zero batch in the BatchNormalization moving statistics (they feed the training=False forward)
+            for m in self.G.modules():
+                if hasattr(m, "moving_mean") and hasattr(m, "moving_var"):
+                    m.moving_mean.zero_()
+                    m.moving_var.fill_(1.0)
         # identical initial weights and spectral-norm state on every replica (MirroredStrategy variables)
         self.dp.broadcast_(self.G.flat_params, self.D.flat_params, self.G.sn_group.out, self.D.sn_group.out)
         # every replica draws its OWN noise / fake labels (MirroredStrategy runs main.py:176-177,194-195 per replica):
