@@ -86,6 +86,10 @@ typedef struct sagan_sn_plan sagan_sn_plan; /* opaque: device descriptor table +
  * workspace) -- call outside the step loop.  `descs_host` is copied. */
 int sagan_sn_plan_create(const sagan_sn_desc* descs_host, int n, int device, sagan_sn_plan** plan_out);
 int sagan_sn_plan_run(sagan_sn_plan* plan, sagan_stream_t stream);
+/* The wrapped layer called with training=False (sample dump, sagan/main.py:333): no power iteration.  sigma is
+ * recomputed from the stored u, v and the CURRENT kernels, sum((u W_mat) * v) [/ factor] (layers.py:62-66), and
+ * W_bar = W / sigma rewritten; u and v are left alone. */
+int sagan_sn_plan_refresh(sagan_sn_plan* plan, sagan_stream_t stream);
 int sagan_sn_plan_destroy(sagan_sn_plan* plan);
 /* Diagnostics: device-side durations (ms, %globaltimer) of the five phases of the plan's most recent run
  * [u W partials, s + ||s||, v W^T partials, t + ||t||, u / sigma / W_bar].  Synchronises the device. */

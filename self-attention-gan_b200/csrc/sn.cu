@@ -530,6 +530,44 @@ extern "C" int sagan_sn_backward_multi(const sagan_sn_bwd_desc* d, int n, int ac
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ refresh (training=False)
+// The wrapped layer called with training=False (the sample dump, sagan/main.py:333): NO power iteration; sigma is
+// recomputed from the STORED u, v and the CURRENT kernel, sigma = sum((u W_mat) * v) [/ factor] (layers.py:62-66), and
+// W_bar = W / sigma (layers.py:68).  u and v are not written.  Off the training path: one CTA per matrix for sigma
+// (fp64 accumulation over the CTA, fixed order), then a grid over the elements.
+constexpr int SNR_THREADS = 512;
+
+__global__ void __launch_bounds__(SNR_THREADS) sn_refresh_sigma_kernel(const SnDev* __restrict__ tab) {
+  const SnDev d = tab[blockIdx.x];
+  __shared__ double red[SNR_THREADS];
+  double acc = 0.0;
+  for (long long e = threadIdx.x; e < d.numel; e += SNR_THREADS) {
+    const int r = (int)(e / d.K), k = (int)(e % d.K);
+    acc += (double)d.u[r] * (double)d.W[e] * (double)d.v[k];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = SNR_THREADS / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float sg = (float)red[0];
+    if (d.factor != 0.f) sg = sg / d.factor;
+    *d.sigma = sg;
+  }
+}
+
+__global__ void __launch_bounds__(256) sn_refresh_scale_kernel(const SnDev* __restrict__ tab) {
+  const SnDev d = tab[blockIdx.y];
+  const float rs = 1.0f / *d.sigma;      // same reciprocal form as phase 3 of the training kernel
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < d.numel; e += (long long)gridDim.x * 256) {
+    const float w = d.W[e] * rs;
+    d.Wbar[e] = w;
+    if (d.Wbar16) d.Wbar16[e] = __float2bfloat16_rn(w);
+  }
+}
+
 struct sagan_sn_plan {
   int n = 0;
   int device = 0;
@@ -643,6 +681,16 @@ extern "C" int sagan_sn_plan_run(sagan_sn_plan* p, sagan_stream_t stream) {
   SAGAN_CUDA(cudaLaunchCooperativeKernel((const void*)sn_power_iter_kernel, dim3(p->grid), dim3(SN_THREADS), args, 0,
                                          (cudaStream_t)stream));
   count_launch();
+  return 0;
+}
+
+extern "C" int sagan_sn_plan_refresh(sagan_sn_plan* p, sagan_stream_t stream) {
+  SAGAN_REQUIRE(p, "sagan_sn_plan_refresh: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  sn_refresh_sigma_kernel<<<p->n, SNR_THREADS, 0, st>>>(p->tab_dev);
+  SAGAN_LAUNCH_CHECK();
+  sn_refresh_scale_kernel<<<dim3(64, p->n), 256, 0, st>>>(p->tab_dev);
+  SAGAN_LAUNCH_CHECK();
   return 0;
 }
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sagan_deterministic_forward": (_I, [_I]),
     "sagan_sn_plan_create": (_I, [C.POINTER(SnDesc), _I, _I, C.POINTER(_P)]),
     "sagan_sn_plan_run": (_I, [_P, _P]),
+    "sagan_sn_plan_refresh": (_I, [_P, _P]),
     "sagan_sn_plan_destroy": (_I, [_P]),
     "sagan_sn_plan_algorithmic_bytes": (C.c_ulonglong, [_P]),
     "sagan_sn_plan_phase_times": (_I, [_P, C.POINTER(C.c_float)]),

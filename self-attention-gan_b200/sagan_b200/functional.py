@@ -360,10 +360,17 @@ class SpectralNormGroup:
         return (wbar, snap[self.off_u[i]:self.off_u[i] + R], snap[self.off_v[i]:self.off_v[i] + K],
                 snap[self.off_s[i]:self.off_s[i] + 1])
 
+    def refresh(self):
+        """training=False: sigma from the stored u, v and the current kernels, W_bar = W / sigma, no iteration."""
+        check(_lib.load().sagan_sn_plan_refresh(self.plan, _stream()), "sagan_sn_plan_refresh")
+
     def normalized(self, update=True):
-        """Returns the list of W_bar tensors (autograd-connected to the raw kernels)."""
+        """Returns the list of W_bar tensors (autograd-connected to the raw kernels).  update=True (training): one
+        power iteration first (layers.py:46 in the oracle's reading); update=False: `refresh` -- u and v stay."""
         if update:
             self.run()
+        else:
+            self.refresh()
         holder = _Snap(self.out.clone())
         return list(_SnGroupFn.apply(self, holder, *self.weights))
 

@@ -103,6 +103,7 @@ class Network(torch.nn.Module):
             self.sn_group = F.SpectralNormGroup(ws, us, [m.Ip for m in self._sn_layers],
                                                 [m.factor for m in self._sn_layers])
             for i, m in enumerate(self._sn_layers):
+                self.sn_group.v(i).copy_(m.v.reshape(-1))     # v travels with u into the network's group
                 m.adopt(self.sn_group, i)
         # parameters that are not spectrally-normalised kernels (biases, BatchNorm gamma / beta, attention gamma,
         # un-normalised head kernels): read through proxies during a forward, see _normalise_all

@@ -246,6 +246,12 @@ class SpectralNormalization(Layer):
             u_init = u_init / (u_init.norm() + 1e-12)
         self._group = F.SpectralNormGroup([w], [u_init], self.Ip, [self.factor])
         self._index = 0
+        # layers.py:36,38: v ~ N(0,1) [1, cols], l2-normalised.  Every training call recomputes v from u before using
+        # it; a training=False call before the first training call reads this one.
+        # (drawn from a private generator so that the default stream -- and with it every initial kernel that follows --
+        # is what it was before v was materialised here)
+        v_init = torch.randn(1, w.numel() // rows, generator=torch.Generator().manual_seed(0x5EED + w.numel()))
+        self._group.v(0).copy_((v_init / (v_init.norm() + 1e-12)).reshape(-1).to(self._group.out.device))
 
     def build(self, input_shape):
         if not self.module.built:

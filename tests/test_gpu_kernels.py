@@ -112,6 +112,35 @@ def test_sn_large_matrix_property(F):
     assert abs(float(sig) - float(t.norm())) < 1e-5 * float(t.norm())
 
 
+def test_sn_refresh_without_iteration(F):
+    """sagan_sn_plan_refresh -- the wrapped layer called with training=False: sigma = sum((u W_mat) * v) [/ factor] from
+    the STORED u, v and the CURRENT kernel, W_bar = W / sigma; u and v untouched (layers.py:62-68 without :58-60)."""
+    shapes = [(4096, 128), (32, 256), (4, 32), (7, 13), (16, 48)]
+    rng = np.random.Generator(np.random.PCG64(23))
+    Ws, us = zip(*[mg.sn_inputs(R, K, 400 + i)[:2] for i, (R, K) in enumerate(shapes)])
+    factors = [None, 2.0, None, 0.5, None]
+    tW = [cu(W) for W in Ws]
+    g = F.SpectralNormGroup(tW, [cu(u) for u in us], 1, factors)
+    g.run()                                                   # a training call: u, v of the ORIGINAL kernels
+    torch.cuda.synchronize()
+    u1 = [g.u(i).cpu().numpy().astype(np.float64) for i in range(len(shapes))]
+    v1 = [g.v(i).cpu().numpy().astype(np.float64) for i in range(len(shapes))]
+    W2 = [W.astype(np.float64) + rng.standard_normal(W.shape) * 0.004 for W in Ws]      # an optimiser step later
+    for t, w in zip(tW, W2):
+        t.copy_(cu(w))
+    g.refresh()
+    torch.cuda.synchronize()
+    for i, (R, K) in enumerate(shapes):
+        w32 = tW[i].cpu().numpy().astype(np.float64)
+        sig = np.sum((u1[i].reshape(1, R) @ osn.matricize(w32)) * v1[i].reshape(1, K))
+        if factors[i]:
+            sig = sig / factors[i]
+        assert abs(float(g.sigma(i).cpu()) - sig) < STRICT_TOL * abs(sig), (R, K)
+        assert rel_l2(g.w_bar(i).cpu().numpy(), w32 / sig) < STRICT_TOL, (R, K)
+        assert np.array_equal(g.u(i).cpu().numpy().astype(np.float64), u1[i])          # not advanced
+        assert np.array_equal(g.v(i).cpu().numpy().astype(np.float64), v1[i])
+
+
 def test_sn_rejects_bad_ip(F):
     W, u, _ = mg.sn_inputs(8, 16, 1)
     with pytest.raises(ValueError, match="positive integer"):

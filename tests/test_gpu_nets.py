@@ -377,7 +377,8 @@ def test_loss_trajectory_free_running_vs_golden(mode_name):
 
 def test_generator_inference_forward_matches_oracle():
     """generator(..., training=False) -- the sample dumps of sagan/main.py:333: BatchNormalization on its moving
-    statistics, spectral normalisation with the stored u / v (no power iteration), nothing advanced."""
+    statistics, spectral normalisation of the CURRENT kernels with the stored u / v (sagan_sn_plan_refresh: no power
+    iteration), nothing advanced."""
     cfg = dict(mg.TEST_CFG)
     orc, tr = make_pair(cfg, attn_sigma=0.37, bias_scale=0.05)
     t64 = lambda a: torch.tensor(a, dtype=torch.float64)
@@ -386,16 +387,24 @@ def test_generator_inference_forward_matches_oracle():
             _, _, ng = mg.step_inputs(cfg, s)
             onets.generator_forward(orc.G, orc.G_sn, t64(ng), cfg, None, True, orc.bn_stats)
             tr.G([cu(ng), None], training=True)
+        # an optimiser step later: the kernels have moved, u / v are those of the last training forward
+        rng = np.random.Generator(np.random.PCG64(99))
+        for k in orc.G:
+            orc.G[k] = orc.G[k] + torch.tensor(rng.standard_normal(tuple(orc.G[k].shape)) * 2e-3, dtype=torch.float64)
+        tr.G.load_keras_weights({k: v.numpy() for k, v in orc.G.items()})
         _, _, ng = mg.step_inputs(cfg, 7)
-        before = [b.clone() for b in _bn_buffers(tr)] + [tr.G.sn_group.out.clone()]
+        before = [b.clone() for b in _bn_buffers(tr)] + [tr.G.sn_group.u(i).clone() for i in range(len(tr.G.sn_group.shapes))] \
+            + [tr.G.sn_group.v(i).clone() for i in range(len(tr.G.sn_group.shapes))]
         ref = onets.generator_forward(orc.G, orc.G_sn, t64(ng), cfg, None, False, orc.bn_stats)
         img = tr.G([cu(ng), None], training=False)
         again = tr.G([cu(ng), None], training=False)
     torch.cuda.synchronize()
     assert rel_l2(img.cpu().numpy(), ref.numpy()) < 2e-5
     assert torch.equal(img, again)
-    for a, b in zip(before, [b for b in _bn_buffers(tr)] + [tr.G.sn_group.out]):
-        assert torch.equal(a, b)                              # neither the moving statistics nor u / v / sigma moved
+    n_sn = len(tr.G.sn_group.shapes)
+    after = [b for b in _bn_buffers(tr)] + [tr.G.sn_group.u(i) for i in range(n_sn)] + [tr.G.sn_group.v(i) for i in range(n_sn)]
+    for a, b in zip(before, after):
+        assert torch.equal(a, b)                              # neither the moving statistics nor u / v moved
     # and it is not the training-mode forward
     with torch.no_grad():
         assert rel_l2(tr.G([cu(ng), None], training=True).cpu().numpy(), ref.numpy()) > 1e-3
