@@ -32,6 +32,10 @@ Sections of the fixture
            wrapper's forward uses the RAW kernel (appendix A.1), so the kernels are pre-scaled to sigma = 1 under the
            stored u, which makes the literal forward equal to the normalised forward the oracle computes.
            Attention is off in these two runs (see attn_* for why) and BatchNormalization runs on batch statistics.
+  wn_*     the weight-normalisation wrapper of sagan/layers.py:6-211 around Conv2D / Dense /
+           Conv2DTranspose: g and bias after the data-dependent / norm initialisation, the effective kernel, two calls.
+  rec_*    get_dataset_from_tfrecord of sagan/dataset.py:12-40: the uint8 record decode in float32 (bit-exact contract),
+           labels, batching with drop_remainder.
   rgen_* / rdis_*  the legacy residual builders models/generator.py:23-43, models/discriminator.py:40-57 the same way,
            at widths where their Attention_Layer sees C = 8, so attention stays IN (identity pool).
 """
@@ -366,6 +370,91 @@ def section_res_builders(tf, ref_layers, out):
         L.MaxPool2D = real_pool
 
 
+WN_CASES = [
+    # (tag, layer ctor, input shape, data_init)
+    ("conv_data", lambda L: L.Conv2D(24, 3, 1, padding="same"), (4, 16, 16, 8), True),
+    ("conv_norm", lambda L: L.Conv2D(24, 3, 1, padding="same"), (4, 16, 16, 8), False),
+    ("conv_s2_data", lambda L: L.Conv2D(16, 4, 2, padding="same"), (3, 12, 12, 5), True),
+    ("dense_data", lambda L: L.Dense(40), (16, 24), True),
+    ("dense_norm", lambda L: L.Dense(40), (16, 24), False),
+    # Conv2DTranspose: the kernel's last axis is the INPUT channel count, so g has cin entries; with data_init=True the
+    # reference multiplies that g by a cout-sized scale (sagan/layers.py:189) and fails unless cin == cout -- norm init only
+    ("deconv_norm", lambda L: L.Conv2DTranspose(8, 4, 2, padding="same", use_bias=False), (2, 6, 6, 12), False),
+]
+
+
+def section_weightnorm(tf, out):
+    """sagan/layers.py (the weight-normalisation wrapper the `sagan/` tree ships under the name SpectralNormalization,
+    SURVEY.md 8f-4), imported unmodified: build, the first call with its data-dependent (sagan/layers.py:159-194) or
+    norm (:152-157) initialisation of g and of the wrapped layer's bias, and a second call."""
+    import importlib.util
+    L = tf.keras.layers
+    spec = importlib.util.spec_from_file_location("ref_sagan_layers", os.path.join(REF, "sagan", "layers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    tags = []
+    for ci, (tag, ctor, in_shape, data_init) in enumerate(WN_CASES):
+        L.seed_initializers(900 + ci)
+        r = rng_of(910 + ci)
+        x = r.standard_normal(in_shape) * 1.3 + 0.2
+        layer = ctor(L)
+        wrap = mod.SpectralNormalization(layer, data_init=data_init)
+        wrap.build(tf.TensorShape(in_shape))
+        wrap.built = True
+        v0 = r.standard_normal(layer.kernel.shape) * 0.2
+        layer.kernel.assign(v0)                                   # == wrap.v (sagan/layers.py:85)
+        if layer.bias is not None:
+            layer.bias.assign(r.standard_normal(layer.bias.shape) * 0.1)
+        if data_init:                                             # the clone made in build() copies the weights (:101)
+            wrap._naked_clone_layer.set_weights(layer.get_weights())
+        p = "wn_%s_" % tag
+        out[p + "x"], out[p + "v"] = x, v0.copy()
+        out[p + "bias0"] = layer.bias.numpy().copy() if layer.bias is not None else np.zeros(0)
+        out[p + "data_init"] = np.int64(data_init)
+        y1 = wrap(tf.Tensor(x)).numpy()
+        out[p + "g"] = wrap.g.numpy().copy()
+        out[p + "bias1"] = layer.bias.numpy().copy() if layer.bias is not None else np.zeros(0)
+        out[p + "kernel1"] = tf._core.raw(layer.kernel).copy()    # l2_normalize(v) * g, what the layer ran with (:124-130)
+        out[p + "y1"] = y1
+        assert bool(wrap._initialized.numpy())
+        out[p + "y2"] = wrap(tf.Tensor(x)).numpy()                # second call: no re-initialisation (:113-114)
+        assert np.array_equal(out[p + "g"], wrap.g.numpy())
+        out[p + "norm_axes"] = np.asarray(wrap.kernel_norm_axes, dtype=np.int64)
+        tags.append(tag)
+    out["wn_tags"] = np.asarray(tags)
+
+
+def section_records(tf, out):
+    """get_dataset_from_tfrecord of sagan/dataset.py:12-40, imported unmodified and run over stand-in records (a dict per
+    record instead of a serialized tf.train.Example, see tfshim/tensorflow/io.py): which features are read, the uint8
+    HWC decode, `cast(float32) * (2. / 255) - 1.` in float32, int64 labels, batches of global_batch_size with the
+    remainder dropped.  Includes every byte value 0..255."""
+    import importlib.util
+    import tempfile
+    spec = importlib.util.spec_from_file_location("ref_sagan_dataset", os.path.join(REF, "sagan", "dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    size, n, batch = 8, 7, 3
+    r = rng_of(95)
+    raw = r.integers(0, 256, (n, size, size, 3), dtype=np.uint8)
+    raw.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)                      # every byte value once
+    labels = r.integers(0, 1000, n).astype(np.int64)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "part-0.tfrecords")
+        open(path, "wb").close()                                                # the reference globs for *.tfrecords
+        tf.data.records[path] = [{"label": int(labels[i]), "image_raw": raw[i].tobytes(),
+                                  "height": size, "width": size, "depth": 3} for i in range(n)]
+        ds = mod.get_dataset_from_tfrecord({"data_path": d, "img_size": size, "data_size": -1, "global_batch_size": batch})
+        batches = list(ds)
+    assert len(batches) == n // batch                                           # drop_remainder
+    imgs = np.concatenate([b[0].numpy() for b in batches])
+    labs = np.concatenate([b[1].numpy() for b in batches])
+    assert imgs.dtype == np.float32 and labs.dtype == np.int64
+    out["rec_raw"], out["rec_labels_in"] = raw, labels
+    out["rec_images"], out["rec_labels"] = imgs, labs
+    out["rec_batch"] = np.int64(batch)
+
+
 def main():
     tf, ref = _import_reference()
     out = {}
@@ -375,6 +464,8 @@ def main():
     section_hinge(tf, out)
     section_builders(tf, ref, out)
     section_res_builders(tf, ref, out)
+    section_weightnorm(tf, out)
+    section_records(tf, out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "(%d arrays, %.0f kB)" % (len(out), os.path.getsize(OUT) / 1e3))
 

@@ -19,6 +19,15 @@ from . import keras  # noqa: F401
 from . import nn  # noqa: F401
 from . import random  # noqa: F401
 from . import math  # noqa: F401
+from . import linalg  # noqa: F401
+from . import debugging  # noqa: F401
+from . import dtypes  # noqa: F401
+from . import compat  # noqa: F401
+from . import io  # noqa: F401
+from . import data  # noqa: F401
+
+string = "string"
+uint8 = "uint8"
 
 float32 = "float32"
 float64 = "float64"
@@ -40,7 +49,7 @@ def _a(x):
 
 
 def reshape(t, shape):
-    return Tensor(_np.reshape(_a(t), [int(s) for s in shape]))
+    return Tensor(_np.reshape(_a(t), [int(s) for s in shape]), keep_dtype=getattr(t, "keep", False))
 
 
 def transpose(t, perm=None):
@@ -84,3 +93,53 @@ def zeros_like(t):
 
 def tanh(t):
     return Tensor(_np.tanh(_a(t)))
+
+
+def tile(t, multiples):
+    return Tensor(_np.tile(_a(t), [int(m) for m in multiples]))
+
+
+def identity(t):
+    return Tensor(_np.array(_a(t)))
+
+
+def cast(t, dtype):
+    """tf.cast; a cast to float32 yields a tensor whose arithmetic STAYS float32 (numpy float32 with Python-float
+    scalars, which is what TensorFlow does with `x * (2. / 255) - 1.` on a float32 tensor)."""
+    return Tensor(_a(t).astype(dtype), keep_dtype=(dtype == "float32"))
+
+
+def cond(pred, true_fn, false_fn):
+    """Eager tf.cond: exactly one branch runs."""
+    return true_fn() if bool(_a(pred)) else false_fn()
+
+
+class _NullContext:
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+name_scope = _NullContext
+
+
+def control_dependencies(ops):
+    """Eager: the operations in `ops` have already run by the time the list exists."""
+    return _NullContext()
+
+
+class CriticalSection:
+    def __init__(self, name=None):
+        self.name = name
+
+    def execute(self, fn):
+        return fn()
+
+
+class VariableSynchronization:
+    AUTO = "auto"

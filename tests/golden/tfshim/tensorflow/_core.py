@@ -6,12 +6,28 @@ class TensorShape(tuple):
     """`Tensor.shape`: indexable like a tuple, with the `as_list()` the reference calls (layers.py:80,94)."""
 
     def as_list(self):
-        return [int(s) for s in self]
+        return [None if s is None else int(s) for s in self]
+
+    @property
+    def rank(self):
+        return len(self)
+
+    def __getitem__(self, k):
+        r = tuple.__getitem__(self, k)
+        return TensorShape(r) if isinstance(k, slice) else r
+
+    def __add__(self, o):
+        return TensorShape(tuple(self) + tuple(o))
+
+    def __radd__(self, o):
+        return TensorShape(tuple(o) + tuple(self))
 
 
 def raw(x):
     if isinstance(x, Tensor):
         return x.a
+    if isinstance(x, (bool, int, float)):
+        return x                      # Python scalars stay "weak": float32 tensor * 2. / 255 is float32, as in TF
     return np.asarray(x)
 
 
@@ -22,11 +38,20 @@ def convert(x):
 class Tensor:
     __array_priority__ = 1000
 
-    def __init__(self, a):
+    def __init__(self, a, keep_dtype=False):
+        """Floating-point data is promoted to float64 unless `keep_dtype` (set by tf.cast(x, tf.float32): the record
+        decode of sagan/dataset.py:34 is float32 arithmetic and is pinned bit for bit)."""
         a = np.asarray(a)
-        if a.dtype.kind == "f":
+        if a.dtype.kind == "f" and not keep_dtype:
             a = a.astype(np.float64)
         self.a = a
+        self.keep = bool(keep_dtype)
+
+    def _w(self, arr):
+        return Tensor(arr, keep_dtype=getattr(self, "keep", False))
+
+    def set_shape(self, shape):
+        assert self.a.size == int(np.prod([int(s) for s in (shape if isinstance(shape, (list, tuple)) else [shape])]))
 
     @property
     def shape(self):
@@ -40,32 +65,32 @@ class Tensor:
         return self.a
 
     def __add__(self, o):
-        return Tensor(self.a + raw(o))
+        return self._w(self.a + raw(o))
 
     __radd__ = __add__
 
     def __sub__(self, o):
-        return Tensor(self.a - raw(o))
+        return self._w(self.a - raw(o))
 
     def __rsub__(self, o):
-        return Tensor(raw(o) - self.a)
+        return self._w(raw(o) - self.a)
 
     def __mul__(self, o):
-        return Tensor(self.a * raw(o))
+        return self._w(self.a * raw(o))
 
     __rmul__ = __mul__
 
     def __truediv__(self, o):
-        return Tensor(self.a / raw(o))
+        return self._w(self.a / raw(o))
 
     def __rtruediv__(self, o):
-        return Tensor(raw(o) / self.a)
+        return self._w(raw(o) / self.a)
 
     def __neg__(self):
-        return Tensor(-self.a)
+        return self._w(-self.a)
 
     def __getitem__(self, k):
-        return Tensor(self.a[k])
+        return self._w(self.a[k])
 
     def __repr__(self):
         return "shim.Tensor(shape=%s)" % (tuple(self.a.shape),)
@@ -78,7 +103,7 @@ class Variable(Tensor):
         self.trainable = trainable
 
     def assign(self, value):
-        v = raw(value)
+        v = np.asarray(raw(value))
         assert tuple(v.shape) == tuple(self.a.shape), (v.shape, self.a.shape)
         self.a = np.array(v, dtype=self.a.dtype)
         return self

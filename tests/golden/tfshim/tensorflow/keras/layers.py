@@ -72,9 +72,11 @@ class Layer:
     def weights(self):
         return list(self._weights)
 
-    def add_weight(self, name=None, shape=(), initializer="glorot_uniform", trainable=True, dtype=None):
-        shape = tuple(int(s) for s in shape)
-        if initializer in ("zero", "zeros"):
+    def add_weight(self, name=None, shape=(), initializer="glorot_uniform", trainable=True, dtype=None, **_distribution):
+        shape = () if shape is None else tuple(int(s) for s in shape)
+        if dtype == "bool":
+            a = np.zeros(shape, dtype=bool)
+        elif initializer in ("zero", "zeros"):
             a = np.zeros(shape)
         elif initializer in ("one", "ones"):
             a = np.ones(shape)
@@ -96,6 +98,20 @@ class Layer:
 
     def call(self, inputs, *args, **kwargs):
         return inputs
+
+    def _track_trackable(self, obj, name=None):
+        return obj
+
+    def get_weights(self):
+        return [np.array(w.numpy()) for w in self._weights]
+
+    def set_weights(self, arrays):
+        assert len(arrays) == len(self._weights)
+        for w, a in zip(self._weights, arrays):
+            w.assign(a)
+
+    def get_config(self):
+        return dict(getattr(self, "_config", {}), trainable=True)
 
     def __call__(self, inputs, *args, **kwargs):
         if not self.built:
@@ -122,6 +138,8 @@ def _activation(name):
 class Conv2D(Layer):
     def __init__(self, filters, kernel_size, strides=1, padding="valid", use_bias=True, activation=None, **kw):
         super().__init__(**kw)
+        self._config = dict(filters=filters, kernel_size=kernel_size, strides=strides, padding=padding,
+                            use_bias=use_bias, activation=activation)
         self.filters, self.kernel_size, self.strides = int(filters), _pair(kernel_size), _pair(strides)
         self.padding, self.use_bias, self.activation = padding.lower(), use_bias, activation
 
@@ -147,6 +165,8 @@ class Conv2D(Layer):
 class Conv2DTranspose(Layer):
     def __init__(self, filters, kernel_size, strides=1, padding="valid", use_bias=True, activation=None, **kw):
         super().__init__(**kw)
+        self._config = dict(filters=filters, kernel_size=kernel_size, strides=strides, padding=padding,
+                            use_bias=use_bias, activation=activation)
         self.filters, self.kernel_size, self.strides = int(filters), _pair(kernel_size), _pair(strides)
         self.padding, self.use_bias, self.activation = padding.lower(), use_bias, activation
 
@@ -179,6 +199,7 @@ class Conv2DTranspose(Layer):
 class Dense(Layer):
     def __init__(self, units, use_bias=True, activation=None, **kw):
         super().__init__(**kw)
+        self._config = dict(units=units, use_bias=use_bias, activation=activation)
         self.units, self.use_bias, self.activation = int(units), use_bias, activation
 
     def build(self, input_shape):
@@ -282,6 +303,33 @@ class Reshape(Layer):
     def call(self, inputs):
         x = raw(inputs)
         return Tensor(x.reshape((x.shape[0],) + self.target_shape))
+
+
+class Wrapper(Layer):
+    """tf.keras.layers.Wrapper: holds `layer`."""
+
+    def __init__(self, layer, **kw):
+        super().__init__(**kw)
+        self.layer = layer
+
+
+class RNN(Layer):
+    pass
+
+
+class InputSpec:
+    def __init__(self, shape=None, **kw):
+        self.shape = shape
+
+
+def serialize(layer):
+    return {"class_name": type(layer).__name__, "config": layer.get_config()}
+
+
+def deserialize(config):
+    cfg = dict(config["config"])
+    cfg.pop("trainable", None)
+    return globals()[config["class_name"]](**cfg)
 
 
 def add(inputs):

@@ -1,6 +1,12 @@
 """tf.math subset."""
+import numpy as np
+
 from ._core import Tensor, raw
 
 
 def divide(x, y):
     return Tensor(raw(x) / raw(y))
+
+
+def sqrt(x):
+    return Tensor(np.sqrt(raw(x)))

@@ -314,6 +314,61 @@ def test_oracle_residual_discriminator_matches_reference_builder(ref):
     assert rel_l2(out.numpy(), ref["rdis_out"]) < 1e-10
 
 
+# tag -> (layer kind, kernel size, stride) of make_reference_vectors.WN_CASES
+WN_LAYERS = {"conv_data": ("conv", 3, 1), "conv_norm": ("conv", 3, 1), "conv_s2_data": ("conv", 4, 2),
+             "dense_data": ("dense", 0, 0), "dense_norm": ("dense", 0, 0), "deconv_norm": ("deconv", 4, 2)}
+
+
+def _wn_apply(kind, stride, x, kernel, bias):
+    """The wrapped Keras layer (no activation) through the oracle's layer functions, fp64."""
+    x, kernel = torch.tensor(x), torch.tensor(kernel)
+    b = torch.tensor(bias) if bias.size else None
+    if kind == "dense":
+        y = x @ kernel
+        return (y + b if b is not None else y).numpy()
+    if kind == "conv":
+        return onets.conv2d_same(x, kernel, b, stride).numpy()
+    y = onets.conv2d_transpose_same(x, kernel, stride)
+    return (y + b if b is not None else y).numpy()
+
+
+def test_oracle_weightnorm_matches_reference_wrapper(ref):
+    """sagan/layers.py:6-211 executed by the reference around Conv2D / Dense / Conv2DTranspose: g and the bias after the
+    data-dependent (:159-194) or norm (:152-157) initialisation, the kernel l2_normalize(v) * g the layer then runs with
+    (:124), the output of the first and of the second call."""
+    from oracle import weightnorm as own
+    assert sorted(ref["wn_tags"]) == sorted(WN_LAYERS)
+    for tag, (kind, k, stride) in WN_LAYERS.items():
+        p = f"wn_{tag}_"
+        x, v, b0 = ref[p + "x"], ref[p + "v"], ref[p + "bias0"]
+        assert list(ref[p + "norm_axes"]) == list(range(v.ndim - 1)), tag          # every axis but the last (:73)
+        if int(ref[p + "data_init"]):
+            g, b1 = own.data_dep_init(_wn_apply(kind, stride, x, v, b0), np.ones(v.shape[-1]), b0 if b0.size else None)
+        else:
+            g, b1 = own.init_norm(v), (b0 if b0.size else None)
+        assert rel_l2(g, ref[p + "g"]) < FP64_TOL, tag
+        if b0.size:
+            assert rel_l2(b1, ref[p + "bias1"]) < 1e-11, tag
+        kern = own.kernel_from_vg(v, g)
+        assert rel_l2(kern, ref[p + "kernel1"]) < FP64_TOL, tag
+        y = _wn_apply(kind, stride, x, kern, ref[p + "bias1"])
+        assert rel_l2(y, ref[p + "y1"]) < 1e-11, tag
+        assert np.array_equal(ref[p + "y1"], ref[p + "y2"]), tag                   # no second initialisation
+
+
+def test_oracle_record_decode_matches_reference_reader(ref):
+    """get_dataset_from_tfrecord (sagan/dataset.py:12-40) run by the reference over 7 stand-in records, batch 3: the
+    float32 images BIT FOR BIT, the int64 labels, and the dropped remainder."""
+    from oracle import weightnorm as own
+    raw, batch = ref["rec_raw"], int(ref["rec_batch"])
+    keep = raw.shape[0] // batch * batch
+    got = own.decode_records(raw[:keep])
+    assert ref["rec_images"].dtype == np.float32 and ref["rec_images"].shape == got.shape == (keep,) + raw.shape[1:]
+    assert np.array_equal(got.view(np.uint32), ref["rec_images"].view(np.uint32))
+    assert ref["rec_labels"].dtype == np.int64 and np.array_equal(ref["rec_labels"], ref["rec_labels_in"][:keep])
+    assert set(np.unique(raw)) == set(range(256))                                  # every byte value is covered
+
+
 # ------------------------------------------------------------------------------------------------- CUDA == reference
 def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
@@ -438,3 +493,45 @@ def test_cuda_residual_nets_match_reference_builders(F, ref):
     torch.cuda.synchronize()
     assert rel_l2(fake.cpu().numpy(), ref["rgen_out"]) < STRICT_TOL
     assert rel_l2(logit.cpu().numpy(), ref["rdis_out"]) < 2e-5        # 19 fp32 conv layers deep, summed over 16 pixels
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(WN_LAYERS))
+def test_cuda_weightnorm_matches_reference_wrapper(F, ref, tag):
+    """nn.WeightNormalization (sagan_wn_fwd + the wrapped layer's kernels) given the reference's v / bias / first batch:
+    the same g, bias and outputs as the reference's wrapper computed."""
+    from sagan_b200 import nn as snn
+    kind, k, stride = WN_LAYERS[tag]
+    p = f"wn_{tag}_"
+    x, v, b0 = ref[p + "x"], ref[p + "v"], ref[p + "bias0"]
+    if kind == "dense":
+        inner = snn.Dense(v.shape[-1])
+    elif kind == "conv":
+        inner = snn.Conv2D(v.shape[-1], k, stride, padding="same")
+    else:
+        inner = snn.Conv2DTranspose(v.shape[-2], k, stride, padding="same", use_bias=False)
+    layer = snn.WeightNormalization(inner, data_init=bool(int(ref[p + "data_init"])))
+    layer.build(tuple(x.shape))
+    with torch.no_grad():
+        layer.v.copy_(cu(v))
+        if b0.size:
+            inner.bias.copy_(cu(b0))
+    tx = cu(x)
+    y1 = layer(tx)
+    y2 = layer(tx)
+    torch.cuda.synchronize()
+    assert rel_l2(layer.g.detach().cpu().numpy(), ref[p + "g"]) < STRICT_TOL
+    if b0.size:
+        assert rel_l2(inner.bias.detach().cpu().numpy(), ref[p + "bias1"]) < 2e-5
+    assert rel_l2(y1.detach().cpu().numpy(), ref[p + "y1"]) < 2e-5
+    assert rel_l2(y2.detach().cpu().numpy(), ref[p + "y2"]) < 2e-5
+
+
+@pytest.mark.gpu
+def test_cuda_record_decode_matches_reference_reader(F, ref):
+    """sagan_u8_to_f32 on the raw record bytes: the reference reader's float32 images bit for bit."""
+    raw, batch = ref["rec_raw"], int(ref["rec_batch"])
+    keep = raw.shape[0] // batch * batch
+    got = F.decode_records(torch.tensor(raw[:keep]).cuda()).cpu().numpy()
+    assert got.dtype == np.float32
+    assert np.array_equal(got.reshape(-1).view(np.uint32), ref["rec_images"].reshape(-1).view(np.uint32))
