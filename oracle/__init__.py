@@ -13,6 +13,8 @@ op like the reference's TF graph) of the reference algorithm:
   * `oracle.nets`       <- /root/reference/sagan/models/generator.py:7-37,
                            /root/reference/sagan/models/discriminator.py:7-36
   * `oracle.train`      <- /root/reference/sagan/main.py:21-27,111-120,171-229
+  * `oracle.resnets`    <- /root/reference/models/generator.py:6-43, models/discriminator.py:6-57
+  * `oracle.weightnorm` <- /root/reference/sagan/layers.py:6-211, sagan/dataset.py:27-40
 
 PARITY: PINNED TO THE REFERENCE'S OWN CODE FOR THE FORWARD PATH, UNPINNED BELOW IT.
 The reference ships no golden vectors, known-answer tests or published numbers
@@ -29,7 +31,10 @@ l2normalize; SpectralNormalization._make_param / update_uv (u, v, sigma,
 W / sigma over two calls, Keras Dense / Conv2D / Conv2DTranspose kernel layouts,
 Ip 1-3, factor); Attention_Layer.build / call; hinge_loss_d / hinge_loss_g;
 get_generator / get_discriminator (patch head and projection head) layer by
-layer.  `tests/test_reference_vectors.py` holds this oracle to those numbers
+layer; the legacy residual builders models/generator.py, models/discriminator.py
+(attention at C = 8 inside); the weight-normalisation wrapper of sagan/layers.py
+(data-dependent and norm initialisation, two calls); the record reader of
+sagan/dataset.py:12-40 (float32 decode, bit for bit).  `tests/test_reference_vectors.py` holds this oracle to those numbers
 at 1e-12 and the CUDA kernels at the north_star tolerances.
 
 Still unpinned (no reference code to execute, or TF itself needed): TensorFlow's

@@ -4,7 +4,8 @@ The reference ships no golden vectors for this path (its tests assert shapes onl
 not installable here, so these vectors are the oracle's own outputs frozen at commit time: they pin
 the oracle against regressions and let the GPU tests compare against fp64 results without re-running
 the fp64 oracle at size.  Inputs are regenerated from numpy PCG64 seeds (bit-reproducible across
-platforms) by the helpers below, which the tests import too.
+platforms) by the helpers below, which the tests import too.  The oracle itself is held to the reference's own
+code by the OTHER fixture, reference_layers.npz (make_reference_vectors.py).
 
     python tests/golden/make_golden.py            # everything except the 100-step trajectory
     python tests/golden/make_golden.py --traj     # also the 100-step loss trajectory (~minutes of CPU)

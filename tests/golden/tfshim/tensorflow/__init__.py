@@ -1,8 +1,9 @@
 """A numpy-backed stand-in for the handful of `tensorflow` symbols the reference's hot-path files touch.
 
 TEST INFRASTRUCTURE ONLY.  TensorFlow cannot be installed in this environment (no network, not in the wheelhouse),
-so the reference's own Python (`/root/reference/layers.py`, the model builders under `/root/reference/sagan/models/`,
-the loss functions of `/root/reference/sagan/main.py`) cannot run as shipped.  This package lets those files be
+so the reference's own Python (`/root/reference/layers.py`, the model builders under `/root/reference/sagan/models/`
+and `/root/reference/models/`, `/root/reference/sagan/layers.py`, `/root/reference/sagan/dataset.py`, the loss functions
+of `/root/reference/sagan/main.py`) cannot run as shipped.  This package lets those files be
 IMPORTED AND EXECUTED UNMODIFIED by `tests/golden/make_reference_vectors.py`: every line of control flow, every
 reshape, transposition, normalisation and reduction executed is the reference's; only the primitive array operations
 underneath (`tf.matmul`, `tf.norm`, `tf.reshape`, `tf.nn.softmax`, Keras `Conv2D` ...) are supplied here, in float64,
