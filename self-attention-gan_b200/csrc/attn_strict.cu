@@ -566,13 +566,6 @@ attn_bwd_finalize_kernel(const float* __restrict__ Wo, const float* __restrict__
   if (threadIdx.x == 0) *dgamma = acc;
 }
 
-static sagan_conv_geom geom_1x1(long long T, int cin, int cout) {
-  sagan_conv_geom g;
-  g.B = 1; g.H = 1; g.W = (int)T; g.Cin = cin; g.Ho = 1; g.Wo = (int)T; g.Cout = cout;
-  g.kh = 1; g.kw = 1; g.stride = 1; g.pad_t = 0; g.pad_l = 0;
-  return g;
-}
-
 template <int C>
 static int attn_fwd_strict_t(const float* X, const float* Wq, const float* bq, const float* Wk, const float* bk,
                              const float* Wv, const float* bv, const float* Wo, const float* bo, const float* gamma,
