@@ -16,7 +16,8 @@ op like the reference's TF graph) of the reference algorithm:
   * `oracle.resnets`    <- /root/reference/models/generator.py:6-43, models/discriminator.py:6-57
   * `oracle.weightnorm` <- /root/reference/sagan/layers.py:6-211, sagan/dataset.py:27-40
 
-PARITY: PINNED TO THE REFERENCE'S OWN CODE FOR THE FORWARD PATH, UNPINNED BELOW IT.
+PARITY: PINNED TO THE REFERENCE'S OWN CODE FOR THE FORWARD PATH, THE STEP SCHEDULE
+AND THE LOSS SCALING; UNPINNED FOR THE GRADIENTS AND THE OPTIMISER ARITHMETIC.
 The reference ships no golden vectors, known-answer tests or published numbers
 for this path (its tests assert output shapes only, test/test_generator.py:26,
 test/test_discriminator.py:28) and its arithmetic primitives live in an absent,
@@ -34,15 +35,17 @@ get_generator / get_discriminator (patch head and projection head) layer by
 layer; the legacy residual builders models/generator.py, models/discriminator.py
 (attention at C = 8 inside); the weight-normalisation wrapper of sagan/layers.py
 (data-dependent and norm initialisation, two calls); the record reader of
-sagan/dataset.py:12-40 (float32 decode, bit for bit).  `tests/test_reference_vectors.py` holds this oracle to those numbers
+sagan/dataset.py:12-40 (float32 decode, bit for bit); Trainer.train_step /
+distributed_train_step of sagan/main.py:171-236 on stub models (call schedule,
+differentiated scalars, reported losses).  `tests/test_reference_vectors.py` holds this oracle to those numbers
 at 1e-12 and the CUDA kernels at the north_star tolerances.
 
 Still unpinned (no reference code to execute, or TF itself needed): TensorFlow's
 own kernels under those calls (matmul / conv / softmax semantics come from the
 stand-in, per their documentation); the gradients (tf.GradientTape; the oracle's
 analytic gradients are checked against torch autograd and finite differences
-instead); Keras Adam / ExponentialDecay and the step schedule of
-sagan/main.py:111-120,171-229 (main.py does not import as shipped); attention at
+instead); Keras Adam / ExponentialDecay (sagan/main.py:111-120: library code,
+restated from its documentation); attention at
 C > 8 in the literal code (its MaxPool2D(2, 1) + raw reshape is ill-formed, see
 make_reference_vectors.py).  The readings chosen where the literal reference
 code is ill-formed are listed in DESIGN.md ("Oracle readings").

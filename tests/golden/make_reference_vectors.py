@@ -36,6 +36,8 @@ Sections of the fixture
            Conv2DTranspose: g and bias after the data-dependent / norm initialisation, the effective kernel, two calls.
   rec_*    get_dataset_from_tfrecord of sagan/dataset.py:12-40: the uint8 record decode in float32 (bit-exact contract),
            labels, batching with drop_remainder.
+  step_*   Trainer.train_step / distributed_train_step of sagan/main.py:171-236 on stub models: the call schedule, the
+           scalars that are differentiated, the reported losses (no gradients: the tape only records).
   rgen_* / rdis_*  the legacy residual builders models/generator.py:23-43, models/discriminator.py:40-57 the same way,
            at widths where their Attention_Layer sees C = 8, so attention stays IN (identity pool).
 """
@@ -455,6 +457,96 @@ def section_records(tf, out):
     out["rec_batch"] = np.int64(batch)
 
 
+def section_train_step(tf, out):
+    """Trainer.train_step and Trainer.distributed_train_step of sagan/main.py:171-236, the two method definitions
+    compiled from the file (the module does not import, appendix A.7) and run on a stand-in `self`: stub generator /
+    discriminator that log their calls and return fixed logits, a GradientTape that records what is differentiated, stub
+    optimisers, a one-replica strategy.  Pins (a) the schedule -- which model is called on what, in which order, with
+    which `training` flag, inside or outside the tape, when each optimiser is applied; (b) the scalar handed to
+    tape.gradient, mean(L) / global_batch_size; (c) the returned per-example losses and the reported means of
+    :216-229.  update_ratio = 2 so that the accumulation of :186,192 shows."""
+    import types
+    src = open(os.path.join(REF, "sagan", "main.py")).read()
+    cls = [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "Trainer"][0]
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("train_step", "distributed_train_step")]
+    assert len(fns) == 2
+    hinge = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("hinge_loss_g", "hinge_loss_d")]
+    ns = {"tf": tf}
+    exec(compile(ast.Module(body=hinge + fns, type_ignores=[]), os.path.join(REF, "sagan", "main.py"), "exec"), ns)
+
+    B, ur, gbs = 4, 2, 8                     # per-replica batch 4, global batch 8 (two replicas' worth), update_ratio 2
+    r = rng_of(77)
+    d_real = [r.standard_normal((B, 4, 4, 1)) * 2 for _ in range(ur)]
+    d_fake = [r.standard_normal((B, 4, 4, 1)) * 2 for _ in range(ur + 1)]       # ur D-phase fakes + the G-phase one
+    log = tf.GradientTape.log
+    log.clear()
+    counters = {"G": 0, "Dreal": 0, "Dfake": 0}
+
+    class Var:
+        def __init__(self, name):
+            self.name = name
+
+    class Gen:
+        trainable_variables = [Var("G/w0"), Var("G/w1")]
+        variables = []
+
+        def __call__(self, inputs, training=None):
+            noise, labels = inputs
+            counters["G"] += 1
+            log.append(("G", tuple(noise.shape), training, "in_tape" if tf.GradientTape.depth else "outside_tape"))
+            t = tf.Tensor(np.full((noise.shape[0], 2, 2, 3), float(counters["G"])))
+            t.is_fake = True
+            return t
+
+    class Dis:
+        trainable_variables = [Var("D/w0")]
+
+        def __call__(self, inputs, training=None):
+            images, labels = inputs
+            fake = getattr(images, "is_fake", False)
+            k = "Dfake" if fake else "Dreal"
+            log.append(("D", "fake" if fake else "real", training, "in_tape" if tf.GradientTape.depth else "outside_tape"))
+            val = (d_fake if fake else d_real)[counters[k]]
+            counters[k] += 1
+            return tf.Tensor(val)
+
+    class Opt:
+        def __init__(self, name):
+            self.name = name
+
+        def apply_gradients(self, grads_and_vars):
+            log.append(("apply", self.name, tuple(v.name for _, v in grads_and_vars)))
+
+    class Strategy:
+        def experimental_run_v2(self, fn, args=()):
+            return fn(*args)
+
+        def reduce(self, op, value, axis=None):
+            assert op == tf.distribute.ReduceOp.SUM
+            if isinstance(value, tuple):                     # a gradient token (main.py:222-226 reduces every G gradient)
+                return value
+            return tf.reduce_sum(value, axis=axis) if axis is not None else value
+
+    reported = {}
+    me = types.SimpleNamespace(
+        config={"update_ratio": ur, "z_dim": 16, "num_classes": 1, "global_batch_size": gbs},
+        generator=Gen(), discriminator=Dis(), optimizer_D=Opt("D"), optimizer_G=Opt("G"),
+        dloss_fn=ns["hinge_loss_d"], gloss_fn=ns["hinge_loss_g"], strategy=Strategy(),
+        metrics={"G_loss": lambda v: reported.__setitem__("G_loss", float(np.mean(v.numpy()))),
+                 "D_loss": lambda v: reported.__setitem__("D_loss", float(np.mean(v.numpy())))})
+    me.train_step = lambda inputs: ns["train_step"](me, inputs)
+    tf.random.set_seed(5)
+    images = tf.Tensor(r.uniform(-1, 1, (B, 8, 8, 3)))
+    labels = tf.Tensor(np.zeros((B,), dtype=np.int32))
+    mean_loss = ns["distributed_train_step"](me, (images, labels))
+    out["step_d_real"], out["step_d_fake"] = np.stack(d_real), np.stack(d_fake)
+    out["step_cfg"] = np.asarray([B, ur, gbs], dtype=np.int64)
+    out["step_log"] = np.asarray([repr(e) for e in log])
+    out["step_grad_scalars"] = np.asarray([e[1] for e in log if e[0] == "gradient"])
+    out["step_mean_D"], out["step_mean_G"] = mean_loss["D_loss"].numpy(), mean_loss["G_loss"].numpy()
+    out["step_reported"] = np.asarray([reported["D_loss"], reported["G_loss"]])
+
+
 def main():
     tf, ref = _import_reference()
     out = {}
@@ -466,6 +558,7 @@ def main():
     section_res_builders(tf, ref, out)
     section_weightnorm(tf, out)
     section_records(tf, out)
+    section_train_step(tf, out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "(%d arrays, %.0f kB)" % (len(out), os.path.getsize(OUT) / 1e3))
 

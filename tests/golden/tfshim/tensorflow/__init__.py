@@ -144,3 +144,34 @@ class CriticalSection:
 
 class VariableSynchronization:
     AUTO = "auto"
+
+
+def constant(value, dtype=None):
+    return Tensor(_np.asarray(value, dtype=_np.float64 if dtype in (None, "float32", "float64") else dtype))
+
+
+class distribute:
+    class ReduceOp:
+        SUM = "sum"
+
+
+class GradientTape:
+    """No automatic differentiation here: the tape records WHAT the reference asks to differentiate (the target scalar,
+    the variable list) and which model calls happened while it was open; `gradient` hands back one opaque token per
+    variable.  Used to pin the step schedule and the loss scaling of sagan/main.py:171-211, not the gradients."""
+    log = []            # shared event log, reset by the fixture script
+    depth = 0
+
+    def __enter__(self):
+        GradientTape.depth += 1
+        GradientTape.log.append(("tape_open",))
+        return self
+
+    def __exit__(self, *exc):
+        GradientTape.depth -= 1
+        GradientTape.log.append(("tape_close",))
+        return False
+
+    def gradient(self, target, sources):
+        GradientTape.log.append(("gradient", float(_a(target)), tuple(getattr(v, "name", "?") for v in sources)))
+        return [("grad", getattr(v, "name", "?")) for v in sources]

@@ -369,6 +369,63 @@ def test_oracle_record_decode_matches_reference_reader(ref):
     assert set(np.unique(raw)) == set(range(256))                                  # every byte value is covered
 
 
+def test_reference_train_step_schedule_and_loss_scaling(ref):
+    """Trainer.train_step / distributed_train_step (sagan/main.py:171-236) run by the reference on stub models, with
+    update_ratio = 2: the schedule our trainers follow, the scalar that is differentiated, the reported losses."""
+    B, ur, gbs = (int(v) for v in ref["step_cfg"])
+    d_phase = ["('G', (4, 16), True, 'outside_tape')",        # :178 fakes for D are generated OUTSIDE the tape, training=True
+               "('tape_open',)",
+               "('D', 'real', True, 'in_tape')",              # :181
+               "('D', 'fake', True, 'in_tape')",              # :182
+               "('tape_close',)",
+               None,                                          # :188 gradient of mean(L) / global_batch wrt D's variables
+               "('apply', 'D', ('D/w0',))"]                   # :190 one Adam step per D iteration
+    g_phase = ["('tape_open',)",
+               "('G', (4, 16), True, 'in_tape')",             # :198
+               "('D', 'fake', True, 'in_tape')",              # :199 D in training mode (its u advances), updated D weights
+               "('tape_close',)",
+               None,                                          # :203
+               "('apply', 'G', ('G/w0', 'G/w1'))"]            # :205
+    want = d_phase * ur + g_phase
+    got = list(ref["step_log"])
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert (g.startswith("('gradient',") if w is None else g == w), (g, w)
+    r, f = torch.tensor(ref["step_d_real"]), torch.tensor(ref["step_d_fake"])
+    scal = [float(otrain.hinge_loss_d(r[i], f[i]).mean() / gbs) for i in range(ur)] + [float(otrain.hinge_loss_g(f[ur]).mean() / gbs)]
+    assert np.allclose(ref["step_grad_scalars"], scal, rtol=1e-13, atol=0)       # :184,201
+    # reported losses (:186,192,216-229): D accumulated over update_ratio and averaged, summed over the batch, divided by
+    # the GLOBAL batch, then the Keras Mean over the remaining [4,4,1]
+    accu = sum(otrain.hinge_loss_d(r[i], f[i]) for i in range(ur)) / ur
+    assert rel_l2((accu.sum(0) / gbs).numpy(), ref["step_mean_D"]) < FP64_TOL
+    assert rel_l2((otrain.hinge_loss_g(f[ur]).sum(0) / gbs).numpy(), ref["step_mean_G"]) < FP64_TOL
+    assert np.allclose(ref["step_reported"], [ref["step_mean_D"].mean(), ref["step_mean_G"].mean()], rtol=1e-13)
+
+
+def test_oracle_train_step_reports_what_the_reference_reports(ref):
+    """oracle.train.OracleTrainer.train_step with its gradient evaluations replaced by the fixture's logits: the same
+    accumulation over update_ratio and the same reported D / G losses as the reference's distributed_train_step."""
+    B, ur, gbs = (int(v) for v in ref["step_cfg"])
+    cfg = dict(z_dim=8, gf_dim=4, df_dim=4, img_size=64, use_attention=False, attn_dim_G=[], use_label=False, batch_size=B,
+               lr_g=2e-4, lr_d=7e-4, decay_rate=0.99, update_ratio=ur)
+    orc = otrain.OracleTrainer(cfg, torch.float64, global_batch_size=gbs)
+    r, f = torch.tensor(ref["step_d_real"]), torch.tensor(ref["step_d_fake"])
+    calls = {"d": 0, "applied": []}
+
+    def d_grads(images, noise, labels=None, fake_labels=None):
+        i = calls["d"]
+        calls["d"] += 1
+        return {}, otrain.hinge_loss_d(r[i], f[i])
+
+    orc.d_grads = d_grads
+    orc.g_grads = lambda noise, fake_labels=None: ({}, otrain.hinge_loss_g(f[ur]))
+    orc.opt_D.apply_gradients = lambda params, grads: calls["applied"].append("D")
+    orc.opt_G.apply_gradients = lambda params, grads: calls["applied"].append("G")
+    rep = orc.train_step(None, [None] * ur, None)
+    assert calls["applied"] == ["D"] * ur + ["G"]
+    assert abs(rep["D_loss"] - ref["step_reported"][0]) < 1e-13 and abs(rep["G_loss"] - ref["step_reported"][1]) < 1e-13
+
+
 # ------------------------------------------------------------------------------------------------- CUDA == reference
 def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
