@@ -38,6 +38,7 @@ Sections of the fixture
            labels, batching with drop_remainder.
   step_*   Trainer.train_step / distributed_train_step of sagan/main.py:171-236 on stub models: the call schedule, the
            scalars that are differentiated, the reported losses (no gradients: the tape only records).
+  config_* the shipped example_configs/*.py dicts as JSON.
   rgen_* / rdis_*  the legacy residual builders models/generator.py:23-43, models/discriminator.py:40-57 the same way,
            at widths where their Attention_Layer sees C = 8, so attention stays IN (identity pool).
 """
@@ -547,6 +548,18 @@ def section_train_step(tf, out):
     out["step_reported"] = np.asarray([reported["D_loss"], reported["G_loss"]])
 
 
+def section_configs(out):
+    """The reference's shipped configuration dicts (example_configs/*.py, what sagan/main.py:352-355 loads), evaluated and
+    stored as JSON: the key set and the values our Trainer has to accept unchanged."""
+    import json
+    import runpy
+    names = sorted(f for f in os.listdir(os.path.join(REF, "example_configs")) if f.endswith(".py"))
+    for f in names:
+        ns = runpy.run_path(os.path.join(REF, "example_configs", f))
+        out["config_" + f[:-3]] = np.asarray(json.dumps(ns["config"], sort_keys=True))
+    out["config_names"] = np.asarray([f[:-3] for f in names])
+
+
 def main():
     tf, ref = _import_reference()
     out = {}
@@ -559,6 +572,7 @@ def main():
     section_weightnorm(tf, out)
     section_records(tf, out)
     section_train_step(tf, out)
+    section_configs(out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "(%d arrays, %.0f kB)" % (len(out), os.path.getsize(OUT) / 1e3))
 

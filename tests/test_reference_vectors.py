@@ -426,6 +426,37 @@ def test_oracle_train_step_reports_what_the_reference_reports(ref):
     assert abs(rep["D_loss"] - ref["step_reported"][0]) < 1e-13 and abs(rep["G_loss"] - ref["step_reported"][1]) < 1e-13
 
 
+# keys of the reference's config dicts that belong to its data pipeline, logging and checkpointing (SURVEY.md section 2:
+# out of scope), i.e. that the layer / train-step path never reads
+CONFIG_KEYS_OUTSIDE_THE_PATH = {"_description", "gpu", "dataset", "data_path", "data_size", "use_image_generator", "epoch",
+                                "num_sample", "summary_step_freq", "log_dir", "ckpt_dir", "img_dir", "loss"}
+
+
+def test_reference_example_configs_are_consumed_unchanged(ref):
+    """example_configs/*.py as shipped: every key is either read by the product's Trainer / model builders or belongs to
+    the reference's IO side; the model keys give the reference's topology (1 227 638 G / 175 438 D parameters at the
+    church64 widths; discriminator.py:23 reads attn_dim_G, so attn_dim_D is accepted and ignored)."""
+    import json
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "self-attention-gan_b200", "sagan_b200")
+    src = "".join(open(os.path.join(pkg, f)).read() for f in ("trainer.py", "nets.py"))
+    read = set(re.findall(r"""(?:cfg|config)(?:\.get\(|\[)["']([A-Za-z_]+)["']""", src))
+    assert list(ref["config_names"]) == ["church64_attn", "test"]
+    for name in ref["config_names"]:
+        cfg = json.loads(str(ref["config_" + name]))
+        unknown = set(cfg) - read - CONFIG_KEYS_OUTSIDE_THE_PATH - {"attn_dim_D"}
+        assert not unknown, (name, unknown)
+        assert cfg["loss"] == "hinge_loss" and cfg["model"] == "vanilla"          # the path that is built
+        for k in ("z_dim", "gf_dim", "df_dim", "use_attention", "attn_dim_G", "use_label", "batch_size", "lr_g", "lr_d",
+                  "decay_rate", "update_ratio", "model"):
+            assert k in read, k
+        cfg.setdefault("img_size", 64)                                            # sagan/main.py derives it from the dataset
+        n_g = sum(int(np.prod(sh)) for _, sh in onets.generator_spec(cfg))
+        n_d = sum(int(np.prod(sh)) for _, sh in onets.discriminator_spec(cfg))
+        if (cfg["gf_dim"], cfg["df_dim"], cfg["z_dim"], cfg["use_attention"]) == (16, 16, 128, True):
+            assert (n_g, n_d) == (1227638, 175438)
+
+
 # ------------------------------------------------------------------------------------------------- CUDA == reference
 def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
