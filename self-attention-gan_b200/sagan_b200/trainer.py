@@ -73,6 +73,9 @@ class Trainer:
         peer-memory exchange + Adam kernel (parallel.PeerAdam), "nccl" = NCCL all-reduce followed by Adam."""
         self.config = dict(config)
         cfg = self.config
+        if cfg.get("loss") == "cross_entropy":               # main.py:122-125 swaps in the cross-entropy pair
+            raise ValueError("config['loss'] = 'cross_entropy': only the hinge losses (sagan/main.py:21-27, what every "
+                             "shipped config uses) are built")
         self.B = cfg["batch_size"]
         self.dp = ReplicaGradientSum(process_group)
         self.world = self.dp.world

@@ -429,7 +429,7 @@ def test_oracle_train_step_reports_what_the_reference_reports(ref):
 # keys of the reference's config dicts that belong to its data pipeline, logging and checkpointing (SURVEY.md section 2:
 # out of scope), i.e. that the layer / train-step path never reads
 CONFIG_KEYS_OUTSIDE_THE_PATH = {"_description", "gpu", "dataset", "data_path", "data_size", "use_image_generator", "epoch",
-                                "num_sample", "summary_step_freq", "log_dir", "ckpt_dir", "img_dir", "loss"}
+                                "num_sample", "summary_step_freq", "log_dir", "ckpt_dir", "img_dir"}
 
 
 def test_reference_example_configs_are_consumed_unchanged(ref):
