@@ -76,6 +76,15 @@ def test_product_has_no_cpu_fallback_and_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+                assert "tfshim" not in src and "import tensorflow" not in src, f      # the stand-in is fixture tooling
+    # ... and the stand-in for tensorflow is reachable from the fixture script alone: bench, smoke and the tests read
+    # the .npz it wrote, never the package
+    for f in ["bench.py", "__graft_entry__.py"] + [os.path.join("tests", t) for t in os.listdir(os.path.join(ROOT, "tests"))
+                                                  if t.endswith(".py")]:
+        src = open(os.path.join(ROOT, f)).read()
+        if f.endswith("test_cabi.py"):
+            continue
+        assert "tfshim" not in src and "import tensorflow" not in src, f
     if not torch.cuda.is_available():
         with pytest.raises(Exception, match="no CPU fallback|CUDA"):
             layers.Dense(4)(torch.zeros(2, 3))
